@@ -1,0 +1,101 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings of the reference engines built into ``oracle/_ref``.
+
+``oracle/_ref/libssba_ref.so`` and ``libpba_ref.so`` are the UNMODIFIED SSBA-3.0 / PBA sources of
+``/root/reference`` compiled by ``oracle/Makefile`` together with the small harnesses
+``oracle/ssba_ref_harness.cpp`` / ``oracle/pba_ref_harness.cpp`` that replay SequenceSFM's own marshalling
+(``src/sfm_ba_ssba.cpp:85-233``, ``src/sfm_ba_pba.cpp:56-166``).  Only ``tests/``, the golden generator,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, "_ref")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def have_ssba() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libssba_ref.so"))
+
+
+def have_pba() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libpba_ref.so"))
+
+
+@dataclass
+class SsbaResult:
+    ret: int                 # what adjustBundle_ssba returns: 0 good / -1 discarded
+    status: int              # 0 TIMEOUT, 1 SMALL_UPDATE, 2 CONVERGED (Math/v3d_optimization.h:16-21)
+    iterations: int
+    trace: np.ndarray        # rows {iter, err, lambda, new_err, rho, accepted}
+    mean_px: tuple[float, float]
+    seconds: float
+    cam_RT: np.ndarray
+    pts: np.ndarray
+
+
+def ssba_adjust(p, *, round_pixels: bool = True, max_iterations: int = 50, trace: bool = True) -> SsbaResult:
+    lib = C.CDLL(os.path.join(REF_DIR, "libssba_ref.so"))
+    cam = np.ascontiguousarray(p.cam_RT, dtype=np.float64).copy()
+    pts = np.ascontiguousarray(p.pts, dtype=np.float64).copy()
+    K5 = np.ascontiguousarray(p.K5, dtype=np.float64)
+    xy = np.ascontiguousarray(p.obs_xy, dtype=np.float64)
+    oc = np.ascontiguousarray(p.obs_cam, dtype=np.int32)
+    op = np.ascontiguousarray(p.obs_pt, dtype=np.int32)
+    cap = max(4, max_iterations + 2)
+    tr = np.full((cap, 6), np.nan)
+    ntr = C.c_int(0); st = C.c_int(0); it = C.c_int(0); secs = C.c_double(0)
+    mean = np.zeros(2)
+    lib.ssba_ref_adjust.restype = C.c_int
+    ret = lib.ssba_ref_adjust(C.c_int(p.N), C.c_int(p.M), C.c_int(p.K), _d(K5), _d(cam), _d(pts), _d(xy), _i(oc), _i(op),
+                              C.c_int(int(round_pixels)), C.c_int(max_iterations),
+                              _d(tr) if trace else None, C.c_int(cap), C.byref(ntr),
+                              C.byref(st), C.byref(it), _d(mean), C.byref(secs))
+    return SsbaResult(ret, st.value, it.value, tr[: ntr.value].copy(), (float(mean[0]), float(mean[1])),
+                      secs.value, cam, pts)
+
+
+@dataclass
+class PbaResult:
+    initial_mse: float
+    final_mse: float
+    lm_iterations: int
+    cg_iterations: int
+    seconds: float
+    return_code: str
+    successful: int
+    cam_RT: np.ndarray
+    pts: np.ndarray
+
+
+def pba_adjust(p, *, double: bool = True, args: tuple[str, ...] = (), threads: int = 0) -> PbaResult:
+    lib = C.CDLL(os.path.join(REF_DIR, "libpba_ref.so"))
+    cam = np.ascontiguousarray(p.cam_RT, dtype=np.float64).copy()
+    pts = np.ascontiguousarray(p.pts, dtype=np.float64).copy()
+    K5 = np.ascontiguousarray(p.K5, dtype=np.float64)
+    xy = np.ascontiguousarray(p.obs_xy, dtype=np.float64)
+    oc = np.ascontiguousarray(p.obs_cam, dtype=np.int32)
+    op = np.ascontiguousarray(p.obs_pt, dtype=np.int32)
+    argv = (C.c_char_p * max(1, len(args)))(*[a.encode() for a in args])
+    stats = np.zeros(8)
+    lib.pba_ref_adjust.restype = C.c_int
+    lib.pba_ref_adjust(C.c_int(p.N), C.c_int(p.M), C.c_int(p.K), _d(K5), None, _d(cam), _d(pts), _d(xy), _i(oc), _i(op),
+                       C.c_int(-3 if double else -2), C.c_int(len(args)), argv, C.c_int(threads), _d(stats))
+    code = int(stats[5])
+    return PbaResult(float(stats[0]), float(stats[1]), int(stats[2]), int(stats[3]), float(stats[4]),
+                     chr(code) if code > 0 else "", int(stats[6]), cam, pts)
