@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s and observations/s of the bundle-adjustment hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--shape venice] [--impl ours|reference]
+
+A *step* is one full Levenberg-Marquardt iteration of the SSBA-personality BA on a synthetic BAL-shaped problem:
+linearisation (residuals, Huber weights, Jacobian blocks, U/V/g), Schur-diagonal preconditioner, 50-step PCG on the
+reduced camera system, back-substitution, cost re-evaluation at the trial point and the on-device accept/reject +
+damping update.  N = 1 runs the Venice shape (1778 cameras / 993 923 points / 5 001 946 observations, the
+configuration BASELINE.json's metric is quoted on); N > 1 partitions the same problem by point (strong scaling), one
+process per GPU under torchrun, NCCL all-reduce of camera-sized buffers only.
+
+value      = LM iterations/s with the problem resident in HBM (timed: b200ba_iterate only; CUDA events, max over ranks)
+e2e        = the same metric through the public entry (host arrays -> b200ba_set_problem -> b200ba_solve(K) ->
+             b200ba_get_result), host<->device copies inside the timed region
+roofline   = algorithmic bytes of one LM iteration (SURVEY.md section 8d model) / measured time, against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json
+cpu_baseline / --impl reference = the reference's own CPU engine (PBA multicore, oracle/_ref/libpba_ref.so; SSBA's
+             sparse LDL cannot factor a Venice-sized system) timed on this box's host cores on the same problem.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CG_STEPS = 50
+
+
+def algorithmic_bytes(N: int, M: int, K: int, T: int = CG_STEPS, s: int = 8) -> dict:
+    """SURVEY.md section 8(d) byte model (fp64, Jacobians recomputed, T CG steps)."""
+    b_lin = K * (8 + 2 * s) + M * 3 * s + M * 9 * s + N * 42 * s
+    b_cg = K * (16 + 4 * s) + M * 12 * s
+    b_back = K * 8 + M * 15 * s
+    b_cost = K * (8 + 2 * s) + M * 3 * s
+    b_upd = M * 6 * s
+    return {"lin": b_lin, "cg_step": b_cg, "back": b_back, "cost": b_cost, "upd": b_upd,
+            "iteration": b_lin + T * b_cg + b_back + b_cost + b_upd}
+
+
+def measured_peak() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.samples: list[tuple[float, float, str]] = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                sm, mx = float(out[0]), float(out[1])
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                rs = [n for n, v in zip(names, out[2:6]) if "Active" in v and "Not" not in v]
+                self.samples.append((sm, mx, ",".join(rs)))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[2].split(",") if r})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_reference(args, world: int, rank: int) -> int:
+    """--impl reference: the reference's own multicore CPU BA (PBA, unmodified, oracle/_ref) on the same problem."""
+    if rank != 0:
+        return 0
+    from oracle import refs
+    from sequencesfm_b200.synth import make_problem, SHAPES
+    if not refs.have_pba():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpba_ref.so not built"}))
+        return 0
+    p = make_problem(args.shape, args.seed)
+    cores = os.cpu_count() or 1
+    lmi = max(1, args.ref_lm_iterations)
+    times = []
+    its = 0
+    for s in range(args.warmup_ref + args.steps_ref):
+        t0 = time.perf_counter()
+        q = refs.pba_adjust(p, double=True, args=("-schur", "-lmi", str(lmi), "-v", "0"), threads=0)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup_ref:
+            times.append(q.seconds if q.seconds > 0 else dt)
+            its += q.lm_iterations
+    total = float(sum(times))
+    value = its / total if total > 0 else 0.0
+    sample = f"PBA --double -schur -lmi {lmi} x{args.steps_ref} runs on {args.shape} ({p.N}/{p.M}/{p.K}), PBA's own optimisation timer, {its} LM iterations"
+    line = {"impl": "reference", "metric": "lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value if value else None, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.shape} shape {p.N} cameras / {p.M} points / {p.K} observations, seed {args.seed}",
+                       "engine": "PBA multicore CPU (reference Thirdparty/pba, -DPBA_NO_GPU), fp64 arrays, implicit Schur PCG"},
+            "observations_per_s": value * p.K,
+            "cpu_baseline": {"value": value, "unit": "LM iterations/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--shape", default="venice")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-lm-iterations", type=int, default=3)
+    ap.add_argument("--steps-ref", type=int, default=1)
+    ap.add_argument("--warmup-ref", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, world, rank)
+
+    import torch
+    import torch.distributed as dist
+    from sequencesfm_b200 import binding
+    from sequencesfm_b200.synth import make_problem, partition_points
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, K_steps = max(3, args.warmup), max(1, args.steps)
+    full = make_problem(args.shape, args.seed)
+    N, M, K = full.N, full.M, full.K
+    if world > 1:
+        j0, j1 = partition_points(full.obs_pt, M, world)[rank]
+        prob = full.slice_points(j0, j1)
+    else:
+        prob = full
+
+    # every step must be a full LM iteration: no early stop inside the timed region
+    opt = binding.default_options(device=local_rank, max_iterations=W + K_steps, min_iterations=10 ** 6,
+                                  gradient_threshold=0.0, cg_max_steps=CG_STEPS, cg_rel_tol=0.0, poll_every=W + K_steps)
+    eng = binding.Engine(opt)
+    if world > 1:
+        idt = torch.zeros(binding.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(binding.Engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    eng.set_problem_from(prob)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel-resident measurement: `value` ----------------
+    eng.begin()
+    eng.iterate(W)                       # warm-up LM iterations (also warms instruction caches / NCCL)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        eng.iterate(K_steps)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = eng.last_iterate_ms()          # CUDA events on the engine's stream around the K timed iterations
+    res = eng.finish()
+    trace = res.trace
+    accepted = int(np.sum(trace[W:W + K_steps, 5] == 1)) if len(trace) >= W + K_steps else int(np.sum(trace[:, 5] == 1))
+    launches_per_iter = res.gpu_launches / max(1, res.iterations)
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    ms_per_step = dev_ms / K_steps
+    value = 1e3 / ms_per_step
+
+    # ---------------- per-kernel timings for the roofline (rank 0, single GPU semantics) ----------------
+    peak, peak_src = measured_peak()
+    ab = algorithmic_bytes(N, M, K)
+    roof = None
+    if True:
+        eng.begin(); eng.iterate(1)
+        names = eng.kernel_names()
+        kt = {n: eng.time_kernel(i, 20) for i, n in enumerate(names)}
+        Kl, Ml = prob.K, prob.M
+        abl = algorithmic_bytes(N, Ml, Kl)
+        cg_ms = kt["cg_point_pass"] + kt["cg_camera_pass"] + kt["camera_reduce6"] + kt["cg_update"]
+        achieved = abl["cg_step"] / (cg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "one PCG step = cg_point_pass + cg_camera_pass (+camera_reduce6, cg_update)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": abl["cg_step"], "ms_per_launch": cg_ms,
+                "share_of_step": CG_STEPS * cg_ms / ms_per_step,
+                "iteration": {"algorithmic_bytes": abl["iteration"], "achieved": abl["iteration"] / (ms_per_step * 1e-3) / 1e9,
+                              "frac": abl["iteration"] / (ms_per_step * 1e-3) / 1e9 / peak},
+                "kernels_ms": kt}
+        eng.finish()
+
+    # ---------------- end-to-end through the public entry: `e2e` ----------------
+    e2e_steps = K_steps
+    opt2 = binding.default_options(device=local_rank, max_iterations=e2e_steps, min_iterations=10 ** 6, gradient_threshold=0.0,
+                                   cg_max_steps=CG_STEPS, cg_rel_tol=0.0, poll_every=e2e_steps, discard_converged=0)
+    eng2 = binding.Engine(opt2)
+    if world > 1:
+        idt = torch.zeros(binding.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(binding.Engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng2.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    barrier()
+    t0 = time.perf_counter()
+    eng2.set_problem_from(prob)
+    r2 = eng2.solve()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    h2d = prob.K * (16 + 16 + 4 + 4) + prob.M * 32 * 2 + N * 96 * 2
+    d2h = prob.M * 32 + N * 96
+    e2e = {"value": r2.iterations / e2e_s, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d / e2e_steps,
+           "d2h_bytes_per_step": d2h / e2e_steps, "seconds_total": e2e_s, "lm_iterations": r2.iterations,
+           "note": "host arrays -> b200ba_set_problem (marshal, sort, upload) -> b200ba_solve -> b200ba_get_result; bytes amortised over the solve's LM iterations"}
+    eng2.close()
+
+    # ---------------- CPU baseline (rank 0, N = 1 only, bounded sample) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refs
+            if refs.have_pba():
+                lmi = 2
+                q = refs.pba_adjust(full, double=True, args=("-schur", "-lmi", str(lmi), "-v", "0"))
+                v = q.lm_iterations / q.seconds if q.seconds > 0 else 0.0
+                cpu = {"value": v, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "reference",
+                       "sample": f"PBA multicore CPU --double -schur -lmi {lmi} on the same {args.shape} problem: {q.lm_iterations} LM iterations, "
+                                 f"{q.cg_iterations} CG steps in {q.seconds:.2f} s (PBA's own optimisation timer)"}
+            else:
+                from oracle import oracle as orc
+                t0 = time.perf_counter()
+                o = orc.solve(full, max_iterations=1)
+                dt = time.perf_counter() - t0
+                cpu = {"value": 1.0 / dt, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+                       "sample": f"oracle/ba_oracle.c, 1 LM iteration (50 PCG steps) on {args.shape}"}
+        except Exception as ex:  # pragma: no cover
+            cpu = {"value": None, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": "lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": K_steps,
+                "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.shape} shape: {N} cameras / {M} points / {K} observations, seed {args.seed}; "
+                                       f"one step = full LM iteration (linearise + Schur-Jacobi preconditioner + {CG_STEPS}-step PCG + "
+                                       f"back-substitution + trial cost + accept/reject)",
+                           "partition": f"by point over {world} rank(s)", "l2": "inputs larger than L2 (per-step working set >= 260 MB vs 126 MB L2)",
+                           "accepted_steps": accepted},
+                "observations_per_s": value * K, "cg_steps_per_s": value * CG_STEPS,
+                "wall_ms_per_step": wall_ms / K_steps,
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_iter * K_steps)),
+                "roofline": roof, "cpu_baseline": cpu,
+                "final_mean_px": res.mean_px[1], "initial_mean_px": res.mean_px[0]}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

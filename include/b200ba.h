@@ -1,0 +1,145 @@
+/* b200ba.h -- C ABI of the B200-native sparse bundle-adjustment engine (libb200ba.so).
+ *
+ * This is the drop-in boundary for SequenceSFM's BA entry point.  The reference interface it replaces
+ * (paths relative to the reference tree):
+ *
+ *   int adjustBundle_ssba(vector<CloudPoint>&, Mat& K, map<int,vector<KeyPoint>>&, map<int,Matx34d>&)   src/sfm_ba.h:29-32
+ *   int adjustBundle_pba (vector<CloudPoint>&, Mat& K, Mat& dist, map<...>&, map<...>&)                 src/sfm_ba.h:39-43
+ *
+ * whose bodies (src/sfm_ba_ssba.cpp:66-286, src/sfm_ba_pba.cpp:33-174) marshal the tracker state into flat
+ * arrays and hand them to SSBA-3.0 (`CommonInternalsMetricBundleOptimizer(...).minimize()`,
+ * Thirdparty/SSBA-3.0/Geometry/v3d_metricbundle.h:150-238) or PBA (`ParallelBA::SetCameraData / SetPointData /
+ * SetProjection / RunBundleAdjustment`, Thirdparty/pba/pba/pba.h:103-108).  The functions below take the same
+ * flat arrays.  adapter/sfm_ba_b200.cpp is the replacement body of the two C++ functions on top of this ABI;
+ * INTEGRATION.md shows the build change.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative B200BA_E_* code and
+ * never throws; host buffers are caller-owned and copied; one handle owns one CUDA device (and optionally one NCCL
+ * rank); a handle is not re-entrant, distinct handles are independent.  There is NO CPU fallback: when no CUDA
+ * device is usable b200ba_create fails with B200BA_E_CUDA.
+ */
+#ifndef B200BA_H
+#define B200BA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BA_VERSION 1
+
+enum {
+    B200BA_OK             =  0,
+    B200BA_E_INVALID      = -1,   /* bad argument / problem (indices out of range, obs_pt decreasing, ...) */
+    B200BA_E_CUDA         = -2,   /* CUDA runtime error, no device, out of memory */
+    B200BA_E_STATE        = -3,   /* call order violated (e.g. solve before set_problem) */
+    B200BA_E_COMM         = -4    /* NCCL unavailable or failed */
+};
+
+/* LM exit status, same numbering as SSBA (Thirdparty/SSBA-3.0/Math/v3d_optimization.h:16-21). */
+enum {
+    B200BA_STATUS_TIMEOUT      = 0,   /* max_iterations reached                          */
+    B200BA_STATUS_SMALL_UPDATE = 1,   /* |delta| < 1e-8 (|params| + 1e-8) after >= min_iterations */
+    B200BA_STATUS_CONVERGED    = 2    /* |J^t e|_inf < gradient_threshold                */
+};
+
+typedef struct b200ba_options {
+    int32_t struct_size;        /* = sizeof(b200ba_options); set by b200ba_default_options            */
+    int32_t device;             /* CUDA device ordinal; -1 = current device                               */
+    /* --- LM control, defaults = what src/sfm_ba_ssba.cpp:193-217 hard-codes --- */
+    int32_t max_iterations;     /* 50                                                                     */
+    int32_t min_iterations;     /* 10   (v3d_optimization.h:28)                                           */
+    double  tau;                /* 1e-3 lambda0 = tau * max diag(J^t J)                                   */
+    double  inlier_px;          /* 2.0  Huber threshold in pixels; <= 0 disables the robustifier          */
+    double  gradient_threshold; /* 1e-8                                                                   */
+    double  update_threshold;   /* 1e-8                                                                   */
+    int32_t round_pixels;       /* 1: measurements rounded to whole pixels like `Point cvp = Point2f`     */
+                                /*    (src/sfm_ba_ssba.cpp:171); 0: keep sub-pixel (src/sfm_ba_pba.cpp:122) */
+    int32_t normalize;          /* 1: ScopedBundleExtrinsicNormalizer (v3d_metricbundle.h:327-375)        */
+    int32_t fix_first_camera;   /* 0 (SSBA: all free); 1 = PBA's SetConstantCamera on camera 0            */
+    int32_t discard_converged;  /* 1: replicate `good_adjustment = (status != 2)` (src/sfm_ba_ssba.cpp:221) */
+    /* --- linear solver: block-Jacobi PCG on the reduced camera system --- */
+    int32_t cg_max_steps;       /* 50                                                                     */
+    double  cg_rel_tol;         /* 0: always run cg_max_steps; > 0: stop when sqrt(r.z / r0.z0) < tol     */
+    int32_t precond;            /* 1: diagonal blocks of S; 0: (U + lambda I)^-1 like PBA                 */
+    /* --- host interaction --- */
+    int32_t poll_every;         /* copy the device status word back every n LM iterations (default 5)     */
+    int32_t reserved[7];
+} b200ba_options;
+
+#define B200BA_TRACE_COLS 8     /* iter, err, lambda, new_err, rho, accepted(1/0/-1), cg_steps, cg_rel_residual */
+
+typedef struct b200ba_report {
+    int32_t status;             /* B200BA_STATUS_*                                                        */
+    int32_t iterations;         /* LM loop iterations executed (accepted + rejected)                      */
+    int32_t ret;                /* what adjustBundle_ssba returns for this outcome: 0 or -1               */
+    int32_t n_trace;            /* rows valid in trace                                                    */
+    int32_t total_cg_steps;
+    int32_t gpu_launches;       /* kernels of this library launched by the call                           */
+    double  mean_px[2];         /* mean reprojection error in pixels before / after (sfm_ba_ssba.cpp:26-51) */
+    double  initial_cost, final_cost;   /* sum of squared weighted residuals (normalised units)           */
+    double  ms_solve;           /* device time of the LM loop (CUDA events)                               */
+    double  ms_h2d, ms_d2h;     /* upload (set_problem) / download (get_result) wall time                 */
+    double* trace;              /* optional caller buffer, trace_cap rows x B200BA_TRACE_COLS; may be NULL */
+    int32_t trace_cap;
+    int32_t reserved[5];
+} b200ba_report;
+
+typedef struct b200ba_handle b200ba_handle;
+
+/* Fill *opt with the SSBA-path defaults (src/sfm_ba_ssba.cpp:193-217). */
+int b200ba_default_options(b200ba_options* opt);
+/* PBA-path preset (src/sfm_ba_pba.cpp:60-62,94,136): camera 0 constant, no robustifier, sub-pixel measurements. */
+int b200ba_pba_preset(b200ba_options* opt);
+
+int b200ba_create(const b200ba_options* opt, b200ba_handle** out);
+void b200ba_destroy(b200ba_handle* h);
+const char* b200ba_last_error(const b200ba_handle* h);   /* h may be NULL: error of the last failed create */
+
+/* Upload one problem.  cam_RT: N x 12 row-major [R|T] world->camera (Pmats, src/sfm_ba_ssba.cpp:130-146);
+ * K5 = {fx, skew, cx, fy, cy} (camIntrinsic, :90-94); pts: M x 3 (pointcloud[j].pt); obs_xy: K x 2 float pixels
+ * (imgpts[frame][kp].pt); obs_cam / obs_pt: K indices, obs_pt non-decreasing (the order :161-182 produces).
+ * In a multi-rank handle (b200ba_comm_init) cameras are replicated and pts / observations are this rank's shard
+ * with obs_pt indexing the local points. */
+int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
+                       const double* cam_RT, const double* K5, const double* pts,
+                       const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt);
+
+/* Whole BA: normalise, run LM until a stop criterion, de-normalise.  Equivalent of opt.minimize() inside the
+ * normaliser scope of src/sfm_ba_ssba.cpp:200-222. */
+int b200ba_solve(b200ba_handle* h, b200ba_report* report);
+
+/* The same, in pieces (bench.py times b200ba_iterate): begin = (re)start from the uploaded parameters and
+ * normalise; iterate = run up to n LM loop iterations; finish = de-normalise and fill the report. */
+int b200ba_begin(b200ba_handle* h);
+int b200ba_iterate(b200ba_handle* h, int32_t n, int32_t* done);
+/* Device time (CUDA events on the engine's stream) of the last b200ba_iterate call, in milliseconds. */
+int b200ba_last_iterate_ms(b200ba_handle* h, double* ms);
+int b200ba_finish(b200ba_handle* h, b200ba_report* report);
+
+/* Download the adjusted cameras / points (what src/sfm_ba_ssba.cpp:250-271 writes back).  When the outcome is
+ * "discarded" (report.ret == -1) the inputs are returned unchanged, like the reference. */
+int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts);
+
+/* ---- multi-GPU: one handle per rank, problem partitioned by point ---- */
+#define B200BA_COMM_ID_BYTES 128
+int b200ba_comm_unique_id(void* id_bytes);    /* rank 0 creates, the launcher broadcasts (e.g. torch.distributed) */
+int b200ba_comm_init(b200ba_handle* h, const void* id_bytes, int32_t rank, int32_t world);
+
+/* ---- stage-level access for parity tests and profiling (not needed by the adapter) ---- */
+/* Linearise at the current (normalised) state after b200ba_begin: any output may be NULL.
+ * cost, w[K], gc[6N], gp[3M], U[36N], V[9M] (full symmetric blocks), lambda0 = tau * max diag. */
+int b200ba_debug_linearize(b200ba_handle* h, double* cost, double* w, double* gc, double* gp,
+                           double* U, double* V, double* lambda0);
+/* Sx = ((U + lambda I) - W (V + lambda I)^-1 W^t) x for the last linearisation; x, Sx: 6N. */
+int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, double* Sx);
+/* Time `reps` launches of one kernel group with CUDA events; which: see b200ba_kernel_name. */
+int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, double* ms_per_launch);
+const char* b200ba_kernel_name(int32_t which);   /* NULL past the last kernel */
+int b200ba_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BA_H */

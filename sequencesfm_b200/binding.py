@@ -1,0 +1,243 @@
+"""ctypes binding of the C ABI in ``include/b200ba.h`` (``sequencesfm_b200/libb200ba.so``).
+
+This is the Python face of the drop-in boundary: plain pointers and sizes cross it, nothing else.  The
+library is the hand-written sm_100a CUDA engine; there is no fallback of any kind -- if the shared object
+is missing or no CUDA device is usable the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200ba.so")
+TRACE_COLS = 8
+COMM_ID_BYTES = 128
+
+STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
+
+# every symbol include/b200ba.h declares (tests check that the library exports each of them)
+ABI_SYMBOLS = [
+    "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
+    "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
+    "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
+    "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("max_iterations", C.c_int32),
+                ("min_iterations", C.c_int32), ("tau", C.c_double), ("inlier_px", C.c_double),
+                ("gradient_threshold", C.c_double), ("update_threshold", C.c_double),
+                ("round_pixels", C.c_int32), ("normalize", C.c_int32), ("fix_first_camera", C.c_int32),
+                ("discard_converged", C.c_int32), ("cg_max_steps", C.c_int32), ("cg_rel_tol", C.c_double),
+                ("precond", C.c_int32), ("poll_every", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class Report(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("ret", C.c_int32), ("n_trace", C.c_int32),
+                ("total_cg_steps", C.c_int32), ("gpu_launches", C.c_int32), ("mean_px", C.c_double * 2),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("ms_solve", C.c_double),
+                ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("trace", C.POINTER(C.c_double)),
+                ("trace_cap", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class B200BAError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200ba error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libb200ba.so (fails loudly when it has not been built: ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built; run `make -C sequencesfm_b200/csrc` (no CPU fallback exists)")
+        lib = C.CDLL(LIB_PATH)
+        lib.b200ba_last_error.restype = C.c_char_p
+        lib.b200ba_last_error.argtypes = [C.c_void_p]
+        lib.b200ba_kernel_name.restype = C.c_char_p
+        lib.b200ba_kernel_name.argtypes = [C.c_int32]
+        lib.b200ba_create.argtypes = [C.POINTER(Options), C.POINTER(C.c_void_p)]
+        lib.b200ba_destroy.argtypes = [C.c_void_p]
+        lib.b200ba_destroy.restype = None
+        _lib = lib
+    return _lib
+
+
+def default_options(preset: str = "ssba", **kw) -> Options:
+    o = Options()
+    lib = load()
+    rc = lib.b200ba_pba_preset(C.byref(o)) if preset == "pba" else lib.b200ba_default_options(C.byref(o))
+    if rc:
+        raise B200BAError(rc, "default options")
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+@dataclass
+class SolveResult:
+    ret: int
+    status: int
+    iterations: int
+    trace: np.ndarray
+    mean_px: tuple[float, float]
+    cam_RT: np.ndarray
+    pts: np.ndarray
+    total_cg_steps: int
+    gpu_launches: int
+    ms_solve: float
+    ms_h2d: float
+    ms_d2h: float
+    initial_cost: float
+    final_cost: float
+    extra: dict = field(default_factory=dict)
+
+
+class Engine:
+    """Thin RAII wrapper over one ``b200ba_handle``."""
+
+    def __init__(self, options: Options | None = None, **kw):
+        self.lib = load()
+        self.opt = options if options is not None else default_options(**kw)
+        self.h = C.c_void_p()
+        rc = self.lib.b200ba_create(C.byref(self.opt), C.byref(self.h))
+        if rc:
+            raise B200BAError(rc, self.lib.b200ba_last_error(None).decode())
+        self.N = self.M = self.K = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.b200ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise B200BAError(rc, self.lib.b200ba_last_error(self.h).decode())
+
+    # -- multi-GPU ------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load().b200ba_comm_unique_id(buf)
+        if rc:
+            raise B200BAError(rc, load().b200ba_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, id_bytes: bytes, rank: int, world: int):
+        self._check(self.lib.b200ba_comm_init(self.h, C.c_char_p(id_bytes), C.c_int32(rank), C.c_int32(world)))
+
+    # -- problem / solve ------------------------------------------------------------------------------
+    def set_problem(self, K5, cam_RT, pts, obs_xy, obs_cam, obs_pt):
+        self._K5 = np.ascontiguousarray(K5, dtype=np.float64)
+        self._cam = np.ascontiguousarray(cam_RT, dtype=np.float64).reshape(-1, 12)
+        self._pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
+        oc = np.ascontiguousarray(obs_cam, dtype=np.int32)
+        op = np.ascontiguousarray(obs_pt, dtype=np.int32)
+        self.N, self.M, self.K = self._cam.shape[0], self._pts.shape[0], oc.shape[0]
+        self._check(self.lib.b200ba_set_problem(self.h, C.c_int32(self.N), C.c_int32(self.M), C.c_int32(self.K),
+                                                _dp(self._cam), _dp(self._K5), _dp(self._pts), _dp(xy), _ip(oc), _ip(op)))
+
+    def set_problem_from(self, p):
+        self.set_problem(p.K5, p.cam_RT, p.pts, p.obs_xy, p.obs_cam, p.obs_pt)
+
+    def _report(self, with_trace=True):
+        rep = Report()
+        cap = self.opt.max_iterations + 2
+        tr = np.full((cap, TRACE_COLS), np.nan)
+        if with_trace:
+            rep.trace = _dp(tr)
+            rep.trace_cap = cap
+        return rep, tr
+
+    def _result(self, rep, tr) -> SolveResult:
+        cam = np.empty((self.N, 12)); pts = np.empty((self.M, 3))
+        self._check(self.lib.b200ba_get_result(self.h, _dp(cam), _dp(pts)))
+        rep2 = Report()
+        return SolveResult(rep.ret, rep.status, rep.iterations, tr[: rep.n_trace].copy(), (rep.mean_px[0], rep.mean_px[1]),
+                           cam, pts, rep.total_cg_steps, rep.gpu_launches, rep.ms_solve, rep.ms_h2d, rep.ms_d2h,
+                           rep.initial_cost, rep.final_cost)
+
+    def solve(self) -> SolveResult:
+        rep, tr = self._report()
+        self._check(self.lib.b200ba_solve(self.h, C.byref(rep)))
+        return self._result(rep, tr)
+
+    def begin(self):
+        self._check(self.lib.b200ba_begin(self.h))
+
+    def iterate(self, n: int) -> bool:
+        done = C.c_int32(0)
+        self._check(self.lib.b200ba_iterate(self.h, C.c_int32(n), C.byref(done)))
+        return bool(done.value)
+
+    def last_iterate_ms(self) -> float:
+        ms = C.c_double(0)
+        self._check(self.lib.b200ba_last_iterate_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def finish(self) -> SolveResult:
+        rep, tr = self._report()
+        self._check(self.lib.b200ba_finish(self.h, C.byref(rep)))
+        return self._result(rep, tr)
+
+    # -- stage-level ----------------------------------------------------------------------------------
+    def debug_linearize(self) -> dict:
+        N, M, K = self.N, self.M, self.K
+        out = {"w": np.zeros(K), "gc": np.zeros((N, 6)), "gp": np.zeros((M, 3)), "U": np.zeros((N, 6, 6)), "V": np.zeros((M, 3, 3))}
+        cost = C.c_double(0); lam0 = C.c_double(0)
+        self._check(self.lib.b200ba_debug_linearize(self.h, C.byref(cost), _dp(out["w"]), _dp(out["gc"]), _dp(out["gp"]),
+                                                    _dp(out["U"]), _dp(out["V"]), C.byref(lam0)))
+        out["cost"] = cost.value; out["lambda0"] = lam0.value
+        return out
+
+    def debug_schur_matvec(self, lam: float, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        Sx = np.zeros_like(x)
+        self._check(self.lib.b200ba_debug_schur_matvec(self.h, C.c_double(lam), _dp(x), _dp(Sx)))
+        return Sx.reshape(self.N, 6)
+
+    def time_kernel(self, which: int, reps: int = 20) -> float:
+        ms = C.c_double(0)
+        self._check(self.lib.b200ba_debug_time_kernel(self.h, C.c_int32(which), C.c_int32(reps), C.byref(ms)))
+        return ms.value
+
+    def kernel_names(self) -> list[str]:
+        out = []
+        i = 0
+        while True:
+            n = self.lib.b200ba_kernel_name(i)
+            if not n:
+                return out
+            out.append(n.decode()); i += 1

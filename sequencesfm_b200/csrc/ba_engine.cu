@@ -1,0 +1,729 @@
+// ba_engine.cu -- host side of libb200ba.so: problem upload, LM driver, C ABI (include/b200ba.h).
+//
+// One handle = one CUDA device (+ optionally one NCCL rank).  The host never touches an observation after
+// upload: it only enqueues kernels; accept/reject, damping and every stop decision live in the device-side
+// LMState (ba_kernels.cuh), polled every `poll_every` LM iterations.
+//
+// Reference lines replaced by each entry point are cited in include/b200ba.h.
+#include "../../include/b200ba.h"
+#include "ba_kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace b200ba;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen: the library has no link-time dependency on NCCL (single-GPU use needs none) ----
+struct NcclApi {
+    void* so = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (so) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { so = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (so) break; }
+        if (!so) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(so, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(so, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(so, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+NcclApi g_nccl;
+
+template <class T> struct DBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release(); n = count;
+        if (!count) return cudaSuccess;
+        return cudaMalloc((void**)&p, sizeof(T) * count);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+} // namespace
+
+struct b200ba_handle {
+    b200ba_options opt{};
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // communicator
+    ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    // host copies of the caller's problem
+    int N = 0, M = 0, K = 0;
+    std::vector<double> h_cam, h_pts;        // as given (un-normalised)
+    double K5[5] = {0, 0, 0, 0, 0};
+    double mean[3] = {0, 0, 0}, scale = 1.0;
+    bool have_problem = false, begun = false, finished = false;
+    // device
+    Dev d{};
+    DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, o_w, c_w, chunk_part, pt_part, trace;
+    DBuf<double2> o_meas, c_meas;
+    DBuf<int> o_cam, pstart, c_pt, chunk_cam, chunk_beg, chunk_end, cam_chunk_beg;
+    DBuf<LMState> st;
+    DBuf<double> norm_buf;
+    LMState h_st{};
+    long long launches = 0;
+    double ms_h2d = 0, ms_d2h = 0, ms_solve = 0, ms_last_iterate = 0;
+    double mean_px[2] = {0, 0};
+    double initial_cost = 0;
+    int trace_cap = 0;
+};
+
+namespace {
+
+int fail(b200ba_handle* h, int code, const char* fmt, ...)
+{
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, B200BA_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(h, B200BA_E_COMM, "%s: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int allreduce(b200ba_handle* h, double* buf, size_t count)
+{
+    if (h->world <= 1) return 0;
+    NC(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream));
+    return 0;
+}
+
+// ---- kernel launch sequences ---------------------------------------------------------------------------
+#define LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+
+int enqueue_linearize(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
+    LAUNCH(k_linearize_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d);
+    LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
+    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0);
+    if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world)) return rc;
+    LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
+    return 0;
+}
+
+int enqueue_precond(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
+    if (h->opt.precond == 1) {
+        LAUNCH(k_schur_diag_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d);
+        LAUNCH((k_camera_reduce<21, 21>), cdiv((long long)d.N * 21, 256), 256, d, d.ar_sd, 0);
+        if (int rc = allreduce(h, d.ar_sd, (size_t)d.N * 21)) return rc;
+    }
+    LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond);
+    return 0;
+}
+
+int enqueue_cg_init(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH(k_cg_point_pass<1>, d.n_pt_blocks, PT_BLOCK, d);
+    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 1);
+    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
+    if (int rc = allreduce(h, d.ar_q, (size_t)d.N * 6)) return rc;
+    LAUNCH(k_cg_init, 1, ONE_CTA, d);
+    return 0;
+}
+
+int enqueue_cg_step(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0);
+    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
+    if (int rc = allreduce(h, d.ar_q, (size_t)d.N * 6)) return rc;
+    LAUNCH(k_cg_update, 1, ONE_CTA, d);
+    return 0;
+}
+
+int enqueue_step_and_decide(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH(k_cg_finish, 1, ONE_CTA, d);
+    LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
+    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1);
+    if (int rc = allreduce(h, d.ar_dec, 4)) return rc;
+    LAUNCH(k_lm_decide, 1, 1, d);
+    return 0;
+}
+
+int enqueue_lm_iteration(b200ba_handle* h)
+{
+    if (int rc = enqueue_linearize(h)) return rc;
+    if (int rc = enqueue_precond(h)) return rc;
+    if (int rc = enqueue_cg_init(h)) return rc;
+    const int steps = h->opt.cg_max_steps;
+    if (h->opt.cg_rel_tol > 0) {
+        // convergence-controlled PCG: poll the device flag between batches of steps
+        int done_steps = 0;
+        while (done_steps < steps) {
+            int batch = std::min(25, steps - done_steps);
+            for (int s = 0; s < batch; ++s) if (int rc = enqueue_cg_step(h)) return rc;
+            done_steps += batch;
+            int active = 0;
+            CU(cudaMemcpyAsync(&active, &h->d.st->cg_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (!active) break;
+        }
+    } else {
+        for (int s = 0; s < steps; ++s) if (int rc = enqueue_cg_step(h)) return rc;
+    }
+    return enqueue_step_and_decide(h);
+}
+
+int mean_reproj(b200ba_handle* h, int which, double* out)
+{
+    Dev& d = h->d;
+    if (d.K == 0 && h->world <= 1) { *out = 0; return 0; }
+    LAUNCH(k_reproj_sum, d.n_pt_blocks, PT_BLOCK, d, which);
+    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 2);
+    double k_local = (double)d.K;
+    CU(cudaMemcpyAsync(d.ar_dec + 1, &k_local, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = allreduce(h, d.ar_dec, 4)) return rc;
+    double s[2];
+    CU(cudaMemcpyAsync(s, d.ar_dec, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = s[1] > 0 ? s[0] / s[1] : 0.0;
+    return 0;
+}
+
+// host-side global sums for the normaliser: local sums go through one tiny all-reduce when world > 1
+int global_sum(b200ba_handle* h, double* vals, int n)
+{
+    if (h->world <= 1) return 0;
+    CU(cudaMemcpyAsync(h->norm_buf.p, vals, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = allreduce(h, h->norm_buf.p, n)) return rc;
+    CU(cudaMemcpyAsync(vals, h->norm_buf.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+void camera_centre(const double* P, double* C)   // -R^t T
+{
+    for (int c = 0; c < 3; ++c) C[c] = -(P[c] * P[3] + P[4 + c] * P[7] + P[8 + c] * P[11]);
+}
+void set_camera_centre(double* P, const double* C)   // T = -R C   (v3d_cameramatrix.h:132)
+{
+    for (int r = 0; r < 3; ++r) P[4 * r + 3] = -1.0 * (P[4 * r] * C[0] + P[4 * r + 1] * C[1] + P[4 * r + 2] * C[2]);
+}
+
+} // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int b200ba_version(void) { return B200BA_VERSION; }
+
+int b200ba_default_options(b200ba_options* o)
+{
+    if (!o) return B200BA_E_INVALID;
+    memset(o, 0, sizeof *o);
+    o->struct_size = (int32_t)sizeof *o;
+    o->device = -1;
+    o->max_iterations = 50; o->min_iterations = 10; o->tau = 1e-3; o->inlier_px = 2.0;
+    o->gradient_threshold = 1e-8; o->update_threshold = 1e-8;
+    o->round_pixels = 1; o->normalize = 1; o->fix_first_camera = 0; o->discard_converged = 1;
+    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5;
+    return 0;
+}
+
+int b200ba_pba_preset(b200ba_options* o)
+{
+    if (int rc = b200ba_default_options(o)) return rc;
+    o->fix_first_camera = 1;      // camera_data[0].SetConstantCamera()   src/sfm_ba_pba.cpp:94
+    o->inlier_px = 0.0;           // PBA has no robustifier                SparseBundleCPU.cpp:1176-1180
+    o->round_pixels = 0;          // float sub-pixel measurements          src/sfm_ba_pba.cpp:122-123
+    o->discard_converged = 0;     // adjustBundle_pba always returns 0     src/sfm_ba_pba.cpp:173
+    return 0;
+}
+
+const char* b200ba_last_error(const b200ba_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b200ba_create(const b200ba_options* opt, b200ba_handle** out)
+{
+    if (!out) return B200BA_E_INVALID;
+    *out = nullptr;
+    b200ba_handle* h = nullptr;
+    b200ba_options o;
+    if (opt) { if (opt->struct_size != (int32_t)sizeof o) return fail(nullptr, B200BA_E_INVALID, "options.struct_size mismatch"); o = *opt; }
+    else b200ba_default_options(&o);
+    if (o.max_iterations < 0 || o.cg_max_steps < 0) return fail(nullptr, B200BA_E_INVALID, "negative iteration count");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200BA_E_CUDA, "no usable CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+    int dev = o.device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, B200BA_E_INVALID, "device %d out of range (%d devices)", dev, ndev);
+    h = new b200ba_handle();
+    h->opt = o; h->device = dev;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        fail(nullptr, B200BA_E_CUDA, "cannot initialise device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+        delete h; return B200BA_E_CUDA;
+    }
+    *out = h;
+    return 0;
+}
+
+void b200ba_destroy(b200ba_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->rt0.release(); h->rt1.release(); h->U.release(); h->gc.release(); h->Minv.release(); h->x.release(); h->r.release();
+    h->z.release(); h->p.release(); h->q.release(); h->ar_lin.release(); h->ar_q.release(); h->ar_sd.release(); h->ar_dec.release();
+    h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_w.release(); h->c_w.release();
+    h->chunk_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
+    h->pstart.release(); h->c_pt.release(); h->chunk_cam.release(); h->chunk_beg.release(); h->chunk_end.release(); h->cam_chunk_beg.release();
+    h->st.release(); h->norm_buf.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int b200ba_comm_unique_id(void* id_bytes)
+{
+    if (!id_bytes) return B200BA_E_INVALID;
+    if (!g_nccl.load()) return fail(nullptr, B200BA_E_COMM, "libnccl.so.2 not loadable: %s", dlerror());
+    static_assert(sizeof(ncclUniqueId) == B200BA_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, B200BA_E_COMM, "ncclGetUniqueId failed");
+    memcpy(id_bytes, &id, sizeof id);
+    return 0;
+}
+
+int b200ba_comm_init(b200ba_handle* h, const void* id_bytes, int32_t rank, int32_t world)
+{
+    if (!h || !id_bytes || world < 1 || rank < 0 || rank >= world) return B200BA_E_INVALID;
+    if (h->have_problem) return fail(h, B200BA_E_STATE, "b200ba_comm_init must precede b200ba_set_problem");
+    if (world == 1) { h->rank = 0; h->world = 1; return 0; }
+    if (!g_nccl.load()) return fail(h, B200BA_E_COMM, "libnccl.so.2 not loadable: %s", dlerror());
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId id; memcpy(&id, id_bytes, sizeof id);
+    NC(g_nccl.CommInitRank(&h->comm, world, id, rank));
+    h->rank = rank; h->world = world;
+    return 0;
+}
+
+int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
+                       const double* cam_RT, const double* K5, const double* pts,
+                       const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (N <= 0 || M < 0 || K < 0 || !cam_RT || !K5 || (M && !pts) || (K && (!obs_xy || !obs_cam || !obs_pt)))
+        return fail(h, B200BA_E_INVALID, "null or empty problem arrays (N=%d M=%d K=%d)", N, M, K);
+    if (h->world <= 1 && (M == 0 || K == 0)) return fail(h, B200BA_E_INVALID, "empty problem (M=%d K=%d)", M, K);
+    if (!(K5[0] != 0.0) || !std::isfinite(K5[0])) return fail(h, B200BA_E_INVALID, "focal length fx must be finite and non-zero");
+    for (int k = 0; k < K; ++k) {
+        if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M) return fail(h, B200BA_E_INVALID, "observation %d: index out of range", k);
+        if (k && obs_pt[k] < obs_pt[k - 1]) return fail(h, B200BA_E_INVALID, "observation %d: obs_pt must be non-decreasing", k);
+    }
+    double t0 = now_ms();
+    CU(cudaSetDevice(h->device));
+    h->N = N; h->M = M; h->K = K;
+    h->h_cam.assign(cam_RT, cam_RT + 12 * (size_t)N);
+    h->h_pts.assign(pts, pts + 3 * (size_t)M);
+    memcpy(h->K5, K5, sizeof h->K5);
+
+    // ---- marshalling (src/sfm_ba_ssba.cpp:88-102,171-178; intrinsic normaliser v3d_metricbundle.h:395-413) ----
+    Dev& d = h->d;
+    const b200ba_options& o = h->opt;
+    double f0 = K5[0], rf = 1.0 / f0;
+    Intrinsics in;
+    in.k00 = K5[0] * rf; in.k01 = K5[1] * rf; in.k02 = K5[2] * rf; in.k11 = K5[3] * rf; in.k12 = K5[4] * rf;
+    double r2 = 1.0 / in.k00;
+    in.k00 *= r2; in.k01 *= r2; in.k02 *= r2; in.k11 *= r2; in.k12 *= r2;
+    in.huber = o.inlier_px > 0 ? o.inlier_px / std::fabs(f0) : 0.0;
+    in.f0 = f0;
+
+    std::vector<double2> meas((size_t)K);
+    for (int k = 0; k < K; ++k) {
+        double x = obs_xy[2 * (size_t)k], y = obs_xy[2 * (size_t)k + 1];
+        if (o.round_pixels) { x = (double)lrintf((float)x); y = (double)lrintf((float)y); }
+        meas[k] = make_double2((x * rf) * r2, (y * rf) * r2);
+    }
+    // CSR by point
+    std::vector<int> pstart((size_t)M + 1, 0);
+    for (int k = 0; k < K; ++k) pstart[obs_pt[k] + 1]++;
+    for (int j = 0; j < M; ++j) pstart[j + 1] += pstart[j];
+    // camera order: stable counting sort by camera (order inside a camera = increasing point index), then chunks
+    std::vector<int> cstart((size_t)N + 1, 0);
+    for (int k = 0; k < K; ++k) cstart[obs_cam[k] + 1]++;
+    for (int i = 0; i < N; ++i) cstart[i + 1] += cstart[i];
+    std::vector<int> c_pt((size_t)K); std::vector<double2> c_meas((size_t)K);
+    {
+        std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+        for (int k = 0; k < K; ++k) { int dst = fill[obs_cam[k]]++; c_pt[dst] = obs_pt[k]; c_meas[dst] = meas[k]; }
+    }
+    std::vector<int> chunk_cam, chunk_beg, chunk_end, cam_chunk_beg((size_t)N + 1, 0);
+    for (int i = 0; i < N; ++i) {
+        cam_chunk_beg[i] = (int)chunk_cam.size();
+        for (int b = cstart[i]; b < cstart[i + 1]; b += CHUNK) {
+            chunk_cam.push_back(i); chunk_beg.push_back(b); chunk_end.push_back(std::min(b + CHUNK, cstart[i + 1]));
+        }
+    }
+    cam_chunk_beg[N] = (int)chunk_cam.size();
+    int n_chunks = (int)chunk_cam.size();
+    int n_pt_blocks = std::max(1, cdiv(M, PT_BLOCK));
+
+    // ---- device allocation ----
+    size_t n6 = 6 * (size_t)N;
+    int world = h->world;
+    h->trace_cap = o.max_iterations + 2;
+    CU(h->rt0.alloc(12 * (size_t)N)); CU(h->rt1.alloc(12 * (size_t)N));
+    CU(h->U.alloc(36 * (size_t)N)); CU(h->Minv.alloc(36 * (size_t)N));
+    CU(h->gc.alloc(n6)); CU(h->x.alloc(n6)); CU(h->r.alloc(n6)); CU(h->z.alloc(n6)); CU(h->p.alloc(n6)); CU(h->q.alloc(n6));
+    CU(h->ar_lin.alloc((size_t)N * PART_STRIDE + 1 + 2 * (size_t)world)); CU(h->ar_q.alloc(n6)); CU(h->ar_sd.alloc(21 * (size_t)N)); CU(h->ar_dec.alloc(4));
+    CU(h->X0.alloc(4 * (size_t)std::max(M, 1))); CU(h->X1.alloc(4 * (size_t)std::max(M, 1)));
+    CU(h->V.alloc(6 * (size_t)std::max(M, 1))); CU(h->Vinv.alloc(6 * (size_t)std::max(M, 1)));
+    CU(h->gp.alloc(4 * (size_t)std::max(M, 1))); CU(h->v.alloc(4 * (size_t)std::max(M, 1)));
+    CU(h->o_w.alloc(std::max(K, 1))); CU(h->c_w.alloc(std::max(K, 1)));
+    CU(h->o_meas.alloc(std::max(K, 1))); CU(h->c_meas.alloc(std::max(K, 1)));
+    CU(h->o_cam.alloc(std::max(K, 1))); CU(h->c_pt.alloc(std::max(K, 1))); CU(h->pstart.alloc((size_t)M + 1));
+    CU(h->chunk_cam.alloc(std::max(n_chunks, 1))); CU(h->chunk_beg.alloc(std::max(n_chunks, 1))); CU(h->chunk_end.alloc(std::max(n_chunks, 1)));
+    CU(h->cam_chunk_beg.alloc((size_t)N + 1));
+    CU(h->chunk_part.alloc((size_t)std::max(n_chunks, 1) * PART_STRIDE)); CU(h->pt_part.alloc(4 * (size_t)n_pt_blocks));
+    CU(h->trace.alloc((size_t)h->trace_cap * TRACE_COLS)); CU(h->st.alloc(1)); CU(h->norm_buf.alloc(16));
+
+    cudaStream_t s = h->stream;
+    if (K) {
+        CU(cudaMemcpyAsync(h->o_meas.p, meas.data(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->c_meas.p, c_meas.data(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->o_cam.p, obs_cam, sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->c_pt.p, c_pt.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(h->o_w.p, 0, sizeof(double) * (size_t)K, s));
+        CU(cudaMemsetAsync(h->c_w.p, 0, sizeof(double) * (size_t)K, s));
+    }
+    CU(cudaMemcpyAsync(h->pstart.p, pstart.data(), sizeof(int) * ((size_t)M + 1), cudaMemcpyHostToDevice, s));
+    if (n_chunks) {
+        CU(cudaMemcpyAsync(h->chunk_cam.p, chunk_cam.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->chunk_beg.p, chunk_beg.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->chunk_end.p, chunk_end.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
+    }
+    CU(cudaMemcpyAsync(h->cam_chunk_beg.p, cam_chunk_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->chunk_part.p, 0, sizeof(double) * (size_t)std::max(n_chunks, 1) * PART_STRIDE, s));
+    CU(cudaMemsetAsync(h->pt_part.p, 0, sizeof(double) * 4 * (size_t)n_pt_blocks, s));
+    CU(cudaMemsetAsync(h->ar_lin.p, 0, sizeof(double) * h->ar_lin.n, s));
+    CU(cudaMemsetAsync(h->ar_sd.p, 0, sizeof(double) * h->ar_sd.n, s));
+    CU(cudaMemsetAsync(h->ar_q.p, 0, sizeof(double) * h->ar_q.n, s));
+    CU(cudaStreamSynchronize(s));
+
+    d = Dev{};
+    d.N = N; d.M = M; d.K = K; d.n_chunks = n_chunks; d.first_free = o.fix_first_camera ? 1 : 0; d.n_pt_blocks = n_pt_blocks;
+    d.world = world; d.rank = h->rank; d.in = in; d.st = h->st.p;
+    d.rt[0] = h->rt0.p; d.rt[1] = h->rt1.p; d.U = h->U.p; d.gc = h->gc.p; d.Minv = h->Minv.p;
+    d.x = h->x.p; d.r = h->r.p; d.z = h->z.p; d.p = h->p.p; d.q = h->q.p;
+    d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
+    d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
+    d.o_cam = h->o_cam.p; d.o_meas = h->o_meas.p; d.o_w = h->o_w.p; d.pstart = h->pstart.p;
+    d.c_pt = h->c_pt.p; d.c_meas = h->c_meas.p; d.c_w = h->c_w.p;
+    d.chunk_cam = h->chunk_cam.p; d.chunk_beg = h->chunk_beg.p; d.chunk_end = h->chunk_end.p; d.cam_chunk_beg = h->cam_chunk_beg.p;
+    d.chunk_part = h->chunk_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
+    h->have_problem = true; h->begun = false; h->finished = false;
+    h->ms_h2d = now_ms() - t0;
+    return 0;
+}
+
+int b200ba_begin(b200ba_handle* h)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->have_problem) return fail(h, B200BA_E_STATE, "b200ba_begin before b200ba_set_problem");
+    CU(cudaSetDevice(h->device));
+    const int N = h->N, M = h->M;
+    const b200ba_options& o = h->opt;
+    std::vector<double> cam(h->h_cam), X4(4 * (size_t)std::max(M, 1), 0.0);
+    const double* P0 = h->h_pts.data();
+    h->mean[0] = h->mean[1] = h->mean[2] = 0; h->scale = 1.0;
+    std::vector<double> C(3 * (size_t)N);
+    for (int i = 0; i < N; ++i) camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i);
+    if (o.normalize) {
+        // ScopedBundleExtrinsicNormalizer ctor (v3d_metricbundle.h:327-356); point sums are global over ranks,
+        // cameras are replicated and counted once.
+        double s[4] = {0, 0, 0, (double)M};
+        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) s[c] += P0[3 * (size_t)j + c];
+        if (int rc = global_sum(h, s, 4)) return rc;
+        double cs[3] = {0, 0, 0};
+        for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) cs[c] += C[3 * (size_t)i + c];
+        // reference adds camera centres first, then points
+        double rn = 1.0 / ((double)N + s[3]);
+        for (int c = 0; c < 3; ++c) h->mean[c] = (cs[c] + s[c]) * rn;
+        double sq[1] = {0};
+        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) { double v = P0[3 * (size_t)j + c] - h->mean[c]; sq[0] += v * v; }
+        if (int rc = global_sum(h, sq, 1)) return rc;
+        double sqc = 0;
+        for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) { C[3 * (size_t)i + c] -= h->mean[c]; sqc += C[3 * (size_t)i + c] * C[3 * (size_t)i + c]; }
+        h->scale = std::sqrt(sqc + sq[0]);
+        double rs = 1.0 / h->scale;
+        for (int i = 0; i < N; ++i) { for (int c = 0; c < 3; ++c) C[3 * (size_t)i + c] *= rs; set_camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i); }
+        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) X4[4 * (size_t)j + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs;
+    } else {
+        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) X4[4 * (size_t)j + c] = P0[3 * (size_t)j + c];
+    }
+    // cached parameter length (v3d_metricbundle.h:37-45), after normalisation
+    double L[1] = {0};
+    for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) L[0] += X4[4 * (size_t)j + c] * X4[4 * (size_t)j + c];
+    if (int rc = global_sum(h, L, 1)) return rc;
+    for (int i = (o.fix_first_camera ? 1 : 0); i < N; ++i) {
+        const double* P = cam.data() + 12 * (size_t)i;
+        L[0] += P[3] * P[3] + P[7] * P[7] + P[11] * P[11] + 3.0;
+    }
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->rt0.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->rt1.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->X0.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->X1.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
+    LMState st{};
+    st.lambda = 1e-3; st.param_length = std::sqrt(L[0]);
+    st.tau = o.tau; st.grad_thr = o.gradient_threshold; st.upd_thr = o.update_threshold; st.cg_tol = o.cg_rel_tol;
+    st.iter = 0; st.status = 0; st.done = (o.max_iterations <= 0) ? 1 : 0; st.compute = 1; st.cur = 0; st.first = 1;
+    st.cg_active = 0; st.solve_ok = 1; st.max_iter = o.max_iterations; st.min_iter = o.min_iterations;
+    st.n_trace = 0; st.trace_cap = h->trace_cap;
+    h->h_st = st;
+    CU(cudaMemcpyAsync(h->st.p, &h->h_st, sizeof st, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    h->launches = 0; h->ms_solve = 0;
+    if (int rc = mean_reproj(h, 0, &h->mean_px[0])) return rc;
+    h->begun = true; h->finished = false;
+    return 0;
+}
+
+int b200ba_iterate(b200ba_handle* h, int32_t n, int32_t* done)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->begun) return fail(h, B200BA_E_STATE, "b200ba_iterate before b200ba_begin");
+    CU(cudaSetDevice(h->device));
+    int poll = h->opt.poll_every > 0 ? h->opt.poll_every : n;
+    int is_done = 0;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int it = 0; it < n && !is_done; ) {
+        int batch = std::min(poll, n - it);
+        for (int b = 0; b < batch; ++b) if (int rc = enqueue_lm_iteration(h)) return rc;
+        it += batch;
+        CU(cudaMemcpyAsync(&is_done, &h->d.st->done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ms_solve += ms; h->ms_last_iterate = ms;
+    CU(cudaGetLastError());
+    if (done) *done = is_done;
+    return 0;
+}
+
+int b200ba_last_iterate_ms(b200ba_handle* h, double* ms)
+{
+    if (!h || !ms) return B200BA_E_INVALID;
+    *ms = h->ms_last_iterate;
+    return 0;
+}
+
+int b200ba_finish(b200ba_handle* h, b200ba_report* rep)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->begun) return fail(h, B200BA_E_STATE, "b200ba_finish before b200ba_begin");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(&h->h_st, h->st.p, sizeof(LMState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (int rc = mean_reproj(h, h->h_st.cur, &h->mean_px[1])) return rc;
+    h->finished = true;
+    if (rep) {
+        double* tr = rep->trace; int cap = rep->trace_cap;
+        rep->status = h->h_st.status; rep->iterations = h->h_st.iter;
+        rep->ret = (h->opt.discard_converged && h->h_st.status == B200BA_STATUS_CONVERGED) ? -1 : 0;
+        rep->total_cg_steps = h->h_st.total_cg;
+        rep->gpu_launches = (int32_t)std::min<long long>(h->launches, 2147483647LL);
+        rep->mean_px[0] = h->mean_px[0]; rep->mean_px[1] = h->mean_px[1];
+        rep->ms_solve = h->ms_solve; rep->ms_h2d = h->ms_h2d; rep->ms_d2h = h->ms_d2h;
+        int n = std::min(h->h_st.n_trace, h->trace_cap);
+        std::vector<double> t((size_t)std::max(n, 1) * TRACE_COLS);
+        if (n) { CU(cudaMemcpy(t.data(), h->trace.p, sizeof(double) * (size_t)n * TRACE_COLS, cudaMemcpyDeviceToHost)); }
+        rep->initial_cost = n ? t[1] : h->h_st.err;
+        rep->final_cost = h->h_st.err;
+        if (n && t[(size_t)(n - 1) * TRACE_COLS + 5] == 1.0) rep->final_cost = t[(size_t)(n - 1) * TRACE_COLS + 3];
+        rep->n_trace = 0;
+        if (tr && cap > 0) { int m = std::min(n, cap); memcpy(tr, t.data(), sizeof(double) * (size_t)m * TRACE_COLS); rep->n_trace = m; }
+    }
+    return 0;
+}
+
+int b200ba_solve(b200ba_handle* h, b200ba_report* rep)
+{
+    if (int rc = b200ba_begin(h)) return rc;
+    int done = 0;
+    if (int rc = b200ba_iterate(h, h->opt.max_iterations, &done)) return rc;
+    return b200ba_finish(h, rep);
+}
+
+int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->finished) return fail(h, B200BA_E_STATE, "b200ba_get_result before b200ba_solve / b200ba_finish");
+    double t0 = now_ms();
+    CU(cudaSetDevice(h->device));
+    const int N = h->N, M = h->M;
+    bool discard = h->opt.discard_converged && h->h_st.status == B200BA_STATUS_CONVERGED;   // src/sfm_ba_ssba.cpp:221,235
+    if (discard) {
+        if (cam_RT) memcpy(cam_RT, h->h_cam.data(), sizeof(double) * 12 * (size_t)N);
+        if (pts) memcpy(pts, h->h_pts.data(), sizeof(double) * 3 * (size_t)M);
+        return 0;
+    }
+    int cur = h->h_st.cur;
+    if (cam_RT) {
+        CU(cudaMemcpy(cam_RT, h->d.rt[cur], sizeof(double) * 12 * (size_t)N, cudaMemcpyDeviceToHost));
+        if (h->opt.normalize)   // ScopedBundleExtrinsicNormalizer dtor (v3d_metricbundle.h:358-375)
+            for (int i = 0; i < N; ++i) {
+                double C[3]; camera_centre(cam_RT + 12 * (size_t)i, C);
+                for (int c = 0; c < 3; ++c) C[c] = C[c] * h->scale + h->mean[c];
+                set_camera_centre(cam_RT + 12 * (size_t)i, C);
+            }
+    }
+    if (pts && M) {
+        std::vector<double> X4(4 * (size_t)M);
+        CU(cudaMemcpy(X4.data(), h->d.X[cur], sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
+        if (h->opt.normalize) for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)j + c] * h->scale + h->mean[c];
+        else for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)j + c];
+    }
+    h->ms_d2h = now_ms() - t0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage-level access
+// ---------------------------------------------------------------------------------------------------------
+int b200ba_debug_linearize(b200ba_handle* h, double* cost, double* w, double* gc, double* gp, double* U, double* V, double* lambda0)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->begun) return fail(h, B200BA_E_STATE, "b200ba_debug_linearize before b200ba_begin");
+    CU(cudaSetDevice(h->device));
+    if (int rc = enqueue_linearize(h)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    LMState st; CU(cudaMemcpy(&st, h->st.p, sizeof st, cudaMemcpyDeviceToHost));
+    const int N = h->N, M = h->M, K = h->K;
+    if (cost) *cost = st.err;
+    if (lambda0) *lambda0 = st.lambda;
+    if (w && K) CU(cudaMemcpy(w, h->o_w.p, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost));
+    if (gc) CU(cudaMemcpy(gc, h->gc.p, sizeof(double) * 6 * (size_t)N, cudaMemcpyDeviceToHost));
+    if (U) CU(cudaMemcpy(U, h->U.p, sizeof(double) * 36 * (size_t)N, cudaMemcpyDeviceToHost));
+    if (gp && M) {
+        std::vector<double> t(4 * (size_t)M); CU(cudaMemcpy(t.data(), h->gp.p, sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) gp[3 * (size_t)j + c] = t[4 * (size_t)j + c];
+    }
+    if (V && M) {
+        std::vector<double> t(6 * (size_t)M); CU(cudaMemcpy(t.data(), h->V.p, sizeof(double) * 6 * (size_t)M, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < M; ++j) {
+            const double* s = t.data() + 6 * (size_t)j; double* o = V + 9 * (size_t)j;
+            o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+        }
+    }
+    return 0;
+}
+
+int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, double* Sx)
+{
+    if (!h || !x || !Sx) return B200BA_E_INVALID;
+    if (!h->begun) return fail(h, B200BA_E_STATE, "b200ba_debug_schur_matvec before b200ba_begin");
+    CU(cudaSetDevice(h->device));
+    Dev& d = h->d;
+    const int N = h->N; size_t n6 = 6 * (size_t)N;
+    LMState st; CU(cudaMemcpy(&st, h->st.p, sizeof st, cudaMemcpyDeviceToHost));
+    LMState sv = st;
+    st.lambda = lambda; st.done = 0; st.cg_active = 1; st.solve_ok = 1;
+    CU(cudaMemcpy(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.p, x, sizeof(double) * n6, cudaMemcpyHostToDevice));
+    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
+    LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0);
+    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
+    if (int rc = allreduce(h, d.ar_q, n6)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<double> U(36 * (size_t)N), wv(n6);
+    CU(cudaMemcpy(U.data(), d.U, sizeof(double) * 36 * (size_t)N, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(wv.data(), d.ar_q, sizeof(double) * n6, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; ++i) for (int a = 0; a < 6; ++a) {
+        double v = lambda * x[6 * (size_t)i + a];
+        for (int b = 0; b < 6; ++b) v += U[36 * (size_t)i + 6 * a + b] * x[6 * (size_t)i + b];
+        Sx[6 * (size_t)i + a] = v - wv[6 * (size_t)i + a];
+    }
+    CU(cudaMemcpy(h->st.p, &sv, sizeof sv, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static const char* kKernelNames[] = {"linearize_points", "linearize_cameras", "cg_point_pass", "cg_camera_pass",
+                                     "camera_reduce6", "cg_update", "schur_diag_cameras", "point_vinv",
+                                     "backsub_cost_points", "precond_invert"};
+const char* b200ba_kernel_name(int32_t which)
+{
+    return (which >= 0 && which < (int)(sizeof kKernelNames / sizeof *kKernelNames)) ? kKernelNames[which] : nullptr;
+}
+
+int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, double* ms_per_launch)
+{
+    if (!h || !ms_per_launch || reps <= 0 || !b200ba_kernel_name(which)) return B200BA_E_INVALID;
+    if (!h->begun) return fail(h, B200BA_E_STATE, "b200ba_debug_time_kernel before b200ba_begin");
+    CU(cudaSetDevice(h->device));
+    Dev& d = h->d;
+    LMState st; CU(cudaMemcpy(&st, h->st.p, sizeof st, cudaMemcpyDeviceToHost));
+    LMState sv = st;
+    st.done = 0; st.compute = 1; st.cg_active = 1; st.solve_ok = 1; st.cg_tol = 0;
+    CU(cudaMemcpy(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice));
+    auto one = [&]() {
+        switch (which) {
+        case 0: LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d); break;
+        case 1: LAUNCH(k_linearize_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d); break;
+        case 2: LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d); break;
+        case 3: LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0); break;
+        case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0); break;
+        case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
+        case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d); break;
+        case 7: LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d); break;
+        case 8: LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d); break;
+        case 9: LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond); break;
+        }
+        return 0;
+    };
+    for (int w = 0; w < 3; ++w) one();
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < reps; ++r) one();
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *ms_per_launch = ms / reps;
+    CU(cudaMemcpy(h->st.p, &sv, sizeof sv, cudaMemcpyHostToDevice));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

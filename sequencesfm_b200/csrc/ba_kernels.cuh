@@ -1,0 +1,792 @@
+// ba_kernels.cuh -- sm_100a device code of the B200 bundle-adjustment engine (fp64).
+//
+// Cost model and LM rules are those of the reference's live path (SSBA-3.0 as driven by
+// src/sfm_ba_ssba.cpp); every kernel cites the reference lines whose arithmetic it carries out.  The
+// organisation is NOT the reference's: nothing per-observation is stored except one weight; Jacobian
+// blocks are recomputed in registers in every pass; the damped normal equations are never assembled --
+// the reduced camera system S = (U + lambda I) - W (V + lambda I)^-1 W^t is applied matrix-free in two
+// sweeps (by point, then by camera) and solved by block-Jacobi PCG; all reductions are segmented
+// (thread-per-point over point-sorted observations, warp-per-chunk over camera-sorted observations with a
+// fixed-order second level) so there is no atomic on any accumulator and results are bit-reproducible.
+//
+// Memory layout (HBM, all fp64 unless noted):
+//   cameras   rt[2]   N x 12   row-major [R|T] (96 B = 3 sectors), current / trial copy selected by st->cur
+//             U, Minv N x 36   full symmetric 6x6 blocks;  gc, x, r, z, p  N x 6
+//   points    X[2]    M x 4    xyz + pad (32 B = 1 sector so a by-camera gather costs one sector)
+//             V, Vinv M x 6    symmetric 3x3 (xx xy xz yy yz zz);  gp, v  M x 4
+//   obs (point order)   o_cam int32, o_meas double2 (normalised), o_w double;  pstart[M+1] CSR offsets
+//   obs (camera order)  c_pt  int32, c_meas double2,             c_w double;  chunk tables (<= CHUNK obs of
+//                       one camera per chunk, chunks of a camera contiguous)
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace b200ba {
+
+constexpr int CHUNK        = 256;   // observations of one camera handled by one warp
+constexpr int PT_BLOCK     = 128;   // threads per block in thread-per-point kernels
+constexpr int CH_BLOCK     = 128;   // threads per block in warp-per-chunk kernels (4 chunks)
+constexpr int PART_STRIDE  = 28;    // doubles per chunk partial: 21 (sym 6x6) + 6 (+1 pad)
+constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side kernels
+constexpr int TRACE_COLS   = 8;
+
+struct Intrinsics {
+    double k00, k01, k02, k11, k12;   // unit-focal-length intrinsics (src/sfm_ba_ssba.cpp:98-102)
+    double huber;                     // 2 / |f0| (src/sfm_ba_ssba.cpp:193); <= 0: robustifier off
+    double f0;
+};
+
+// Device-resident LM / CG control block: all accept/reject and stop decisions are taken on the device
+// (reference keeps them in host scalars, v3d_optimization.cpp:879-978).
+struct LMState {
+    double lambda, err, new_err, rho;
+    double rz, rz0, cg_rel;
+    double d2c, denomc;
+    double param_length;
+    double tau, grad_thr, upd_thr, cg_tol;
+    int iter, status, done, compute, cur, first;
+    int cg_active, cg_steps, solve_ok, total_cg;
+    int max_iter, min_iter, n_trace, trace_cap;
+};
+
+struct Dev {
+    int N, M, K, n_chunks, first_free, n_pt_blocks, world, rank;
+    Intrinsics in;
+    LMState* st;
+    double* rt[2];
+    double *U, *gc, *Minv, *x, *r, *z, *p, *q;
+    double* ar_lin;     // [N x 28 | cost | ginf slots(world) | vmax slots(world)]  all-reduced after linearisation
+    double* ar_q;       // N x 6  reduced sum_k W_k v_j, all-reduced every CG step
+    double* ar_sd;      // N x 21 Schur-diagonal correction, all-reduced
+    double* ar_dec;     // [d2p, denomp, new_cost, pad]
+    double* X[2];
+    double *V, *gp, *Vinv, *v;
+    int* o_cam; double2* o_meas; double* o_w; int* pstart;
+    int* c_pt; double2* c_meas; double* c_w;
+    int *chunk_cam, *chunk_beg, *chunk_end, *cam_chunk_beg;
+    double* chunk_part;   // n_chunks x PART_STRIDE
+    double* pt_part;      // n_pt_blocks x 4
+    double* trace;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// deterministic block reductions (fixed butterfly + fixed-order cross-warp sum); result valid in all threads
+template <int NT> __device__ __forceinline__ double block_sum(double v, double* sm)
+{
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0;
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) t += sm[i];
+    return t;
+}
+template <int NT> __device__ __forceinline__ double block_max(double v, double* sm)
+{
+    v = warp_max(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double t = sm[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; ++i) t = fmax(t, sm[i]);
+    return t;
+}
+
+struct Cam { double R[9], T[3]; };
+__device__ __forceinline__ void load_cam(const double* __restrict__ rt, int i, Cam& c)
+{
+    const double2* s = reinterpret_cast<const double2*>(rt + 12 * (size_t)i);
+    double2 a = __ldg(s), b = __ldg(s + 1), d = __ldg(s + 2), e = __ldg(s + 3), f = __ldg(s + 4), g = __ldg(s + 5);
+    c.R[0] = a.x; c.R[1] = a.y; c.R[2] = b.x; c.T[0] = b.y;
+    c.R[3] = d.x; c.R[4] = d.y; c.R[5] = e.x; c.T[1] = e.y;
+    c.R[6] = f.x; c.R[7] = f.y; c.R[8] = g.x; c.T[2] = g.y;
+}
+__device__ __forceinline__ void load3p(const double* __restrict__ base, int j, double X[3])   // padded 4-double record
+{
+    const double2* s = reinterpret_cast<const double2*>(base + 4 * (size_t)j);
+    double2 a = __ldg(s), b = __ldg(s + 1);
+    X[0] = a.x; X[1] = a.y; X[2] = b.x;
+}
+__device__ __forceinline__ void load6(const double* __restrict__ base, int i, double v[6])
+{
+    const double2* s = reinterpret_cast<const double2*>(base + 6 * (size_t)i);
+    double2 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+
+// Per-observation geometry: camera-space point, residual, Huber weight, weighted projection Jacobian.
+//   residual  e = K^ (XX / z) - m                         v3d_metricbundle.h:185-209
+//   weight    w = 1 | sqrt(thr / |e|)                     v3d_metricbundle.h:49-57
+//   dp/dXX    [[f/z, 0, -f x/z^2], [0, ar f/z, -ar f y/z^2]]   v3d_metricbundle.cpp:126-141 (skew ignored, as there)
+// The weighted 2x3 matrix is kept as (a, b, c, d):  [[a, 0, b], [0, c, d]].
+struct Obs {
+    double e0, e1, w;          // unweighted residual, weight
+    double a, b, c, d;         // w * dp/dXX
+    double r0, r1, r2;         // R X  (= XX - T), the lever arm of the rotation derivative
+};
+__device__ __forceinline__ void obs_residual(const Cam& cm, const double X[3], double2 m, const Intrinsics& in,
+                                             double& e0, double& e1, double& x, double& y, double& iz,
+                                             double& r0, double& r1, double& r2)
+{
+    r0 = cm.R[0] * X[0] + cm.R[1] * X[1] + cm.R[2] * X[2];
+    r1 = cm.R[3] * X[0] + cm.R[4] * X[1] + cm.R[5] * X[2];
+    r2 = cm.R[6] * X[0] + cm.R[7] * X[1] + cm.R[8] * X[2];
+    x = r0 + cm.T[0]; y = r1 + cm.T[1];
+    double z = r2 + cm.T[2];
+    iz = 1.0 / z;
+    double u = x * iz, v = y * iz;
+    e0 = in.k00 * u + in.k01 * v + in.k02 - m.x;
+    e1 = in.k11 * v + in.k12 - m.y;
+}
+__device__ __forceinline__ double huber_weight(double e0, double e1, double thr)
+{
+    if (thr <= 0.0) return 1.0;
+    double n = sqrt(e0 * e0 + e1 * e1);
+    return (n < thr) ? 1.0 : sqrt(thr / n);
+}
+// full geometry with the weight recomputed from the residual
+__device__ __forceinline__ void obs_full(const Cam& cm, const double X[3], double2 m, const Intrinsics& in, Obs& o)
+{
+    double x, y, iz;
+    obs_residual(cm, X, m, in, o.e0, o.e1, x, y, iz, o.r0, o.r1, o.r2);
+    o.w = huber_weight(o.e0, o.e1, in.huber);
+    double f = in.k00, ar = in.k11 / in.k00;
+    double wf = o.w * f * iz;
+    o.a = wf; o.b = -wf * x * iz; o.c = ar * wf; o.d = -ar * wf * y * iz;
+}
+// geometry for the CG sweeps: weight given (stored at linearisation), no measurement needed
+__device__ __forceinline__ void obs_jac(const Cam& cm, const double X[3], double w, const Intrinsics& in, Obs& o)
+{
+    o.r0 = cm.R[0] * X[0] + cm.R[1] * X[1] + cm.R[2] * X[2];
+    o.r1 = cm.R[3] * X[0] + cm.R[4] * X[1] + cm.R[5] * X[2];
+    o.r2 = cm.R[6] * X[0] + cm.R[7] * X[1] + cm.R[8] * X[2];
+    double x = o.r0 + cm.T[0], y = o.r1 + cm.T[1], z = o.r2 + cm.T[2];
+    double iz = 1.0 / z;
+    double f = in.k00, ar = in.k11 / in.k00;
+    double wf = w * f * iz;
+    o.w = w;
+    o.a = wf; o.b = -wf * x * iz; o.c = ar * wf; o.d = -ar * wf * y * iz;
+}
+// rows of the weighted camera Jacobian A~ = w dp/dXX [I | -[R X]x]   (poseDerivatives, v3d_metricbundle.cpp:52-71;
+// parameter order t then omega)
+__device__ __forceinline__ void jac_rows_A(const Obs& o, double A0[6], double A1[6])
+{
+    A0[0] = o.a; A0[1] = 0.0; A0[2] = o.b; A0[3] = o.b * o.r1; A0[4] = o.a * o.r2 - o.b * o.r0; A0[5] = -o.a * o.r1;
+    A1[0] = 0.0; A1[1] = o.c; A1[2] = o.d; A1[3] = o.d * o.r1 - o.c * o.r2; A1[4] = -o.d * o.r0; A1[5] = o.c * o.r0;
+}
+// rows of the weighted point Jacobian B~ = w dp/dXX R
+__device__ __forceinline__ void jac_rows_B(const Obs& o, const Cam& cm, double B0[3], double B1[3])
+{
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        B0[c] = o.a * cm.R[c] + o.b * cm.R[6 + c];
+        B1[c] = o.c * cm.R[3 + c] + o.d * cm.R[6 + c];
+    }
+}
+// t = A~ p   (2-vector);  p = (pt, pw):  A~ p = P~ (pt + pw x r)
+__device__ __forceinline__ void apply_A(const Obs& o, const double p[6], double& t0, double& t1)
+{
+    double s0 = p[0] + (p[4] * o.r2 - p[5] * o.r1);
+    double s1 = p[1] + (p[5] * o.r0 - p[3] * o.r2);
+    double s2 = p[2] + (p[3] * o.r1 - p[4] * o.r0);
+    t0 = o.a * s0 + o.b * s2;
+    t1 = o.c * s1 + o.d * s2;
+}
+// h = P~^t y  (camera-space 3-vector)
+__device__ __forceinline__ void apply_Pt(const Obs& o, double y0, double y1, double h[3])
+{
+    h[0] = o.a * y0; h[1] = o.c * y1; h[2] = o.b * y0 + o.d * y1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1  linearize_points: one thread per point over its (contiguous) observations.
+//     residual + Huber weight (stored), cost, V_j = sum B~^t B~, g_p,j = sum B~^t (-w e)
+//     (v3d_optimization.cpp:512-524, 543-558, 616-630).  Block partials: cost, max|g_p|, max diag V.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
+{
+    __shared__ double sm[PT_BLOCK / 32];
+    const LMState* st = d.st;
+    if (st->done || !st->compute) return;
+    int j = blockIdx.x * PT_BLOCK + threadIdx.x;
+    double cost = 0, gmax = 0, vmax = -1e30;
+    if (j < d.M) {
+        const double* Xb = d.X[st->cur]; const double* rt = d.rt[st->cur];
+        double X[3]; load3p(Xb, j, X);
+        double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        int k0 = d.pstart[j], k1 = d.pstart[j + 1];
+        for (int k = k0; k < k1; ++k) {
+            Cam cm; load_cam(rt, __ldg(d.o_cam + k), cm);
+            Obs o; obs_full(cm, X, __ldg(d.o_meas + k), d.in, o);
+            d.o_w[k] = o.w;
+            double we0 = o.w * o.e0, we1 = o.w * o.e1;
+            cost += we0 * we0 + we1 * we1;
+            double B0[3], B1[3]; jac_rows_B(o, cm, B0, B1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] += B0[c] * (-we0) + B1[c] * (-we1);
+            V[0] += B0[0] * B0[0] + B1[0] * B1[0]; V[1] += B0[0] * B0[1] + B1[0] * B1[1]; V[2] += B0[0] * B0[2] + B1[0] * B1[2];
+            V[3] += B0[1] * B0[1] + B1[1] * B1[1]; V[4] += B0[1] * B0[2] + B1[1] * B1[2]; V[5] += B0[2] * B0[2] + B1[2] * B1[2];
+        }
+        double2* Vo = reinterpret_cast<double2*>(d.V + 6 * (size_t)j);
+        Vo[0] = make_double2(V[0], V[1]); Vo[1] = make_double2(V[2], V[3]); Vo[2] = make_double2(V[4], V[5]);
+        double2* go = reinterpret_cast<double2*>(d.gp + 4 * (size_t)j);
+        go[0] = make_double2(g[0], g[1]); go[1] = make_double2(g[2], 0.0);
+        gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+        vmax = fmax(V[0], fmax(V[3], V[5]));
+    }
+    cost = block_sum<PT_BLOCK>(cost, sm);
+    gmax = block_max<PT_BLOCK>(gmax, sm);
+    vmax = block_max<PT_BLOCK>(vmax, sm);
+    if (threadIdx.x == 0) {
+        double* o = d.pt_part + 4 * (size_t)blockIdx.x;
+        o[0] = cost; o[1] = gmax; o[2] = vmax; o[3] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2  linearize_cameras: one warp per chunk of <= CHUNK camera-sorted observations of one camera.
+//     U_i += A~^t A~ (21 unique), g_c,i += A~^t (-w e)   (v3d_optimization.cpp:530-541, 600-614); the weight is
+//     recomputed from the residual and stored in camera order for the CG sweeps.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
+{
+    const LMState* st = d.st;
+    if (st->done || !st->compute) return;
+    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ch >= d.n_chunks) return;
+    int i = d.chunk_cam[ch];
+    double acc[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = 0;
+    if (i >= d.first_free) {
+        const double* Xb = d.X[st->cur];
+        Cam cm; load_cam(d.rt[st->cur], i, cm);
+        int k1 = d.chunk_end[ch];
+        for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
+            double X[3]; load3p(Xb, __ldg(d.c_pt + k), X);
+            Obs o; obs_full(cm, X, __ldg(d.c_meas + k), d.in, o);
+            d.c_w[k] = o.w;
+            double A0[6], A1[6]; jac_rows_A(o, A0, A1);
+            double we0 = -o.w * o.e0, we1 = -o.w * o.e1;
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) acc[q++] += A0[a] * A0[b] + A1[a] * A1[b];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[21 + a] += A0[a] * we0 + A1[a] * we1;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+        double* o = d.chunk_part + PART_STRIDE * (size_t)ch;
+#pragma unroll
+        for (int q = 0; q < 27; ++q) o[q] = acc[q];
+    }
+}
+
+// second level of every by-camera reduction: fixed-order sum of a camera's chunk partials
+template <int NV, int OSTRIDE>
+__global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_compute)
+{
+    const LMState* st = d.st;
+    if (st->done || (need_compute && !st->compute)) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = t / NV, c = t - i * NV;
+    if (i >= d.N) return;
+    double s = 0;
+    for (int ch = d.cam_chunk_beg[i]; ch < d.cam_chunk_beg[i + 1]; ++ch) s += d.chunk_part[PART_STRIDE * (size_t)ch + c];
+    out[(size_t)i * OSTRIDE + c] = s;
+}
+
+// reduce the per-block partials of a thread-per-point kernel in a fixed order (single CTA).
+// mode 0 (linearisation): out = ar_lin tail  [cost | ginf slot(rank) | vmax slot(rank)]
+// mode 1 (decision):      out = ar_dec       [d2p, denomp, new_cost]
+// mode 2 (statistics):    like 1 but runs regardless of st->done (mean reprojection error)
+__global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mode)
+{
+    __shared__ double sm[ONE_CTA / 32];
+    const LMState* st = d.st;
+    if ((mode != 2 && st->done) || (mode == 0 && !st->compute)) return;
+    double a = 0, b = 0.0, c = (mode == 0) ? -1e30 : 0.0;
+    for (int i = threadIdx.x; i < d.n_pt_blocks; i += ONE_CTA) {
+        const double* p = d.pt_part + 4 * (size_t)i;
+        a += p[0];
+        if (mode == 0) { b = fmax(b, p[1]); c = fmax(c, p[2]); } else { b += p[1]; c += p[2]; }
+    }
+    a = block_sum<ONE_CTA>(a, sm);
+    if (mode == 0) { b = block_max<ONE_CTA>(b, sm); c = block_max<ONE_CTA>(c, sm); }
+    else           { b = block_sum<ONE_CTA>(b, sm); c = block_sum<ONE_CTA>(c, sm); }
+    if (threadIdx.x == 0) {
+        if (mode == 0) {
+            double* o = d.ar_lin + (size_t)d.N * PART_STRIDE;
+            o[0] = a;
+            for (int r = 0; r < d.world; ++r) { o[1 + r] = (r == d.rank) ? b : 0.0; o[1 + d.world + r] = (r == d.rank) ? c : 0.0; }
+        } else {
+            d.ar_dec[0] = a; d.ar_dec[1] = b; d.ar_dec[2] = c; d.ar_dec[3] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4  lm_prepare (single CTA): unpack U / g_c, |J^t e|_inf stop (v3d_optimization.cpp:587), lambda0 on the
+//     first linearisation (v3d_optimization.cpp:711-782).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
+{
+    __shared__ double sm[ONE_CTA / 32];
+    LMState* st = d.st;
+    if (st->done) return;
+    if (st->compute) {
+        double gmax = 0, umax = -1e30;
+        for (int i = threadIdx.x; i < d.N; i += ONE_CTA) {
+            const double* s = d.ar_lin + (size_t)i * PART_STRIDE;
+            double* U = d.U + 36 * (size_t)i;
+            int q = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int b = a; b < 6; ++b) { double v = s[q++]; U[6 * a + b] = v; U[6 * b + a] = v; }
+            for (int a = 0; a < 6; ++a) {
+                double g = s[21 + a];
+                d.gc[6 * (size_t)i + a] = g;
+                if (i >= d.first_free) { gmax = fmax(gmax, fabs(g)); umax = fmax(umax, U[7 * a]); }
+            }
+        }
+        gmax = block_max<ONE_CTA>(gmax, sm);
+        umax = block_max<ONE_CTA>(umax, sm);
+        if (threadIdx.x == 0) {
+            const double* t = d.ar_lin + (size_t)d.N * PART_STRIDE;
+            double gp = 0, vm = -1e30;
+            for (int r = 0; r < d.world; ++r) { gp = fmax(gp, t[1 + r]); vm = fmax(vm, t[1 + d.world + r]); }
+            st->err = t[0];
+            double ginf = fmax(gmax, gp);
+            if (ginf < st->grad_thr) { st->status = 2; st->done = 1; }
+            if (st->first) { st->lambda = st->tau * fmax(umax, vm); st->first = 0; }
+        }
+    }
+    if (threadIdx.x == 0) { st->solve_ok = 1; }
+}
+
+// K5  point_vinv: (V_j + lambda I)^-1 in registers (adjugate / determinant); not positive definite => the
+//     step is rejected like an LDL failure (v3d_optimization.cpp:869-874).
+__global__ void __launch_bounds__(256) k_point_vinv(Dev d)
+{
+    LMState* st = d.st;
+    if (st->done) return;
+    int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= d.M) return;
+    double V[6]; load6(d.V, j, V);
+    double l = st->lambda;
+    double a = V[0] + l, b = V[1], c = V[2], e = V[3] + l, f = V[4], g = V[5] + l;
+    double c00 = e * g - f * f, c01 = c * f - b * g, c02 = b * f - c * e;
+    double det = a * c00 + b * c01 + c * c02;
+    bool ok = (det > 0) && (a > 0) && (a * e - b * b > 0);
+    double id = 1.0 / det;
+    double2* o = reinterpret_cast<double2*>(d.Vinv + 6 * (size_t)j);
+    o[0] = make_double2(c00 * id, c01 * id);
+    o[1] = make_double2(c02 * id, (a * g - c * c) * id);
+    o[2] = make_double2((b * c - a * f) * id, (a * e - b * b) * id);
+    if (!ok) st->solve_ok = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6  schur_diag_cameras: warp per chunk, sum_k W_k (V+lambda I)^-1 W_k^t (21 unique), W_k = A~^t B~.
+//     Gives the diagonal blocks of S for the block-Jacobi preconditioner.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
+{
+    const LMState* st = d.st;
+    if (st->done) return;
+    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ch >= d.n_chunks) return;
+    int i = d.chunk_cam[ch];
+    double acc[21];
+#pragma unroll
+    for (int q = 0; q < 21; ++q) acc[q] = 0;
+    if (i >= d.first_free) {
+        const double* Xb = d.X[st->cur];
+        Cam cm; load_cam(d.rt[st->cur], i, cm);
+        int k1 = d.chunk_end[ch];
+        for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
+            int j = __ldg(d.c_pt + k);
+            double X[3]; load3p(Xb, j, X);
+            Obs o; obs_jac(cm, X, __ldg(d.c_w + k), d.in, o);
+            double Vi[6]; load6(d.Vinv, j, Vi);
+            // camera-space covariance  C = R Vinv R^t (sym 3x3), then G = P~ C P~^t (sym 2x2), then
+            // W Vinv W^t = A~^t G A~  because W = A~^t P~ R.
+            double RV[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double r0 = cm.R[3 * r], r1 = cm.R[3 * r + 1], r2 = cm.R[3 * r + 2];
+                RV[3 * r]     = r0 * Vi[0] + r1 * Vi[1] + r2 * Vi[2];
+                RV[3 * r + 1] = r0 * Vi[1] + r1 * Vi[3] + r2 * Vi[4];
+                RV[3 * r + 2] = r0 * Vi[2] + r1 * Vi[4] + r2 * Vi[5];
+            }
+            double C00 = RV[0] * cm.R[0] + RV[1] * cm.R[1] + RV[2] * cm.R[2];
+            double C02 = RV[0] * cm.R[6] + RV[1] * cm.R[7] + RV[2] * cm.R[8];
+            double C01 = RV[0] * cm.R[3] + RV[1] * cm.R[4] + RV[2] * cm.R[5];
+            double C11 = RV[3] * cm.R[3] + RV[4] * cm.R[4] + RV[5] * cm.R[5];
+            double C12 = RV[3] * cm.R[6] + RV[4] * cm.R[7] + RV[5] * cm.R[8];
+            double C22 = RV[6] * cm.R[6] + RV[7] * cm.R[7] + RV[8] * cm.R[8];
+            // G = P C P^t with P = [[a,0,b],[0,c,d]]
+            double G00 = o.a * o.a * C00 + 2.0 * o.a * o.b * C02 + o.b * o.b * C22;
+            double G01 = o.a * o.c * C01 + o.a * o.d * C02 + o.b * o.c * C12 + o.b * o.d * C22;
+            double G11 = o.c * o.c * C11 + 2.0 * o.c * o.d * C12 + o.d * o.d * C22;
+            double A0[6], A1[6]; jac_rows_A(o, A0, A1);
+            // A^t G A : rows combined  Y0 = G00 A0 + G01 A1, Y1 = G01 A0 + G11 A1;  result[a][b] = A0[a] Y0[b] + A1[a] Y1[b]
+            double Y0[6], Y1[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) { Y0[a] = G00 * A0[a] + G01 * A1[a]; Y1[a] = G01 * A0[a] + G11 * A1[a]; }
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) acc[q++] += A0[a] * Y0[b] + A1[a] * Y1[b];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 21; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+        double* o = d.chunk_part + PART_STRIDE * (size_t)ch;
+#pragma unroll
+        for (int q = 0; q < 21; ++q) o[q] = acc[q];
+    }
+}
+
+// K7  precond_invert: one thread per camera, M_i = (U_i + lambda I - [precond] sum W Vinv W^t)^-1 by Cholesky.
+__global__ void __launch_bounds__(128) k_precond_invert(Dev d, int precond)
+{
+    LMState* st = d.st;
+    if (st->done) return;
+    int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= d.N) return;
+    double L[36];
+    const double* U = d.U + 36 * (size_t)i;
+    double lam = st->lambda;
+#pragma unroll
+    for (int a = 0; a < 36; ++a) L[a] = U[a];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) L[7 * a] += lam;
+    if (precond == 1) {
+        const double* s = d.ar_sd + 21 * (size_t)i;
+        int q = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { double v = s[q++]; L[6 * a + b] -= v; if (a != b) L[6 * b + a] -= v; }
+    }
+    bool ok = true;
+    for (int j = 0; j < 6; ++j) {
+        double dd = L[7 * j];
+        for (int k = 0; k < j; ++k) dd -= L[6 * j + k] * L[6 * j + k];
+        if (!(dd > 0)) { ok = false; dd = 1.0; }
+        dd = sqrt(dd); L[7 * j] = dd;
+        for (int r = j + 1; r < 6; ++r) {
+            double v = L[6 * r + j];
+            for (int k = 0; k < j; ++k) v -= L[6 * r + k] * L[6 * j + k];
+            L[6 * r + j] = v / dd;
+        }
+    }
+    double* Mi = d.Minv + 36 * (size_t)i;
+    for (int c = 0; c < 6; ++c) {
+        double x[6];
+        for (int r = 0; r < 6; ++r) { double v = (r == c) ? 1.0 : 0.0; for (int k = 0; k < r; ++k) v -= L[6 * r + k] * x[k]; x[r] = v / L[7 * r]; }
+        for (int r = 5; r >= 0; --r) { double v = x[r]; for (int k = r + 1; k < 6; ++k) v -= L[6 * k + r] * x[k]; x[r] = v / L[7 * r]; }
+        for (int r = 0; r < 6; ++r) Mi[6 * r + c] = x[r];
+    }
+    if (!ok) st->solve_ok = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K8  cg_point_pass: v_j = (V+lambda I)^-1 u_j with
+//       MODE 0: u_j = sum_k W_k^t p_i(k) = sum_k R^t P~^t P~ (pt + pw x r)     (first half of S p)
+//       MODE 1: u_j = g_p,j                                                     (for the reduced rhs)
+//       MODE 2: u_j = g_p,j - sum_k W_k^t x_i(k)  -> delta_p, trial point, trial cost, |delta_p|^2, delta_p.g_p
+//                                                                               (back-substitution + cost re-evaluation,
+//                                                                                v3d_optimization.cpp:908-921)
+// ------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
+{
+    __shared__ double sm[PT_BLOCK / 32];
+    const LMState* st = d.st;
+    if (st->done) return;
+    if (MODE == 0 && !st->cg_active) return;
+    if (MODE != 0 && !st->solve_ok) return;
+    int j = blockIdx.x * PT_BLOCK + threadIdx.x;
+    double d2 = 0, dg = 0, cost = 0;
+    if (j < d.M) {
+        int cur = st->cur;
+        double u[3] = {0, 0, 0}, X[3], g[3];
+        if (MODE != 1) load3p(d.X[cur], j, X);
+        if (MODE != 0) load3p(d.gp, j, g);
+        int k0 = d.pstart[j], k1 = d.pstart[j + 1];
+        if (MODE != 1) {
+            const double* vec = (MODE == 0) ? d.p : d.x;
+            const double* rt = d.rt[cur];
+            for (int k = k0; k < k1; ++k) {
+                int i = __ldg(d.o_cam + k);
+                Cam cm; load_cam(rt, i, cm);
+                Obs o; obs_jac(cm, X, __ldg(d.o_w + k), d.in, o);
+                double p[6]; load6(vec, i, p);
+                double t0, t1; apply_A(o, p, t0, t1);
+                if (i < d.first_free) { t0 = 0; t1 = 0; }
+                double h[3]; apply_Pt(o, t0, t1, h);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) u[c] += cm.R[c] * h[0] + cm.R[3 + c] * h[1] + cm.R[6 + c] * h[2];
+            }
+        }
+        if (MODE == 1) { u[0] = g[0]; u[1] = g[1]; u[2] = g[2]; }
+        if (MODE == 2) { u[0] = g[0] - u[0]; u[1] = g[1] - u[1]; u[2] = g[2] - u[2]; }
+        double Vi[6]; load6(d.Vinv, j, Vi);
+        double v0 = Vi[0] * u[0] + Vi[1] * u[1] + Vi[2] * u[2];
+        double v1 = Vi[1] * u[0] + Vi[3] * u[1] + Vi[4] * u[2];
+        double v2 = Vi[2] * u[0] + Vi[4] * u[1] + Vi[5] * u[2];
+        if (MODE != 2) {
+            double2* o = reinterpret_cast<double2*>(d.v + 4 * (size_t)j);
+            o[0] = make_double2(v0, v1); o[1] = make_double2(v2, 0.0);
+        } else {
+            d2 = v0 * v0 + v1 * v1 + v2 * v2;
+            dg = v0 * g[0] + v1 * g[1] + v2 * g[2];
+            double Xn[3] = {X[0] + v0, X[1] + v1, X[2] + v2};           // updateParametersB, v3d_metricbundle.cpp:42-50
+            double2* o = reinterpret_cast<double2*>(d.X[cur ^ 1] + 4 * (size_t)j);
+            o[0] = make_double2(Xn[0], Xn[1]); o[1] = make_double2(Xn[2], 0.0);
+            const double* rtn = d.rt[cur ^ 1];                          // trial cameras written by k_cg_finish
+            for (int k = k0; k < k1; ++k) {
+                Cam cm; load_cam(rtn, __ldg(d.o_cam + k), cm);
+                double e0, e1, x, y, iz, r0, r1, r2;
+                obs_residual(cm, Xn, __ldg(d.o_meas + k), d.in, e0, e1, x, y, iz, r0, r1, r2);
+                double w = huber_weight(e0, e1, d.in.huber);            // weights re-evaluated at the trial point (:917)
+                double a = w * e0, b = w * e1;
+                cost += a * a + b * b;
+            }
+        }
+    }
+    if (MODE == 2) {
+        d2 = block_sum<PT_BLOCK>(d2, sm);
+        dg = block_sum<PT_BLOCK>(dg, sm);
+        cost = block_sum<PT_BLOCK>(cost, sm);
+        if (threadIdx.x == 0) {
+            double* o = d.pt_part + 4 * (size_t)blockIdx.x;
+            o[0] = d2; o[1] = dg; o[2] = cost; o[3] = 0;
+        }
+    }
+}
+
+// K9  cg_camera_pass: warp per chunk, sum_k W_k v_j(k) = sum_k A~^t P~ R v_j   (second half of S p)
+__global__ void __launch_bounds__(CH_BLOCK) k_cg_camera_pass(Dev d, int rhs_pass)
+{
+    const LMState* st = d.st;
+    if (st->done) return;
+    if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
+    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ch >= d.n_chunks) return;
+    int i = d.chunk_cam[ch];
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (i >= d.first_free) {
+        const double* Xb = d.X[st->cur];
+        Cam cm; load_cam(d.rt[st->cur], i, cm);
+        int k1 = d.chunk_end[ch];
+        for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
+            int j = __ldg(d.c_pt + k);
+            double X[3], v[3]; load3p(Xb, j, X); load3p(d.v, j, v);
+            Obs o; obs_jac(cm, X, __ldg(d.c_w + k), d.in, o);
+            double g0 = cm.R[0] * v[0] + cm.R[1] * v[1] + cm.R[2] * v[2];
+            double g1 = cm.R[3] * v[0] + cm.R[4] * v[1] + cm.R[5] * v[2];
+            double g2 = cm.R[6] * v[0] + cm.R[7] * v[1] + cm.R[8] * v[2];
+            double y0 = o.a * g0 + o.b * g2, y1 = o.c * g1 + o.d * g2;
+            double h[3]; apply_Pt(o, y0, y1, h);
+            acc[0] += h[0]; acc[1] += h[1]; acc[2] += h[2];
+            acc[3] += o.r1 * h[2] - o.r2 * h[1];       // r x h
+            acc[4] += o.r2 * h[0] - o.r0 * h[2];
+            acc[5] += o.r0 * h[1] - o.r1 * h[0];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+        double* o = d.chunk_part + PART_STRIDE * (size_t)ch;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) o[q] = acc[q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Camera-side PCG (single CTA; camera-sized vectors only).  Structure after PBA's implicit-Schur PCG
+// (SparseBundleCPU.cpp:3323-3450) with additive damping and S-block / U-block Jacobi preconditioner.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double matvec6_row(const double* __restrict__ Mblk, const double* __restrict__ v6, int a)
+{
+    const double* r = Mblk + 6 * a;
+    return r[0] * v6[0] + r[1] * v6[1] + r[2] * v6[2] + r[3] * v6[3] + r[4] * v6[4] + r[5] * v6[5];
+}
+
+// K10 cg_init: rhs = g_c - W Vinv g_p ; x = 0 ; r = rhs ; z = M r ; p = z
+__global__ void __launch_bounds__(ONE_CTA) k_cg_init(Dev d)
+{
+    __shared__ double sm[ONE_CTA / 32];
+    LMState* st = d.st;
+    if (st->done) return;
+    int n6 = 6 * d.N;
+    bool ok = st->solve_ok != 0;
+    if (ok) for (int e = threadIdx.x; e < n6; e += ONE_CTA) { d.x[e] = 0.0; d.r[e] = d.gc[e] - d.ar_q[e]; }
+    __syncthreads();
+    double rz = 0;
+    if (ok) for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
+        int i = e / 6, a = e - 6 * i;
+        double z = matvec6_row(d.Minv + 36 * (size_t)i, d.r + 6 * (size_t)i, a);
+        d.z[e] = z; d.p[e] = z; rz += d.r[e] * z;
+    }
+    rz = block_sum<ONE_CTA>(rz, sm);
+    if (threadIdx.x == 0) {
+        st->rz = rz; st->rz0 = rz; st->cg_rel = 0; st->cg_steps = 0;
+        st->cg_active = (ok && rz > 0) ? 1 : 0;
+    }
+}
+
+// K11 cg_update: q = (U + lambda I) p - sum W v ; alpha = r.z / p.q ; x += alpha p ; r -= alpha q ; z = M r ;
+//     beta = r.z' / r.z ; p = z + beta p
+__global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
+{
+    __shared__ double sm[ONE_CTA / 32];
+    LMState* st = d.st;
+    if (st->done || !st->cg_active) return;
+    int n6 = 6 * d.N;
+    double lam = st->lambda, rz = st->rz, rz0 = st->rz0, tol = st->cg_tol;
+    double pq = 0;
+    for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
+        int i = e / 6, a = e - 6 * i;
+        double q = lam * d.p[e] + matvec6_row(d.U + 36 * (size_t)i, d.p + 6 * (size_t)i, a) - d.ar_q[e];
+        d.q[e] = q; pq += d.p[e] * q;
+    }
+    pq = block_sum<ONE_CTA>(pq, sm);
+    if (!(pq > 0) || !isfinite(pq)) {                      // breakdown: keep x, first-step breakdown = failed solve
+        if (threadIdx.x == 0) { st->cg_active = 0; if (st->cg_steps == 0) st->solve_ok = 0; }
+        return;
+    }
+    double alpha = rz / pq;
+    for (int e = threadIdx.x; e < n6; e += ONE_CTA) { d.x[e] += alpha * d.p[e]; d.r[e] -= alpha * d.q[e]; }
+    __syncthreads();
+    double rzn = 0;
+    for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
+        int i = e / 6, a = e - 6 * i;
+        double z = matvec6_row(d.Minv + 36 * (size_t)i, d.r + 6 * (size_t)i, a);
+        d.z[e] = z; rzn += d.r[e] * z;
+    }
+    rzn = block_sum<ONE_CTA>(rzn, sm);
+    double rel = sqrt(fabs(rzn) / rz0);
+    bool stop = (tol > 0 && rel < tol) || !(rzn > 0);
+    if (!stop) {
+        double beta = rzn / rz;
+        for (int e = threadIdx.x; e < n6; e += ONE_CTA) d.p[e] = d.z[e] + beta * d.p[e];
+    }
+    if (threadIdx.x == 0) {
+        st->cg_steps += 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
+        if (stop) st->cg_active = 0;
+    }
+}
+
+// K12 cg_finish: delta_c = x; trial cameras T += dt, R <- Rodrigues(dw) R (v3d_metricbundle.cpp:17-39,
+//     v3d_mathutilities.h:173-194); camera part of |delta|^2 and delta . J^t e.
+__global__ void __launch_bounds__(ONE_CTA) k_cg_finish(Dev d)
+{
+    __shared__ double sm[ONE_CTA / 32];
+    LMState* st = d.st;
+    if (st->done) return;
+    bool ok = st->solve_ok != 0;
+    int cur = st->cur;
+    double d2 = 0, dg = 0;
+    int bad = 0;
+    if (ok) for (int i = threadIdx.x; i < d.N; i += ONE_CTA) {
+        double x[6];
+        for (int a = 0; a < 6; ++a) { x[a] = d.x[6 * (size_t)i + a]; d2 += x[a] * x[a]; dg += x[a] * d.gc[6 * (size_t)i + a]; if (!isfinite(x[a])) bad = 1; }
+        const double* s = d.rt[cur] + 12 * (size_t)i; double* o = d.rt[cur ^ 1] + 12 * (size_t)i;
+        double R[9] = {s[0], s[1], s[2], s[4], s[5], s[6], s[8], s[9], s[10]};
+        double T[3] = {s[3] + x[0], s[7] + x[1], s[11] + x[2]};
+        double w0 = x[3], w1 = x[4], w2 = x[5];
+        double th = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+        double dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (fabs(th) > 1e-6) {
+            double J[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0}, J2[9];
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) J2[3 * r + c] = J[3 * r] * J[c] + J[3 * r + 1] * J[3 + c] + J[3 * r + 2] * J[6 + c];
+            double c1 = sin(th) / th, c2 = (1.0 - cos(th)) / (th * th);
+            for (int a = 0; a < 9; ++a) dR[a] += c1 * J[a] + c2 * J2[a];
+        }
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) o[4 * r + c] = dR[3 * r] * R[c] + dR[3 * r + 1] * R[3 + c] + dR[3 * r + 2] * R[6 + c];
+            o[4 * r + 3] = T[r];
+        }
+    }
+    d2 = block_sum<ONE_CTA>(d2, sm);
+    dg = block_sum<ONE_CTA>(dg, sm);
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) { st->d2c = d2; st->denomc = dg; if (bad) st->solve_ok = 0; }
+}
+
+// K13 lm_decide (one thread): update stop test, gain ratio, accept/reject, damping update
+//     (v3d_optimization.cpp:879-978, v3d_optimization.h:49-50,60-64).
+__global__ void k_lm_decide(Dev d)
+{
+    LMState* st = d.st;
+    if (st->done) return;
+    int it = st->iter;
+    double* tr = (d.trace && st->n_trace < st->trace_cap) ? d.trace + TRACE_COLS * (size_t)st->n_trace : nullptr;
+    double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (tr) { tr[0] = it; tr[1] = st->err; tr[2] = st->lambda; tr[3] = nan; tr[4] = nan; tr[5] = 0; tr[6] = st->cg_steps; tr[7] = st->cg_rel; st->n_trace += 1; }
+    bool accept = false;
+    if (st->solve_ok) {
+        double d2 = st->d2c + d.ar_dec[0], denom2 = st->denomc + d.ar_dec[1], new_err = d.ar_dec[2];
+        if (it >= st->min_iter && sqrt(d2) < st->upd_thr * (st->param_length + st->upd_thr)) {
+            st->status = 1; st->done = 1;
+            if (tr) tr[5] = -1;
+            return;
+        }
+        double rho = (st->err - new_err) / (st->lambda * d2 + denom2);
+        st->new_err = new_err; st->rho = rho;
+        accept = rho > 0;
+        if (tr) { tr[3] = new_err; tr[4] = rho; tr[5] = accept ? 1 : 0; }
+    }
+    if (accept) { st->lambda = fmax(1e-10, st->lambda * 0.1); st->compute = 1; st->cur ^= 1; }
+    else        { st->lambda *= 10.0; st->compute = 0; }
+    st->iter = it + 1;
+    if (it + 1 >= st->max_iter) st->done = 1;
+}
+
+// mean reprojection error in pixels, the reference's own self-check (src/sfm_ba_ssba.cpp:26-51):
+// block partial sums of f0 * |e_k| (unweighted), thread per point.
+__global__ void __launch_bounds__(PT_BLOCK) k_reproj_sum(Dev d, int which)
+{
+    __shared__ double sm[PT_BLOCK / 32];
+    int j = blockIdx.x * PT_BLOCK + threadIdx.x;
+    double s = 0;
+    if (j < d.M) {
+        double X[3]; load3p(d.X[which], j, X);
+        for (int k = d.pstart[j]; k < d.pstart[j + 1]; ++k) {
+            Cam cm; load_cam(d.rt[which], __ldg(d.o_cam + k), cm);
+            double e0, e1, x, y, iz, r0, r1, r2;
+            obs_residual(cm, X, __ldg(d.o_meas + k), d.in, e0, e1, x, y, iz, r0, r1, r2);
+            s += d.in.f0 * sqrt(e0 * e0 + e1 * e1);
+        }
+    }
+    s = block_sum<PT_BLOCK>(s, sm);
+    if (threadIdx.x == 0) d.pt_part[4 * (size_t)blockIdx.x] = s;
+}
+
+} // namespace b200ba

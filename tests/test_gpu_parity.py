@@ -1,0 +1,222 @@
+"""GPU (-m gpu): the CUDA engine through the C ABI against the CPU oracle, the committed SSBA golden vectors, and
+size-independent properties at the benchmark's full size.  Tolerances are the north star's: per-iteration cost within
+1e-9 relative (fp64) inside the parity window (tests/util.py), final reprojection RMS within 1e-3 of the PBA run."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from sequencesfm_b200 import ba, binding
+from sequencesfm_b200.synth import make_problem
+from tests.util import COST_RTOL, golden_problem, load_golden, parity_window, rel, rel_cost_diff
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _solve(p, **kw):
+    with binding.Engine(**kw) as eng:
+        eng.set_problem_from(p)
+        return eng.solve()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# stage level: one linearisation and one Schur product
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,seed,kw", [("tiny", 1, {}), ("small", 2, {"outlier_frac": 0.03}),
+                                            ("ladybug", 1, {"fy_ratio": 1.01, "pp": (3.0, -2.0)}),
+                                            ((40, 3000, 6000), 7, {})])
+def test_linearisation_blocks_match_oracle(shape, seed, kw):
+    p = make_problem(shape, seed, **kw)
+    o = oracle.linearize(p)
+    with binding.Engine() as eng:
+        eng.set_problem_from(p)
+        eng.begin()
+        g = eng.debug_linearize()
+        x = np.random.default_rng(1).normal(size=(p.N, 6))
+        for lam in (o["lambda0"], 1e-6 * o["lambda0"]):
+            Sx = eng.debug_schur_matvec(lam, x)
+            oS = oracle.linearize(p, x=x.reshape(-1), lam=lam)["Sx"]
+            assert rel(Sx, oS) < 1e-11
+    assert abs(g["cost"] - o["cost"]) < 1e-13 * o["cost"]            # SSBA's first printed |residual|^2
+    assert abs(g["lambda0"] - o["lambda0"]) < 1e-13 * o["lambda0"]
+    assert np.array_equal(g["w"] == 1.0, o["w"] == 1.0)               # same inlier / outlier split
+    for k in ("w", "gc", "gp", "U", "V"):
+        assert rel(g[k], o[k]) < 1e-12, k                             # A_k^t A_k, B_k^t B_k, J^t e of v3d_optimization.cpp:530-630
+
+
+def test_schur_operator_is_symmetric_and_linear():
+    p = make_problem("ladybug", 4)
+    rng = np.random.default_rng(2)
+    with binding.Engine() as eng:
+        eng.set_problem_from(p); eng.begin(); g = eng.debug_linearize()
+        lam = g["lambda0"]
+        x, y = rng.normal(size=(p.N, 6)), rng.normal(size=(p.N, 6))
+        Sx, Sy = eng.debug_schur_matvec(lam, x), eng.debug_schur_matvec(lam, y)
+        Sxy = eng.debug_schur_matvec(lam, 2.0 * x - 3.0 * y)
+    assert abs(np.sum(y * Sx) - np.sum(x * Sy)) < 1e-11 * abs(np.sum(y * Sx))
+    assert rel(Sxy, 2.0 * Sx - 3.0 * Sy) < 1e-12
+    assert np.sum(x * Sx) > 0                                            # positive definite with damping
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full solves
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ssba_tiny_s1", "ssba_tiny_s2", "ssba_tiny_s3", "ssba_small_s1", "ssba_small_s2",
+                                  "ssba_small_s3", "ssba_ladybug_s1", "ssba_ladybug_s2", "ssba_ladybug_s3"])
+def test_cost_trajectory_matches_reference_golden(name):
+    """Tightly converged PCG (parity mode) reproduces the reference SSBA run: per-iteration cost <= 1e-9 relative."""
+    fx = load_golden(name)
+    p = golden_problem(fx)
+    r = _solve(p, cg_max_steps=4000, cg_rel_tol=1e-13)
+    ref = fx["trace"]
+    k = parity_window(r.trace, ref)
+    assert k >= min(8, len(ref) - 1), (k, len(ref))
+    d = rel_cost_diff(r.trace, ref, k)
+    assert d.max() < COST_RTOL, d
+    assert np.allclose(r.trace[:k, 2], ref[:k, 2], rtol=1e-9)           # damping schedule
+    assert abs(r.mean_px[0] - fx["mean_px"][0]) < 1e-9 * fx["mean_px"][0]
+    assert abs(r.mean_px[1] - fx["mean_px"][1]) < 1e-5 * fx["mean_px"][1]
+    if k == len(ref) and r.iterations == fx["iterations"]:
+        assert r.status == fx["status"] and r.ret == fx["ret"]
+        assert np.allclose(r.cam_RT[:3], np.array(fx["cam_RT_head"]), atol=1e-7)
+        assert np.allclose(r.pts[:5], np.array(fx["pts_head"]), atol=1e-7)
+
+
+def test_trafalgar_trajectory_matches_reference_golden():
+    fx = load_golden("ssba_trafalgar_s1")
+    p = golden_problem(fx)
+    r = _solve(p)                                                        # throughput mode: fixed 50 PCG steps
+    k = parity_window(r.trace, fx["trace"])
+    assert k >= 8
+    assert rel_cost_diff(r.trace, fx["trace"], min(k, 8)).max() < 1e-8
+    rt = _solve(p, cg_max_steps=2000, cg_rel_tol=1e-13, max_iterations=12)
+    k = parity_window(rt.trace, fx["trace"])
+    assert k >= 8
+    assert rel_cost_diff(rt.trace, fx["trace"], k).max() < COST_RTOL
+    # final RMS against the reference PBA run on the same inputs (north star: "within a stated tolerance" = 1e-3)
+    g = fx["pba_double_schur"]
+    q = _solve(p, **{"fix_first_camera": 1, "inlier_px": 0.0, "round_pixels": 0, "discard_converged": 0})
+    mse = q.final_cost * p.K5[0] ** 2 / p.K
+    assert abs(np.sqrt(mse) - np.sqrt(g["final_mse"])) < 1e-3 * np.sqrt(g["final_mse"])
+
+
+@pytest.mark.parametrize("shape,seed,kw,opts", [
+    ("small", 5, {}, {}),
+    ("small", 6, {"outlier_frac": 0.05}, {"precond": 0}),
+    ("ladybug", 5, {}, {"fix_first_camera": 1, "inlier_px": 0.0, "round_pixels": 0}),
+    ((30, 400, 800), 8, {}, {}),                                         # every point seen exactly twice
+])
+def test_fifty_step_mode_matches_oracle(shape, seed, kw, opts):
+    """Same algorithm on both sides (fixed 50-step PCG): the GPU follows the CPU restatement."""
+    p = make_problem(shape, seed, **kw)
+    r = _solve(p, **opts)
+    c = oracle.solve(p, **opts)
+    k = parity_window(r.trace, c.trace)
+    assert k >= min(8, len(c.trace) - 1)
+    assert rel_cost_diff(r.trace, c.trace, min(k, 10)).max() < COST_RTOL
+    assert abs(r.mean_px[1] - c.mean_px[1]) < 1e-5 * c.mean_px[1]
+    assert np.array_equal(r.trace[:k, 6], c.trace[:k, 6])               # same PCG step counts
+
+
+def test_status_and_discard_convention():
+    p = make_problem("tiny", 9)
+    r = _solve(p, max_iterations=1)
+    assert (r.status, r.iterations, r.ret) == (0, 1, 0)
+    # gradient-converged result is discarded like the reference (src/sfm_ba_ssba.cpp:221,235)
+    r = _solve(p, gradient_threshold=1e30)
+    assert (r.status, r.ret) == (2, -1)
+    assert np.array_equal(r.cam_RT, p.cam_RT) and np.array_equal(r.pts, p.pts)
+    r = _solve(p, gradient_threshold=1e30, discard_converged=0)
+    assert (r.status, r.ret) == (2, 0)
+    # converged run is idempotent: solving again from the result does not move the cost
+    a = _solve(p)
+    q = p.copy(); q.cam_RT, q.pts = a.cam_RT, a.pts
+    b = _solve(q)
+    assert abs(b.trace[0, 1] - a.final_cost) < 1e-8 * a.final_cost
+    assert b.final_cost <= b.trace[0, 1] * (1 + 1e-12)
+
+
+def test_invalid_inputs_are_rejected():
+    p = make_problem("tiny", 1)
+    with binding.Engine() as eng:
+        bad = p.obs_pt.copy(); bad[[3, 40]] = bad[[40, 3]]
+        with pytest.raises(binding.B200BAError) as e:
+            eng.set_problem(p.K5, p.cam_RT, p.pts, p.obs_xy, p.obs_cam, bad)
+        assert e.value.code == -1 and "non-decreasing" in str(e.value)
+        badc = p.obs_cam.copy(); badc[0] = p.N
+        with pytest.raises(binding.B200BAError):
+            eng.set_problem(p.K5, p.cam_RT, p.pts, p.obs_xy, badc, p.obs_pt)
+        with pytest.raises(binding.B200BAError) as e:
+            eng.solve()
+        assert e.value.code == -3
+        with pytest.raises(binding.B200BAError):
+            eng.set_problem(p.K5, p.cam_RT, p.pts, p.obs_xy[:0], p.obs_cam[:0], p.obs_pt[:0])
+        # a camera that sees nothing and ragged track lengths are fine
+        keep = p.obs_cam != 2
+        eng.set_problem(p.K5, p.cam_RT, p.pts, p.obs_xy[keep], p.obs_cam[keep], p.obs_pt[keep])
+        r = eng.solve()
+        assert r.final_cost < r.initial_cost
+        assert np.allclose(r.cam_RT[2, [0, 1, 2, 4, 5, 6, 8, 9, 10]], p.cam_RT[2, [0, 1, 2, 4, 5, 6, 8, 9, 10]], atol=1e-12)
+
+
+def test_python_mirror_and_cpp_adapter_agree(tmp_path):
+    """adjustBundle_ssba through the Python mirror and through adapter/sfm_ba_b200.cpp (built against the shim
+    headers) see the same marshalled problem and write back the same numbers."""
+    from tests.test_abi_and_host import _tracker_containers
+    p = make_problem("small", 4)
+    cloud, Kmat, imgpts, Pmats = _tracker_containers(p)
+    rep = {}
+    assert ba.adjustBundle_ssba(cloud, Kmat, imgpts, Pmats, report=rep) == 0
+    direct = _solve(p)
+    assert np.array_equal(rep["result"].trace[:, 1], direct.trace[:, 1])
+    exe = str(tmp_path / "test_adapter")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", f"-I{ROOT}/adapter/shim", f"-I{ROOT}/include",
+                           f"{ROOT}/adapter/test_adapter.cpp", f"{ROOT}/adapter/sfm_ba_b200.cpp",
+                           f"-L{ROOT}/sequencesfm_b200", "-lb200ba", f"-Wl,-rpath,{ROOT}/sequencesfm_b200", "-o", exe])
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    with open(fin, "w") as f:
+        f.write(f"{p.N} {p.M} {p.K} " + " ".join(repr(float(v)) for v in p.K5) + "\n")
+        for row in p.cam_RT: f.write(" ".join(repr(float(v)) for v in row) + "\n")
+        for row in p.pts: f.write(" ".join(repr(float(v)) for v in row) + "\n")
+        for k in range(p.K): f.write(f"{p.obs_cam[k]} {p.obs_pt[k]} {float(p.obs_xy[k, 0])!r} {float(p.obs_xy[k, 1])!r}\n")
+    subprocess.check_call([exe, "ssba", str(fin), str(fout)])
+    vals = open(fout).read().split()
+    assert int(vals[0]) == 0
+    arr = np.array(vals[1:], dtype=np.float64)
+    cam = arr[: 12 * p.N].reshape(p.N, 12); pts = arr[12 * p.N:].reshape(p.M, 3)
+    assert np.allclose(cam, direct.cam_RT, rtol=0, atol=1e-13) and np.allclose(pts, direct.pts, rtol=0, atol=1e-13)
+    assert np.allclose(np.array([Pmats[k].reshape(12) for k in sorted(Pmats)]), direct.cam_RT, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the benchmark's full size: properties that do not need the oracle
+# ---------------------------------------------------------------------------------------------------------
+def test_venice_shape_properties():
+    p = make_problem("venice", 1)
+    with binding.Engine(max_iterations=6) as eng:
+        eng.set_problem_from(p)
+        eng.begin()
+        g = eng.debug_linearize()
+        # checksum-of-checksums: the by-camera and by-point reductions see the same observations:
+        # sum_i trace(U_i[:3,:3]) (translation block = sum of P^t P) equals sum_j trace(R_i V_j R_i^t)-type invariant;
+        # use the simpler identity sum_i g_c,i[0:3] . t = ...: both gradients come from the same residual vector, so
+        # the cost recomputed from weights must match and J^t e must vanish for a gauge direction (global translation):
+        # a translation of all points by d and of every camera centre by d leaves residuals unchanged:
+        # sum_j g_p,j - sum_i R_i^t g_c,i[0:3] = 0.
+        RT = None
+        r = eng.solve()
+    # global-translation gauge invariance of the gradient, evaluated with the normalised rotations (unchanged by normalisation)
+    R = p.cam_RT.reshape(-1, 3, 4)[:, :, :3]
+    lhs = g["gp"].sum(axis=0)
+    rhs = np.einsum("nji,nj->i", R, g["gc"][:, :3])
+    assert np.abs(lhs - rhs).max() < 1e-9 * max(np.abs(g["gp"]).sum(), 1.0)
+    assert np.all(np.diff(r.trace[:, 1]) <= 0) or np.all(r.trace[:, 5] == 1)
+    acc = r.trace[:, 5] == 1
+    assert acc.sum() >= 4
+    assert np.all(r.trace[acc, 3] < r.trace[acc, 1])                    # accepted steps decrease the cost
+    assert r.mean_px[1] < 0.7 and r.mean_px[0] > 2.0
+    assert r.gpu_launches > 0
