@@ -81,7 +81,15 @@ struct b200ba_handle {
     Dev d{};
     DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, o_w, c_w, chunk_part, pt_part, trace;
     DBuf<double2> o_meas, c_meas;
-    DBuf<int> o_cam, pstart, c_pt, chunk_cam, chunk_beg, chunk_end, cam_chunk_beg;
+    DBuf<int> o_cam, slice_base, slice_deg, c_pt, chunk_cam, chunk_beg, chunk_end, cam_chunk_beg;
+    DBuf<double> ptab, part_pq, part_rz, c_r0, c_r1, c_r2;
+    DBuf<int> tab_wr;
+    std::vector<int> orig_of_new, entry_of_obs;      // SELL permutation (new point index -> caller's), obs -> padded entry
+    int Kp = 0;                                      // padded SELL entries
+    int num_sms = 148, tab_grid = 0, step_grid = 0;
+    bool use_tab = false, use_coop = false, use_graph = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long launches_per_graph = 0;
     DBuf<LMState> st;
     DBuf<double> norm_buf;
     LMState h_st{};
@@ -120,6 +128,7 @@ int allreduce(b200ba_handle* h, double* buf, size_t count)
 int enqueue_linearize(b200ba_handle* h)
 {
     Dev& d = h->d;
+    if (h->use_tab) LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
     LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
     LAUNCH(k_linearize_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d);
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
@@ -142,24 +151,55 @@ int enqueue_precond(b200ba_handle* h)
     return 0;
 }
 
+int enqueue_camera_half(b200ba_handle* h, int rhs_pass);
+int enqueue_camera_sums(b200ba_handle* h);
+
 int enqueue_cg_init(b200ba_handle* h)
 {
     Dev& d = h->d;
     LAUNCH(k_cg_point_pass<1>, d.n_pt_blocks, PT_BLOCK, d);
-    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 1);
-    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
-    if (int rc = allreduce(h, d.ar_q, (size_t)d.N * 6)) return rc;
+    if (int rc = enqueue_camera_half(h, 1)) return rc;
+    if (int rc = enqueue_camera_sums(h)) return rc;
     LAUNCH(k_cg_init, 1, ONE_CTA, d);
+    return 0;
+}
+
+// sum_k W_k v_j by camera (chunked, warp per chunk)
+int enqueue_camera_half(b200ba_handle* h, int rhs_pass)
+{
+    Dev& d = h->d;
+    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, rhs_pass);
+    return 0;
+}
+// second level -> ar_q (+ all-reduce over ranks)
+int enqueue_camera_sums(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
+    return allreduce(h, d.ar_q, (size_t)d.N * 6);
+}
+
+int launch_camera_step(b200ba_handle* h, int sums_ready)
+{
+    Dev& d = h->d;
+    double* ppq = h->part_pq.p; double* prz = h->part_rz.p;
+    void* args[] = {(void*)&d, (void*)&sums_ready, (void*)&ppq, (void*)&prz};
+    CU(cudaLaunchCooperativeKernel((const void*)k_cg_camera_step, dim3(h->step_grid), dim3(STEP_BLOCK), args, 0, h->stream));
+    h->launches++;
     return 0;
 }
 
 int enqueue_cg_step(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
-    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0);
-    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
-    if (int rc = allreduce(h, d.ar_q, (size_t)d.N * 6)) return rc;
+    if (h->use_tab) {
+        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, (size_t)d.N * TAB_STRIDE * sizeof(double), h->stream>>>(d);
+        h->launches++;
+    } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    if (int rc = enqueue_camera_half(h, 0)) return rc;
+    if (h->use_coop && h->world <= 1) return launch_camera_step(h, 0);
+    if (int rc = enqueue_camera_sums(h)) return rc;
+    if (h->use_coop) return launch_camera_step(h, 1);
     LAUNCH(k_cg_update, 1, ONE_CTA, d);
     return 0;
 }
@@ -175,7 +215,35 @@ int enqueue_step_and_decide(b200ba_handle* h)
     return 0;
 }
 
+int enqueue_lm_iteration_raw(b200ba_handle* h);
+
+// One LM iteration = a fixed kernel sequence (all data-dependent decisions are device-side flags), so in the
+// fixed-step mode it is captured once into a CUDA graph and replayed.
 int enqueue_lm_iteration(b200ba_handle* h)
+{
+    if (!h->use_graph || h->opt.cg_rel_tol > 0) return enqueue_lm_iteration_raw(h);
+    if (!h->graph_exec) {
+        cudaGraph_t g = nullptr;
+        long long before = h->launches;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->use_graph = false; return enqueue_lm_iteration_raw(h); }
+        int rc = enqueue_lm_iteration_raw(h);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        h->launches_per_graph = h->launches - before;
+        h->launches = before;
+        if (rc || e != cudaSuccess || !g || cudaGraphInstantiate(&h->graph_exec, g, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            h->graph_exec = nullptr; h->use_graph = false;
+            return enqueue_lm_iteration_raw(h);
+        }
+        cudaGraphDestroy(g);
+    }
+    CU(cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->launches_per_graph;
+    return 0;
+}
+
+int enqueue_lm_iteration_raw(b200ba_handle* h)
 {
     if (int rc = enqueue_linearize(h)) return rc;
     if (int rc = enqueue_precond(h)) return rc;
@@ -304,8 +372,10 @@ void b200ba_destroy(b200ba_handle* h)
     h->z.release(); h->p.release(); h->q.release(); h->ar_lin.release(); h->ar_q.release(); h->ar_sd.release(); h->ar_dec.release();
     h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_w.release(); h->c_w.release();
     h->chunk_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
-    h->pstart.release(); h->c_pt.release(); h->chunk_cam.release(); h->chunk_beg.release(); h->chunk_end.release(); h->cam_chunk_beg.release();
-    h->st.release(); h->norm_buf.release();
+    h->c_pt.release(); h->chunk_cam.release(); h->chunk_beg.release(); h->chunk_end.release(); h->cam_chunk_beg.release();
+    h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->part_pq.release(); h->part_rz.release();
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    h->c_r0.release(); h->c_r1.release(); h->c_r2.release(); h->tab_wr.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -373,18 +443,45 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (o.round_pixels) { x = (double)lrintf((float)x); y = (double)lrintf((float)y); }
         meas[k] = make_double2((x * rf) * r2, (y * rf) * r2);
     }
-    // CSR by point
+    // ---- by-point layout: SELL-32, points sorted by track length (descending, stable) ----
     std::vector<int> pstart((size_t)M + 1, 0);
     for (int k = 0; k < K; ++k) pstart[obs_pt[k] + 1]++;
     for (int j = 0; j < M; ++j) pstart[j + 1] += pstart[j];
-    // camera order: stable counting sort by camera (order inside a camera = increasing point index), then chunks
+    int maxdeg = 0;
+    for (int j = 0; j < M; ++j) maxdeg = std::max(maxdeg, pstart[j + 1] - pstart[j]);
+    std::vector<int> bucket((size_t)maxdeg + 2, 0);
+    for (int j = 0; j < M; ++j) bucket[maxdeg - (pstart[j + 1] - pstart[j]) + 1]++;
+    for (int b = 0; b <= maxdeg; ++b) bucket[b + 1] += bucket[b];
+    h->orig_of_new.assign((size_t)M, 0);
+    for (int j = 0; j < M; ++j) h->orig_of_new[bucket[maxdeg - (pstart[j + 1] - pstart[j])]++] = j;
+    const int n_slices = cdiv(std::max(M, 1), 32);
+    std::vector<int> slice_base((size_t)n_slices + 1, 0), slice_deg((size_t)n_slices, 0);
+    for (int g = 0; g < n_slices; ++g) {
+        int j0 = 32 * g;
+        int dg = j0 < M ? pstart[h->orig_of_new[j0] + 1] - pstart[h->orig_of_new[j0]] : 0;
+        slice_deg[g] = dg; slice_base[g + 1] = slice_base[g] + 32 * dg;
+    }
+    const int Kp = slice_base[n_slices];
+    h->Kp = Kp;
+    std::vector<int> o_cam_p((size_t)std::max(Kp, 1), -1);
+    std::vector<double2> o_meas_p((size_t)std::max(Kp, 1), make_double2(0.0, 0.0));
+    h->entry_of_obs.assign((size_t)K, 0);
+    // camera order: stable counting sort by camera over the NEW point order, then chunks of <= CHUNK
     std::vector<int> cstart((size_t)N + 1, 0);
     for (int k = 0; k < K; ++k) cstart[obs_cam[k] + 1]++;
     for (int i = 0; i < N; ++i) cstart[i + 1] += cstart[i];
     std::vector<int> c_pt((size_t)K); std::vector<double2> c_meas((size_t)K);
     {
         std::vector<int> fill(cstart.begin(), cstart.end() - 1);
-        for (int k = 0; k < K; ++k) { int dst = fill[obs_cam[k]]++; c_pt[dst] = obs_pt[k]; c_meas[dst] = meas[k]; }
+        for (int jn = 0; jn < M; ++jn) {
+            const int j = h->orig_of_new[jn], g = jn >> 5, l = jn & 31;
+            for (int k = pstart[j], sl = 0; k < pstart[j + 1]; ++k, ++sl) {
+                const int kk = slice_base[g] + 32 * sl + l;
+                o_cam_p[kk] = obs_cam[k]; o_meas_p[kk] = meas[k]; h->entry_of_obs[k] = kk;
+                const int dst = fill[obs_cam[k]]++;
+                c_pt[dst] = jn; c_meas[dst] = meas[k];
+            }
+        }
     }
     std::vector<int> chunk_cam, chunk_beg, chunk_end, cam_chunk_beg((size_t)N + 1, 0);
     for (int i = 0; i < N; ++i) {
@@ -397,35 +494,40 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     int n_chunks = (int)chunk_cam.size();
     int n_pt_blocks = std::max(1, cdiv(M, PT_BLOCK));
 
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+
     // ---- device allocation ----
     size_t n6 = 6 * (size_t)N;
     int world = h->world;
     h->trace_cap = o.max_iterations + 2;
+    const size_t Mp = (size_t)std::max(M, 1), Kc = (size_t)std::max(K, 1), Kpp = (size_t)std::max(Kp, 1);
     CU(h->rt0.alloc(12 * (size_t)N)); CU(h->rt1.alloc(12 * (size_t)N));
     CU(h->U.alloc(36 * (size_t)N)); CU(h->Minv.alloc(36 * (size_t)N));
     CU(h->gc.alloc(n6)); CU(h->x.alloc(n6)); CU(h->r.alloc(n6)); CU(h->z.alloc(n6)); CU(h->p.alloc(n6)); CU(h->q.alloc(n6));
     CU(h->ar_lin.alloc((size_t)N * PART_STRIDE + 1 + 2 * (size_t)world)); CU(h->ar_q.alloc(n6)); CU(h->ar_sd.alloc(21 * (size_t)N)); CU(h->ar_dec.alloc(4));
-    CU(h->X0.alloc(4 * (size_t)std::max(M, 1))); CU(h->X1.alloc(4 * (size_t)std::max(M, 1)));
-    CU(h->V.alloc(6 * (size_t)std::max(M, 1))); CU(h->Vinv.alloc(6 * (size_t)std::max(M, 1)));
-    CU(h->gp.alloc(4 * (size_t)std::max(M, 1))); CU(h->v.alloc(4 * (size_t)std::max(M, 1)));
-    CU(h->o_w.alloc(std::max(K, 1))); CU(h->c_w.alloc(std::max(K, 1)));
-    CU(h->o_meas.alloc(std::max(K, 1))); CU(h->c_meas.alloc(std::max(K, 1)));
-    CU(h->o_cam.alloc(std::max(K, 1))); CU(h->c_pt.alloc(std::max(K, 1))); CU(h->pstart.alloc((size_t)M + 1));
+    CU(h->X0.alloc(4 * Mp)); CU(h->X1.alloc(4 * Mp));
+    CU(h->V.alloc(6 * Mp)); CU(h->Vinv.alloc(6 * Mp)); CU(h->gp.alloc(4 * Mp)); CU(h->v.alloc(4 * Mp));
+    CU(h->o_w.alloc(Kpp)); CU(h->c_w.alloc(Kc)); CU(h->o_meas.alloc(Kpp)); CU(h->c_meas.alloc(Kc));
+    CU(h->o_cam.alloc(Kpp)); CU(h->c_pt.alloc(Kc)); CU(h->slice_base.alloc((size_t)n_slices + 1)); CU(h->slice_deg.alloc((size_t)n_slices));
     CU(h->chunk_cam.alloc(std::max(n_chunks, 1))); CU(h->chunk_beg.alloc(std::max(n_chunks, 1))); CU(h->chunk_end.alloc(std::max(n_chunks, 1)));
     CU(h->cam_chunk_beg.alloc((size_t)N + 1));
     CU(h->chunk_part.alloc((size_t)std::max(n_chunks, 1) * PART_STRIDE)); CU(h->pt_part.alloc(4 * (size_t)n_pt_blocks));
     CU(h->trace.alloc((size_t)h->trace_cap * TRACE_COLS)); CU(h->st.alloc(1)); CU(h->norm_buf.alloc(16));
-
+    CU(h->ptab.alloc((size_t)N * TAB_STRIDE));
     cudaStream_t s = h->stream;
+    CU(h->c_r0.alloc(Kc)); CU(h->c_r1.alloc(Kc)); CU(h->c_r2.alloc(Kc));
+    CU(cudaMemsetAsync(h->c_r0.p, 0, sizeof(double) * Kc, s)); CU(cudaMemsetAsync(h->c_r1.p, 0, sizeof(double) * Kc, s)); CU(cudaMemsetAsync(h->c_r2.p, 0, sizeof(double) * Kc, s));
+    CU(cudaMemcpyAsync(h->o_meas.p, o_meas_p.data(), sizeof(double2) * Kpp, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->o_cam.p, o_cam_p.data(), sizeof(int) * Kpp, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->o_w.p, 0, sizeof(double) * Kpp, s));
     if (K) {
-        CU(cudaMemcpyAsync(h->o_meas.p, meas.data(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->c_meas.p, c_meas.data(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->o_cam.p, obs_cam, sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->c_pt.p, c_pt.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(h->o_w.p, 0, sizeof(double) * (size_t)K, s));
         CU(cudaMemsetAsync(h->c_w.p, 0, sizeof(double) * (size_t)K, s));
     }
-    CU(cudaMemcpyAsync(h->pstart.p, pstart.data(), sizeof(int) * ((size_t)M + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->slice_base.p, slice_base.data(), sizeof(int) * ((size_t)n_slices + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->slice_deg.p, slice_deg.data(), sizeof(int) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
     if (n_chunks) {
         CU(cudaMemcpyAsync(h->chunk_cam.p, chunk_cam.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->chunk_beg.p, chunk_beg.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
@@ -437,16 +539,52 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     CU(cudaMemsetAsync(h->ar_lin.p, 0, sizeof(double) * h->ar_lin.n, s));
     CU(cudaMemsetAsync(h->ar_sd.p, 0, sizeof(double) * h->ar_sd.n, s));
     CU(cudaMemsetAsync(h->ar_q.p, 0, sizeof(double) * h->ar_q.n, s));
+    CU(cudaMemsetAsync(h->ptab.p, 0, sizeof(double) * h->ptab.n, s));
     CU(cudaStreamSynchronize(s));
+
+    // ---- execution plan: shared-memory camera table, cooperative camera-side step, CUDA graph ----
+    const size_t tab_bytes = (size_t)N * TAB_STRIDE * sizeof(double);
+    h->use_tab = tab_bytes + 1024 <= (size_t)prop.sharedMemPerBlockOptin && getenv("B200BA_NO_TAB") == nullptr;
+    if (h->use_tab) {
+        if (cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes) != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
+        h->tab_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB_BLOCK / 32)));
+    }
+    // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue)
+    int tab_warps = std::max(1, h->tab_grid) * (TAB_BLOCK / 32);
+    {
+        std::vector<int> wr((size_t)tab_warps + 1, n_slices);
+        long long total = 0; for (int g = 0; g < n_slices; ++g) total += slice_deg[g] + 1;
+        long long acc = 0; int w = 0; wr[0] = 0;
+        for (int g = 0; g < n_slices && w + 1 < tab_warps; ++g) {
+            acc += slice_deg[g] + 1;
+            while (w + 1 < tab_warps && acc * tab_warps >= total * (long long)(w + 1)) wr[++w] = g + 1;
+        }
+        for (int q = w + 1; q <= tab_warps; ++q) wr[q] = n_slices;
+        CU(h->tab_wr.alloc(wr.size()));
+        CU(cudaMemcpy(h->tab_wr.p, wr.data(), sizeof(int) * wr.size(), cudaMemcpyHostToDevice));
+    }
+    h->step_grid = cdiv((long long)N * 6, STEP_BLOCK);
+    {
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_camera_step, STEP_BLOCK, 0);
+        h->use_coop = coop && (long long)per_sm * h->num_sms >= h->step_grid && getenv("B200BA_NO_COOP") == nullptr;
+    }
+    CU(h->part_pq.alloc((size_t)h->step_grid)); CU(h->part_rz.alloc((size_t)h->step_grid));
+    h->use_graph = getenv("B200BA_NO_GRAPH") == nullptr;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
 
     d = Dev{};
     d.N = N; d.M = M; d.K = K; d.n_chunks = n_chunks; d.first_free = o.fix_first_camera ? 1 : 0; d.n_pt_blocks = n_pt_blocks;
-    d.world = world; d.rank = h->rank; d.in = in; d.st = h->st.p;
+    d.world = world; d.rank = h->rank; d.n_slices = n_slices; d.tab_ok = h->use_tab ? 1 : 0; d.in = in; d.st = h->st.p;
     d.rt[0] = h->rt0.p; d.rt[1] = h->rt1.p; d.U = h->U.p; d.gc = h->gc.p; d.Minv = h->Minv.p;
     d.x = h->x.p; d.r = h->r.p; d.z = h->z.p; d.p = h->p.p; d.q = h->q.p;
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
-    d.o_cam = h->o_cam.p; d.o_meas = h->o_meas.p; d.o_w = h->o_w.p; d.pstart = h->pstart.p;
+    d.o_cam = h->o_cam.p; d.o_meas = h->o_meas.p; d.o_w = h->o_w.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
+    d.ptab = h->ptab.p;
+    d.c_r0 = h->c_r0.p; d.c_r1 = h->c_r1.p; d.c_r2 = h->c_r2.p;
+    d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_pt = h->c_pt.p; d.c_meas = h->c_meas.p; d.c_w = h->c_w.p;
     d.chunk_cam = h->chunk_cam.p; d.chunk_beg = h->chunk_beg.p; d.chunk_end = h->chunk_end.p; d.cam_chunk_beg = h->cam_chunk_beg.p;
     d.chunk_part = h->chunk_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
@@ -486,13 +624,17 @@ int b200ba_begin(b200ba_handle* h)
         h->scale = std::sqrt(sqc + sq[0]);
         double rs = 1.0 / h->scale;
         for (int i = 0; i < N; ++i) { for (int c = 0; c < 3; ++c) C[3 * (size_t)i + c] *= rs; set_camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i); }
-        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) X4[4 * (size_t)j + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs;
+        for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs; }
     } else {
-        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) X4[4 * (size_t)j + c] = P0[3 * (size_t)j + c];
+        for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = P0[3 * (size_t)j + c]; }
     }
-    // cached parameter length (v3d_metricbundle.h:37-45), after normalisation
+    // cached parameter length (v3d_metricbundle.h:37-45), after normalisation (summed in the caller's point order)
     double L[1] = {0};
-    for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) L[0] += X4[4 * (size_t)j + c] * X4[4 * (size_t)j + c];
+    {
+        std::vector<int> new_of_orig((size_t)M);
+        for (int jn = 0; jn < M; ++jn) new_of_orig[h->orig_of_new[jn]] = jn;
+        for (int j = 0; j < M; ++j) { const int jn = new_of_orig[j]; for (int c = 0; c < 3; ++c) L[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; }
+    }
     if (int rc = global_sum(h, L, 1)) return rc;
     for (int i = (o.fix_first_camera ? 1 : 0); i < N; ++i) {
         const double* P = cam.data() + 12 * (size_t)i;
@@ -612,8 +754,8 @@ int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts)
     if (pts && M) {
         std::vector<double> X4(4 * (size_t)M);
         CU(cudaMemcpy(X4.data(), h->d.X[cur], sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
-        if (h->opt.normalize) for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)j + c] * h->scale + h->mean[c];
-        else for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)j + c];
+        if (h->opt.normalize) for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)jn + c] * h->scale + h->mean[c]; }
+        else for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)jn + c]; }
     }
     h->ms_d2h = now_ms() - t0;
     return 0;
@@ -633,17 +775,20 @@ int b200ba_debug_linearize(b200ba_handle* h, double* cost, double* w, double* gc
     const int N = h->N, M = h->M, K = h->K;
     if (cost) *cost = st.err;
     if (lambda0) *lambda0 = st.lambda;
-    if (w && K) CU(cudaMemcpy(w, h->o_w.p, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost));
+    if (w && K) {
+        std::vector<double> t((size_t)h->Kp); CU(cudaMemcpy(t.data(), h->o_w.p, sizeof(double) * (size_t)h->Kp, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < K; ++k) w[k] = t[h->entry_of_obs[k]];
+    }
     if (gc) CU(cudaMemcpy(gc, h->gc.p, sizeof(double) * 6 * (size_t)N, cudaMemcpyDeviceToHost));
     if (U) CU(cudaMemcpy(U, h->U.p, sizeof(double) * 36 * (size_t)N, cudaMemcpyDeviceToHost));
     if (gp && M) {
         std::vector<double> t(4 * (size_t)M); CU(cudaMemcpy(t.data(), h->gp.p, sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
-        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) gp[3 * (size_t)j + c] = t[4 * (size_t)j + c];
+        for (int jn = 0; jn < M; ++jn) for (int c = 0; c < 3; ++c) gp[3 * (size_t)h->orig_of_new[jn] + c] = t[4 * (size_t)jn + c];
     }
     if (V && M) {
         std::vector<double> t(6 * (size_t)M); CU(cudaMemcpy(t.data(), h->V.p, sizeof(double) * 6 * (size_t)M, cudaMemcpyDeviceToHost));
-        for (int j = 0; j < M; ++j) {
-            const double* s = t.data() + 6 * (size_t)j; double* o = V + 9 * (size_t)j;
+        for (int jn = 0; jn < M; ++jn) {
+            const double* s = t.data() + 6 * (size_t)jn; double* o = V + 9 * (size_t)h->orig_of_new[jn];
             o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
         }
     }
@@ -663,10 +808,17 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
     CU(cudaMemcpy(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.p, x, sizeof(double) * n6, cudaMemcpyHostToDevice));
     LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
-    LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
-    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0);
-    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
-    if (int rc = allreduce(h, d.ar_q, n6)) return rc;
+    if (h->use_tab) {
+        // exercise the shared-memory-table sweep: scatter x into the packed table's p-slots
+        std::vector<double> tab((size_t)N * TAB_STRIDE);
+        CU(cudaMemcpy(tab.data(), d.ptab, sizeof(double) * tab.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; ++i) for (int a = 0; a < 6; ++a) tab[(size_t)i * TAB_STRIDE + 7 + a] = x[6 * (size_t)i + a];
+        CU(cudaMemcpy(d.ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, (size_t)d.N * TAB_STRIDE * sizeof(double), h->stream>>>(d);
+        h->launches++;
+    } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    if (int rc = enqueue_camera_half(h, 0)) return rc;
+    if (int rc = enqueue_camera_sums(h)) return rc;
     CU(cudaStreamSynchronize(h->stream));
     std::vector<double> U(36 * (size_t)N), wv(n6);
     CU(cudaMemcpy(U.data(), d.U, sizeof(double) * 36 * (size_t)N, cudaMemcpyDeviceToHost));
@@ -682,7 +834,8 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
 
 static const char* kKernelNames[] = {"linearize_points", "linearize_cameras", "cg_point_pass", "cg_camera_pass",
                                      "camera_reduce6", "cg_update", "schur_diag_cameras", "point_vinv",
-                                     "backsub_cost_points", "precond_invert"};
+                                     "backsub_cost_points", "precond_invert", "cg_point_pass_generic", "cg_camera_step_fused", "cg_step",
+                                     "cg_camera_pass_generic"};
 const char* b200ba_kernel_name(int32_t which)
 {
     return (which >= 0 && which < (int)(sizeof kKernelNames / sizeof *kKernelNames)) ? kKernelNames[which] : nullptr;
@@ -702,8 +855,16 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
         switch (which) {
         case 0: LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d); break;
         case 1: LAUNCH(k_linearize_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d); break;
-        case 2: LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d); break;
-        case 3: LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0); break;
+        case 2: if (h->use_tab) { k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, (size_t)d.N * TAB_STRIDE * sizeof(double), h->stream>>>(d); h->launches++; }
+                else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+                break;
+        case 10: LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d); break;
+        case 11: if (h->use_coop) { if (int rc = launch_camera_step(h, 0)) return rc; } else LAUNCH(k_cg_update, 1, ONE_CTA, d);
+                 CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
+        case 12: if (int rc = enqueue_cg_step(h)) return rc;
+                 CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
+        case 3: if (int rc = enqueue_camera_half(h, 0)) return rc; break;
+        case 13: LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0); break;
         case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0); break;
         case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d); break;

@@ -14,10 +14,14 @@
 //             U, Minv N x 36   full symmetric 6x6 blocks;  gc, x, r, z, p  N x 6
 //   points    X[2]    M x 4    xyz + pad (32 B = 1 sector so a by-camera gather costs one sector)
 //             V, Vinv M x 6    symmetric 3x3 (xx xy xz yy yz zz);  gp, v  M x 4
-//   obs (point order)   o_cam int32, o_meas double2 (normalised), o_w double;  pstart[M+1] CSR offsets
+//   obs (point order)   SELL-32: points are sorted by track length (descending) and grouped in slices of 32; slot s of
+//                       lane l of slice g lives at slice_base[g] + 32 s + l.  One thread owns one point, every lane of a
+//                       warp runs the same trip count and every load of o_cam (int32, -1 = padding), o_meas (double2,
+//                       normalised) and o_w (double) is a fully coalesced 128/256/512-byte row.
 //   obs (camera order)  c_pt  int32, c_meas double2,             c_w double;  chunk tables (<= CHUNK obs of
 //                       one camera per chunk, chunks of a camera contiguous)
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -30,6 +34,10 @@ constexpr int CH_BLOCK     = 128;   // threads per block in warp-per-chunk kerne
 constexpr int PART_STRIDE  = 28;    // doubles per chunk partial: 21 (sym 6x6) + 6 (+1 pad)
 constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side kernels
 constexpr int TRACE_COLS   = 8;
+constexpr int TAB_STRIDE   = 14;    // doubles per camera in the packed table: quaternion 4, T 3, p 6, pad 1 (112 B = 7 x 16 B)
+constexpr int TAB_BLOCK    = 768;   // threads of the persistent shared-memory-table CG point sweep (1 CTA / SM, <= 85 registers)
+constexpr int STEP_BLOCK   = 192;   // threads of the cooperative camera-side CG kernel: 32 cameras x 6 components
+constexpr int MAX_SMEM     = 227 * 1024;
 
 struct Intrinsics {
     double k00, k01, k02, k11, k12;   // unit-focal-length intrinsics (src/sfm_ba_ssba.cpp:98-102)
@@ -51,7 +59,7 @@ struct LMState {
 };
 
 struct Dev {
-    int N, M, K, n_chunks, first_free, n_pt_blocks, world, rank;
+    int N, M, K, n_chunks, first_free, n_pt_blocks, world, rank, n_slices, tab_ok;
     Intrinsics in;
     LMState* st;
     double* rt[2];
@@ -62,8 +70,12 @@ struct Dev {
     double* ar_dec;     // [d2p, denomp, new_cost, pad]
     double* X[2];
     double *V, *gp, *Vinv, *v;
-    int* o_cam; double2* o_meas; double* o_w; int* pstart;
+    int* o_cam; double2* o_meas; double* o_w; int *slice_base, *slice_deg;
+    double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
     int* c_pt; double2* c_meas; double* c_w;
+    double *c_r0, *c_r1, *c_r2;   // R_i X_j per observation (camera order), written at linearisation: the CG sweep streams it instead of gathering X_j
+    int* tab_wr;                  // [tab_warps + 1] contiguous slice ranges of the persistent CG point sweep's warps (balanced by rows)
+    int tab_warps;
     int *chunk_cam, *chunk_beg, *chunk_end, *cam_chunk_beg;
     double* chunk_part;   // n_chunks x PART_STRIDE
     double* pt_part;      // n_pt_blocks x 4
@@ -131,6 +143,49 @@ __device__ __forceinline__ void load6(const double* __restrict__ base, int i, do
     const double2* s = reinterpret_cast<const double2*>(base + 6 * (size_t)i);
     double2 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y;
+}
+
+// 256-bit gather of one padded 4-double record (LDG.E.256 on sm_100a: one L1 wavefront per lane instead of two)
+__device__ __forceinline__ void load3p_256(const double* __restrict__ base, int j, double X[3])
+{
+    double pad;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(X[0]), "=d"(X[1]), "=d"(X[2]), "=d"(pad) : "l"(base + 4 * (size_t)j));
+    (void)pad;
+}
+// L2 residency control.  Per PCG step ~260 MB stream through a 126 MB L2 while the point-sized vector that is GATHERED
+// (v: 32 MB) must stay resident, otherwise every gather becomes a random 32-byte DRAM access.  Streams are loaded
+// evict_first / no L1 allocation; gathered arrays are loaded and stored evict_last.
+__device__ __forceinline__ uint64_t policy_evict_last()  { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol)
+{
+    int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ double ldg_stream(const double* p, uint64_t pol)
+{
+    double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ void load3p_256_keep(const double* __restrict__ base, int j, double X[3], uint64_t pol)
+{
+    double pad;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(X[0]), "=d"(X[1]), "=d"(X[2]), "=d"(pad) : "l"(base + 4 * (size_t)j), "l"(pol));
+    (void)pad;
+}
+__device__ __forceinline__ void store4_keep(double* p, double a, double b, double c, double e, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(e), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// SELL-32 addressing: first entry and (warp-uniform) trip count of point j
+__device__ __forceinline__ void slice_of(const Dev& d, int j, int& k0, int& deg)
+{
+    int g = j >> 5;
+    if (g < d.n_slices) { k0 = __ldg(d.slice_base + g) + (j & 31); deg = __ldg(d.slice_deg + g); }
+    else { k0 = 0; deg = 0; }
 }
 
 // Per-observation geometry: camera-space point, residual, Huber weight, weighted projection Jacobian.
@@ -229,13 +284,15 @@ __global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
     if (st->done || !st->compute) return;
     int j = blockIdx.x * PT_BLOCK + threadIdx.x;
     double cost = 0, gmax = 0, vmax = -1e30;
-    if (j < d.M) {
+    int k0, deg; slice_of(d, j, k0, deg);
+    {
         const double* Xb = d.X[st->cur]; const double* rt = d.rt[st->cur];
-        double X[3]; load3p(Xb, j, X);
+        double X[3] = {0, 0, 0}; if (j < d.M) load3p(Xb, j, X);
         double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-        int k0 = d.pstart[j], k1 = d.pstart[j + 1];
-        for (int k = k0; k < k1; ++k) {
-            Cam cm; load_cam(rt, __ldg(d.o_cam + k), cm);
+        for (int s = 0, k = k0; s < deg; ++s, k += 32) {
+            int ci = __ldg(d.o_cam + k);
+            if (ci < 0) continue;
+            Cam cm; load_cam(rt, ci, cm);
             Obs o; obs_full(cm, X, __ldg(d.o_meas + k), d.in, o);
             d.o_w[k] = o.w;
             double we0 = o.w * o.e0, we1 = o.w * o.e1;
@@ -246,12 +303,14 @@ __global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
             V[0] += B0[0] * B0[0] + B1[0] * B1[0]; V[1] += B0[0] * B0[1] + B1[0] * B1[1]; V[2] += B0[0] * B0[2] + B1[0] * B1[2];
             V[3] += B0[1] * B0[1] + B1[1] * B1[1]; V[4] += B0[1] * B0[2] + B1[1] * B1[2]; V[5] += B0[2] * B0[2] + B1[2] * B1[2];
         }
-        double2* Vo = reinterpret_cast<double2*>(d.V + 6 * (size_t)j);
-        Vo[0] = make_double2(V[0], V[1]); Vo[1] = make_double2(V[2], V[3]); Vo[2] = make_double2(V[4], V[5]);
-        double2* go = reinterpret_cast<double2*>(d.gp + 4 * (size_t)j);
-        go[0] = make_double2(g[0], g[1]); go[1] = make_double2(g[2], 0.0);
-        gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
-        vmax = fmax(V[0], fmax(V[3], V[5]));
+        if (j < d.M) {
+            double2* Vo = reinterpret_cast<double2*>(d.V + 6 * (size_t)j);
+            Vo[0] = make_double2(V[0], V[1]); Vo[1] = make_double2(V[2], V[3]); Vo[2] = make_double2(V[4], V[5]);
+            double2* go = reinterpret_cast<double2*>(d.gp + 4 * (size_t)j);
+            go[0] = make_double2(g[0], g[1]); go[1] = make_double2(g[2], 0.0);
+            gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+            vmax = fmax(V[0], fmax(V[3], V[5]));
+        }
     }
     cost = block_sum<PT_BLOCK>(cost, sm);
     gmax = block_max<PT_BLOCK>(gmax, sm);
@@ -284,7 +343,7 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
         for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
             double X[3]; load3p(Xb, __ldg(d.c_pt + k), X);
             Obs o; obs_full(cm, X, __ldg(d.c_meas + k), d.in, o);
-            d.c_w[k] = o.w;
+            d.c_w[k] = o.w; d.c_r0[k] = o.r0; d.c_r1[k] = o.r1; d.c_r2[k] = o.r2;
             double A0[6], A1[6]; jac_rows_A(o, A0, A1);
             double we0 = -o.w * o.e0, we1 = -o.w * o.e1;
             int q = 0;
@@ -537,12 +596,13 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
         double u[3] = {0, 0, 0}, X[3], g[3];
         if (MODE != 1) load3p(d.X[cur], j, X);
         if (MODE != 0) load3p(d.gp, j, g);
-        int k0 = d.pstart[j], k1 = d.pstart[j + 1];
+        int k0, deg; slice_of(d, j, k0, deg);
         if (MODE != 1) {
             const double* vec = (MODE == 0) ? d.p : d.x;
             const double* rt = d.rt[cur];
-            for (int k = k0; k < k1; ++k) {
+            for (int s = 0, k = k0; s < deg; ++s, k += 32) {
                 int i = __ldg(d.o_cam + k);
+                if (i < 0) continue;
                 Cam cm; load_cam(rt, i, cm);
                 Obs o; obs_jac(cm, X, __ldg(d.o_w + k), d.in, o);
                 double p[6]; load6(vec, i, p);
@@ -569,8 +629,10 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
             double2* o = reinterpret_cast<double2*>(d.X[cur ^ 1] + 4 * (size_t)j);
             o[0] = make_double2(Xn[0], Xn[1]); o[1] = make_double2(Xn[2], 0.0);
             const double* rtn = d.rt[cur ^ 1];                          // trial cameras written by k_cg_finish
-            for (int k = k0; k < k1; ++k) {
-                Cam cm; load_cam(rtn, __ldg(d.o_cam + k), cm);
+            for (int s = 0, k = k0; s < deg; ++s, k += 32) {
+                int i = __ldg(d.o_cam + k);
+                if (i < 0) continue;
+                Cam cm; load_cam(rtn, i, cm);
                 double e0, e1, x, y, iz, r0, r1, r2;
                 obs_residual(cm, Xn, __ldg(d.o_meas + k), d.in, e0, e1, x, y, iz, r0, r1, r2);
                 double w = huber_weight(e0, e1, d.in.huber);            // weights re-evaluated at the trial point (:917)
@@ -590,8 +652,30 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
     }
 }
 
-// K9  cg_camera_pass: warp per chunk, sum_k W_k v_j(k) = sum_k A~^t P~ R v_j   (second half of S p)
-__global__ void __launch_bounds__(CH_BLOCK) k_cg_camera_pass(Dev d, int rhs_pass)
+// K9  cg_camera_pass: warp per chunk, sum_k W_k v_j(k) = sum_k A~^t P~ R v_j   (second half of S p).
+//     Per observation the sweep streams (point index 4 B, weight 8 B, cached R X 24 B: coalesced) and gathers ONE
+//     32-byte record v_j (LDG.256, kept L2-resident with evict_last).  It is bound by memory latency, so three
+//     observations' gathers are in flight per lane before any arithmetic, and the streams are fetched one batch ahead.
+//     (A cp.async / shared-memory landing zone with all 8 rows in flight was measured SLOWER: two 16-byte LDGSTS per
+//     record double the L2 sector requests.)
+__device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in, double r0, double r1, double r2, const double v[3], double w, double acc[6])
+{
+    const double x = r0 + cm.T[0], y = r1 + cm.T[1], z = r2 + cm.T[2];
+    const double iz = 1.0 / z;
+    const double wf = w * in.k00 * iz, ar = in.k11 / in.k00;
+    const double pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
+    const double g0 = cm.R[0] * v[0] + cm.R[1] * v[1] + cm.R[2] * v[2];
+    const double g1 = cm.R[3] * v[0] + cm.R[4] * v[1] + cm.R[5] * v[2];
+    const double g2 = cm.R[6] * v[0] + cm.R[7] * v[1] + cm.R[8] * v[2];
+    const double y0 = pa * g0 + pb * g2, y1 = pc * g1 + pd * g2;
+    const double h0 = pa * y0, h1 = pc * y1, h2 = pb * y0 + pd * y1;
+    acc[0] += h0; acc[1] += h1; acc[2] += h2;
+    acc[3] += r1 * h2 - r2 * h1;       // r x h
+    acc[4] += r2 * h0 - r0 * h2;
+    acc[5] += r0 * h1 - r1 * h0;
+}
+constexpr int CP_DEPTH = 3;            // observations in flight per lane
+__global__ void __launch_bounds__(CH_BLOCK, 4) k_cg_camera_pass(Dev d, int rhs_pass)
 {
     const LMState* st = d.st;
     if (st->done) return;
@@ -601,22 +685,34 @@ __global__ void __launch_bounds__(CH_BLOCK) k_cg_camera_pass(Dev d, int rhs_pass
     int i = d.chunk_cam[ch];
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (i >= d.first_free) {
-        const double* Xb = d.X[st->cur];
+        const double* vb = d.v;
         Cam cm; load_cam(d.rt[st->cur], i, cm);
-        int k1 = d.chunk_end[ch];
-        for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
-            int j = __ldg(d.c_pt + k);
-            double X[3], v[3]; load3p(Xb, j, X); load3p(d.v, j, v);
-            Obs o; obs_jac(cm, X, __ldg(d.c_w + k), d.in, o);
-            double g0 = cm.R[0] * v[0] + cm.R[1] * v[1] + cm.R[2] * v[2];
-            double g1 = cm.R[3] * v[0] + cm.R[4] * v[1] + cm.R[5] * v[2];
-            double g2 = cm.R[6] * v[0] + cm.R[7] * v[1] + cm.R[8] * v[2];
-            double y0 = o.a * g0 + o.b * g2, y1 = o.c * g1 + o.d * g2;
-            double h[3]; apply_Pt(o, y0, y1, h);
-            acc[0] += h[0]; acc[1] += h[1]; acc[2] += h[2];
-            acc[3] += o.r1 * h[2] - o.r2 * h[1];       // r x h
-            acc[4] += o.r2 * h[0] - o.r0 * h[2];
-            acc[5] += o.r0 * h[1] - o.r1 * h[0];
+        const int k1 = d.chunk_end[ch];
+        const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
+        int jn[CP_DEPTH]; double wn[CP_DEPTH], an[CP_DEPTH], bn[CP_DEPTH], cn[CP_DEPTH];
+        int k = d.chunk_beg[ch] + lane;
+#pragma unroll
+        for (int u = 0; u < CP_DEPTH; ++u) {
+            const int kk = k + 32 * u; const bool on = kk < k1;
+            jn[u] = on ? ldg_stream(d.c_pt + kk, strm) : -1; wn[u] = on ? ldg_stream(d.c_w + kk, strm) : 0.0;
+            an[u] = on ? ldg_stream(d.c_r0 + kk, strm) : 0.0; bn[u] = on ? ldg_stream(d.c_r1 + kk, strm) : 0.0; cn[u] = on ? ldg_stream(d.c_r2 + kk, strm) : 1.0;
+        }
+        for (; k < k1; k += 32 * CP_DEPTH) {
+            int j[CP_DEPTH]; double w[CP_DEPTH], r0[CP_DEPTH], r1[CP_DEPTH], r2[CP_DEPTH], v[CP_DEPTH][3];
+#pragma unroll
+            for (int u = 0; u < CP_DEPTH; ++u) {
+                j[u] = jn[u]; w[u] = wn[u]; r0[u] = an[u]; r1[u] = bn[u]; r2[u] = cn[u];
+                if (j[u] >= 0) load3p_256_keep(vb, j[u], v[u], keep);
+            }
+#pragma unroll
+            for (int u = 0; u < CP_DEPTH; ++u) {
+                const int kk = k + 32 * (CP_DEPTH + u); const bool on = kk < k1;
+                jn[u] = on ? ldg_stream(d.c_pt + kk, strm) : -1; wn[u] = on ? ldg_stream(d.c_w + kk, strm) : 0.0;
+                an[u] = on ? ldg_stream(d.c_r0 + kk, strm) : 0.0; bn[u] = on ? ldg_stream(d.c_r1 + kk, strm) : 0.0; cn[u] = on ? ldg_stream(d.c_r2 + kk, strm) : 1.0;
+            }
+#pragma unroll
+            for (int u = 0; u < CP_DEPTH; ++u)
+                if (j[u] >= 0) cam_pass_one(cm, d.in, r0[u], r1[u], r2[u], v[u], w[u], acc);
         }
     }
 #pragma unroll
@@ -652,7 +748,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_init(Dev d)
     if (ok) for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
         int i = e / 6, a = e - 6 * i;
         double z = matvec6_row(d.Minv + 36 * (size_t)i, d.r + 6 * (size_t)i, a);
-        d.z[e] = z; d.p[e] = z; rz += d.r[e] * z;
+        d.z[e] = z; d.p[e] = z; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = z; rz += d.r[e] * z;
     }
     rz = block_sum<ONE_CTA>(rz, sm);
     if (threadIdx.x == 0) {
@@ -695,10 +791,221 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
     bool stop = (tol > 0 && rel < tol) || !(rzn > 0);
     if (!stop) {
         double beta = rzn / rz;
-        for (int e = threadIdx.x; e < n6; e += ONE_CTA) d.p[e] = d.z[e] + beta * d.p[e];
+        for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
+            double pn = d.z[e] + beta * d.p[e];
+            d.p[e] = pn; d.ptab[(size_t)(e / 6) * TAB_STRIDE + 7 + (e % 6)] = pn;
+        }
     }
     if (threadIdx.x == 0) {
         st->cg_steps += 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
+        if (stop) st->cg_active = 0;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Shared-memory camera table for the by-point CG sweep.
+//
+// In the by-point sweep every observation needs its camera's R, T and p (18 doubles = 5 sectors of L2 traffic and,
+// worse, 6 uncoalesced LDG.128 per lane = 192 L1 wavefronts per warp: ncu showed the generic sweep bound by L1
+// wavefronts at 70 %).  For problems up to MAX_SMEM / 112 B = 2075 cameras (Venice: 1778) the whole camera side fits
+// in one SM's shared memory once R is carried as a unit quaternion: 14 doubles per camera, staged with TMA bulk
+// copies (cp.async.bulk, one mbarrier), read with 7 LDS.128 per observation.  k_build_ptab converts R -> quaternion
+// once per linearisation; the CG kernels keep the p-part current.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_build_ptab(Dev d)
+{
+    const LMState* st = d.st;
+    if (st->done || !st->compute) return;
+    int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= d.N) return;
+    const double* s = d.rt[st->cur] + 12 * (size_t)i;
+    double R0 = s[0], R1 = s[1], R2 = s[2], R3 = s[4], R4 = s[5], R5 = s[6], R6 = s[8], R7 = s[9], R8 = s[10];
+    double w, x, y, z, tr = R0 + R4 + R8;
+    if (tr > 0) { double q = sqrt(tr + 1.0) * 2.0; w = 0.25 * q; x = (R7 - R5) / q; y = (R2 - R6) / q; z = (R3 - R1) / q; }
+    else if (R0 > R4 && R0 > R8) { double q = sqrt(1.0 + R0 - R4 - R8) * 2.0; w = (R7 - R5) / q; x = 0.25 * q; y = (R1 + R3) / q; z = (R2 + R6) / q; }
+    else if (R4 > R8) { double q = sqrt(1.0 + R4 - R0 - R8) * 2.0; w = (R2 - R6) / q; x = (R1 + R3) / q; y = 0.25 * q; z = (R5 + R7) / q; }
+    else { double q = sqrt(1.0 + R8 - R0 - R4) * 2.0; w = (R3 - R1) / q; x = (R2 + R6) / q; y = (R5 + R7) / q; z = 0.25 * q; }
+    double n = 1.0 / sqrt(w * w + x * x + y * y + z * z);
+    double* o = d.ptab + (size_t)i * TAB_STRIDE;
+    o[0] = w * n; o[1] = x * n; o[2] = y * n; o[3] = z * n; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// K8'  cg_point_pass_tab: persistent (one 768-thread CTA per SM), camera table in shared memory, one thread per point.
+//      Computes v_j = (V+lambda I)^-1 sum_k W_k^t p_i(k)  (MODE 0 of k_cg_point_pass).
+__global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;
+    double2* tab = reinterpret_cast<double2*>(smem_raw);
+    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* Xb = d.X[st->cur];
+    const double ar = d.in.k11 / d.in.k00, f = d.in.k00;
+    const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
+    // Each warp owns a CONTIGUOUS range of slices (balanced by rows on the host), so its o_cam / o_w rows form one
+    // contiguous stream: the two-rows-ahead register prefetch runs straight across slice boundaries, and the next
+    // slice's X / Vinv are requested one slice early.
+    const int wid = blockIdx.x * (TAB_BLOCK / 32) + warp;
+    if (wid >= d.tab_warps) return;
+    int g = __ldg(d.tab_wr + wid);
+    const int g_end = __ldg(d.tab_wr + wid + 1);
+    if (g >= g_end) return;
+    int k = __ldg(d.slice_base + g) + lane;
+    const int k_end = __ldg(d.slice_base + g_end) + lane;
+    int rows_left = __ldg(d.slice_deg + g);
+    int deg_next = g + 1 < g_end ? __ldg(d.slice_deg + g + 1) : 0;
+    double X[3] = {0, 0, 0}, Xn[3] = {0, 0, 0};
+    if (32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, keep);
+    if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, keep);
+    int cam_n = k < k_end ? ldg_stream(d.o_cam + k, strm) : -1, cam_n2 = k + 32 < k_end ? ldg_stream(d.o_cam + k + 32, strm) : -1;
+    double w_n = k < k_end ? ldg_stream(d.o_w + k, strm) : 0.0, w_n2 = k + 32 < k_end ? ldg_stream(d.o_w + k + 32, strm) : 0.0;
+    double u0 = 0, u1 = 0, u2 = 0;
+    for (;;) {
+        if (rows_left == 0) {                                   // slice boundary (warp-uniform): finish point 32 g + lane
+            const int j = 32 * g + lane;
+            if (j < d.M) {
+                double Vi[6]; load6(d.Vinv, j, Vi);
+                store4_keep(d.v + 4 * (size_t)j, Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2,
+                            Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0, keep);
+            }
+            if (++g >= g_end) break;
+            rows_left = deg_next; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; u0 = u1 = u2 = 0;
+            if (g + 1 < g_end) {
+                deg_next = __ldg(d.slice_deg + g + 1);
+                if (32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, keep);
+                if (lane == 0) { const int nj = min(32, d.M - 32 * (g + 1)); if (nj > 0) prefetch_l2_bulk(d.Vinv + 6 * (size_t)(32 * (g + 1)), (uint32_t)nj * 48u); }
+            }
+            continue;
+        }
+        const int cam = cam_n; const double w = w_n;
+        cam_n = cam_n2; w_n = w_n2;
+        if (k + 64 < k_end) { cam_n2 = ldg_stream(d.o_cam + k + 64, strm); w_n2 = ldg_stream(d.o_w + k + 64, strm); }
+        else { cam_n2 = -1; w_n2 = 0.0; }
+        --rows_left; k += 32;
+        if (cam < 0) continue;
+        const double2* t = tab + 7 * cam;
+        const double2 a0 = t[0], a1 = t[1], a2 = t[2], a3 = t[3], a4 = t[4], a5 = t[5], a6 = t[6];
+        const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
+        // r = R X by the quaternion sandwich  r = X + qw t + qv x t,  t = 2 qv x X   (no 3x3 matrix in registers)
+        const double tx = 2.0 * (qy * X[2] - qz * X[1]), ty = 2.0 * (qz * X[0] - qx * X[2]), tz = 2.0 * (qx * X[1] - qy * X[0]);
+        const double r0 = X[0] + qw * tx + (qy * tz - qz * ty);
+        const double r1 = X[1] + qw * ty + (qz * tx - qx * tz);
+        const double r2 = X[2] + qw * tz + (qx * ty - qy * tx);
+        const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
+        const double iz = 1.0 / z;
+        const double wf = w * f * iz;
+        const double pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
+        // t = A~ p,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x)
+        const double s0 = a3.y + (a5.y * r2 - a6.x * r1);
+        const double s1 = a4.x + (a6.x * r0 - a5.x * r2);
+        const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
+        const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
+        const double h0 = pa * t0, h1 = pc * t1, h2 = pb * t0 + pd * t1;
+        // u += R^t h : inverse rotation = sandwich with the conjugate quaternion
+        const double gx = 2.0 * (qz * h1 - qy * h2), gy = 2.0 * (qx * h2 - qz * h0), gz = 2.0 * (qy * h0 - qx * h1);
+        u0 += h0 + qw * gx + (qz * gy - qy * gz);
+        u1 += h1 + qw * gy + (qx * gz - qz * gx);
+        u2 += h2 + qw * gz + (qy * gx - qx * gy);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K11' cg_camera_step: the whole camera side of one PCG step in ONE cooperative kernel (grid-wide syncs instead of
+//      three kernel boundaries): second-level chunk sums, q = (U + lambda I) p - sum W v, alpha, x, r, z = M r, beta, p.
+//      One thread per (camera, component); a block owns 32 cameras.  Dot products: fixed-order block partials,
+//      summed in the same fixed order by every warp, so every thread sees identical scalars.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double grid_total(const double* part, int n)
+{
+    double s = 0;
+    for (int b = (threadIdx.x & 31); b < n; b += 32) s += part[b];
+    return warp_sum(s);
+}
+__global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_ready, double* part_pq, double* part_rz)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sv[STEP_BLOCK];
+    __shared__ double sm[STEP_BLOCK / 32];
+    LMState* st = d.st;
+    if (st->done || !st->cg_active) return;                      // uniform over the grid
+    const double lam = st->lambda, rz = st->rz, rz0 = st->rz0, tol = st->cg_tol;
+    const int steps = st->cg_steps;
+    const int e = blockIdx.x * STEP_BLOCK + threadIdx.x, n6 = 6 * d.N;
+    const bool on = e < n6;
+    const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;    // lc: first thread of this camera inside the block
+    double pe = on ? d.p[e] : 0.0;
+    sv[threadIdx.x] = pe;
+    __syncthreads();
+    double q = 0;
+    if (on) {
+        double s = 0;
+        if (sums_ready == 1) s = d.ar_q[e];
+        else for (int ch = d.cam_chunk_beg[i]; ch < d.cam_chunk_beg[i + 1]; ++ch) s += d.chunk_part[PART_STRIDE * (size_t)ch + a];
+        q = lam * pe + matvec6_row(d.U + 36 * (size_t)i, sv + lc, a) - s;
+    }
+    double bp = block_sum<STEP_BLOCK>(pe * q, sm);
+    if (threadIdx.x == 0) part_pq[blockIdx.x] = bp;
+    grid.sync();
+    const double pq = grid_total(part_pq, gridDim.x);
+    if (!(pq > 0) || !isfinite(pq)) {                            // breakdown (uniform): keep x; first-step breakdown = failed solve
+        if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; }
+        return;
+    }
+    const double alpha = rz / pq;
+    double re = 0, xe = 0;
+    if (on) { xe = d.x[e] + alpha * pe; re = d.r[e] - alpha * q; d.x[e] = xe; d.r[e] = re; }
+    __syncthreads();
+    sv[threadIdx.x] = re;
+    __syncthreads();
+    double z = on ? matvec6_row(d.Minv + 36 * (size_t)i, sv + lc, a) : 0.0;
+    double br = block_sum<STEP_BLOCK>(re * z, sm);
+    if (threadIdx.x == 0) part_rz[blockIdx.x] = br;
+    grid.sync();
+    const double rzn = grid_total(part_rz, gridDim.x);
+    const double rel = sqrt(fabs(rzn) / rz0);
+    const bool stop = (tol > 0 && rel < tol) || !(rzn > 0);
+    if (!stop && on) {
+        double pn = z + (rzn / rz) * pe;
+        d.p[e] = pn; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = pn;
+    }
+    if (e == 0) {
+        st->cg_steps = steps + 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
         if (stop) st->cg_active = 0;
     }
 }
@@ -778,8 +1085,11 @@ __global__ void __launch_bounds__(PT_BLOCK) k_reproj_sum(Dev d, int which)
     double s = 0;
     if (j < d.M) {
         double X[3]; load3p(d.X[which], j, X);
-        for (int k = d.pstart[j]; k < d.pstart[j + 1]; ++k) {
-            Cam cm; load_cam(d.rt[which], __ldg(d.o_cam + k), cm);
+        int k0, deg; slice_of(d, j, k0, deg);
+        for (int sl = 0, k = k0; sl < deg; ++sl, k += 32) {
+            int i = __ldg(d.o_cam + k);
+            if (i < 0) continue;
+            Cam cm; load_cam(d.rt[which], i, cm);
             double e0, e1, x, y, iz, r0, r1, r2;
             obs_residual(cm, X, __ldg(d.o_meas + k), d.in, e0, e1, x, y, iz, r0, r1, r2);
             s += d.in.f0 * sqrt(e0 * e0 + e1 * e1);
