@@ -571,7 +571,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->use_coop = coop && (long long)per_sm * h->num_sms >= h->step_grid && getenv("B200BA_NO_COOP") == nullptr;
     }
     CU(h->part_pq.alloc((size_t)h->step_grid)); CU(h->part_rz.alloc((size_t)h->step_grid));
-    h->use_graph = getenv("B200BA_NO_GRAPH") == nullptr;
+    // NCCL collectives are enqueued eagerly (outside any capture): graph replay is used for the single-rank engine only
+    h->use_graph = getenv("B200BA_NO_GRAPH") == nullptr && h->world <= 1;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
 
     d = Dev{};

@@ -1,0 +1,57 @@
+"""torchrun --nproc-per-node N tools/multi_gpu_check.py [shape]: point-partitioned solve on N GPUs vs the same solve on one GPU
+(rank 0 also runs the single-GPU engine): per-iteration costs must agree to 1e-9, results to 1e-9."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from sequencesfm_b200 import binding
+from sequencesfm_b200.synth import make_problem, partition_points
+
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+shape = sys.argv[1] if len(sys.argv) > 1 else "ladybug"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+p = make_problem(shape, 1, outlier_frac=0.01)
+j0, j1 = partition_points(p.obs_pt, p.M, world)[rank]
+shard = p.slice_points(j0, j1)
+def mark(m):
+    print(f"[rank {rank}] {m}", flush=True)
+mark("process group up")
+eng = binding.Engine(device=lr, max_iterations=iters)
+idt = torch.zeros(binding.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt.copy_(torch.frombuffer(bytearray(binding.Engine.comm_unique_id()), dtype=torch.uint8))
+dist.broadcast(idt, 0)
+mark("id broadcast")
+eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+mark("comm_init done")
+eng.set_problem_from(shard)
+mark("set_problem done")
+eng.begin(); mark("begin done")
+eng.iterate(1); mark("iterate(1) done")
+torch.cuda.synchronize(); dist.barrier()
+t0 = time.time()
+r = eng.solve()
+mark("solve done")
+torch.cuda.synchronize(); dist.barrier()
+dt = time.time() - t0
+# gather point results
+pts = [None] * world
+dist.all_gather_object(pts, r.pts)
+if rank == 0:
+    allpts = np.concatenate(pts, axis=0)
+    with binding.Engine(device=lr, max_iterations=iters) as e1:
+        e1.set_problem_from(p)
+        t0 = time.time(); s = e1.solve(); d1 = time.time() - t0
+    n = min(len(r.trace), len(s.trace))
+    rel = np.abs(r.trace[:n, 1] - s.trace[:n, 1]) / s.trace[:n, 1]
+    out = {"world": world, "shape": shape, "iters": [r.iterations, s.iterations], "status": [r.status, s.status],
+           "max_rel_cost_diff": float(rel.max()), "accept_equal": bool(np.array_equal(r.trace[:n, 5], s.trace[:n, 5])),
+           "cam_diff": float(np.abs(r.cam_RT - s.cam_RT).max()), "pts_diff": float(np.abs(allpts - s.pts).max()),
+           "ms_solve_multi": r.ms_solve, "ms_solve_single": s.ms_solve, "wall_multi": dt, "wall_single": d1,
+           "mean_px": [r.mean_px, s.mean_px]}
+    print(json.dumps(out))
+    assert out["max_rel_cost_diff"] < 1e-9 and out["cam_diff"] < 1e-8 and out["pts_diff"] < 1e-8, out
+eng.close()
+dist.barrier(); dist.destroy_process_group()
