@@ -258,6 +258,7 @@ def main() -> int:
     d2h = prob.M * 32 + N * 96
     e2e = {"value": r2.iterations / e2e_s, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d / e2e_steps,
            "d2h_bytes_per_step": d2h / e2e_steps, "seconds_total": e2e_s, "lm_iterations": r2.iterations,
+           "ms_set_problem": r2.ms_h2d, "ms_solve_device": r2.ms_solve, "ms_get_result": r2.ms_d2h,
            "note": "host arrays -> b200ba_set_problem (marshal, sort, upload) -> b200ba_solve -> b200ba_get_result; bytes amortised over the solve's LM iterations"}
     eng2.close()
 

@@ -17,7 +17,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace b200ba;
@@ -50,16 +53,33 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+// One device arena per problem: every buffer is carved out of a single cudaMalloc (40 separate allocations cost
+// 40-100 ms per set_problem) and zeroed with a single memset.
+struct Arena {
+    char* base = nullptr; size_t cap = 0, off = 0;
+    void* take(size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return base ? (void*)(base + o) : nullptr; }
+};
 template <class T> struct DBuf {
-    T* p = nullptr; size_t n = 0;
+    T* p = nullptr; size_t n = 0; bool owned = false;
     cudaError_t alloc(size_t count)
     {
-        release(); n = count;
+        release(); n = count; owned = true;
         if (!count) return cudaSuccess;
         return cudaMalloc((void**)&p, sizeof(T) * count);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t take(Arena& a, size_t count) { release(); n = count; owned = false; p = (T*)a.take(sizeof(T) * count); return cudaSuccess; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = false; }
 };
+
+// fork-join helper for the host-side layout build (std::thread: no OpenMP runtime dependency)
+template <class F> void parallel_for(int nthreads, F&& fn)
+{
+    if (nthreads <= 1) { fn(0, 1); return; }
+    std::vector<std::thread> th; th.reserve(nthreads - 1);
+    for (int t = 1; t < nthreads; ++t) th.emplace_back([&fn, t, nthreads] { fn(t, nthreads); });
+    fn(0, nthreads);
+    for (auto& x : th) x.join();
+}
 
 } // namespace
 
@@ -92,6 +112,7 @@ struct b200ba_handle {
     long long launches_per_graph = 0;
     DBuf<LMState> st;
     DBuf<double> norm_buf;
+    Arena arena;
     LMState h_st{};
     long long launches = 0;
     double ms_h2d = 0, ms_d2h = 0, ms_solve = 0, ms_last_iterate = 0;
@@ -375,6 +396,7 @@ void b200ba_destroy(b200ba_handle* h)
     h->c_pt.release(); h->chunk_cam.release(); h->chunk_beg.release(); h->chunk_end.release(); h->cam_chunk_beg.release();
     h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->part_pq.release(); h->part_rz.release();
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->arena.base) cudaFree(h->arena.base);
     h->c_r0.release(); h->c_r1.release(); h->c_r2.release(); h->tab_wr.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -415,11 +437,28 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         return fail(h, B200BA_E_INVALID, "null or empty problem arrays (N=%d M=%d K=%d)", N, M, K);
     if (h->world <= 1 && (M == 0 || K == 0)) return fail(h, B200BA_E_INVALID, "empty problem (M=%d K=%d)", M, K);
     if (!(K5[0] != 0.0) || !std::isfinite(K5[0])) return fail(h, B200BA_E_INVALID, "focal length fx must be finite and non-zero");
-    for (int k = 0; k < K; ++k) {
-        if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M) return fail(h, B200BA_E_INVALID, "observation %d: index out of range", k);
-        if (k && obs_pt[k] < obs_pt[k - 1]) return fail(h, B200BA_E_INVALID, "observation %d: obs_pt must be non-decreasing", k);
+    const int T = (K > 200000) ? (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
+    {
+        std::atomic<long long> bad(-1);
+        parallel_for(T, [&](int t, int nt) {
+            const long long k0 = (long long)K * t / nt, k1 = (long long)K * (t + 1) / nt;
+            for (long long k = k0; k < k1; ++k)
+                if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M || (k && obs_pt[k] < obs_pt[k - 1])) {
+                    long long cur = bad.load();
+                    while ((cur < 0 || k < cur) && !bad.compare_exchange_weak(cur, k)) {}
+                    break;
+                }
+        });
+        const long long k = bad.load();
+        if (k >= 0) {
+            if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M) return fail(h, B200BA_E_INVALID, "observation %lld: index out of range", k);
+            return fail(h, B200BA_E_INVALID, "observation %lld: obs_pt must be non-decreasing", k);
+        }
     }
     double t0 = now_ms();
+    const bool verbose = getenv("B200BA_VERBOSE") != nullptr;
+    double tm = t0;
+    auto lap = [&](const char* what) { if (verbose) { double t = now_ms(); fprintf(stderr, "[b200ba] set_problem %-28s %8.2f ms\n", what, t - tm); tm = t; } };
     CU(cudaSetDevice(h->device));
     h->N = N; h->M = M; h->K = K;
     h->h_cam.assign(cam_RT, cam_RT + 12 * (size_t)N);
@@ -437,12 +476,16 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     in.huber = o.inlier_px > 0 ? o.inlier_px / std::fabs(f0) : 0.0;
     in.f0 = f0;
 
-    std::vector<double2> meas((size_t)K);
-    for (int k = 0; k < K; ++k) {
-        double x = obs_xy[2 * (size_t)k], y = obs_xy[2 * (size_t)k + 1];
-        if (o.round_pixels) { x = (double)lrintf((float)x); y = (double)lrintf((float)y); }
-        meas[k] = make_double2((x * rf) * r2, (y * rf) * r2);
-    }
+    std::unique_ptr<double2[]> meas(new double2[(size_t)std::max(K, 1)]);
+    parallel_for(T, [&](int t, int nt) {
+        const long long k0 = (long long)K * t / nt, k1 = (long long)K * (t + 1) / nt;
+        for (long long k = k0; k < k1; ++k) {
+            double x = obs_xy[2 * (size_t)k], y = obs_xy[2 * (size_t)k + 1];
+            if (o.round_pixels) { x = (double)lrintf((float)x); y = (double)lrintf((float)y); }
+            meas[k] = make_double2((x * rf) * r2, (y * rf) * r2);
+        }
+    });
+    lap("validate + measurements");
     // ---- by-point layout: SELL-32, points sorted by track length (descending, stable) ----
     std::vector<int> pstart((size_t)M + 1, 0);
     for (int k = 0; k < K; ++k) pstart[obs_pt[k] + 1]++;
@@ -463,25 +506,44 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     }
     const int Kp = slice_base[n_slices];
     h->Kp = Kp;
-    std::vector<int> o_cam_p((size_t)std::max(Kp, 1), -1);
-    std::vector<double2> o_meas_p((size_t)std::max(Kp, 1), make_double2(0.0, 0.0));
-    h->entry_of_obs.assign((size_t)K, 0);
-    // camera order: stable counting sort by camera over the NEW point order, then chunks of <= CHUNK
+    std::unique_ptr<int[]> o_cam_p(new int[(size_t)std::max(Kp, 1)]);
+    std::unique_ptr<double2[]> o_meas_p(new double2[(size_t)std::max(Kp, 1)]);
+    h->entry_of_obs.resize((size_t)K);
+    // camera order: stable counting sort by camera over the NEW point order (parallel: per-thread histograms over
+    // contiguous blocks of slices, exclusive scan over threads, then placement), then chunks of <= CHUNK
     std::vector<int> cstart((size_t)N + 1, 0);
-    for (int k = 0; k < K; ++k) cstart[obs_cam[k] + 1]++;
-    for (int i = 0; i < N; ++i) cstart[i + 1] += cstart[i];
-    std::vector<int> c_pt((size_t)K); std::vector<double2> c_meas((size_t)K);
+    std::unique_ptr<int[]> c_pt(new int[(size_t)std::max(K, 1)]);
+    std::unique_ptr<double2[]> c_meas(new double2[(size_t)std::max(K, 1)]);
     {
-        std::vector<int> fill(cstart.begin(), cstart.end() - 1);
-        for (int jn = 0; jn < M; ++jn) {
-            const int j = h->orig_of_new[jn], g = jn >> 5, l = jn & 31;
-            for (int k = pstart[j], sl = 0; k < pstart[j + 1]; ++k, ++sl) {
-                const int kk = slice_base[g] + 32 * sl + l;
-                o_cam_p[kk] = obs_cam[k]; o_meas_p[kk] = meas[k]; h->entry_of_obs[k] = kk;
-                const int dst = fill[obs_cam[k]]++;
-                c_pt[dst] = jn; c_meas[dst] = meas[k];
+        std::vector<std::vector<int>> cnt((size_t)T, std::vector<int>((size_t)N, 0));
+        auto slice_range = [&](int t, int nt, int& g0, int& g1) { g0 = (int)((long long)n_slices * t / nt); g1 = (int)((long long)n_slices * (t + 1) / nt); };
+        parallel_for(T, [&](int t, int nt) {
+            int g0, g1; slice_range(t, nt, g0, g1);
+            std::vector<int>& c = cnt[t];
+            for (int jn = 32 * g0; jn < std::min(M, 32 * g1); ++jn) {
+                const int j = h->orig_of_new[jn];
+                for (int k = pstart[j]; k < pstart[j + 1]; ++k) c[obs_cam[k]]++;
             }
+        });
+        for (int i = 0; i < N; ++i) {
+            int run = cstart[i];
+            for (int t = 0; t < T; ++t) { int c = cnt[t][i]; cnt[t][i] = run; run += c; }
+            cstart[i + 1] = run;
         }
+        parallel_for(T, [&](int t, int nt) {
+            int g0, g1; slice_range(t, nt, g0, g1);
+            std::vector<int>& fill = cnt[t];
+            for (int e = slice_base[g0]; e < slice_base[g1]; ++e) { o_cam_p[e] = -1; o_meas_p[e] = make_double2(0.0, 0.0); }
+            for (int jn = 32 * g0; jn < std::min(M, 32 * g1); ++jn) {
+                const int j = h->orig_of_new[jn], g = jn >> 5, l = jn & 31;
+                for (int k = pstart[j], sl = 0; k < pstart[j + 1]; ++k, ++sl) {
+                    const int kk = slice_base[g] + 32 * sl + l;
+                    o_cam_p[kk] = obs_cam[k]; o_meas_p[kk] = meas[k]; h->entry_of_obs[k] = kk;
+                    const int dst = fill[obs_cam[k]]++;
+                    c_pt[dst] = jn; c_meas[dst] = meas[k];
+                }
+            }
+        });
     }
     std::vector<int> chunk_cam, chunk_beg, chunk_end, cam_chunk_beg((size_t)N + 1, 0);
     for (int i = 0; i < N; ++i) {
@@ -494,37 +556,49 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     int n_chunks = (int)chunk_cam.size();
     int n_pt_blocks = std::max(1, cdiv(M, PT_BLOCK));
 
-    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device));
-    h->num_sms = prop.multiProcessorCount;
+    lap("SELL + camera order build");
+    int smem_optin = 0, n_sm = 0;
+    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    h->num_sms = n_sm;
+    lap("device attributes");
 
     // ---- device allocation ----
     size_t n6 = 6 * (size_t)N;
     int world = h->world;
     h->trace_cap = o.max_iterations + 2;
     const size_t Mp = (size_t)std::max(M, 1), Kc = (size_t)std::max(K, 1), Kpp = (size_t)std::max(Kp, 1);
-    CU(h->rt0.alloc(12 * (size_t)N)); CU(h->rt1.alloc(12 * (size_t)N));
-    CU(h->U.alloc(36 * (size_t)N)); CU(h->Minv.alloc(36 * (size_t)N));
-    CU(h->gc.alloc(n6)); CU(h->x.alloc(n6)); CU(h->r.alloc(n6)); CU(h->z.alloc(n6)); CU(h->p.alloc(n6)); CU(h->q.alloc(n6));
-    CU(h->ar_lin.alloc((size_t)N * PART_STRIDE + 1 + 2 * (size_t)world)); CU(h->ar_q.alloc(n6)); CU(h->ar_sd.alloc(21 * (size_t)N)); CU(h->ar_dec.alloc(4));
-    CU(h->X0.alloc(4 * Mp)); CU(h->X1.alloc(4 * Mp));
-    CU(h->V.alloc(6 * Mp)); CU(h->Vinv.alloc(6 * Mp)); CU(h->gp.alloc(4 * Mp)); CU(h->v.alloc(4 * Mp));
-    CU(h->o_w.alloc(Kpp)); CU(h->c_w.alloc(Kc)); CU(h->o_meas.alloc(Kpp)); CU(h->c_meas.alloc(Kc));
-    CU(h->o_cam.alloc(Kpp)); CU(h->c_pt.alloc(Kc)); CU(h->slice_base.alloc((size_t)n_slices + 1)); CU(h->slice_deg.alloc((size_t)n_slices));
-    CU(h->chunk_cam.alloc(std::max(n_chunks, 1))); CU(h->chunk_beg.alloc(std::max(n_chunks, 1))); CU(h->chunk_end.alloc(std::max(n_chunks, 1)));
-    CU(h->cam_chunk_beg.alloc((size_t)N + 1));
-    CU(h->chunk_part.alloc((size_t)std::max(n_chunks, 1) * PART_STRIDE)); CU(h->pt_part.alloc(4 * (size_t)n_pt_blocks));
-    CU(h->trace.alloc((size_t)h->trace_cap * TRACE_COLS)); CU(h->st.alloc(1)); CU(h->norm_buf.alloc(16));
-    CU(h->ptab.alloc((size_t)N * TAB_STRIDE));
+    if (h->arena.base) { cudaFree(h->arena.base); h->arena = Arena(); }
+    int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (TAB_BLOCK / 32);
+    const int step_grid = cdiv((long long)N * 6, STEP_BLOCK);
+    for (int pass = 0; pass < 2; ++pass) {
+        Arena& A = h->arena;
+        A.off = 0;
+        h->rt0.take(A, 12 * (size_t)N); h->rt1.take(A, 12 * (size_t)N);
+        h->U.take(A, 36 * (size_t)N); h->Minv.take(A, 36 * (size_t)N);
+        h->gc.take(A, n6); h->x.take(A, n6); h->r.take(A, n6); h->z.take(A, n6); h->p.take(A, n6); h->q.take(A, n6);
+        h->ar_lin.take(A, (size_t)N * PART_STRIDE + 1 + 2 * (size_t)world); h->ar_q.take(A, n6); h->ar_sd.take(A, 21 * (size_t)N); h->ar_dec.take(A, 4);
+        h->X0.take(A, 4 * Mp); h->X1.take(A, 4 * Mp);
+        h->V.take(A, 6 * Mp); h->Vinv.take(A, 6 * Mp); h->gp.take(A, 4 * Mp); h->v.take(A, 4 * Mp);
+        h->o_w.take(A, Kpp); h->c_w.take(A, Kc); h->o_meas.take(A, Kpp); h->c_meas.take(A, Kc);
+        h->o_cam.take(A, Kpp); h->c_pt.take(A, Kc); h->slice_base.take(A, (size_t)n_slices + 1); h->slice_deg.take(A, (size_t)n_slices);
+        h->chunk_cam.take(A, std::max(n_chunks, 1)); h->chunk_beg.take(A, std::max(n_chunks, 1)); h->chunk_end.take(A, std::max(n_chunks, 1));
+        h->cam_chunk_beg.take(A, (size_t)N + 1);
+        h->chunk_part.take(A, (size_t)std::max(n_chunks, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)n_pt_blocks);
+        h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
+        h->ptab.take(A, (size_t)N * TAB_STRIDE);
+        h->c_r0.take(A, Kc); h->c_r1.take(A, Kc); h->c_r2.take(A, Kc);
+        h->tab_wr.take(A, (size_t)tab_warps_cap + 1); h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
+        if (pass == 0) { A.cap = A.off; CU(cudaMalloc((void**)&A.base, A.cap)); }
+    }
+    lap("cudaMalloc");
     cudaStream_t s = h->stream;
-    CU(h->c_r0.alloc(Kc)); CU(h->c_r1.alloc(Kc)); CU(h->c_r2.alloc(Kc));
-    CU(cudaMemsetAsync(h->c_r0.p, 0, sizeof(double) * Kc, s)); CU(cudaMemsetAsync(h->c_r1.p, 0, sizeof(double) * Kc, s)); CU(cudaMemsetAsync(h->c_r2.p, 0, sizeof(double) * Kc, s));
-    CU(cudaMemcpyAsync(h->o_meas.p, o_meas_p.data(), sizeof(double2) * Kpp, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->o_cam.p, o_cam_p.data(), sizeof(int) * Kpp, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(h->o_w.p, 0, sizeof(double) * Kpp, s));
+    CU(cudaMemsetAsync(h->arena.base, 0, h->arena.cap, s));
+    CU(cudaMemcpyAsync(h->o_meas.p, o_meas_p.get(), sizeof(double2) * Kpp, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->o_cam.p, o_cam_p.get(), sizeof(int) * Kpp, cudaMemcpyHostToDevice, s));
     if (K) {
-        CU(cudaMemcpyAsync(h->c_meas.p, c_meas.data(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->c_pt.p, c_pt.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(h->c_w.p, 0, sizeof(double) * (size_t)K, s));
+        CU(cudaMemcpyAsync(h->c_meas.p, c_meas.get(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->c_pt.p, c_pt.get(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
     }
     CU(cudaMemcpyAsync(h->slice_base.p, slice_base.data(), sizeof(int) * ((size_t)n_slices + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->slice_deg.p, slice_deg.data(), sizeof(int) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
@@ -534,17 +608,12 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         CU(cudaMemcpyAsync(h->chunk_end.p, chunk_end.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
     }
     CU(cudaMemcpyAsync(h->cam_chunk_beg.p, cam_chunk_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(h->chunk_part.p, 0, sizeof(double) * (size_t)std::max(n_chunks, 1) * PART_STRIDE, s));
-    CU(cudaMemsetAsync(h->pt_part.p, 0, sizeof(double) * 4 * (size_t)n_pt_blocks, s));
-    CU(cudaMemsetAsync(h->ar_lin.p, 0, sizeof(double) * h->ar_lin.n, s));
-    CU(cudaMemsetAsync(h->ar_sd.p, 0, sizeof(double) * h->ar_sd.n, s));
-    CU(cudaMemsetAsync(h->ar_q.p, 0, sizeof(double) * h->ar_q.n, s));
-    CU(cudaMemsetAsync(h->ptab.p, 0, sizeof(double) * h->ptab.n, s));
     CU(cudaStreamSynchronize(s));
 
+    lap("upload");
     // ---- execution plan: shared-memory camera table, cooperative camera-side step, CUDA graph ----
     const size_t tab_bytes = (size_t)N * TAB_STRIDE * sizeof(double);
-    h->use_tab = tab_bytes + 1024 <= (size_t)prop.sharedMemPerBlockOptin && getenv("B200BA_NO_TAB") == nullptr;
+    h->use_tab = tab_bytes + 1024 <= (size_t)smem_optin && getenv("B200BA_NO_TAB") == nullptr;
     if (h->use_tab) {
         if (cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes) != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
         h->tab_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB_BLOCK / 32)));
@@ -560,7 +629,6 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             while (w + 1 < tab_warps && acc * tab_warps >= total * (long long)(w + 1)) wr[++w] = g + 1;
         }
         for (int q = w + 1; q <= tab_warps; ++q) wr[q] = n_slices;
-        CU(h->tab_wr.alloc(wr.size()));
         CU(cudaMemcpy(h->tab_wr.p, wr.data(), sizeof(int) * wr.size(), cudaMemcpyHostToDevice));
     }
     h->step_grid = cdiv((long long)N * 6, STEP_BLOCK);
@@ -570,7 +638,6 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_camera_step, STEP_BLOCK, 0);
         h->use_coop = coop && (long long)per_sm * h->num_sms >= h->step_grid && getenv("B200BA_NO_COOP") == nullptr;
     }
-    CU(h->part_pq.alloc((size_t)h->step_grid)); CU(h->part_rz.alloc((size_t)h->step_grid));
     // NCCL collectives are enqueued eagerly (outside any capture): graph replay is used for the single-rank engine only
     h->use_graph = getenv("B200BA_NO_GRAPH") == nullptr && h->world <= 1;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -589,6 +656,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.c_pt = h->c_pt.p; d.c_meas = h->c_meas.p; d.c_w = h->c_w.p;
     d.chunk_cam = h->chunk_cam.p; d.chunk_beg = h->chunk_beg.p; d.chunk_end = h->chunk_end.p; d.cam_chunk_beg = h->cam_chunk_beg.p;
     d.chunk_part = h->chunk_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
+    lap("plan");
     h->have_problem = true; h->begun = false; h->finished = false;
     h->ms_h2d = now_ms() - t0;
     return 0;
