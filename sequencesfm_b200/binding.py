@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ba.so")
+LIB_PATH = os.environ.get("B200BA_LIB", os.path.join(_HERE, "libb200ba.so"))   # override: kernel-variant experiments
 TRACE_COLS = 8
 COMM_ID_BYTES = 128
 

@@ -35,7 +35,10 @@ constexpr int PART_STRIDE  = 28;    // doubles per chunk partial: 21 (sym 6x6) +
 constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side kernels
 constexpr int TRACE_COLS   = 8;
 constexpr int TAB_STRIDE   = 14;    // doubles per camera in the packed table: quaternion 4, T 3, p 6, pad 1 (112 B = 7 x 16 B)
-constexpr int TAB_BLOCK    = 768;   // threads of the persistent shared-memory-table CG point sweep (1 CTA / SM, <= 85 registers)
+#ifndef B200BA_TAB_BLOCK
+#define B200BA_TAB_BLOCK 768
+#endif
+constexpr int TAB_BLOCK    = B200BA_TAB_BLOCK;   // threads of the persistent shared-memory-table CG point sweep (1 CTA / SM, <= 85 registers)
 constexpr int STEP_BLOCK   = 192;   // threads of the cooperative camera-side CG kernel: 32 cameras x 6 components
 constexpr int MAX_SMEM     = 227 * 1024;
 
@@ -683,19 +686,21 @@ __device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in
     acc[4] += r2 * h0 - r0 * h2;
     acc[5] += r0 * h1 - r1 * h0;
 }
-constexpr int CP_DEPTH = 3;            // observations in flight per lane
-__global__ void __launch_bounds__(CH_BLOCK, 4) k_cg_camera_pass(Dev d, int rhs_pass)
+#ifndef B200BA_CP_DEPTH
+#define B200BA_CP_DEPTH 3
+#endif
+#ifndef B200BA_CP_MINB
+#define B200BA_CP_MINB 4
+#endif
+constexpr int CP_DEPTH = B200BA_CP_DEPTH;   // observations in flight per lane
+// one chunk (<= CHUNK observations of camera chunk_cam[ch]) by one warp; writes the chunk partial
+__device__ __forceinline__ void camera_chunk(const Dev& d, int ch, int lane, int cur)
 {
-    const LMState* st = d.st;
-    if (st->done) return;
-    if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
-    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (ch >= d.n_chunks) return;
-    int i = d.chunk_cam[ch];
+    const int i = d.chunk_cam[ch];
     double acc[6] = {0, 0, 0, 0, 0, 0};
     if (i >= d.first_free) {
         const double* vb = d.v;
-        Cam cm; load_cam(d.rt[st->cur], i, cm);
+        Cam cm; load_cam(d.rt[cur], i, cm);
         const int k1 = d.chunk_end[ch];
         const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
         int jn[CP_DEPTH]; double wn[CP_DEPTH], an[CP_DEPTH], bn[CP_DEPTH], cn[CP_DEPTH];
@@ -731,6 +736,15 @@ __global__ void __launch_bounds__(CH_BLOCK, 4) k_cg_camera_pass(Dev d, int rhs_p
 #pragma unroll
         for (int q = 0; q < 6; ++q) o[q] = acc[q];
     }
+}
+__global__ void __launch_bounds__(CH_BLOCK, B200BA_CP_MINB) k_cg_camera_pass(Dev d, int rhs_pass)
+{
+    const LMState* st = d.st;
+    if (st->done) return;
+    if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
+    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ch >= d.n_chunks) return;
+    camera_chunk(d, ch, lane, st->cur);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -965,16 +979,12 @@ __device__ __forceinline__ double grid_total(const double* part, int n)
     for (int b = (threadIdx.x & 31); b < n; b += 32) s += part[b];
     return warp_sum(s);
 }
-__global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_ready, double* part_pq, double* part_rz)
+// phases of the camera-side step (after the by-camera partial sums exist); every thread of the grid must call it
+__device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_groups::grid_group& grid, int sums_ready,
+                                                   double* part_pq, double* part_rz, int step_blocks, double* sv, double* sm,
+                                                   double lam, double rz, double rz0, double tol, int steps)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sv[STEP_BLOCK];
-    __shared__ double sm[STEP_BLOCK / 32];
     LMState* st = d.st;
-    if (st->done || !st->cg_active) return;                      // uniform over the grid
-    const double lam = st->lambda, rz = st->rz, rz0 = st->rz0, tol = st->cg_tol;
-    const int steps = st->cg_steps;
     const int e = blockIdx.x * STEP_BLOCK + threadIdx.x, n6 = 6 * d.N;
     const bool on = e < n6;
     const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;    // lc: first thread of this camera inside the block
@@ -989,9 +999,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
         q = lam * pe + matvec6_row(d.U + 36 * (size_t)i, sv + lc, a) - s;
     }
     double bp = block_sum<STEP_BLOCK>(pe * q, sm);
-    if (threadIdx.x == 0) part_pq[blockIdx.x] = bp;
+    if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_pq[blockIdx.x] = bp;
     grid.sync();
-    const double pq = grid_total(part_pq, gridDim.x);
+    const double pq = grid_total(part_pq, step_blocks);
     if (!(pq > 0) || !isfinite(pq)) {                            // breakdown (uniform): keep x; first-step breakdown = failed solve
         if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; }
         return;
@@ -1004,9 +1014,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
     __syncthreads();
     double z = on ? matvec6_row(d.Minv + 36 * (size_t)i, sv + lc, a) : 0.0;
     double br = block_sum<STEP_BLOCK>(re * z, sm);
-    if (threadIdx.x == 0) part_rz[blockIdx.x] = br;
+    if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_rz[blockIdx.x] = br;
     grid.sync();
-    const double rzn = grid_total(part_rz, gridDim.x);
+    const double rzn = grid_total(part_rz, step_blocks);
     const double rel = sqrt(fabs(rzn) / rz0);
     const bool stop = (tol > 0 && rel < tol) || !(rzn > 0);
     if (!stop && on) {
@@ -1017,6 +1027,16 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
         st->cg_steps = steps + 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
         if (stop) st->cg_active = 0;
     }
+}
+__global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_ready, double* part_pq, double* part_rz)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sv[STEP_BLOCK];
+    __shared__ double sm[STEP_BLOCK / 32];
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;                      // uniform over the grid
+    camera_step_phases(d, grid, sums_ready, part_pq, part_rz, gridDim.x, sv, sm, st->lambda, st->rz, st->rz0, st->cg_tol, st->cg_steps);
 }
 
 // K12 cg_finish: delta_c = x; trial cameras T += dt, R <- Rodrigues(dw) R (v3d_metricbundle.cpp:17-39,
