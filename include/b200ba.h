@@ -65,7 +65,10 @@ typedef struct b200ba_options {
     int32_t precond;            /* 1: diagonal blocks of S; 0: (U + lambda I)^-1 like PBA                 */
     /* --- host interaction --- */
     int32_t poll_every;         /* copy the device status word back every n LM iterations (default 5)     */
-    int32_t reserved[7];
+    /* --- layout --- */
+    int32_t lane_window;        /* 64: candidate window of the bank-conflict-aware grouping of points into     */
+                                /*     quarter-warps for the shared-memory camera table; 0 = keep input order  */
+    int32_t reserved[6];
 } b200ba_options;
 
 #define B200BA_TRACE_COLS 8     /* iter, err, lambda, new_err, rho, accepted(1/0/-1), cg_steps, cg_rel_residual */

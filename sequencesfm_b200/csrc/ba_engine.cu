@@ -340,7 +340,7 @@ int b200ba_default_options(b200ba_options* o)
     o->max_iterations = 50; o->min_iterations = 10; o->tau = 1e-3; o->inlier_px = 2.0;
     o->gradient_threshold = 1e-8; o->update_threshold = 1e-8;
     o->round_pixels = 1; o->normalize = 1; o->fix_first_camera = 0; o->discard_converged = 1;
-    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5;
+    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5; o->lane_window = 64;
     return 0;
 }
 
@@ -497,6 +497,62 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     for (int b = 0; b <= maxdeg; ++b) bucket[b + 1] += bucket[b];
     h->orig_of_new.assign((size_t)M, 0);
     for (int j = 0; j < M; ++j) h->orig_of_new[bucket[maxdeg - (pstart[j + 1] - pstart[j])]++] = j;
+    // ---- bank-conflict-aware lane grouping (shared-memory camera table) ----
+    // In k_cg_point_pass_tab the 8 lanes of a quarter-warp read the same 16-byte field of 8 different camera records;
+    // the bank group of a record is (camera index mod 8), so random cameras collide 2.6-fold on average (ncu: 63 % of the
+    // sweep's shared-memory wavefronts were conflicts).  Points of equal track length are interchangeable, so they are
+    // regrouped greedily (candidate window lane_window) such that the cameras met by a quarter-warp in each slot have
+    // distinct residues mod 8 as far as possible (measured 2.6 -> ~1.7).  Only the point permutation changes.
+    if (o.lane_window > 0 && K > 0 && getenv("B200BA_NO_LANE_OPT") == nullptr) {
+        const int W = std::min(o.lane_window, 1024);
+        std::vector<int>& ord = h->orig_of_new;
+        auto degree = [&](int jn) { const int j = ord[jn]; return pstart[j + 1] - pstart[j]; };
+        parallel_for(T, [&](int t, int nt) {
+            long long a = (long long)(M / 32) * t / nt * 32, b = (t + 1 == nt) ? M : (long long)(M / 32) * (t + 1) / nt * 32;
+            std::vector<int> run, out, pool; std::vector<unsigned long long> key;
+            for (long long r0 = a; r0 < b;) {
+                const int dg = degree((int)r0);
+                long long r1 = r0; while (r1 < b && degree((int)r1) == dg) ++r1;
+                const int n = (int)(r1 - r0), ds = std::min(dg, 16);
+                if (n >= 16 && ds > 0) {
+                    run.assign(ord.begin() + r0, ord.begin() + r1);
+                    key.resize(n);
+                    for (int q = 0; q < n; ++q) { unsigned long long kq = 0; const int j = run[q]; for (int sl = 0; sl < ds; ++sl) kq |= (unsigned long long)(obs_cam[pstart[j] + sl] & 7) << (3 * sl); key[q] = kq; }
+                    out.clear(); out.reserve(n); pool.clear();
+                    int next = 0;
+                    while (next < n && (int)pool.size() < W) pool.push_back(next++);
+                    unsigned char cnt[16][8]; unsigned char mx[16];
+                    int group = (8 - (int)(r0 & 7)) & 7;          // first (partial) group completes the quarter-warp the run starts in
+                    if (group == 0) group = 8;
+                    for (; !pool.empty(); group = 8) {
+                        memset(cnt, 0, sizeof cnt); memset(mx, 0, sizeof mx);
+                        for (int g8 = 0; g8 < group && !pool.empty(); ++g8) {
+                            int best = 0;
+                            if (g8 > 0) {
+                                int best_score = 1 << 30;
+                                for (int c = 0; c < (int)pool.size(); ++c) {
+                                    const unsigned long long kq = key[pool[c]];
+                                    int inc = 0, sum = 0;
+                                    for (int sl = 0; sl < ds; ++sl) { const int c1 = cnt[sl][(kq >> (3 * sl)) & 7] + 1; inc += c1 > mx[sl] ? c1 - mx[sl] : 0; sum += c1; }
+                                    const int score = inc * 256 + sum;
+                                    if (score < best_score) { best_score = score; best = c; if (inc == 0 && sum == ds) break; }
+                                }
+                            }
+                            const int q = pool[best];
+                            pool.erase(pool.begin() + best);
+                            const unsigned long long kq = key[q];
+                            for (int sl = 0; sl < ds; ++sl) { unsigned char& c = cnt[sl][(kq >> (3 * sl)) & 7]; ++c; if (c > mx[sl]) mx[sl] = c; }
+                            out.push_back(run[q]);
+                            if (next < n) pool.push_back(next++);
+                        }
+                    }
+                    std::copy(out.begin(), out.end(), ord.begin() + r0);
+                }
+                r0 = r1;
+            }
+        });
+        lap("lane grouping");
+    }
     const int n_slices = cdiv(std::max(M, 1), 32);
     std::vector<int> slice_base((size_t)n_slices + 1, 0), slice_deg((size_t)n_slices, 0);
     for (int g = 0; g < n_slices; ++g) {

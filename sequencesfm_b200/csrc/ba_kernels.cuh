@@ -28,7 +28,10 @@
 
 namespace b200ba {
 
-constexpr int CHUNK        = 256;   // observations of one camera handled by one warp
+#ifndef B200BA_CHUNK
+#define B200BA_CHUNK 512
+#endif
+constexpr int CHUNK        = B200BA_CHUNK;   // observations of one camera handled by one warp
 constexpr int PT_BLOCK     = 128;   // threads per block in thread-per-point kernels
 constexpr int CH_BLOCK     = 128;   // threads per block in warp-per-chunk kernels (4 chunks)
 constexpr int PART_STRIDE  = 28;    // doubles per chunk partial: 21 (sym 6x6) + 6 (+1 pad)
