@@ -644,7 +644,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
         h->ptab.take(A, (size_t)N * TAB_STRIDE);
         h->c_r0.take(A, Kc); h->c_r1.take(A, Kc); h->c_r2.take(A, Kc);
-        h->tab_wr.take(A, (size_t)tab_warps_cap + 1); h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
+        h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8); h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
         if (pass == 0) { A.cap = A.off; CU(cudaMalloc((void**)&A.base, A.cap)); }
     }
     lap("cudaMalloc");
@@ -674,7 +674,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes) != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
         h->tab_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB_BLOCK / 32)));
     }
-    // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue)
+    // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
+    // one 32-byte header per warp: {first slice, end slice, first entry, end entry, deg(first), deg(first+1), 0, 0}
     int tab_warps = std::max(1, h->tab_grid) * (TAB_BLOCK / 32);
     {
         std::vector<int> wr((size_t)tab_warps + 1, n_slices);
@@ -685,7 +686,14 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             while (w + 1 < tab_warps && acc * tab_warps >= total * (long long)(w + 1)) wr[++w] = g + 1;
         }
         for (int q = w + 1; q <= tab_warps; ++q) wr[q] = n_slices;
-        CU(cudaMemcpy(h->tab_wr.p, wr.data(), sizeof(int) * wr.size(), cudaMemcpyHostToDevice));
+        std::vector<int> hdr((size_t)tab_warps * 8, 0);
+        for (int q = 0; q < tab_warps; ++q) {
+            const int g0 = wr[q], g1 = wr[q + 1];
+            int* o = hdr.data() + 8 * (size_t)q;
+            o[0] = g0; o[1] = g1; o[2] = slice_base[g0]; o[3] = slice_base[g1];
+            o[4] = g0 < n_slices ? slice_deg[g0] : 0; o[5] = g0 + 1 < g1 ? slice_deg[g0 + 1] : 0;
+        }
+        CU(cudaMemcpy(h->tab_wr.p, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice));
     }
     h->step_grid = cdiv((long long)N * 6, STEP_BLOCK);
     {
