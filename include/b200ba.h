@@ -117,6 +117,9 @@ int b200ba_solve(b200ba_handle* h, b200ba_report* report);
  * normalise; iterate = run up to n LM loop iterations; finish = de-normalise and fill the report. */
 int b200ba_begin(b200ba_handle* h);
 int b200ba_iterate(b200ba_handle* h, int32_t n, int32_t* done);
+/* Put the device state back to what b200ba_begin produced (device-to-device copy of the normalised start point, LM
+ * state reset) without touching the host: lets a benchmark time many full LM iterations from the same start. */
+int b200ba_restart(b200ba_handle* h);
 /* Device time (CUDA events on the engine's stream) of the last b200ba_iterate call, in milliseconds. */
 int b200ba_last_iterate_ms(b200ba_handle* h, double* ms);
 int b200ba_finish(b200ba_handle* h, b200ba_report* report);

@@ -70,6 +70,11 @@ def ssba_adjust(p, *, round_pixels: bool = True, max_iterations: int = 50, trace
                       secs.value, cam, pts)
 
 
+class _noop:
+    def __enter__(self): return self
+    def __exit__(self, *a): pass
+
+
 @dataclass
 class PbaResult:
     initial_mse: float
@@ -83,7 +88,24 @@ class PbaResult:
     pts: np.ndarray
 
 
-def pba_adjust(p, *, double: bool = True, args: tuple[str, ...] = (), threads: int = 0) -> PbaResult:
+class _quiet_stdout:
+    """PBA and SSBA print banners with std::cout / printf even at verbosity 0; keep them off the caller's stdout
+    (bench.py must print exactly one JSON line)."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *a):
+        C.CDLL(None).fflush(None)          # drain the C / C++ stdio buffers into /dev/null before restoring fd 1
+        os.dup2(self._saved, 1)
+        os.close(self._null); os.close(self._saved)
+
+
+def pba_adjust(p, *, double: bool = True, args: tuple[str, ...] = (), threads: int = 0, quiet: bool = True) -> PbaResult:
     lib = C.CDLL(os.path.join(REF_DIR, "libpba_ref.so"))
     cam = np.ascontiguousarray(p.cam_RT, dtype=np.float64).copy()
     pts = np.ascontiguousarray(p.pts, dtype=np.float64).copy()
@@ -94,8 +116,10 @@ def pba_adjust(p, *, double: bool = True, args: tuple[str, ...] = (), threads: i
     argv = (C.c_char_p * max(1, len(args)))(*[a.encode() for a in args])
     stats = np.zeros(8)
     lib.pba_ref_adjust.restype = C.c_int
-    lib.pba_ref_adjust(C.c_int(p.N), C.c_int(p.M), C.c_int(p.K), _d(K5), None, _d(cam), _d(pts), _d(xy), _i(oc), _i(op),
-                       C.c_int(-3 if double else -2), C.c_int(len(args)), argv, C.c_int(threads), _d(stats))
+    ctx = _quiet_stdout() if quiet else _noop()
+    with ctx:
+        lib.pba_ref_adjust(C.c_int(p.N), C.c_int(p.M), C.c_int(p.K), _d(K5), None, _d(cam), _d(pts), _d(xy), _i(oc), _i(op),
+                           C.c_int(-3 if double else -2), C.c_int(len(args)), argv, C.c_int(threads), _d(stats))
     code = int(stats[5])
     return PbaResult(float(stats[0]), float(stats[1]), int(stats[2]), int(stats[3]), float(stats[4]),
                      chr(code) if code > 0 else "", int(stats[6]), cam, pts)

@@ -22,7 +22,7 @@ STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 # every symbol include/b200ba.h declares (tests check that the library exports each of them)
 ABI_SYMBOLS = [
     "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
-    "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
+    "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
     "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
 ]
@@ -201,6 +201,9 @@ class Engine:
         done = C.c_int32(0)
         self._check(self.lib.b200ba_iterate(self.h, C.c_int32(n), C.byref(done)))
         return bool(done.value)
+
+    def restart(self):
+        self._check(self.lib.b200ba_restart(self.h))
 
     def last_iterate_ms(self) -> float:
         ms = C.c_double(0)

@@ -102,7 +102,7 @@ struct b200ba_handle {
     DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, o_w, c_w, chunk_part, pt_part, trace;
     DBuf<double2> o_meas, c_meas;
     DBuf<int> o_cam, slice_base, slice_deg, c_pt, chunk_cam, chunk_beg, chunk_end, cam_chunk_beg;
-    DBuf<double> ptab, part_pq, part_rz, c_r0, c_r1, c_r2;
+    DBuf<double> ptab, part_pq, part_rz, c_r0, c_r1, c_r2, X_init, rt_init;
     DBuf<int> tab_wr;
     std::vector<int> orig_of_new, entry_of_obs;      // SELL permutation (new point index -> caller's), obs -> padded entry
     int Kp = 0;                                      // padded SELL entries
@@ -113,7 +113,7 @@ struct b200ba_handle {
     DBuf<LMState> st;
     DBuf<double> norm_buf;
     Arena arena;
-    LMState h_st{};
+    LMState h_st{}, h_st_init{};
     long long launches = 0;
     double ms_h2d = 0, ms_d2h = 0, ms_solve = 0, ms_last_iterate = 0;
     double mean_px[2] = {0, 0};
@@ -643,7 +643,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->chunk_part.take(A, (size_t)std::max(n_chunks, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)n_pt_blocks);
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
         h->ptab.take(A, (size_t)N * TAB_STRIDE);
-        h->c_r0.take(A, Kc); h->c_r1.take(A, Kc); h->c_r2.take(A, Kc);
+        h->c_r0.take(A, Kc); h->c_r1.take(A, Kc); h->c_r2.take(A, Kc); h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8); h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
         if (pass == 0) { A.cap = A.off; CU(cudaMalloc((void**)&A.base, A.cap)); }
     }
@@ -778,18 +778,38 @@ int b200ba_begin(b200ba_handle* h)
     CU(cudaMemcpyAsync(h->rt1.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->X0.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->X1.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->X_init.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(h->rt_init.p, h->rt0.p, sizeof(double) * 12 * (size_t)N, cudaMemcpyDeviceToDevice, s));
     LMState st{};
     st.lambda = 1e-3; st.param_length = std::sqrt(L[0]);
     st.tau = o.tau; st.grad_thr = o.gradient_threshold; st.upd_thr = o.update_threshold; st.cg_tol = o.cg_rel_tol;
     st.iter = 0; st.status = 0; st.done = (o.max_iterations <= 0) ? 1 : 0; st.compute = 1; st.cur = 0; st.first = 1;
     st.cg_active = 0; st.solve_ok = 1; st.max_iter = o.max_iterations; st.min_iter = o.min_iterations;
     st.n_trace = 0; st.trace_cap = h->trace_cap;
-    h->h_st = st;
+    h->h_st = st; h->h_st_init = st;
     CU(cudaMemcpyAsync(h->st.p, &h->h_st, sizeof st, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
     h->launches = 0; h->ms_solve = 0;
     if (int rc = mean_reproj(h, 0, &h->mean_px[0])) return rc;
     h->begun = true; h->finished = false;
+    return 0;
+}
+
+int b200ba_restart(b200ba_handle* h)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->begun) return fail(h, B200BA_E_STATE, "b200ba_restart before b200ba_begin");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t xb = sizeof(double) * 4 * (size_t)std::max(h->M, 1), rb = sizeof(double) * 12 * (size_t)h->N;
+    CU(cudaMemcpyAsync(h->X0.p, h->X_init.p, xb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(h->X1.p, h->X_init.p, xb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(h->rt0.p, h->rt_init.p, rb, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(h->rt1.p, h->rt_init.p, rb, cudaMemcpyDeviceToDevice, s));
+    LMState st = h->h_st_init;
+    CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    h->finished = false;
     return 0;
 }
 
