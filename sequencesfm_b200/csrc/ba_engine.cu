@@ -99,14 +99,17 @@ struct b200ba_handle {
     bool have_problem = false, begun = false, finished = false;
     // device
     Dev d{};
-    DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, o_w, c_w, chunk_part, pt_part, trace;
+    DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, o_w, seg_part, pt_part, trace;
     DBuf<double2> o_meas, c_meas;
-    DBuf<int> o_cam, slice_base, slice_deg, c_pt, chunk_cam, chunk_beg, chunk_end, cam_chunk_beg;
-    DBuf<double> ptab, part_pq, part_rz, c_r0, c_r1, c_r2, X_init, rt_init;
+    DBuf<int> o_cam, slice_base, slice_deg, row_j, cam_seg_beg;
+    DBuf<int2> row_hdr;
+    DBuf<unsigned char> c_rec;
+    DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
     DBuf<int> tab_wr;
     std::vector<int> orig_of_new, entry_of_obs;      // SELL permutation (new point index -> caller's), obs -> padded entry
     int Kp = 0;                                      // padded SELL entries
-    int num_sms = 148, tab_grid = 0, step_grid = 0;
+    int num_sms = 148, tab_grid = 0, step_grid = 0, cam_grid = 0;
+    size_t tab_smem = 0;
     bool use_tab = false, use_coop = false, use_graph = false;
     cudaGraphExec_t graph_exec = nullptr;
     long long launches_per_graph = 0;
@@ -151,7 +154,7 @@ int enqueue_linearize(b200ba_handle* h)
     Dev& d = h->d;
     if (h->use_tab) LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
     LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
-    LAUNCH(k_linearize_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d);
+    LAUNCH(k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world)) return rc;
@@ -164,7 +167,7 @@ int enqueue_precond(b200ba_handle* h)
     Dev& d = h->d;
     LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
     if (h->opt.precond == 1) {
-        LAUNCH(k_schur_diag_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d);
+        LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
         LAUNCH((k_camera_reduce<21, 21>), cdiv((long long)d.N * 21, 256), 256, d, d.ar_sd, 0);
         if (int rc = allreduce(h, d.ar_sd, (size_t)d.N * 21)) return rc;
     }
@@ -185,11 +188,12 @@ int enqueue_cg_init(b200ba_handle* h)
     return 0;
 }
 
-// sum_k W_k v_j by camera (chunked, warp per chunk)
+// sum_k W_k v_j by camera (persistent row sweep, TMA-staged row records)
 int enqueue_camera_half(b200ba_handle* h, int rhs_pass)
 {
     Dev& d = h->d;
-    LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, rhs_pass);
+    k_cg_camera_pass<<<h->cam_grid, CW * 32, CAMPASS_SMEM, h->stream>>>(d, rhs_pass);
+    h->launches++;
     return 0;
 }
 // second level -> ar_q (+ all-reduce over ranks)
@@ -214,7 +218,7 @@ int enqueue_cg_step(b200ba_handle* h)
 {
     Dev& d = h->d;
     if (h->use_tab) {
-        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, (size_t)d.N * TAB_STRIDE * sizeof(double), h->stream>>>(d);
+        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d);
         h->launches++;
     } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
@@ -391,13 +395,13 @@ void b200ba_destroy(b200ba_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->rt0.release(); h->rt1.release(); h->U.release(); h->gc.release(); h->Minv.release(); h->x.release(); h->r.release();
     h->z.release(); h->p.release(); h->q.release(); h->ar_lin.release(); h->ar_q.release(); h->ar_sd.release(); h->ar_dec.release();
-    h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_w.release(); h->c_w.release();
-    h->chunk_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
-    h->c_pt.release(); h->chunk_cam.release(); h->chunk_beg.release(); h->chunk_end.release(); h->cam_chunk_beg.release();
+    h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_w.release();
+    h->seg_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
+    h->row_j.release(); h->row_hdr.release(); h->c_rec.release(); h->cam_seg_beg.release();
     h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->part_pq.release(); h->part_rz.release();
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->arena.base) cudaFree(h->arena.base);
-    h->c_r0.release(); h->c_r1.release(); h->c_r2.release(); h->tab_wr.release();
+    h->tab_wr.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -475,6 +479,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     in.k00 *= r2; in.k01 *= r2; in.k02 *= r2; in.k11 *= r2; in.k12 *= r2;
     in.huber = o.inlier_px > 0 ? o.inlier_px / std::fabs(f0) : 0.0;
     in.f0 = f0;
+    in.ar = in.k11 / in.k00;
 
     std::unique_ptr<double2[]> meas(new double2[(size_t)std::max(K, 1)]);
     parallel_for(T, [&](int t, int nt) {
@@ -565,11 +570,17 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     std::unique_ptr<int[]> o_cam_p(new int[(size_t)std::max(Kp, 1)]);
     std::unique_ptr<double2[]> o_meas_p(new double2[(size_t)std::max(Kp, 1)]);
     h->entry_of_obs.resize((size_t)K);
+    int smem_optin = 0, n_sm = 0;
+    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    h->num_sms = n_sm;
     // camera order: stable counting sort by camera over the NEW point order (parallel: per-thread histograms over
-    // contiguous blocks of slices, exclusive scan over threads, then placement), then chunks of <= CHUNK
-    std::vector<int> cstart((size_t)N + 1, 0);
-    std::unique_ptr<int[]> c_pt(new int[(size_t)std::max(K, 1)]);
-    std::unique_ptr<double2[]> c_meas(new double2[(size_t)std::max(K, 1)]);
+    // contiguous blocks of slices, exclusive scan over threads, then placement).  Every camera's run is padded to whole
+    // ROWS of 32 observations (point index -1 = padding); see REC_* in ba_kernels.cuh.
+    std::vector<int> row_beg((size_t)N + 1, 0);
+    std::unique_ptr<int[]> row_j;
+    std::unique_ptr<double2[]> c_meas;
+    int n_rows = 0;
     {
         std::vector<std::vector<int>> cnt((size_t)T, std::vector<int>((size_t)N, 0));
         auto slice_range = [&](int t, int nt, int& g0, int& g1) { g0 = (int)((long long)n_slices * t / nt); g1 = (int)((long long)n_slices * (t + 1) / nt); };
@@ -582,10 +593,17 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             }
         });
         for (int i = 0; i < N; ++i) {
-            int run = cstart[i];
+            int run = 32 * row_beg[i];
             for (int t = 0; t < T; ++t) { int c = cnt[t][i]; cnt[t][i] = run; run += c; }
-            cstart[i + 1] = run;
+            row_beg[i + 1] = row_beg[i] + (run - 32 * row_beg[i] + 31) / 32;
         }
+        n_rows = row_beg[N];
+        const size_t ne = 32 * (size_t)std::max(n_rows, 1);
+        row_j.reset(new int[ne]); c_meas.reset(new double2[ne]);
+        parallel_for(T, [&](int t, int nt) {
+            const size_t e0 = ne * t / nt, e1 = ne * (t + 1) / nt;
+            for (size_t e = e0; e < e1; ++e) { row_j[e] = -1; c_meas[e] = make_double2(0.0, 0.0); }
+        });
         parallel_for(T, [&](int t, int nt) {
             int g0, g1; slice_range(t, nt, g0, g1);
             std::vector<int>& fill = cnt[t];
@@ -596,34 +614,36 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
                     const int kk = slice_base[g] + 32 * sl + l;
                     o_cam_p[kk] = obs_cam[k]; o_meas_p[kk] = meas[k]; h->entry_of_obs[k] = kk;
                     const int dst = fill[obs_cam[k]]++;
-                    c_pt[dst] = jn; c_meas[dst] = meas[k];
+                    row_j[dst] = jn; c_meas[dst] = meas[k];
                 }
             }
         });
     }
-    std::vector<int> chunk_cam, chunk_beg, chunk_end, cam_chunk_beg((size_t)N + 1, 0);
-    for (int i = 0; i < N; ++i) {
-        cam_chunk_beg[i] = (int)chunk_cam.size();
-        for (int b = cstart[i]; b < cstart[i + 1]; b += CHUNK) {
-            chunk_cam.push_back(i); chunk_beg.push_back(b); chunk_end.push_back(std::min(b + CHUNK, cstart[i + 1]));
+    // virtual warps (equal row ranges) and segments (runs of one camera inside one virtual warp's range)
+    const int n_vwarps = std::max(1, n_sm) * CW;
+    std::vector<int2> row_hdr((size_t)std::max(n_rows, 1), make_int2(0, 0));
+    std::vector<int> cam_seg_beg((size_t)N + 1, 0);
+    int n_segs = 0;
+    {
+        for (int i = 0; i < N; ++i) for (int r = row_beg[i]; r < row_beg[i + 1]; ++r) row_hdr[r].x = i;
+        int seg = -1;
+        for (int v = 0; v < n_vwarps; ++v) {
+            const int rb = (int)((long long)n_rows * v / n_vwarps), re = (int)((long long)n_rows * (v + 1) / n_vwarps);
+            for (int r = rb; r < re; ++r) { if (r == rb || row_hdr[r].x != row_hdr[r - 1].x) ++seg; row_hdr[r].y = seg; }
         }
+        n_segs = seg + 1;
+        cam_seg_beg[N] = n_segs;
+        for (int i = N - 1; i >= 0; --i) cam_seg_beg[i] = row_beg[i + 1] > row_beg[i] ? row_hdr[row_beg[i]].y : cam_seg_beg[i + 1];
     }
-    cam_chunk_beg[N] = (int)chunk_cam.size();
-    int n_chunks = (int)chunk_cam.size();
     int n_pt_blocks = std::max(1, cdiv(M, PT_BLOCK));
 
-    lap("SELL + camera order build");
-    int smem_optin = 0, n_sm = 0;
-    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
-    h->num_sms = n_sm;
-    lap("device attributes");
+    lap("SELL + camera rows build");
 
     // ---- device allocation ----
     size_t n6 = 6 * (size_t)N;
     int world = h->world;
     h->trace_cap = o.max_iterations + 2;
-    const size_t Mp = (size_t)std::max(M, 1), Kc = (size_t)std::max(K, 1), Kpp = (size_t)std::max(Kp, 1);
+    const size_t Mp = (size_t)std::max(M, 1), Kpp = (size_t)std::max(Kp, 1), Rp = (size_t)std::max(n_rows, 1);
     if (h->arena.base) { cudaFree(h->arena.base); h->arena = Arena(); }
     int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (TAB_BLOCK / 32);
     const int step_grid = cdiv((long long)N * 6, STEP_BLOCK);
@@ -636,14 +656,14 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->ar_lin.take(A, (size_t)N * PART_STRIDE + 1 + 2 * (size_t)world); h->ar_q.take(A, n6); h->ar_sd.take(A, 21 * (size_t)N); h->ar_dec.take(A, 4);
         h->X0.take(A, 4 * Mp); h->X1.take(A, 4 * Mp);
         h->V.take(A, 6 * Mp); h->Vinv.take(A, 6 * Mp); h->gp.take(A, 4 * Mp); h->v.take(A, 4 * Mp);
-        h->o_w.take(A, Kpp); h->c_w.take(A, Kc); h->o_meas.take(A, Kpp); h->c_meas.take(A, Kc);
-        h->o_cam.take(A, Kpp); h->c_pt.take(A, Kc); h->slice_base.take(A, (size_t)n_slices + 1); h->slice_deg.take(A, (size_t)n_slices);
-        h->chunk_cam.take(A, std::max(n_chunks, 1)); h->chunk_beg.take(A, std::max(n_chunks, 1)); h->chunk_end.take(A, std::max(n_chunks, 1));
-        h->cam_chunk_beg.take(A, (size_t)N + 1);
-        h->chunk_part.take(A, (size_t)std::max(n_chunks, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)n_pt_blocks);
+        h->o_w.take(A, Kpp); h->o_meas.take(A, Kpp); h->c_meas.take(A, 32 * Rp);
+        h->o_cam.take(A, Kpp); h->slice_base.take(A, (size_t)n_slices + 1); h->slice_deg.take(A, (size_t)n_slices);
+        h->c_rec.take(A, Rp * REC_BYTES + 16); h->row_j.take(A, 32 * Rp); h->row_hdr.take(A, Rp);
+        h->cam_seg_beg.take(A, (size_t)N + 1);
+        h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)n_pt_blocks);
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
         h->ptab.take(A, (size_t)N * TAB_STRIDE);
-        h->c_r0.take(A, Kc); h->c_r1.take(A, Kc); h->c_r2.take(A, Kc); h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
+        h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8); h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
         if (pass == 0) { A.cap = A.off; CU(cudaMalloc((void**)&A.base, A.cap)); }
     }
@@ -652,26 +672,28 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     CU(cudaMemsetAsync(h->arena.base, 0, h->arena.cap, s));
     CU(cudaMemcpyAsync(h->o_meas.p, o_meas_p.get(), sizeof(double2) * Kpp, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->o_cam.p, o_cam_p.get(), sizeof(int) * Kpp, cudaMemcpyHostToDevice, s));
-    if (K) {
-        CU(cudaMemcpyAsync(h->c_meas.p, c_meas.get(), sizeof(double2) * (size_t)K, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->c_pt.p, c_pt.get(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, s));
+    if (n_rows) {
+        CU(cudaMemcpyAsync(h->c_meas.p, c_meas.get(), sizeof(double2) * 32 * (size_t)n_rows, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->row_j.p, row_j.get(), sizeof(int) * 32 * (size_t)n_rows, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->row_hdr.p, row_hdr.data(), sizeof(int2) * (size_t)n_rows, cudaMemcpyHostToDevice, s));
     }
     CU(cudaMemcpyAsync(h->slice_base.p, slice_base.data(), sizeof(int) * ((size_t)n_slices + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->slice_deg.p, slice_deg.data(), sizeof(int) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
-    if (n_chunks) {
-        CU(cudaMemcpyAsync(h->chunk_cam.p, chunk_cam.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->chunk_beg.p, chunk_beg.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->chunk_end.p, chunk_end.data(), sizeof(int) * (size_t)n_chunks, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->cam_seg_beg.p, cam_seg_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+    if (n_rows) {
+        Dev dr{}; dr.n_rows = n_rows; dr.c_rec = h->c_rec.p;
+        k_fill_rows<<<cdiv(n_rows, 8), 256, 0, s>>>(dr, h->row_hdr.p, h->row_j.p);
     }
-    CU(cudaMemcpyAsync(h->cam_chunk_beg.p, cam_chunk_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
 
     lap("upload");
     // ---- execution plan: shared-memory camera table, cooperative camera-side step, CUDA graph ----
     const size_t tab_bytes = (size_t)N * TAB_STRIDE * sizeof(double);
-    h->use_tab = tab_bytes + 1024 <= (size_t)smem_optin && getenv("B200BA_NO_TAB") == nullptr;
+    h->tab_smem = ((tab_bytes + 127) & ~(size_t)127) + TAB_RING_BYTES;       // camera table + per-warp stream rings
+    h->use_tab = h->tab_smem + 256 <= (size_t)smem_optin && getenv("B200BA_NO_TAB") == nullptr;
     if (h->use_tab) {
-        if (cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes) != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
+        if (cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem) != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
         h->tab_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB_BLOCK / 32)));
     }
     // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
@@ -695,6 +717,9 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         }
         CU(cudaMemcpy(h->tab_wr.p, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice));
     }
+    if ((size_t)CAMPASS_SMEM > (size_t)smem_optin) return fail(h, B200BA_E_CUDA, "device offers %d bytes of shared memory per block, the by-camera sweep needs %d", smem_optin, CAMPASS_SMEM);
+    CU(cudaFuncSetAttribute(k_cg_camera_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CAMPASS_SMEM));
+    h->cam_grid = cdiv(n_vwarps, CW);
     h->step_grid = cdiv((long long)N * 6, STEP_BLOCK);
     {
         int per_sm = 0, coop = 0;
@@ -707,7 +732,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
 
     d = Dev{};
-    d.N = N; d.M = M; d.K = K; d.n_chunks = n_chunks; d.first_free = o.fix_first_camera ? 1 : 0; d.n_pt_blocks = n_pt_blocks;
+    d.N = N; d.M = M; d.K = K; d.n_rows = n_rows; d.n_vwarps = n_vwarps; d.n_segs = n_segs; d.first_free = o.fix_first_camera ? 1 : 0; d.n_pt_blocks = n_pt_blocks;
     d.world = world; d.rank = h->rank; d.n_slices = n_slices; d.tab_ok = h->use_tab ? 1 : 0; d.in = in; d.st = h->st.p;
     d.rt[0] = h->rt0.p; d.rt[1] = h->rt1.p; d.U = h->U.p; d.gc = h->gc.p; d.Minv = h->Minv.p;
     d.x = h->x.p; d.r = h->r.p; d.z = h->z.p; d.p = h->p.p; d.q = h->q.p;
@@ -715,11 +740,10 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
     d.o_cam = h->o_cam.p; d.o_meas = h->o_meas.p; d.o_w = h->o_w.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
     d.ptab = h->ptab.p;
-    d.c_r0 = h->c_r0.p; d.c_r1 = h->c_r1.p; d.c_r2 = h->c_r2.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
-    d.c_pt = h->c_pt.p; d.c_meas = h->c_meas.p; d.c_w = h->c_w.p;
-    d.chunk_cam = h->chunk_cam.p; d.chunk_beg = h->chunk_beg.p; d.chunk_end = h->chunk_end.p; d.cam_chunk_beg = h->cam_chunk_beg.p;
-    d.chunk_part = h->chunk_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
+    d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
+    d.cam_seg_beg = h->cam_seg_beg.p;
+    d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
     lap("plan");
     h->have_problem = true; h->begun = false; h->finished = false;
     h->ms_h2d = now_ms() - t0;
@@ -967,7 +991,7 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
         CU(cudaMemcpy(tab.data(), d.ptab, sizeof(double) * tab.size(), cudaMemcpyDeviceToHost));
         for (int i = 0; i < N; ++i) for (int a = 0; a < 6; ++a) tab[(size_t)i * TAB_STRIDE + 7 + a] = x[6 * (size_t)i + a];
         CU(cudaMemcpy(d.ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
-        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, (size_t)d.N * TAB_STRIDE * sizeof(double), h->stream>>>(d);
+        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d);
         h->launches++;
     } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
@@ -1007,8 +1031,8 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
     auto one = [&]() {
         switch (which) {
         case 0: LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d); break;
-        case 1: LAUNCH(k_linearize_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d); break;
-        case 2: if (h->use_tab) { k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, (size_t)d.N * TAB_STRIDE * sizeof(double), h->stream>>>(d); h->launches++; }
+        case 1: LAUNCH(k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;
+        case 2: if (h->use_tab) { k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d); h->launches++; }
                 else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
                 break;
         case 10: LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d); break;
@@ -1017,10 +1041,10 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
         case 12: if (int rc = enqueue_cg_step(h)) return rc;
                  CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 3: if (int rc = enqueue_camera_half(h, 0)) return rc; break;
-        case 13: LAUNCH(k_cg_camera_pass, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d, 0); break;
+        case 13: if (int rc = enqueue_camera_half(h, 0)) return rc; break;
         case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0); break;
         case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
-        case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_chunks, CH_BLOCK / 32), CH_BLOCK, d); break;
+        case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;
         case 7: LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d); break;
         case 8: LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d); break;
         case 9: LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond); break;

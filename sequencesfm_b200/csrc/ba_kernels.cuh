@@ -6,7 +6,7 @@
 // blocks are recomputed in registers in every pass; the damped normal equations are never assembled --
 // the reduced camera system S = (U + lambda I) - W (V + lambda I)^-1 W^t is applied matrix-free in two
 // sweeps (by point, then by camera) and solved by block-Jacobi PCG; all reductions are segmented
-// (thread-per-point over point-sorted observations, warp-per-chunk over camera-sorted observations with a
+// (thread-per-point over point-sorted observations, warp-per-row-range over camera-sorted observations with a
 // fixed-order second level) so there is no atomic on any accumulator and results are bit-reproducible.
 //
 // Memory layout (HBM, all fp64 unless noted):
@@ -18,8 +18,14 @@
 //                       lane l of slice g lives at slice_base[g] + 32 s + l.  One thread owns one point, every lane of a
 //                       warp runs the same trip count and every load of o_cam (int32, -1 = padding), o_meas (double2,
 //                       normalised) and o_w (double) is a fully coalesced 128/256/512-byte row.
-//   obs (camera order)  c_pt  int32, c_meas double2,             c_w double;  chunk tables (<= CHUNK obs of
-//                       one camera per chunk, chunks of a camera contiguous)
+//   obs (camera order)  ROW RECORDS: every camera's observations are padded to a multiple of 32 and cut into rows of 32;
+//                       one row is ONE contiguous 1168-byte record  [cam, segment | 32 x point index (int32, -1 = padding) |
+//                       32 x weight | 32 x (R X).x | .y | .z]  so that a single TMA bulk copy stages everything the CG
+//                       by-camera sweep streams for 32 observations, and the linearisation writes weight / cached R X back
+//                       with coalesced 256-byte stores.  c_meas (double2, same row order) is only read by the linearisation.
+//                       The rows are split evenly over n_vwarps "virtual warps"; a SEGMENT is a maximal run of rows of one
+//                       camera inside one virtual warp's range and owns one partial-sum slot (seg_part), so the second level
+//                       of every by-camera reduction is a fixed-order sum over cam_seg_beg[i] .. cam_seg_beg[i+1].
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -28,13 +34,32 @@
 
 namespace b200ba {
 
-#ifndef B200BA_CHUNK
-#define B200BA_CHUNK 512
-#endif
-constexpr int CHUNK        = B200BA_CHUNK;   // observations of one camera handled by one warp
 constexpr int PT_BLOCK     = 128;   // threads per block in thread-per-point kernels
-constexpr int CH_BLOCK     = 128;   // threads per block in warp-per-chunk kernels (4 chunks)
-constexpr int PART_STRIDE  = 28;    // doubles per chunk partial: 21 (sym 6x6) + 6 (+1 pad)
+constexpr int CH_BLOCK     = 128;   // threads per block in the by-camera row sweeps of the linearisation (4 virtual warps)
+constexpr int PART_STRIDE  = 28;    // doubles per segment partial: 21 (sym 6x6) + 6 (+1 pad)
+// camera-order row record (bytes)
+constexpr int REC_HDR      = 0;                 // int32 cam, int32 segment, 2 x pad
+constexpr int REC_J        = 16;                // 32 x int32 point index (new order), -1 = padding
+constexpr int REC_W        = REC_J + 128;       // 32 x f64 IRLS weight
+constexpr int REC_R0       = REC_W + 256;       // 32 x f64 (R X).x, .y, .z cached at linearisation
+constexpr int REC_R1       = REC_R0 + 256;
+constexpr int REC_R2       = REC_R1 + 256;
+constexpr int REC_BYTES    = REC_R2 + 256;      // 1168 = 73 x 16
+#ifndef B200BA_CW
+#define B200BA_CW 16
+#endif
+#ifndef B200BA_CG
+#define B200BA_CG 2
+#endif
+#ifndef B200BA_CNS
+#define B200BA_CNS 4
+#endif
+constexpr int CW  = B200BA_CW;      // warps per CTA of the persistent CG by-camera sweep = virtual warps per SM
+constexpr int CG  = B200BA_CG;      // rows per stage = rows whose arithmetic is interleaved (ILP) = gathers per register set
+constexpr int CNS = B200BA_CNS;     // stages staged in shared memory per warp (TMA ring, one mbarrier each)
+static_assert(CNS >= 3, "two stages are in use (gather front, arithmetic) while a third is being refilled");
+constexpr int STAGE_BYTES  = CG * REC_BYTES;
+constexpr int CAMPASS_SMEM = CW * CNS * STAGE_BYTES + CW * CNS * 8;
 constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side kernels
 constexpr int TRACE_COLS   = 8;
 constexpr int TAB_STRIDE   = 14;    // doubles per camera in the packed table: quaternion 4, T 3, p 6, pad 1 (112 B = 7 x 16 B)
@@ -49,6 +74,7 @@ struct Intrinsics {
     double k00, k01, k02, k11, k12;   // unit-focal-length intrinsics (src/sfm_ba_ssba.cpp:98-102)
     double huber;                     // 2 / |f0| (src/sfm_ba_ssba.cpp:193); <= 0: robustifier off
     double f0;
+    double ar;                        // k11 / k00 (aspect ratio), precomputed so that kernels read it from the constant bank
 };
 
 // Device-resident LM / CG control block: all accept/reject and stop decisions are taken on the device
@@ -65,7 +91,7 @@ struct LMState {
 };
 
 struct Dev {
-    int N, M, K, n_chunks, first_free, n_pt_blocks, world, rank, n_slices, tab_ok;
+    int N, M, K, n_rows, n_vwarps, n_segs, first_free, n_pt_blocks, world, rank, n_slices, tab_ok;
     Intrinsics in;
     LMState* st;
     double* rt[2];
@@ -78,12 +104,12 @@ struct Dev {
     double *V, *gp, *Vinv, *v;
     int* o_cam; double2* o_meas; double* o_w; int *slice_base, *slice_deg;
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
-    int* c_pt; double2* c_meas; double* c_w;
-    double *c_r0, *c_r1, *c_r2;   // R_i X_j per observation (camera order), written at linearisation: the CG sweep streams it instead of gathering X_j
+    unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
+    double2* c_meas;              // n_rows x 32 normalised measurements in row order
     int* tab_wr;                  // [tab_warps + 1] contiguous slice ranges of the persistent CG point sweep's warps (balanced by rows)
     int tab_warps;
-    int *chunk_cam, *chunk_beg, *chunk_end, *cam_chunk_beg;
-    double* chunk_part;   // n_chunks x PART_STRIDE
+    int* cam_seg_beg;     // N + 1: segments of camera i
+    double* seg_part;     // n_segs x PART_STRIDE
     double* pt_part;      // n_pt_blocks x 4
     double* trace;
 };
@@ -172,6 +198,14 @@ __device__ __forceinline__ void load3p_256(const double* __restrict__ base, int 
 // evict_first / no L1 allocation; gathered arrays are loaded and stored evict_last.
 __device__ __forceinline__ uint64_t policy_evict_last()  { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ int ldg_stream(const int* p)
+{
+    int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ double ldg_stream(const double* p)
+{
+    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
 __device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol)
 {
     int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
@@ -195,6 +229,43 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// ---- mbarrier / TMA bulk-copy helpers (sm_90+ PTX; the only async-copy engine used here is cp.async.bulk) ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// The spin loop is written in C++ (not as branches inside the asm block) so that the compiler sees it and places a
+// reconvergence point behind it: lanes can leave a try_wait loop in different trips, and with asm-internal branches the
+// warp stayed split for the rest of the kernel (ncu: every instruction of the sweep executed twice).
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred P1;\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+    __syncwarp();
+}
+
 // SELL-32 addressing: first entry and (warp-uniform) trip count of point j
 __device__ __forceinline__ void slice_of(const Dev& d, int j, int& k0, int& deg)
 {
@@ -239,7 +310,7 @@ __device__ __forceinline__ void obs_full(const Cam& cm, const double X[3], doubl
     double x, y, iz;
     obs_residual(cm, X, m, in, o.e0, o.e1, x, y, iz, o.r0, o.r1, o.r2);
     o.w = huber_weight(o.e0, o.e1, in.huber);
-    double f = in.k00, ar = in.k11 / in.k00;
+    double f = in.k00, ar = in.ar;
     double wf = o.w * f * iz;
     o.a = wf; o.b = -wf * x * iz; o.c = ar * wf; o.d = -ar * wf * y * iz;
 }
@@ -251,7 +322,7 @@ __device__ __forceinline__ void obs_jac(const Cam& cm, const double X[3], double
     o.r2 = cm.R[6] * X[0] + cm.R[7] * X[1] + cm.R[8] * X[2];
     double x = o.r0 + cm.T[0], y = o.r1 + cm.T[1], z = o.r2 + cm.T[2];
     double iz = fast_rcp(z);
-    double f = in.k00, ar = in.k11 / in.k00;
+    double f = in.k00, ar = in.ar;
     double wf = w * f * iz;
     o.w = w;
     o.a = wf; o.b = -wf * x * iz; o.c = ar * wf; o.d = -ar * wf * y * iz;
@@ -337,49 +408,74 @@ __global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2  linearize_cameras: one warp per chunk of <= CHUNK camera-sorted observations of one camera.
-//     U_i += A~^t A~ (21 unique), g_c,i += A~^t (-w e)   (v3d_optimization.cpp:530-541, 600-614); the weight is
-//     recomputed from the residual and stored in camera order for the CG sweeps.
+// By-camera row sweeps.  Virtual warp v owns rows [vrow(v), vrow(v+1)); a row holds 32 observations of ONE camera; the
+// record header names the camera and the segment (= partial-sum slot).  A segment change flushes the warp's
+// accumulators (fixed butterfly) and loads the next camera.
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int vrow(const Dev& d, int v) { return (int)((long long)d.n_rows * v / d.n_vwarps); }
+template <int NACC> __device__ __forceinline__ void seg_flush(const Dev& d, int seg, double (&acc)[NACC], int lane)
+{
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+        double* o = d.seg_part + PART_STRIDE * (size_t)seg;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) o[q] = acc[q];
+    }
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) acc[q] = 0.0;
+}
+
+// K2  linearize_cameras: U_i += A~^t A~ (21 unique), g_c,i += A~^t (-w e)   (v3d_optimization.cpp:530-541, 600-614); the
+//     weight is recomputed from the residual and written, with the lever arm R X, into the row record for the CG sweeps.
 __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 {
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
-    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (ch >= d.n_chunks) return;
-    int i = d.chunk_cam[ch];
-    double acc[27];
+    const int lane = threadIdx.x & 31, wpb = CH_BLOCK / 32, nw = gridDim.x * wpb;
+    const int cur = st->cur;
+    const double* Xb = d.X[cur];
+    const double* rt = d.rt[cur];
+    for (int vw = blockIdx.x * wpb + (threadIdx.x >> 5); vw < d.n_vwarps; vw += nw) {
+        const int rb = vrow(d, vw), re = vrow(d, vw + 1);
+        int seg = -1, cam = 0;
+        Cam cm;
+        double acc[27];
 #pragma unroll
-    for (int q = 0; q < 27; ++q) acc[q] = 0;
-    if (i >= d.first_free) {
-        const double* Xb = d.X[st->cur];
-        Cam cm; load_cam(d.rt[st->cur], i, cm);
-        int k1 = d.chunk_end[ch];
-        for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
-            double X[3]; load3p(Xb, __ldg(d.c_pt + k), X);
-            Obs o; obs_full(cm, X, __ldg(d.c_meas + k), d.in, o);
-            d.c_w[k] = o.w; d.c_r0[k] = o.r0; d.c_r1[k] = o.r1; d.c_r2[k] = o.r2;
-            double A0[6], A1[6]; jac_rows_A(o, A0, A1);
-            double we0 = -o.w * o.e0, we1 = -o.w * o.e1;
-            int q = 0;
+        for (int q = 0; q < 27; ++q) acc[q] = 0;
+        for (int r = rb; r < re; ++r) {
+            unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
+            const int2 h = __ldg(reinterpret_cast<const int2*>(rec + REC_HDR));
+            const int j = __ldg(reinterpret_cast<const int*>(rec + REC_J) + lane);
+            const double2 m = __ldg(d.c_meas + 32 * (size_t)r + lane);
+            double X[3] = {0, 0, 1};
+            if (j >= 0) load3p(Xb, j, X);
+            if (h.y != seg) {
+                if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
+                seg = h.y; cam = h.x; load_cam(rt, cam, cm);
+            }
+            if (j >= 0 && cam >= d.first_free) {
+                Obs o; obs_full(cm, X, m, d.in, o);
+                reinterpret_cast<double*>(rec + REC_W)[lane] = o.w;
+                reinterpret_cast<double*>(rec + REC_R0)[lane] = o.r0;
+                reinterpret_cast<double*>(rec + REC_R1)[lane] = o.r1;
+                reinterpret_cast<double*>(rec + REC_R2)[lane] = o.r2;
+                double A0[6], A1[6]; jac_rows_A(o, A0, A1);
+                const double we0 = -o.w * o.e0, we1 = -o.w * o.e1;
+                int q = 0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+                for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int b = a; b < 6; ++b) acc[q++] += A0[a] * A0[b] + A1[a] * A1[b];
+                    for (int b = a; b < 6; ++b) acc[q++] += A0[a] * A0[b] + A1[a] * A1[b];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) acc[21 + a] += A0[a] * we0 + A1[a] * we1;
+                for (int a = 0; a < 6; ++a) acc[21 + a] += A0[a] * we0 + A1[a] * we1;
+            }
         }
-    }
-#pragma unroll
-    for (int q = 0; q < 27; ++q) acc[q] = warp_sum(acc[q]);
-    if (lane == 0) {
-        double* o = d.chunk_part + PART_STRIDE * (size_t)ch;
-#pragma unroll
-        for (int q = 0; q < 27; ++q) o[q] = acc[q];
+        if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
     }
 }
 
-// second level of every by-camera reduction: fixed-order sum of a camera's chunk partials
+// second level of every by-camera reduction: fixed-order sum of a camera's segment partials
 template <int NV, int OSTRIDE>
 __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_compute)
 {
@@ -389,7 +485,7 @@ __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_comput
     int i = t / NV, c = t - i * NV;
     if (i >= d.N) return;
     double s = 0;
-    for (int ch = d.cam_chunk_beg[i]; ch < d.cam_chunk_beg[i + 1]; ++ch) s += d.chunk_part[PART_STRIDE * (size_t)ch + c];
+    for (int sg = d.cam_seg_beg[i]; sg < d.cam_seg_beg[i + 1]; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + c];
     out[(size_t)i * OSTRIDE + c] = s;
 }
 
@@ -483,66 +579,76 @@ __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K6  schur_diag_cameras: warp per chunk, sum_k W_k (V+lambda I)^-1 W_k^t (21 unique), W_k = A~^t B~.
-//     Gives the diagonal blocks of S for the block-Jacobi preconditioner.
+// K6  schur_diag_cameras: row sweep, sum_k W_k (V+lambda I)^-1 W_k^t (21 unique), W_k = A~^t B~.
+//     Gives the diagonal blocks of S for the block-Jacobi preconditioner.  Streams the row records (weight, cached
+//     R X) and gathers (V_j + lambda I)^-1.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
 {
     const LMState* st = d.st;
     if (st->done) return;
-    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (ch >= d.n_chunks) return;
-    int i = d.chunk_cam[ch];
-    double acc[21];
+    const int lane = threadIdx.x & 31, wpb = CH_BLOCK / 32, nw = gridDim.x * wpb;
+    const double* rt = d.rt[st->cur];
+    const double f = d.in.k00, ar = d.in.ar;
+    for (int vw = blockIdx.x * wpb + (threadIdx.x >> 5); vw < d.n_vwarps; vw += nw) {
+        const int rb = vrow(d, vw), re = vrow(d, vw + 1);
+        int seg = -1, cam = 0;
+        Cam cm;
+        double acc[21];
 #pragma unroll
-    for (int q = 0; q < 21; ++q) acc[q] = 0;
-    if (i >= d.first_free) {
-        const double* Xb = d.X[st->cur];
-        Cam cm; load_cam(d.rt[st->cur], i, cm);
-        int k1 = d.chunk_end[ch];
-        for (int k = d.chunk_beg[ch] + lane; k < k1; k += 32) {
-            int j = __ldg(d.c_pt + k);
-            double X[3]; load3p(Xb, j, X);
-            Obs o; obs_jac(cm, X, __ldg(d.c_w + k), d.in, o);
-            double Vi[6]; load6(d.Vinv, j, Vi);
-            // camera-space covariance  C = R Vinv R^t (sym 3x3), then G = P~ C P~^t (sym 2x2), then
-            // W Vinv W^t = A~^t G A~  because W = A~^t P~ R.
-            double RV[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                double r0 = cm.R[3 * r], r1 = cm.R[3 * r + 1], r2 = cm.R[3 * r + 2];
-                RV[3 * r]     = r0 * Vi[0] + r1 * Vi[1] + r2 * Vi[2];
-                RV[3 * r + 1] = r0 * Vi[1] + r1 * Vi[3] + r2 * Vi[4];
-                RV[3 * r + 2] = r0 * Vi[2] + r1 * Vi[4] + r2 * Vi[5];
+        for (int q = 0; q < 21; ++q) acc[q] = 0;
+        for (int r = rb; r < re; ++r) {
+            const unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
+            const int2 h = __ldg(reinterpret_cast<const int2*>(rec + REC_HDR));
+            const int j = __ldg(reinterpret_cast<const int*>(rec + REC_J) + lane);
+            double Vi[6] = {0, 0, 0, 0, 0, 0};
+            if (j >= 0) load6(d.Vinv, j, Vi);
+            if (h.y != seg) {
+                if (seg >= 0) seg_flush<21>(d, seg, acc, lane);
+                seg = h.y; cam = h.x; load_cam(rt, cam, cm);
             }
-            double C00 = RV[0] * cm.R[0] + RV[1] * cm.R[1] + RV[2] * cm.R[2];
-            double C02 = RV[0] * cm.R[6] + RV[1] * cm.R[7] + RV[2] * cm.R[8];
-            double C01 = RV[0] * cm.R[3] + RV[1] * cm.R[4] + RV[2] * cm.R[5];
-            double C11 = RV[3] * cm.R[3] + RV[4] * cm.R[4] + RV[5] * cm.R[5];
-            double C12 = RV[3] * cm.R[6] + RV[4] * cm.R[7] + RV[5] * cm.R[8];
-            double C22 = RV[6] * cm.R[6] + RV[7] * cm.R[7] + RV[8] * cm.R[8];
-            // G = P C P^t with P = [[a,0,b],[0,c,d]]
-            double G00 = o.a * o.a * C00 + 2.0 * o.a * o.b * C02 + o.b * o.b * C22;
-            double G01 = o.a * o.c * C01 + o.a * o.d * C02 + o.b * o.c * C12 + o.b * o.d * C22;
-            double G11 = o.c * o.c * C11 + 2.0 * o.c * o.d * C12 + o.d * o.d * C22;
-            double A0[6], A1[6]; jac_rows_A(o, A0, A1);
-            // A^t G A : rows combined  Y0 = G00 A0 + G01 A1, Y1 = G01 A0 + G11 A1;  result[a][b] = A0[a] Y0[b] + A1[a] Y1[b]
-            double Y0[6], Y1[6];
+            if (j >= 0 && cam >= d.first_free) {
+                Obs o;
+                o.w = __ldg(reinterpret_cast<const double*>(rec + REC_W) + lane);
+                o.r0 = __ldg(reinterpret_cast<const double*>(rec + REC_R0) + lane);
+                o.r1 = __ldg(reinterpret_cast<const double*>(rec + REC_R1) + lane);
+                o.r2 = __ldg(reinterpret_cast<const double*>(rec + REC_R2) + lane);
+                const double x = o.r0 + cm.T[0], y = o.r1 + cm.T[1], z = o.r2 + cm.T[2];
+                const double iz = fast_rcp(z), wf = o.w * f * iz;
+                o.a = wf; o.b = -wf * x * iz; o.c = ar * wf; o.d = -ar * wf * y * iz;
+                // camera-space covariance  C = R Vinv R^t (sym 3x3), then G = P~ C P~^t (sym 2x2), then
+                // W Vinv W^t = A~^t G A~  because W = A~^t P~ R.
+                double RV[9];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) { Y0[a] = G00 * A0[a] + G01 * A1[a]; Y1[a] = G01 * A0[a] + G11 * A1[a]; }
-            int q = 0;
+                for (int q = 0; q < 3; ++q) {
+                    const double r0 = cm.R[3 * q], r1 = cm.R[3 * q + 1], r2 = cm.R[3 * q + 2];
+                    RV[3 * q]     = r0 * Vi[0] + r1 * Vi[1] + r2 * Vi[2];
+                    RV[3 * q + 1] = r0 * Vi[1] + r1 * Vi[3] + r2 * Vi[4];
+                    RV[3 * q + 2] = r0 * Vi[2] + r1 * Vi[4] + r2 * Vi[5];
+                }
+                const double C00 = RV[0] * cm.R[0] + RV[1] * cm.R[1] + RV[2] * cm.R[2];
+                const double C02 = RV[0] * cm.R[6] + RV[1] * cm.R[7] + RV[2] * cm.R[8];
+                const double C01 = RV[0] * cm.R[3] + RV[1] * cm.R[4] + RV[2] * cm.R[5];
+                const double C11 = RV[3] * cm.R[3] + RV[4] * cm.R[4] + RV[5] * cm.R[5];
+                const double C12 = RV[3] * cm.R[6] + RV[4] * cm.R[7] + RV[5] * cm.R[8];
+                const double C22 = RV[6] * cm.R[6] + RV[7] * cm.R[7] + RV[8] * cm.R[8];
+                // G = P C P^t with P = [[a,0,b],[0,c,d]]
+                const double G00 = o.a * o.a * C00 + 2.0 * o.a * o.b * C02 + o.b * o.b * C22;
+                const double G01 = o.a * o.c * C01 + o.a * o.d * C02 + o.b * o.c * C12 + o.b * o.d * C22;
+                const double G11 = o.c * o.c * C11 + 2.0 * o.c * o.d * C12 + o.d * o.d * C22;
+                double A0[6], A1[6]; jac_rows_A(o, A0, A1);
+                // A^t G A : rows combined  Y0 = G00 A0 + G01 A1, Y1 = G01 A0 + G11 A1;  result[a][b] = A0[a] Y0[b] + A1[a] Y1[b]
+                double Y0[6], Y1[6];
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+                for (int a = 0; a < 6; ++a) { Y0[a] = G00 * A0[a] + G01 * A1[a]; Y1[a] = G01 * A0[a] + G11 * A1[a]; }
+                int q = 0;
 #pragma unroll
-                for (int b = a; b < 6; ++b) acc[q++] += A0[a] * Y0[b] + A1[a] * Y1[b];
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a; b < 6; ++b) acc[q++] += A0[a] * Y0[b] + A1[a] * Y1[b];
+            }
         }
-    }
-#pragma unroll
-    for (int q = 0; q < 21; ++q) acc[q] = warp_sum(acc[q]);
-    if (lane == 0) {
-        double* o = d.chunk_part + PART_STRIDE * (size_t)ch;
-#pragma unroll
-        for (int q = 0; q < 21; ++q) o[q] = acc[q];
+        if (seg >= 0) seg_flush<21>(d, seg, acc, lane);
     }
 }
 
@@ -667,17 +773,23 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
     }
 }
 
-// K9  cg_camera_pass: warp per chunk, sum_k W_k v_j(k) = sum_k A~^t P~ R v_j   (second half of S p).
-//     Per observation the sweep streams (point index 4 B, weight 8 B, cached R X 24 B: coalesced) and gathers ONE
-//     32-byte record v_j (LDG.256, kept L2-resident with evict_last).  It is bound by memory latency, so three
-//     observations' gathers are in flight per lane before any arithmetic, and the streams are fetched one batch ahead.
-//     (A cp.async / shared-memory landing zone with all 8 rows in flight was measured SLOWER: two 16-byte LDGSTS per
-//     record double the L2 sector requests.)
-__device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in, double r0, double r1, double r2, const double v[3], double w, double acc[6])
+// K9  cg_camera_pass: sum_k W_k v_j(k) = sum_k A~^t P~ R v_j   (second half of S p), persistent row sweep.
+//     Per observation the sweep STREAMS 36 bytes (point index, weight, cached R X) and GATHERS one 32-byte record v_j
+//     (LDG.256, kept L2-resident with evict_last).  ncu showed the first version (warp per chunk, 3 gathers per lane in
+//     flight, streams through registers, 128 registers) bound by gather latency: 43 % of its stall samples sat on the
+//     first use of v_j.  Here the stream never touches a register before it is needed: each warp owns a ring of CNS
+//     stages of CG row records in shared memory, each filled by ONE TMA bulk copy (cp.async.bulk + mbarrier, issued by
+//     lane 0 two stages ahead of the gather front), and the registers hold two sets of CG outstanding v_j gathers per
+//     lane: the gathers of stage t+1 are issued before the arithmetic of stage t, whose CG rows are computed in one
+//     basic block (CG independent dependency chains per lane - a row-at-a-time version of this loop was issue-bound).
+//     (Measured dead ends: a cp.async landing zone for the gathers doubles the L2 sector requests - two 16-byte LDGSTS
+//     per record; a point-tile sweep with v in shared memory is barrier-bound.)
+// contribution of one observation; `ok` false (padding / past the end): w must be 0 and v finite, z is replaced by 1
+__device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in, bool ok, double r0, double r1, double r2, const double v[3], double w, double acc[6])
 {
-    const double x = r0 + cm.T[0], y = r1 + cm.T[1], z = r2 + cm.T[2];
+    const double x = r0 + cm.T[0], y = r1 + cm.T[1], z = ok ? r2 + cm.T[2] : 1.0;
     const double iz = fast_rcp(z);
-    const double wf = w * in.k00 * iz, ar = in.k11 / in.k00;
+    const double wf = w * in.k00 * iz, ar = in.ar;
     const double pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
     const double g0 = cm.R[0] * v[0] + cm.R[1] * v[1] + cm.R[2] * v[2];
     const double g1 = cm.R[3] * v[0] + cm.R[4] * v[1] + cm.R[5] * v[2];
@@ -689,65 +801,106 @@ __device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in
     acc[4] += r2 * h0 - r0 * h2;
     acc[5] += r0 * h1 - r1 * h0;
 }
-#ifndef B200BA_CP_DEPTH
-#define B200BA_CP_DEPTH 3
-#endif
-#ifndef B200BA_CP_MINB
-#define B200BA_CP_MINB 4
-#endif
-constexpr int CP_DEPTH = B200BA_CP_DEPTH;   // observations in flight per lane
-// one chunk (<= CHUNK observations of camera chunk_cam[ch]) by one warp; writes the chunk partial
-__device__ __forceinline__ void camera_chunk(const Dev& d, int ch, int lane, int cur)
+__global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pass)
 {
-    const int i = d.chunk_cam[ch];
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    if (i >= d.first_free) {
-        const double* vb = d.v;
-        Cam cm; load_cam(d.rt[cur], i, cm);
-        const int k1 = d.chunk_end[ch];
-        const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
-        int jn[CP_DEPTH]; double wn[CP_DEPTH], an[CP_DEPTH], bn[CP_DEPTH], cn[CP_DEPTH];
-        int k = d.chunk_beg[ch] + lane;
-#pragma unroll
-        for (int u = 0; u < CP_DEPTH; ++u) {
-            const int kk = k + 32 * u; const bool on = kk < k1;
-            jn[u] = on ? ldg_stream(d.c_pt + kk, strm) : -1; wn[u] = on ? ldg_stream(d.c_w + kk, strm) : 0.0;
-            an[u] = on ? ldg_stream(d.c_r0 + kk, strm) : 0.0; bn[u] = on ? ldg_stream(d.c_r1 + kk, strm) : 0.0; cn[u] = on ? ldg_stream(d.c_r2 + kk, strm) : 1.0;
-        }
-        for (; k < k1; k += 32 * CP_DEPTH) {
-            int j[CP_DEPTH]; double w[CP_DEPTH], r0[CP_DEPTH], r1[CP_DEPTH], r2[CP_DEPTH], v[CP_DEPTH][3];
-#pragma unroll
-            for (int u = 0; u < CP_DEPTH; ++u) {
-                j[u] = jn[u]; w[u] = wn[u]; r0[u] = an[u]; r1[u] = bn[u]; r2[u] = cn[u];
-                if (j[u] >= 0) load3p_256_keep(vb, j[u], v[u], keep);
-            }
-#pragma unroll
-            for (int u = 0; u < CP_DEPTH; ++u) {
-                const int kk = k + 32 * (CP_DEPTH + u); const bool on = kk < k1;
-                jn[u] = on ? ldg_stream(d.c_pt + kk, strm) : -1; wn[u] = on ? ldg_stream(d.c_w + kk, strm) : 0.0;
-                an[u] = on ? ldg_stream(d.c_r0 + kk, strm) : 0.0; bn[u] = on ? ldg_stream(d.c_r1 + kk, strm) : 0.0; cn[u] = on ? ldg_stream(d.c_r2 + kk, strm) : 1.0;
-            }
-#pragma unroll
-            for (int u = 0; u < CP_DEPTH; ++u)
-                if (j[u] >= 0) cam_pass_one(cm, d.in, r0[u], r1[u], r2[u], v[u], w[u], acc);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) acc[q] = warp_sum(acc[q]);
-    if (lane == 0) {
-        double* o = d.chunk_part + PART_STRIDE * (size_t)ch;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) o[q] = acc[q];
-    }
-}
-__global__ void __launch_bounds__(CH_BLOCK, B200BA_CP_MINB) k_cg_camera_pass(Dev d, int rhs_pass)
-{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const LMState* st = d.st;
     if (st->done) return;
     if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
-    int ch = blockIdx.x * (CH_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (ch >= d.n_chunks) return;
-    camera_chunk(d, ch, lane, st->cur);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vw = blockIdx.x * CW + warp;
+    if (vw >= d.n_vwarps) return;                       // no CTA-wide barrier below: warps are independent
+    const int rb = vrow(d, vw), n = vrow(d, vw + 1) - rb;
+    if (n <= 0) return;
+    const int nst = (n + CG - 1) / CG;                  // stages of this warp's range
+    unsigned char* buf = smem_raw + (size_t)warp * CNS * STAGE_BYTES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)CW * CNS * STAGE_BYTES) + warp * CNS;
+    const unsigned char* src = d.c_rec + (size_t)rb * REC_BYTES;
+    const uint64_t strm = policy_evict_first(), keep = policy_evict_last();
+    // stage t = rows [t CG, t CG + CG) of the range, one bulk copy into ring slot t % CNS
+    auto arm = [&](int t) {
+        const int sl = t % CNS;
+        const uint32_t bytes = (uint32_t)min(CG, n - t * CG) * REC_BYTES;
+        mbar_expect_tx(&bar[sl], bytes);
+        bulk_g2s_hint(buf + sl * STAGE_BYTES, src + (size_t)t * STAGE_BYTES, bytes, &bar[sl], strm);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < CNS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        for (int t = 0; t < CNS && t < nst; ++t) arm(t);
+    }
+    __syncwarp();
+    const double* vb = d.v;
+    const double* rt = d.rt[st->cur];
+    const int first_free = d.first_free;
+    int seg = -1, cam = 0;
+    Cam cm;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    // gather front: point indices of stage t from shared memory, CG gathers per lane into one register set
+    auto issue = [&](int t, int (&jj)[CG], double (&vv)[CG][3]) {
+        const int sl = t % CNS;
+        mbar_wait(&bar[sl], (uint32_t)(t / CNS) & 1u);
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+            jj[g] = (t * CG + g < n) ? reinterpret_cast<const int*>(buf + sl * STAGE_BYTES + g * REC_BYTES + REC_J)[lane] : -1;
+            vv[g][0] = vv[g][1] = vv[g][2] = 0.0;
+            if (jj[g] >= 0) load3p_256_keep(vb, jj[g], vv[g], keep);
+        }
+    };
+    // arithmetic of stage t, then hand its ring slot back to the TMA
+    auto compute = [&](int t, const int (&jj)[CG], const double (&vv)[CG][3]) {
+        const int sl = t % CNS;
+        const unsigned char* sb = buf + sl * STAGE_BYTES;
+        int2 h[CG];
+        bool same = (t * CG + CG <= n);
+#pragma unroll
+        for (int g = 0; g < CG; ++g) { h[g] = *reinterpret_cast<const int2*>(sb + g * REC_BYTES + REC_HDR); same = same && (h[g].y == seg); }
+        if (same) {                                      // whole stage inside the current segment: one basic block, CG-way ILP
+            if (cam >= first_free) {
+                double w[CG], r0[CG], r1[CG], r2[CG];
+#pragma unroll
+                for (int g = 0; g < CG; ++g) {
+                    const unsigned char* rec = sb + g * REC_BYTES;
+                    w[g] = reinterpret_cast<const double*>(rec + REC_W)[lane];
+                    r0[g] = reinterpret_cast<const double*>(rec + REC_R0)[lane];
+                    r1[g] = reinterpret_cast<const double*>(rec + REC_R1)[lane];
+                    r2[g] = reinterpret_cast<const double*>(rec + REC_R2)[lane];
+                }
+#pragma unroll
+                for (int g = 0; g < CG; ++g) cam_pass_one(cm, d.in, jj[g] >= 0, r0[g], r1[g], r2[g], vv[g], w[g], acc);
+            }
+        } else {                                         // segment boundary or ragged end inside the stage: row by row
+#pragma unroll
+            for (int g = 0; g < CG; ++g) {
+                if (t * CG + g < n) {
+                    if (h[g].y != seg) {
+                        if (seg >= 0) seg_flush<6>(d, seg, acc, lane);
+                        seg = h[g].y; cam = h[g].x; load_cam(rt, cam, cm);
+                    }
+                    if (cam >= first_free) {
+                        const unsigned char* rec = sb + g * REC_BYTES;
+                        cam_pass_one(cm, d.in, jj[g] >= 0, reinterpret_cast<const double*>(rec + REC_R0)[lane], reinterpret_cast<const double*>(rec + REC_R1)[lane],
+                                     reinterpret_cast<const double*>(rec + REC_R2)[lane], vv[g], reinterpret_cast<const double*>(rec + REC_W)[lane], acc);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                    // every lane is done with this ring slot
+        if (lane == 0 && t + CNS < nst) { fence_proxy_async(); arm(t + CNS); }
+    };
+    int jA[CG], jB[CG]; double vA[CG][3], vB[CG][3];
+    issue(0, jA, vA);
+    for (int t = 0; t < nst; t += 2) {
+        if (t + 1 < nst) issue(t + 1, jB, vB);
+        compute(t, jA, vA);
+        if (t + 1 < nst) {
+            if (t + 2 < nst) issue(t + 2, jA, vA);
+            compute(t + 1, jB, vB);
+        }
+    }
+    if (seg >= 0) seg_flush<6>(d, seg, acc, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -857,35 +1010,69 @@ __global__ void __launch_bounds__(128) k_build_ptab(Dev d)
     o[0] = w * n; o[1] = x * n; o[2] = y * n; o[3] = z * n; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
 }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+// one warp per row: scatter the uploaded compact row table (header, 32 point indices) into the row records
+__global__ void __launch_bounds__(256) k_fill_rows(Dev d, const int2* __restrict__ row_hdr, const int* __restrict__ row_j)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }"
-                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= d.n_rows) return;
+    unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
+    if (lane == 0) { const int2 h = row_hdr[r]; *reinterpret_cast<int4*>(rec + REC_HDR) = make_int4(h.x, h.y, 0, 0); }
+    reinterpret_cast<int*>(rec + REC_J)[lane] = row_j[32 * (size_t)r + lane];
 }
 
 // K8'  cg_point_pass_tab: persistent (one 768-thread CTA per SM), camera table in shared memory, one thread per point.
 //      Computes v_j = (V+lambda I)^-1 sum_k W_k^t p_i(k)  (MODE 0 of k_cg_point_pass).
+//
+//      Each warp owns a CONTIGUOUS range of slices (balanced by rows on the host), so its o_cam / o_w rows form one
+//      contiguous stream.  THREE rows are always in flight in three fixed register pairs (c0,w0) (c1,w1) (c2,w2) that are
+//      consumed round-robin by a loop unrolled by three: ncu on the previous version (two pairs ROTATED through
+//      registers every row) showed 25 % of all stall samples on the rotation's moves, which have to wait for the
+//      in-flight load they copy - the effective prefetch distance was one row.  (V_j + lambda I)^-1 of the slice being
+//      finished is requested in the middle of the slice's last row body (after the table fields are dead, before the
+//      back-rotation), the next slice's X one slice ahead; the warp's header is one 32-byte record and all start-up
+//      loads are issued BEFORE waiting for the TMA'd camera table.
+struct TabRow { double h0, h1, h2, qw, qx, qy, qz; };
+// first half of a row body: forward rotation, projection Jacobian, t = A~ p, h = P~^t t  (table fields die here)
+__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
+{
+    const double2* t = tab + 7 * cam;
+    const double2 a0 = t[0], a1 = t[1], a2 = t[2], a3 = t[3], a4 = t[4], a5 = t[5], a6 = t[6];
+    const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
+    // r = R X by the quaternion sandwich  r = X + qw t + qv x t,  t = 2 qv x X   (no 3x3 matrix in registers)
+    const double tx = 2.0 * (qy * X[2] - qz * X[1]), ty = 2.0 * (qz * X[0] - qx * X[2]), tz = 2.0 * (qx * X[1] - qy * X[0]);
+    const double r0 = X[0] + qw * tx + (qy * tz - qz * ty);
+    const double r1 = X[1] + qw * ty + (qz * tx - qx * tz);
+    const double r2 = X[2] + qw * tz + (qx * ty - qy * tx);
+    const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
+    const double iz = fast_rcp(z);
+    const double wf = w * in.k00 * iz;
+    const double pa = wf, pb = -wf * x * iz, pc = in.ar * wf, pd = -in.ar * wf * y * iz;
+    // t = A~ p,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x)
+    const double s0 = a3.y + (a5.y * r2 - a6.x * r1);
+    const double s1 = a4.x + (a6.x * r0 - a5.x * r2);
+    const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
+    const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
+    o.h0 = pa * t0; o.h1 = pc * t1; o.h2 = pb * t0 + pd * t1;
+    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz;
+}
+// second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion
+__device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
+{
+    const double gx = 2.0 * (o.qz * o.h1 - o.qy * o.h2), gy = 2.0 * (o.qx * o.h2 - o.qz * o.h0), gz = 2.0 * (o.qy * o.h0 - o.qx * o.h1);
+    u0 += o.h0 + o.qw * gx + (o.qz * gy - o.qy * gz);
+    u1 += o.h1 + o.qw * gy + (o.qx * gz - o.qz * gx);
+    u2 += o.h2 + o.qw * gz + (o.qy * gx - o.qx * gy);
+}
+constexpr int PR = 3;                                            // rows of the o_cam / o_w stream staged per warp
+constexpr int PR_ROW_BYTES = 128 + 256;                          // 32 x int32 camera index | 32 x f64 weight
+constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * PR * (PR_ROW_BYTES + 8);   // rings + their mbarriers
 __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
     if (st->done || !st->cg_active) return;
-    double2* tab = reinterpret_cast<double2*>(smem_raw);
+    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
     const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -898,84 +1085,90 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* Xb = d.X[st->cur];
-    const double ar = d.in.k11 / d.in.k00, f = d.in.k00;
-    const uint64_t keep = policy_evict_last(), strm = policy_evict_first();
-    // Each warp owns a CONTIGUOUS range of slices (balanced by rows on the host), so its o_cam / o_w rows form one
-    // contiguous stream: the two-rows-ahead register prefetch runs straight across slice boundaries, and the next
-    // slice's X is requested one slice early.  The warp's header {first slice, end slice, first entry, end entry,
-    // first two trip counts} is one 32-byte record, and all start-up loads are issued BEFORE waiting for the TMA'd
-    // camera table so that the two latencies overlap (ncu: 25 % of the sweep's stall samples sat on this chain).
     const int wid = blockIdx.x * (TAB_BLOCK / 32) + warp;
     const bool active = wid < d.tab_warps;
-    int g = 0, g_end = 0, k = 0, k_end = 0, rows_left = 0, deg_next = 0;
+    int g = 0, g_end = 0, k0 = 0, n_rows = 0, rows_left = 0, deg_next = 0;
     if (active) {
         const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
-        g = ha.x; g_end = ha.y; k = ha.z + lane; k_end = ha.w + lane; rows_left = hb.x; deg_next = hb.y;
+        g = ha.x; g_end = ha.y; k0 = ha.z; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
     }
-    double X[3] = {0, 0, 0}, Xn[3] = {0, 0, 0};
-    int cam_n = -1, cam_n2 = -1; double w_n = 0.0, w_n2 = 0.0;
-    if (g < g_end) {
-        if (32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, keep);
-        if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, keep);
-        if (k < k_end) { cam_n = ldg_stream(d.o_cam + k, strm); w_n = ldg_stream(d.o_w + k, strm); }
-        if (k + 32 < k_end) { cam_n2 = ldg_stream(d.o_cam + k + 32, strm); w_n2 = ldg_stream(d.o_w + k + 32, strm); }
+    // The warp's o_cam / o_w rows form one contiguous stream (it owns a contiguous range of slices).  The stream is staged
+    // by the TMA into a private ring of PR rows (two bulk copies per row on one mbarrier, issued by lane 0, PR rows
+    // ahead); a row's two values are read into registers at the top of its body and the slot is re-armed at once.
+    // (Prefetching the stream through REGISTERS does not survive ptxas: whatever the source says - rotation, unrolled
+    // copies, a phase switch - the loop-carried value is copied, the copy waits for the load it was meant to overlap,
+    // and ncu showed 12-25 % of all stall samples on that move.)
+    const uint32_t tab_bytes = (total + 127u) & ~127u;
+    unsigned char* ring = smem_raw + tab_bytes + (size_t)warp * PR * PR_ROW_BYTES;
+    uint64_t* rbar = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + (size_t)(TAB_BLOCK / 32) * PR * PR_ROW_BYTES) + warp * PR;
+    auto arm = [&](int r, int slot) {                            // lane 0 only
+        const size_t e = (size_t)k0 + 32 * (size_t)r;
+        mbar_expect_tx(&rbar[slot], PR_ROW_BYTES);
+        bulk_g2s(ring + slot * PR_ROW_BYTES, d.o_cam + e, 128, &rbar[slot]);
+        bulk_g2s(ring + slot * PR_ROW_BYTES + 128, d.o_w + e, 256, &rbar[slot]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < PR; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&rbar[q])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        for (int q = 0; q < PR && q < n_rows; ++q) arm(q, q);
     }
+    double X[3] = {0, 0, 0};
+    if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
     __syncthreads();
     mbar_wait(&bar, 0);
     if (g >= g_end) return;
     double u0 = 0, u1 = 0, u2 = 0;
-    for (;;) {
-        if (rows_left == 0) {                                   // slice boundary (warp-uniform): finish point 32 g + lane
-            const int j = 32 * g + lane;
-            if (j < d.M) {
-                double Vi[6]; load6(d.Vinv, j, Vi);
-                store4_keep(d.v + 4 * (size_t)j, Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2,
-                            Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0, keep);
+    // Requests what the END of slice g needs: its inverse block and the next slice's X.  Called in the middle of the
+    // slice's last row body (after the table fields are dead, before the back-rotation), consumed by finish().
+    auto request = [&](double Vi[6], double Xn[3]) {
+        if (32 * g + lane < d.M) load6(d.Vinv, 32 * g + lane, Vi);
+        if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, policy_evict_last());
+    };
+    // finish point 32 g + lane and step to the next slice; false: the warp's range is done
+    auto finish = [&](const double Vi[6], const double Xn[3]) -> bool {
+        const int j = 32 * g + lane;
+        if (j < d.M)
+            store4_keep(d.v + 4 * (size_t)j, Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2,
+                        Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0, policy_evict_last());
+        if (++g >= g_end) return false;
+        rows_left = deg_next; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; u0 = u1 = u2 = 0;
+        if (g + 1 < g_end) {
+            deg_next = __ldg(d.slice_deg + g + 1);
+            if (lane == 0) {                                     // L2 prefetch of what the next request() will ask for
+                const int nj = min(32, d.M - 32 * (g + 1));
+                if (nj > 0) { prefetch_l2_bulk(d.Vinv + 6 * (size_t)(32 * (g + 1)), (uint32_t)nj * 48u); prefetch_l2_bulk(Xb + 4 * (size_t)(32 * (g + 1)), (uint32_t)nj * 32u); }
             }
-            if (++g >= g_end) break;
-            rows_left = deg_next; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; u0 = u1 = u2 = 0;
-            if (g + 1 < g_end) {
-                deg_next = __ldg(d.slice_deg + g + 1);
-                if (32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, keep);
-                if (lane == 0) { const int nj = min(32, d.M - 32 * (g + 1)); if (nj > 0) prefetch_l2_bulk(d.Vinv + 6 * (size_t)(32 * (g + 1)), (uint32_t)nj * 48u); }
-            }
-            continue;
         }
-        const int cam = cam_n; const double w = w_n;
-        cam_n = cam_n2; w_n = w_n2;
-        if (k + 64 < k_end) { cam_n2 = ldg_stream(d.o_cam + k + 64, strm); w_n2 = ldg_stream(d.o_w + k + 64, strm); }
-        else { cam_n2 = -1; w_n2 = 0.0; }
-        --rows_left; k += 32;
-        if (cam < 0) continue;
-        const double2* t = tab + 7 * cam;
-        const double2 a0 = t[0], a1 = t[1], a2 = t[2], a3 = t[3], a4 = t[4], a5 = t[5], a6 = t[6];
-        const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
-        // r = R X by the quaternion sandwich  r = X + qw t + qv x t,  t = 2 qv x X   (no 3x3 matrix in registers)
-        const double tx = 2.0 * (qy * X[2] - qz * X[1]), ty = 2.0 * (qz * X[0] - qx * X[2]), tz = 2.0 * (qx * X[1] - qy * X[0]);
-        const double r0 = X[0] + qw * tx + (qy * tz - qz * ty);
-        const double r1 = X[1] + qw * ty + (qz * tx - qx * tz);
-        const double r2 = X[2] + qw * tz + (qx * ty - qy * tx);
-        const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
-        const double iz = fast_rcp(z);
-        const double wf = w * f * iz;
-        const double pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
-        // t = A~ p,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x)
-        const double s0 = a3.y + (a5.y * r2 - a6.x * r1);
-        const double s1 = a4.x + (a6.x * r0 - a5.x * r2);
-        const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
-        const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
-        const double h0 = pa * t0, h1 = pc * t1, h2 = pb * t0 + pd * t1;
-        // u += R^t h : inverse rotation = sandwich with the conjugate quaternion
-        const double gx = 2.0 * (qz * h1 - qy * h2), gy = 2.0 * (qx * h2 - qz * h0), gz = 2.0 * (qy * h0 - qx * h1);
-        u0 += h0 + qw * gx + (qz * gy - qy * gz);
-        u1 += h1 + qw * gy + (qx * gz - qz * gx);
-        u2 += h2 + qw * gz + (qy * gx - qx * gy);
+        return true;
+    };
+    int r = 0, slot = 0; uint32_t par = 0;
+    for (;;) {
+        while (rows_left == 0) {                                 // slice without observations (warp-uniform)
+            double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+            request(Vi, Xn);
+            if (!finish(Vi, Xn)) return;
+        }
+        mbar_wait(&rbar[slot], par);
+        const int cam = reinterpret_cast<const int*>(ring + slot * PR_ROW_BYTES)[lane];
+        const double w = reinterpret_cast<const double*>(ring + slot * PR_ROW_BYTES + 128)[lane];
+        __syncwarp();                                            // both values of every lane are in registers: refill the slot
+        if (lane == 0 && r + PR < n_rows) { fence_proxy_async(); arm(r + PR, slot); }
+        ++r; if (++slot == PR) { slot = 0; par ^= 1u; }
+        const bool last = (--rows_left == 0);                    // warp-uniform
+        TabRow o;
+        if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
+        double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+        if (last) request(Vi, Xn);
+        if (cam >= 0) tab_row_bwd(o, u0, u1, u2);
+        if (last && !finish(Vi, Xn)) return;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // K11' cg_camera_step: the whole camera side of one PCG step in ONE cooperative kernel (grid-wide syncs instead of
-//      three kernel boundaries): second-level chunk sums, q = (U + lambda I) p - sum W v, alpha, x, r, z = M r, beta, p.
+//      three kernel boundaries): second-level segment sums, q = (U + lambda I) p - sum W v, alpha, x, r, z = M r, beta, p.
 //      One thread per (camera, component); a block owns 32 cameras.  Dot products: fixed-order block partials,
 //      summed in the same fixed order by every warp, so every thread sees identical scalars.
 // ------------------------------------------------------------------------------------------------------
@@ -1001,7 +1194,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     if (on) {
         double s = 0;
         if (sums_ready == 1) s = d.ar_q[e];
-        else for (int ch = d.cam_chunk_beg[i]; ch < d.cam_chunk_beg[i + 1]; ++ch) s += d.chunk_part[PART_STRIDE * (size_t)ch + a];
+        else for (int sg = d.cam_seg_beg[i]; sg < d.cam_seg_beg[i + 1]; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + a];
         q = lam * pe + matvec6_row(d.U + 36 * (size_t)i, sv + lc, a) - s;
     }
     double bp = block_sum<STEP_BLOCK>(pe * q, sm);

@@ -8,4 +8,4 @@ p = make_problem(shape, 1)
 eng = binding.Engine(max_iterations=2)
 eng.set_problem_from(p); eng.begin(); eng.debug_linearize()
 for i, n in enumerate(eng.kernel_names()):
-    print(n, eng.time_kernel(i, 3))
+    print(n, eng.time_kernel(i, 20))
