@@ -99,11 +99,11 @@ struct b200ba_handle {
     bool have_problem = false, begun = false, finished = false;
     // device
     Dev d{};
-    DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, o_w, seg_part, pt_part, trace;
+    DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, seg_part, pt_part, trace;
     DBuf<double2> o_meas, c_meas;
     DBuf<int> o_cam, slice_base, slice_deg, row_j, cam_seg_beg;
     DBuf<int2> row_hdr;
-    DBuf<unsigned char> c_rec;
+    DBuf<unsigned char> c_rec, o_rec;
     DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
     DBuf<int> tab_wr;
     std::vector<int> orig_of_new, entry_of_obs;      // SELL permutation (new point index -> caller's), obs -> padded entry
@@ -395,7 +395,7 @@ void b200ba_destroy(b200ba_handle* h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->rt0.release(); h->rt1.release(); h->U.release(); h->gc.release(); h->Minv.release(); h->x.release(); h->r.release();
     h->z.release(); h->p.release(); h->q.release(); h->ar_lin.release(); h->ar_q.release(); h->ar_sd.release(); h->ar_dec.release();
-    h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_w.release();
+    h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_rec.release();
     h->seg_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
     h->row_j.release(); h->row_hdr.release(); h->c_rec.release(); h->cam_seg_beg.release();
     h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->part_pq.release(); h->part_rz.release();
@@ -656,7 +656,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->ar_lin.take(A, (size_t)N * PART_STRIDE + 1 + 2 * (size_t)world); h->ar_q.take(A, n6); h->ar_sd.take(A, 21 * (size_t)N); h->ar_dec.take(A, 4);
         h->X0.take(A, 4 * Mp); h->X1.take(A, 4 * Mp);
         h->V.take(A, 6 * Mp); h->Vinv.take(A, 6 * Mp); h->gp.take(A, 4 * Mp); h->v.take(A, 4 * Mp);
-        h->o_w.take(A, Kpp); h->o_meas.take(A, Kpp); h->c_meas.take(A, 32 * Rp);
+        h->o_rec.take(A, (Kpp / 32 + 1) * OREC_BYTES); h->o_meas.take(A, Kpp); h->c_meas.take(A, 32 * Rp);
         h->o_cam.take(A, Kpp); h->slice_base.take(A, (size_t)n_slices + 1); h->slice_deg.take(A, (size_t)n_slices);
         h->c_rec.take(A, Rp * REC_BYTES + 16); h->row_j.take(A, 32 * Rp); h->row_hdr.take(A, Rp);
         h->cam_seg_beg.take(A, (size_t)N + 1);
@@ -680,6 +680,10 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     CU(cudaMemcpyAsync(h->slice_base.p, slice_base.data(), sizeof(int) * ((size_t)n_slices + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->slice_deg.p, slice_deg.data(), sizeof(int) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->cam_seg_beg.p, cam_seg_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+    if (Kp) {
+        Dev dr{}; dr.o_rec = h->o_rec.p;
+        k_fill_orows<<<cdiv(Kp / 32, 8), 256, 0, s>>>(dr, h->o_cam.p, Kp / 32);
+    }
     if (n_rows) {
         Dev dr{}; dr.n_rows = n_rows; dr.c_rec = h->c_rec.p;
         k_fill_rows<<<cdiv(n_rows, 8), 256, 0, s>>>(dr, h->row_hdr.p, h->row_j.p);
@@ -738,7 +742,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.x = h->x.p; d.r = h->r.p; d.z = h->z.p; d.p = h->p.p; d.q = h->q.p;
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
-    d.o_cam = h->o_cam.p; d.o_meas = h->o_meas.p; d.o_w = h->o_w.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
+    d.o_rec = h->o_rec.p; d.o_meas = h->o_meas.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
     d.ptab = h->ptab.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
@@ -953,8 +957,9 @@ int b200ba_debug_linearize(b200ba_handle* h, double* cost, double* w, double* gc
     if (cost) *cost = st.err;
     if (lambda0) *lambda0 = st.lambda;
     if (w && K) {
-        std::vector<double> t((size_t)h->Kp); CU(cudaMemcpy(t.data(), h->o_w.p, sizeof(double) * (size_t)h->Kp, cudaMemcpyDeviceToHost));
-        for (int k = 0; k < K; ++k) w[k] = t[h->entry_of_obs[k]];
+        std::vector<unsigned char> t((size_t)(h->Kp / 32) * OREC_BYTES);
+        CU(cudaMemcpy(t.data(), h->o_rec.p, t.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < K; ++k) { const int e = h->entry_of_obs[k]; memcpy(&w[k], t.data() + (size_t)(e >> 5) * OREC_BYTES + 128 + 8 * (e & 31), sizeof(double)); }
     }
     if (gc) CU(cudaMemcpy(gc, h->gc.p, sizeof(double) * 6 * (size_t)N, cudaMemcpyDeviceToHost));
     if (U) CU(cudaMemcpy(U, h->U.p, sizeof(double) * 36 * (size_t)N, cudaMemcpyDeviceToHost));

@@ -15,9 +15,10 @@
 //   points    X[2]    M x 4    xyz + pad (32 B = 1 sector so a by-camera gather costs one sector)
 //             V, Vinv M x 6    symmetric 3x3 (xx xy xz yy yz zz);  gp, v  M x 4
 //   obs (point order)   SELL-32: points are sorted by track length (descending) and grouped in slices of 32; slot s of
-//                       lane l of slice g lives at slice_base[g] + 32 s + l.  One thread owns one point, every lane of a
-//                       warp runs the same trip count and every load of o_cam (int32, -1 = padding), o_meas (double2,
-//                       normalised) and o_w (double) is a fully coalesced 128/256/512-byte row.
+//                       lane l of slice g is entry slice_base[g] + 32 s + l.  One thread owns one point, every lane of a
+//                       warp runs the same trip count.  32 consecutive entries form one 384-byte ROW RECORD
+//                       [32 x camera index (int32, -1 = padding) | 32 x IRLS weight (f64)] (o_rec) so that the CG by-point
+//                       sweep stages a row with a single TMA bulk copy; o_meas (double2, normalised) is a flat array.
 //   obs (camera order)  ROW RECORDS: every camera's observations are padded to a multiple of 32 and cut into rows of 32;
 //                       one row is ONE contiguous 1168-byte record  [cam, segment | 32 x point index (int32, -1 = padding) |
 //                       32 x weight | 32 x (R X).x | .y | .z]  so that a single TMA bulk copy stages everything the CG
@@ -45,6 +46,7 @@ constexpr int REC_R0       = REC_W + 256;       // 32 x f64 (R X).x, .y, .z cach
 constexpr int REC_R1       = REC_R0 + 256;
 constexpr int REC_R2       = REC_R1 + 256;
 constexpr int REC_BYTES    = REC_R2 + 256;      // 1168 = 73 x 16
+constexpr int OREC_BYTES   = 128 + 256;         // point-order row record: 32 x int32 camera index | 32 x f64 weight
 #ifndef B200BA_CW
 #define B200BA_CW 16
 #endif
@@ -64,9 +66,12 @@ constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side ker
 constexpr int TRACE_COLS   = 8;
 constexpr int TAB_STRIDE   = 14;    // doubles per camera in the packed table: quaternion 4, T 3, p 6, pad 1 (112 B = 7 x 16 B)
 #ifndef B200BA_TAB_BLOCK
-#define B200BA_TAB_BLOCK 768
+#define B200BA_TAB_BLOCK 640
+#ifndef B200BA_TAB_MAXNREG
+#define B200BA_TAB_MAXNREG 96
 #endif
-constexpr int TAB_BLOCK    = B200BA_TAB_BLOCK;   // threads of the persistent shared-memory-table CG point sweep (1 CTA / SM, <= 85 registers)
+#endif
+constexpr int TAB_BLOCK    = B200BA_TAB_BLOCK;   // threads of the persistent shared-memory-table CG point sweep (1 CTA / SM; 640 x 96 registers measured faster than 768 x 80, which spills)
 constexpr int STEP_BLOCK   = 192;   // threads of the cooperative camera-side CG kernel: 32 cameras x 6 components
 constexpr int MAX_SMEM     = 227 * 1024;
 
@@ -102,7 +107,8 @@ struct Dev {
     double* ar_dec;     // [d2p, denomp, new_cost, pad]
     double* X[2];
     double *V, *gp, *Vinv, *v;
-    int* o_cam; double2* o_meas; double* o_w; int *slice_base, *slice_deg;
+    unsigned char* o_rec;         // (padded entries / 32) x OREC_BYTES point-order row records [32 x camera index | 32 x weight]
+    double2* o_meas; int *slice_base, *slice_deg;
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
@@ -274,6 +280,10 @@ __device__ __forceinline__ void slice_of(const Dev& d, int j, int& k0, int& deg)
     else { k0 = 0; deg = 0; }
 }
 
+// point-order row records: camera index / weight of entry k
+__device__ __forceinline__ const int* o_cam_ptr(const Dev& d, int k) { return reinterpret_cast<const int*>(d.o_rec + (size_t)(k >> 5) * OREC_BYTES) + (k & 31); }
+__device__ __forceinline__ double* o_w_ptr(const Dev& d, int k) { return reinterpret_cast<double*>(d.o_rec + (size_t)(k >> 5) * OREC_BYTES + 128) + (k & 31); }
+
 // Per-observation geometry: camera-space point, residual, Huber weight, weighted projection Jacobian.
 //   residual  e = K^ (XX / z) - m                         v3d_metricbundle.h:185-209
 //   weight    w = 1 | sqrt(thr / |e|)                     v3d_metricbundle.h:49-57
@@ -376,11 +386,11 @@ __global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
         double X[3] = {0, 0, 0}; if (j < d.M) load3p(Xb, j, X);
         double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
         for (int s = 0, k = k0; s < deg; ++s, k += 32) {
-            int ci = __ldg(d.o_cam + k);
+            int ci = __ldg(o_cam_ptr(d, k));
             if (ci < 0) continue;
             Cam cm; load_cam(rt, ci, cm);
             Obs o; obs_full(cm, X, __ldg(d.o_meas + k), d.in, o);
-            d.o_w[k] = o.w;
+            *o_w_ptr(d, k) = o.w;
             double we0 = o.w * o.e0, we1 = o.w * o.e1;
             cost += we0 * we0 + we1 * we1;
             double B0[3], B1[3]; jac_rows_B(o, cm, B0, B1);
@@ -443,13 +453,8 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
         double acc[27];
 #pragma unroll
         for (int q = 0; q < 27; ++q) acc[q] = 0;
-        for (int r = rb; r < re; ++r) {
-            unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
-            const int2 h = __ldg(reinterpret_cast<const int2*>(rec + REC_HDR));
-            const int j = __ldg(reinterpret_cast<const int*>(rec + REC_J) + lane);
-            const double2 m = __ldg(d.c_meas + 32 * (size_t)r + lane);
-            double X[3] = {0, 0, 1};
-            if (j >= 0) load3p(Xb, j, X);
+        // one row: segment bookkeeping, geometry, write-back of weight / lever arm, accumulation
+        auto do_row = [&](unsigned char* rec, int2 h, int j, double2 m, const double X[3]) {
             if (h.y != seg) {
                 if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
                 seg = h.y; cam = h.x; load_cam(rt, cam, cm);
@@ -470,6 +475,23 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 #pragma unroll
                 for (int a = 0; a < 6; ++a) acc[21 + a] += A0[a] * we0 + A1[a] * we1;
             }
+        };
+        // two rows per trip: both rows' index / measurement loads and both X gathers are issued before any arithmetic
+        for (int r = rb; r < re; r += 2) {
+            unsigned char* rec0 = d.c_rec + (size_t)r * REC_BYTES;
+            unsigned char* rec1 = rec0 + REC_BYTES;
+            const bool two = r + 1 < re;
+            const int2 h0 = __ldg(reinterpret_cast<const int2*>(rec0 + REC_HDR));
+            const int j0 = __ldg(reinterpret_cast<const int*>(rec0 + REC_J) + lane);
+            const int2 h1 = two ? __ldg(reinterpret_cast<const int2*>(rec1 + REC_HDR)) : h0;
+            const int j1 = two ? __ldg(reinterpret_cast<const int*>(rec1 + REC_J) + lane) : -1;
+            const double2 m0 = __ldg(d.c_meas + 32 * (size_t)r + lane);
+            const double2 m1 = two ? __ldg(d.c_meas + 32 * (size_t)(r + 1) + lane) : m0;
+            double X0[3] = {0, 0, 1}, X1[3] = {0, 0, 1};
+            if (j0 >= 0) load3p_256(Xb, j0, X0);
+            if (j1 >= 0) load3p_256(Xb, j1, X1);
+            do_row(rec0, h0, j0, m0, X0);
+            if (two) do_row(rec1, h1, j1, m1, X1);
         }
         if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
     }
@@ -597,12 +619,7 @@ __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
         double acc[21];
 #pragma unroll
         for (int q = 0; q < 21; ++q) acc[q] = 0;
-        for (int r = rb; r < re; ++r) {
-            const unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
-            const int2 h = __ldg(reinterpret_cast<const int2*>(rec + REC_HDR));
-            const int j = __ldg(reinterpret_cast<const int*>(rec + REC_J) + lane);
-            double Vi[6] = {0, 0, 0, 0, 0, 0};
-            if (j >= 0) load6(d.Vinv, j, Vi);
+        auto do_row = [&](const unsigned char* rec, int2 h, int j, const double Vi[6]) {
             if (h.y != seg) {
                 if (seg >= 0) seg_flush<21>(d, seg, acc, lane);
                 seg = h.y; cam = h.x; load_cam(rt, cam, cm);
@@ -647,6 +664,15 @@ __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
 #pragma unroll
                     for (int b = a; b < 6; ++b) acc[q++] += A0[a] * Y0[b] + A1[a] * Y1[b];
             }
+        };
+        // (two rows of loads per trip, as in k_linearize_cameras, measured SLOWER here: 196 vs 112 us at 156 registers)
+        for (int r = rb; r < re; ++r) {
+            const unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
+            const int2 h = __ldg(reinterpret_cast<const int2*>(rec + REC_HDR));
+            const int j = __ldg(reinterpret_cast<const int*>(rec + REC_J) + lane);
+            double Vi[6] = {0, 0, 0, 0, 0, 0};
+            if (j >= 0) load6(d.Vinv, j, Vi);
+            do_row(rec, h, j, Vi);
         }
         if (seg >= 0) seg_flush<21>(d, seg, acc, lane);
     }
@@ -722,10 +748,10 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
             const double* vec = (MODE == 0) ? d.p : d.x;
             const double* rt = d.rt[cur];
             for (int s = 0, k = k0; s < deg; ++s, k += 32) {
-                int i = __ldg(d.o_cam + k);
+                int i = __ldg(o_cam_ptr(d, k));
                 if (i < 0) continue;
                 Cam cm; load_cam(rt, i, cm);
-                Obs o; obs_jac(cm, X, __ldg(d.o_w + k), d.in, o);
+                Obs o; obs_jac(cm, X, __ldg(o_w_ptr(d, k)), d.in, o);
                 double p[6]; load6(vec, i, p);
                 double t0, t1; apply_A(o, p, t0, t1);
                 if (i < d.first_free) { t0 = 0; t1 = 0; }
@@ -751,7 +777,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
             o[0] = make_double2(Xn[0], Xn[1]); o[1] = make_double2(Xn[2], 0.0);
             const double* rtn = d.rt[cur ^ 1];                          // trial cameras written by k_cg_finish
             for (int s = 0, k = k0; s < deg; ++s, k += 32) {
-                int i = __ldg(d.o_cam + k);
+                int i = __ldg(o_cam_ptr(d, k));
                 if (i < 0) continue;
                 Cam cm; load_cam(rtn, i, cm);
                 double e0, e1, x, y, iz, r0, r1, r2;
@@ -1010,6 +1036,14 @@ __global__ void __launch_bounds__(128) k_build_ptab(Dev d)
     o[0] = w * n; o[1] = x * n; o[2] = y * n; o[3] = z * n; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
 }
 
+// one warp per point-order row: camera indices into the row record (the weights are written by the linearisation)
+__global__ void __launch_bounds__(256) k_fill_orows(Dev d, const int* __restrict__ o_cam, int n_orows)
+{
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= n_orows) return;
+    reinterpret_cast<int*>(d.o_rec + (size_t)r * OREC_BYTES)[lane] = o_cam[32 * (size_t)r + lane];
+}
+
 // one warp per row: scatter the uploaded compact row table (header, 32 point indices) into the row records
 __global__ void __launch_bounds__(256) k_fill_rows(Dev d, const int2* __restrict__ row_hdr, const int* __restrict__ row_j)
 {
@@ -1038,11 +1072,11 @@ __device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int
     const double2* t = tab + 7 * cam;
     const double2 a0 = t[0], a1 = t[1], a2 = t[2], a3 = t[3], a4 = t[4], a5 = t[5], a6 = t[6];
     const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
-    // r = R X by the quaternion sandwich  r = X + qw t + qv x t,  t = 2 qv x X   (no 3x3 matrix in registers)
-    const double tx = 2.0 * (qy * X[2] - qz * X[1]), ty = 2.0 * (qz * X[0] - qx * X[2]), tz = 2.0 * (qx * X[1] - qy * X[0]);
-    const double r0 = X[0] + qw * tx + (qy * tz - qz * ty);
-    const double r1 = X[1] + qw * ty + (qz * tx - qx * tz);
-    const double r2 = X[2] + qw * tz + (qx * ty - qy * tx);
+    // r = R X by the quaternion sandwich  r = X + 2 (qw t + qv x t),  t = qv x X   (no 3x3 matrix in registers)
+    const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];      // t = qv x X
+    const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);                                         // r = X + 2 (qw t + qv x t)
+    const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
+    const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
     const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
     const double iz = fast_rcp(z);
     const double wf = w * in.k00 * iz;
@@ -1058,15 +1092,20 @@ __device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int
 // second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion
 __device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
 {
-    const double gx = 2.0 * (o.qz * o.h1 - o.qy * o.h2), gy = 2.0 * (o.qx * o.h2 - o.qz * o.h0), gz = 2.0 * (o.qy * o.h0 - o.qx * o.h1);
-    u0 += o.h0 + o.qw * gx + (o.qz * gy - o.qy * gz);
-    u1 += o.h1 + o.qw * gy + (o.qx * gz - o.qz * gx);
-    u2 += o.h2 + o.qw * gz + (o.qy * gx - o.qx * gy);
+    const double gx = o.qz * o.h1 - o.qy * o.h2, gy = o.qx * o.h2 - o.qz * o.h0, gz = o.qy * o.h0 - o.qx * o.h1;   // g = -qv x h
+    u0 += fma(2.0, o.qw * gx + (o.qz * gy - o.qy * gz), o.h0);
+    u1 += fma(2.0, o.qw * gy + (o.qx * gz - o.qz * gx), o.h1);
+    u2 += fma(2.0, o.qw * gz + (o.qy * gx - o.qx * gy), o.h2);
 }
-constexpr int PR = 3;                                            // rows of the o_cam / o_w stream staged per warp
-constexpr int PR_ROW_BYTES = 128 + 256;                          // 32 x int32 camera index | 32 x f64 weight
-constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * PR * (PR_ROW_BYTES + 8);   // rings + their mbarriers
+constexpr int PR = 3;                                            // rows of the point-order stream staged per warp
+constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * PR * (OREC_BYTES + 8);   // rings + their mbarriers
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+#ifdef B200BA_TAB_MAXNREG
+__global__ void __maxnreg__(B200BA_TAB_MAXNREG) k_cg_point_pass_tab(Dev d)
+#else
 __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
+#endif
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -1087,32 +1126,34 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
     const double* Xb = d.X[st->cur];
     const int wid = blockIdx.x * (TAB_BLOCK / 32) + warp;
     const bool active = wid < d.tab_warps;
-    int g = 0, g_end = 0, k0 = 0, n_rows = 0, rows_left = 0, deg_next = 0;
+    int g = 0, g_end = 0, n_rows = 0, rows_left = 0, deg_next = 0;
+    const unsigned char* src_rows = d.o_rec;
     if (active) {
         const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
-        g = ha.x; g_end = ha.y; k0 = ha.z; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
+        g = ha.x; g_end = ha.y; src_rows += (size_t)(ha.z >> 5) * OREC_BYTES; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
     }
-    // The warp's o_cam / o_w rows form one contiguous stream (it owns a contiguous range of slices).  The stream is staged
-    // by the TMA into a private ring of PR rows (two bulk copies per row on one mbarrier, issued by lane 0, PR rows
-    // ahead); a row's two values are read into registers at the top of its body and the slot is re-armed at once.
+    // The warp's point-order row records form one contiguous stream (it owns a contiguous range of slices).  The stream
+    // is staged by the TMA into a private ring of PR rows (one bulk copy per row, issued by lane 0, PR rows ahead); a
+    // row's two values are read into registers at the top of its body and the slot is re-armed at the top of the next trip.
     // (Prefetching the stream through REGISTERS does not survive ptxas: whatever the source says - rotation, unrolled
     // copies, a phase switch - the loop-carried value is copied, the copy waits for the load it was meant to overlap,
-    // and ncu showed 12-25 % of all stall samples on that move.)
+    // and ncu showed 12-25 % of all stall samples on that move.)  All ring addresses are 32-bit shared-window offsets
+    // kept in registers; generic pointers made ptxas rebuild them every row.
     const uint32_t tab_bytes = (total + 127u) & ~127u;
-    unsigned char* ring = smem_raw + tab_bytes + (size_t)warp * PR * PR_ROW_BYTES;
-    uint64_t* rbar = reinterpret_cast<uint64_t*>(smem_raw + tab_bytes + (size_t)(TAB_BLOCK / 32) * PR * PR_ROW_BYTES) + warp * PR;
-    auto arm = [&](int r, int slot) {                            // lane 0 only
-        const size_t e = (size_t)k0 + 32 * (size_t)r;
-        mbar_expect_tx(&rbar[slot], PR_ROW_BYTES);
-        bulk_g2s(ring + slot * PR_ROW_BYTES, d.o_cam + e, 128, &rbar[slot]);
-        bulk_g2s(ring + slot * PR_ROW_BYTES + 128, d.o_w + e, 256, &rbar[slot]);
+    const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (PR * OREC_BYTES);
+    const uint32_t rbar = smem_u32(smem_raw) + tab_bytes + (uint32_t)(TAB_BLOCK / 32) * (PR * OREC_BYTES) + (uint32_t)warp * (PR * 8);
+    auto arm = [&](int slot) {                                   // lane 0 only: next unrequested row -> ring slot
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar + 8u * slot), "r"(OREC_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(ring + (uint32_t)slot * OREC_BYTES), "l"(src_rows), "r"(OREC_BYTES), "r"(rbar + 8u * slot) : "memory");
+        src_rows += OREC_BYTES; --n_rows;
     };
     if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < PR; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&rbar[q])), "r"(1) : "memory");
+        for (int q = 0; q < PR; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar + 8u * q), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        for (int q = 0; q < PR && q < n_rows; ++q) arm(q, q);
+        for (int q = 0; q < PR - 1 && n_rows > 0; ++q) arm(q);     // the main loop requests row t + PR - 1 at the top of trip t
     }
     double X[3] = {0, 0, 0};
     if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
@@ -1143,22 +1184,31 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         }
         return true;
     };
-    int r = 0, slot = 0; uint32_t par = 0;
+    int slot = 0; uint32_t par = 0;                              // n_rows: rows not yet requested (meaningful in lane 0)
     for (;;) {
         while (rows_left == 0) {                                 // slice without observations (warp-uniform)
-            double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+            double Vi[6], Xn[3];
             request(Vi, Xn);
             if (!finish(Vi, Xn)) return;
         }
-        mbar_wait(&rbar[slot], par);
-        const int cam = reinterpret_cast<const int*>(ring + slot * PR_ROW_BYTES)[lane];
-        const double w = reinterpret_cast<const double*>(ring + slot * PR_ROW_BYTES + 128)[lane];
-        __syncwarp();                                            // both values of every lane are in registers: refill the slot
-        if (lane == 0 && r + PR < n_rows) { fence_proxy_async(); arm(r + PR, slot); }
-        ++r; if (++slot == PR) { slot = 0; par ^= 1u; }
+        // refill the slot consumed by the previous trip (its two reads have been used by that trip's arithmetic, so the
+        // refill cannot overtake them and no proxy fence is needed); the ring therefore runs PR - 1 rows ahead
+        if (lane == 0 && n_rows > 0) arm(slot == 0 ? PR - 1 : slot - 1);
+        {                                                        // wait for the row (compiler-visible loop + reconvergence)
+            uint32_t ok;
+            do {
+                asm volatile("{\n .reg .pred P1;\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }"
+                             : "=r"(ok) : "r"(rbar + 8u * slot), "r"(par) : "memory");
+            } while (!ok);
+            __syncwarp();
+        }
+        const uint32_t ca = ring + (uint32_t)slot * OREC_BYTES + 4u * lane;
+        const int cam = lds_s32(ca);
+        const double w = lds_f64(ca + 128u + 4u * lane);
         const bool last = (--rows_left == 0);                    // warp-uniform
         TabRow o;
         if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
+        if (++slot == PR) { slot = 0; par ^= 1u; }
         double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
         if (last) request(Vi, Xn);
         if (cam >= 0) tab_row_bwd(o, u0, u1, u2);
@@ -1315,7 +1365,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_reproj_sum(Dev d, int which)
         double X[3]; load3p(d.X[which], j, X);
         int k0, deg; slice_of(d, j, k0, deg);
         for (int sl = 0, k = k0; sl < deg; ++sl, k += 32) {
-            int i = __ldg(d.o_cam + k);
+            int i = __ldg(o_cam_ptr(d, k));
             if (i < 0) continue;
             Cam cm; load_cam(d.rt[which], i, cm);
             double e0, e1, x, y, iz, r0, r1, r2;
