@@ -196,11 +196,7 @@ def main() -> int:
                                   gradient_threshold=0.0, cg_max_steps=CG_STEPS, cg_rel_tol=0.0, poll_every=64)
     eng = binding.Engine(opt)
     if world > 1:
-        idt = torch.zeros(binding.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(binding.Engine.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        eng.comm_setup_torch(rank, world, N)
     eng.set_problem_from(prob)
 
     def barrier():
@@ -270,11 +266,7 @@ def main() -> int:
                                    cg_max_steps=CG_STEPS, cg_rel_tol=0.0, poll_every=e2e_steps, discard_converged=0)
     eng2 = binding.Engine(opt2)
     if world > 1:
-        idt = torch.zeros(binding.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(binding.Engine.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        eng2.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        eng2.comm_setup_torch(rank, world, N)
     barrier()
     t0 = time.perf_counter()
     eng2.set_problem_from(prob)

@@ -132,6 +132,17 @@ int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts);
 #define B200BA_COMM_ID_BYTES 128
 int b200ba_comm_unique_id(void* id_bytes);    /* rank 0 creates, the launcher broadcasts (e.g. torch.distributed) */
 int b200ba_comm_init(b200ba_handle* h, const void* id_bytes, int32_t rank, int32_t world);
+/* Optional, after b200ba_comm_init and before b200ba_set_problem: NVLink peer-memory collectives.  Every rank allocates an
+ * exchange window sized for problems of up to max_cameras cameras and returns its CUDA IPC handle; the launcher
+ * all-gathers the world x B200BA_PEER_HANDLE_BYTES handles and every rank maps its peers.  From then on the per-PCG-step
+ * all-reduce of the camera sums runs INSIDE the camera-side step kernel (publish, flag, peer loads over NVLink, summed in
+ * rank order) and the once-per-iteration reductions as two small kernels, so a multi-rank LM iteration has no host-side
+ * collective call and is replayed as one CUDA graph.  Without these two calls every collective is an NCCL all-reduce.
+ * All ranks must have returned from b200ba_solve / b200ba_finish before any rank calls b200ba_destroy (launcher barrier).
+ * The reference has no counterpart (SSBA and PBA are single-process). */
+#define B200BA_PEER_HANDLE_BYTES 64
+int b200ba_comm_peer_handle(b200ba_handle* h, int32_t max_cameras, void* handle_bytes);
+int b200ba_comm_open_peers(b200ba_handle* h, const void* all_handles);
 
 /* ---- stage-level access for parity tests and profiling (not needed by the adapter) ---- */
 /* Linearise at the current (normalised) state after b200ba_begin: any output may be NULL.

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200BA_LIB", os.path.join(_HERE, "libb200ba.so"))   # override: kernel-variant experiments
 TRACE_COLS = 8
 COMM_ID_BYTES = 128
+PEER_HANDLE_BYTES = 64
 
 STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 
@@ -23,7 +24,7 @@ STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 ABI_SYMBOLS = [
     "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
-    "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
+    "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
     "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
 ]
 
@@ -156,6 +157,31 @@ class Engine:
 
     def comm_init(self, id_bytes: bytes, rank: int, world: int):
         self._check(self.lib.b200ba_comm_init(self.h, C.c_char_p(id_bytes), C.c_int32(rank), C.c_int32(world)))
+
+    def comm_peer_handle(self, max_cameras: int) -> bytes:
+        """Allocate this rank's NVLink exchange window; returns its CUDA IPC handle (all-gather it over the launcher)."""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._check(self.lib.b200ba_comm_peer_handle(self.h, C.c_int32(max_cameras), buf))
+        return buf.raw
+
+    def comm_open_peers(self, all_handles: bytes):
+        self._check(self.lib.b200ba_comm_open_peers(self.h, C.c_char_p(all_handles)))
+
+    def comm_setup_torch(self, rank: int, world: int, max_cameras: int, peer_windows: bool = True):
+        """Launcher plumbing over an initialised torch.distributed NCCL group: broadcast the NCCL id, create the
+        communicator and (optionally) exchange the NVLink peer-window handles."""
+        import torch
+        import torch.distributed as dist
+        idt = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        self.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        if peer_windows and world > 1 and os.environ.get("B200BA_NO_P2P") is None:
+            mine = torch.frombuffer(bytearray(self.comm_peer_handle(max_cameras)), dtype=torch.uint8).cuda()
+            allh = [torch.zeros(PEER_HANDLE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            self.comm_open_peers(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
 
     # -- problem / solve ------------------------------------------------------------------------------
     def set_problem(self, K5, cam_RT, pts, obs_xy, obs_cam, obs_pt):

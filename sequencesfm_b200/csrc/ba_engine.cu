@@ -91,6 +91,9 @@ struct b200ba_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // communicator
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    // NVLink peer-memory exchange (struct P2P in ba_kernels.cuh)
+    unsigned char* win_own = nullptr; void* win_peer[P2P_MAX_WORLD] = {nullptr}; size_t win_cap = 0; bool p2p_ready = false;
+    unsigned long long* p2p_ctl = nullptr;           // [seq | done_blocks | err] device words
     // host copies of the caller's problem
     int N = 0, M = 0, K = 0;
     std::vector<double> h_cam, h_pts;        // as given (un-normalised)
@@ -139,9 +142,20 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-int allreduce(b200ba_handle* h, double* buf, size_t count)
+// Sum over ranks, in place.  `need`: 0 = unconditional, 1 = skipped on device once the solve is done, 2 = skipped as well
+// when the iteration does not re-linearise (the same device-side flags on every rank).  With the peer windows mapped this
+// is two small kernels (no host-side collective call, graph-capturable); otherwise NCCL.
+int allreduce(b200ba_handle* h, double* buf, size_t count, int need = 0)
 {
     if (h->world <= 1) return 0;
+    if (h->p2p_ready) {
+        if (count > h->win_cap) return fail(h, B200BA_E_COMM, "peer window too small (%zu > %zu doubles)", count, h->win_cap);
+        const int grid = (int)std::min<size_t>(64, (count + 255) / 256);
+        k_p2p_publish<<<grid, 256, 0, h->stream>>>(h->d, buf, (int)count, need);
+        k_p2p_reduce<<<grid, 256, 0, h->stream>>>(h->d, buf, (int)count, need);
+        h->launches += 2;
+        return 0;
+    }
     NC(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream));
     return 0;
 }
@@ -157,7 +171,7 @@ int enqueue_linearize(b200ba_handle* h)
     LAUNCH(k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0);
-    if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world)) return rc;
+    if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
     LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
     return 0;
 }
@@ -169,7 +183,7 @@ int enqueue_precond(b200ba_handle* h)
     if (h->opt.precond == 1) {
         LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
         LAUNCH((k_camera_reduce<21, 21>), cdiv((long long)d.N * 21, 256), 256, d, d.ar_sd, 0);
-        if (int rc = allreduce(h, d.ar_sd, (size_t)d.N * 21)) return rc;
+        if (int rc = allreduce(h, d.ar_sd, (size_t)d.N * 21, 1)) return rc;
     }
     LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond);
     return 0;
@@ -201,7 +215,7 @@ int enqueue_camera_sums(b200ba_handle* h)
 {
     Dev& d = h->d;
     LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
-    return allreduce(h, d.ar_q, (size_t)d.N * 6);
+    return allreduce(h, d.ar_q, (size_t)d.N * 6, 1);
 }
 
 int launch_camera_step(b200ba_handle* h, int sums_ready)
@@ -223,6 +237,7 @@ int enqueue_cg_step(b200ba_handle* h)
     } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
     if (h->use_coop && h->world <= 1) return launch_camera_step(h, 0);
+    if (h->use_coop && h->p2p_ready) return launch_camera_step(h, 2);      // all-reduce fused into the step kernel (NVLink peer loads)
     if (int rc = enqueue_camera_sums(h)) return rc;
     if (h->use_coop) return launch_camera_step(h, 1);
     LAUNCH(k_cg_update, 1, ONE_CTA, d);
@@ -235,7 +250,7 @@ int enqueue_step_and_decide(b200ba_handle* h)
     LAUNCH(k_cg_finish, 1, ONE_CTA, d);
     LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1);
-    if (int rc = allreduce(h, d.ar_dec, 4)) return rc;
+    if (int rc = allreduce(h, d.ar_dec, 4, 1)) return rc;
     LAUNCH(k_lm_decide, 1, 1, d);
     return 0;
 }
@@ -392,6 +407,9 @@ void b200ba_destroy(b200ba_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < P2P_MAX_WORLD; ++r) if (h->win_peer[r]) cudaIpcCloseMemHandle(h->win_peer[r]);
+    if (h->win_own) cudaFree(h->win_own);
+    if (h->p2p_ctl) cudaFree(h->p2p_ctl);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->rt0.release(); h->rt1.release(); h->U.release(); h->gc.release(); h->Minv.release(); h->x.release(); h->r.release();
     h->z.release(); h->p.release(); h->q.release(); h->ar_lin.release(); h->ar_q.release(); h->ar_sd.release(); h->ar_dec.release();
@@ -429,6 +447,46 @@ int b200ba_comm_init(b200ba_handle* h, const void* id_bytes, int32_t rank, int32
     ncclUniqueId id; memcpy(&id, id_bytes, sizeof id);
     NC(g_nccl.CommInitRank(&h->comm, world, id, rank));
     h->rank = rank; h->world = world;
+    return 0;
+}
+
+int b200ba_comm_peer_handle(b200ba_handle* h, int32_t max_cameras, void* handle_bytes)
+{
+    if (!h || !handle_bytes || max_cameras <= 0) return B200BA_E_INVALID;
+    if (h->world <= 1) return fail(h, B200BA_E_STATE, "b200ba_comm_peer_handle needs a multi-rank handle (b200ba_comm_init first)");
+    if (h->world > P2P_MAX_WORLD) return fail(h, B200BA_E_INVALID, "peer windows support at most %d ranks", P2P_MAX_WORLD);
+    if (h->have_problem) return fail(h, B200BA_E_STATE, "b200ba_comm_peer_handle must precede b200ba_set_problem");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200BA_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    CU(cudaSetDevice(h->device));
+    if (h->win_own) { cudaFree(h->win_own); h->win_own = nullptr; }
+    h->win_cap = (size_t)max_cameras * PART_STRIDE + 1 + 2 * (size_t)h->world + 16;
+    const size_t bytes = P2P_HDR_BYTES + 2 * (size_t)h->world * h->win_cap * sizeof(double);
+    CU(cudaMalloc((void**)&h->win_own, bytes));
+    CU(cudaMemset(h->win_own, 0, bytes));
+    if (!h->p2p_ctl) { CU(cudaMalloc((void**)&h->p2p_ctl, 64)); CU(cudaMemset(h->p2p_ctl, 0, 64)); }
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, h->win_own));
+    memcpy(handle_bytes, &hd, sizeof hd);
+    return 0;
+}
+
+int b200ba_comm_open_peers(b200ba_handle* h, const void* all_handles)
+{
+    if (!h || !all_handles) return B200BA_E_INVALID;
+    if (!h->win_own) return fail(h, B200BA_E_STATE, "b200ba_comm_open_peers before b200ba_comm_peer_handle");
+    CU(cudaSetDevice(h->device));
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) continue;
+        cudaIpcMemHandle_t hd; memcpy(&hd, (const char*)all_handles + (size_t)r * B200BA_PEER_HANDLE_BYTES, sizeof hd);
+        cudaError_t e = cudaIpcOpenMemHandle(&h->win_peer[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q) if (h->win_peer[q]) { cudaIpcCloseMemHandle(h->win_peer[q]); h->win_peer[q] = nullptr; }
+            return fail(h, B200BA_E_COMM, "cudaIpcOpenMemHandle(rank %d): %s (collectives stay on NCCL)", r, cudaGetErrorString(e));
+        }
+    }
+    h->p2p_ready = true;
     return 0;
 }
 
@@ -731,12 +789,20 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_camera_step, STEP_BLOCK, 0);
         h->use_coop = coop && (long long)per_sm * h->num_sms >= h->step_grid && getenv("B200BA_NO_COOP") == nullptr;
     }
-    // NCCL collectives are enqueued eagerly (outside any capture): graph replay is used for the single-rank engine only
-    h->use_graph = getenv("B200BA_NO_GRAPH") == nullptr && h->world <= 1;
+    // NCCL collectives are enqueued eagerly (outside any capture); with the peer windows mapped the multi-rank iteration
+    // contains no host-side collective and is captured like the single-rank one
+    h->use_graph = getenv("B200BA_NO_GRAPH") == nullptr && (h->world <= 1 || h->p2p_ready);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
 
     d = Dev{};
     d.N = N; d.M = M; d.K = K; d.n_rows = n_rows; d.n_vwarps = n_vwarps; d.n_segs = n_segs; d.first_free = o.fix_first_camera ? 1 : 0; d.n_pt_blocks = n_pt_blocks;
+    if (h->p2p_ready) {
+        if ((size_t)N * PART_STRIDE + 1 + 2 * (size_t)world > h->win_cap)
+            return fail(h, B200BA_E_COMM, "peer windows were sized for fewer cameras (capacity %zu doubles, need %zu)", h->win_cap, (size_t)N * PART_STRIDE + 1 + 2 * (size_t)world);
+        d.p2p.on = 1; d.p2p.world = world; d.p2p.rank = h->rank; d.p2p.cap = h->win_cap;
+        for (int r = 0; r < world; ++r) d.p2p.win[r] = (r == h->rank) ? h->win_own : (unsigned char*)h->win_peer[r];
+        d.p2p.seq = h->p2p_ctl; d.p2p.done_blocks = (unsigned int*)(h->p2p_ctl + 1); d.p2p.err = (int*)(h->p2p_ctl + 2);
+    }
     d.world = world; d.rank = h->rank; d.n_slices = n_slices; d.tab_ok = h->use_tab ? 1 : 0; d.in = in; d.st = h->st.p;
     d.rt[0] = h->rt0.p; d.rt[1] = h->rt1.p; d.U = h->U.p; d.gc = h->gc.p; d.Minv = h->Minv.p;
     d.x = h->x.p; d.r = h->r.p; d.z = h->z.p; d.p = h->p.p; d.q = h->q.p;
@@ -855,6 +921,10 @@ int b200ba_iterate(b200ba_handle* h, int32_t n, int32_t* done)
         it += batch;
         CU(cudaMemcpyAsync(&is_done, &h->d.st->done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        if (h->p2p_ready) {
+            int perr = 0; CU(cudaMemcpy(&perr, h->d.p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
+            if (perr) return fail(h, B200BA_E_COMM, "a peer rank did not publish its contribution in time (peer-memory all-reduce)");
+        }
     }
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaEventSynchronize(h->ev1));

@@ -95,7 +95,28 @@ struct LMState {
     int max_iter, min_iter, n_trace, trace_cap;
 };
 
+// NVLink peer-memory exchange window (multi-rank), PUSH design.  Every rank owns one window
+//   [ flag[2][world] (uint64, 64 bytes apart) | data[2][world][cap] (f64) ]
+// allocated with cudaMalloc and mapped into every peer through CUDA IPC.  Collective number c (the same on every rank: all
+// ranks run the same kernel sequence and take the same device-side decisions) uses half c & 1.  A rank STORES its
+// contribution into slot [c & 1][own rank] of EVERY window (its own included) - posted NVLink writes - and then raises
+// flag [c & 1][own rank] = c + 1 in every window (release, system scope).  A receiver polls and reads only ITS OWN memory:
+// when all world flags of the half have arrived it sums the world slots in rank order - identical bits on every rank, one
+// one-way NVLink trip, no host call.  (The first version pulled: remote flag polls + remote loads = two round trips,
+// measured 16 us per PCG step at 2 GPUs.)  Half c & 1 is rewritten at collective c + 2, which a rank only starts after it
+// has seen every flag of c + 1, i.e. after every peer has finished reading c.
+constexpr int P2P_MAX_WORLD = 8;
+constexpr int P2P_HDR_BYTES = 2 * P2P_MAX_WORLD * 64;
+struct P2P {
+    int on, world, rank, pad;
+    unsigned long long cap;                  // doubles per slot
+    unsigned char* win[P2P_MAX_WORLD];       // win[rank] = own window, others = peer mappings
+    unsigned long long* seq;                 // device counter of collectives executed (own memory)
+    unsigned int* done_blocks;               // last-block-done counter of k_p2p_reduce
+    int* err;                                // set when a peer's flag did not arrive (spin limit)
+};
 struct Dev {
+    P2P p2p;
     int N, M, K, n_rows, n_vwarps, n_segs, first_free, n_pt_blocks, world, rank, n_slices, tab_ok;
     Intrinsics in;
     LMState* st;
@@ -930,6 +951,81 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Peer-memory all-reduce (see struct P2P)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double* p2p_data(const P2P& x, int dst, unsigned long long c, int src)
+{
+    return reinterpret_cast<double*>(x.win[dst] + P2P_HDR_BYTES) + ((c & 1ull) * x.world + src) * x.cap;
+}
+__device__ __forceinline__ unsigned long long* p2p_flag(const P2P& x, int dst, unsigned long long c, int src)
+{
+    return reinterpret_cast<unsigned long long*>(x.win[dst] + 64 * ((c & 1ull) * P2P_MAX_WORLD + src));
+}
+// element e of this rank's contribution -> every window
+__device__ __forceinline__ void p2p_push(const P2P& x, unsigned long long c, size_t e, double v)
+{
+    for (int r = 0; r < x.world; ++r) p2p_data(x, r, c, x.rank)[e] = v;
+}
+// Threads 0 .. world-1 of ONE block, after every push of the grid has been ordered before them (grid sync / kernel
+// boundary): raise this rank's flag in every window.
+__device__ __forceinline__ void p2p_raise_flags(const P2P& x, unsigned long long c)
+{
+    const int r = threadIdx.x;
+    if (r < x.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p2p_flag(x, r, c, x.rank)), "l"(c + 1ull) : "memory");
+    }
+}
+// threads 0 .. world-1 of a block each wait for one source's flag IN THE OWN WINDOW; bounded spin (about a second) so that a
+// dead peer cannot hang the GPU
+__device__ __forceinline__ void p2p_wait_all(const P2P& x, unsigned long long c)
+{
+    const int r = threadIdx.x;
+    if (r < x.world) {
+        const unsigned long long* f = p2p_flag(x, x.rank, c, r);
+        unsigned long long v = 0; unsigned int spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= c + 1ull) break;
+            if (++spins > (1u << 25)) { *x.err = 1; break; }
+            if (spins > 4096u) __nanosleep(32);
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ double p2p_sum(const P2P& x, unsigned long long c, size_t e)
+{
+    double s = 0;
+    for (int r = 0; r < x.world; ++r) s += __ldcv(p2p_data(x, x.rank, c, r) + e);   // fixed rank order; .cv: never a stale L1 line
+    return s;
+}
+// generic all-reduce (sum) of buf[0..count): push, then flag + reduce in place.  Two kernels: the boundary orders the
+// pushes of all blocks before the flags.
+__global__ void __launch_bounds__(256) k_p2p_publish(Dev d, const double* __restrict__ buf, int count, int need)
+{
+    const LMState* st = d.st;
+    if (need == 1 && st->done) return;
+    if (need == 2 && (st->done || !st->compute)) return;
+    const unsigned long long c = *d.p2p.seq;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < count; e += gridDim.x * 256) p2p_push(d.p2p, c, (size_t)e, buf[e]);
+}
+__global__ void __launch_bounds__(256) k_p2p_reduce(Dev d, double* __restrict__ buf, int count, int need)
+{
+    const LMState* st = d.st;
+    if (need == 1 && st->done) return;
+    if (need == 2 && (st->done || !st->compute)) return;
+    const unsigned long long c = *d.p2p.seq;
+    if (blockIdx.x == 0) p2p_raise_flags(d.p2p, c);
+    p2p_wait_all(d.p2p, c);
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < count; e += gridDim.x * 256) buf[e] = p2p_sum(d.p2p, c, (size_t)e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(d.p2p.done_blocks, 1u) == gridDim.x - 1) { *d.p2p.done_blocks = 0; *d.p2p.seq = c + 1ull; __threadfence(); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Camera-side PCG (single CTA; camera-sized vectors only).  Structure after PBA's implicit-Schur PCG
 // (SparseBundleCPU.cpp:3323-3450) with additive damping and S-block / U-block Jacobi preconditioner.
 // ------------------------------------------------------------------------------------------------------
@@ -1240,19 +1336,29 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     double pe = on ? d.p[e] : 0.0;
     sv[threadIdx.x] = pe;
     __syncthreads();
-    double q = 0;
+    double q = 0, s = 0;
     if (on) {
-        double s = 0;
         if (sums_ready == 1) s = d.ar_q[e];
         else for (int sg = d.cam_seg_beg[i]; sg < d.cam_seg_beg[i + 1]; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + a];
-        q = lam * pe + matvec6_row(d.U + 36 * (size_t)i, sv + lc, a) - s;
     }
+    unsigned long long coll = 0;
+    if (sums_ready == 2) {
+        // multi-rank: the all-reduce of the 6N camera sums happens HERE, over NVLink peer memory, between the second-level
+        // sum and the q = S p assembly - push into every window, grid sync, raise the flags, poll the own window, sum its slots
+        coll = *d.p2p.seq;
+        if (on) p2p_push(d.p2p, coll, (size_t)e, s);
+        grid.sync();
+        if (blockIdx.x == 0) p2p_raise_flags(d.p2p, coll);
+        p2p_wait_all(d.p2p, coll);
+        if (on) s = p2p_sum(d.p2p, coll, (size_t)e);
+    }
+    if (on) q = lam * pe + matvec6_row(d.U + 36 * (size_t)i, sv + lc, a) - s;
     double bp = block_sum<STEP_BLOCK>(pe * q, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_pq[blockIdx.x] = bp;
     grid.sync();
     const double pq = grid_total(part_pq, step_blocks);
     if (!(pq > 0) || !isfinite(pq)) {                            // breakdown (uniform): keep x; first-step breakdown = failed solve
-        if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; }
+        if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; if (sums_ready == 2) *d.p2p.seq = coll + 1ull; }
         return;
     }
     const double alpha = rz / pq;
@@ -1275,6 +1381,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     if (e == 0) {
         st->cg_steps = steps + 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
         if (stop) st->cg_active = 0;
+        if (sums_ready == 2) *d.p2p.seq = coll + 1ull;           // every thread read the counter before the first grid sync
     }
 }
 __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_ready, double* part_pq, double* part_rz)
