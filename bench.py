@@ -47,6 +47,27 @@ def algorithmic_bytes(N: int, M: int, K: int, T: int = CG_STEPS, s: int = 8) -> 
             "iteration": b_lin + T * b_cg + b_back + b_cost + b_upd}
 
 
+def kernel_models(N: int, M: int, K: int, s: int = 8) -> dict:
+    """Per-kernel split of the same byte model (the survey's by-point / by-camera halves of B_cg, B_lin split over the two
+    linearisation sweeps in proportion to what each half of the fused-sweep model reads and writes)."""
+    return {"cg_point_pass": K * (8 + 2 * s) + M * 9 * s,            # index + y + points + V^-1
+            "cg_camera_pass": K * (8 + 2 * s) + M * 3 * s,           # index + y + points
+            "linearize": K * (8 + 2 * s) + M * 3 * s + M * 9 * s + N * 42 * s,
+            "backsub_cost_points": (K * 8 + M * 15 * s) + (K * (8 + 2 * s) + M * 3 * s)}
+
+
+def ncu_traffic() -> tuple[dict, str | None]:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full digest (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "ncu_r1_final_summary.json")
+    try:
+        out = {}
+        for d in json.load(open(path)):
+            out[d["Kernel Name"].split("(")[0].replace("void ", "")] = d["dram_traffic_bytes_per_launch"]
+        return out, "profiles/ncu_r1_final_summary.json"
+    except Exception:
+        return {}, None
+
+
 def measured_peak() -> tuple[float, str]:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -251,9 +272,25 @@ def main() -> int:
         abl = algorithmic_bytes(N, Ml, Kl)
         cg_ms = kt["cg_step"]
         achieved = abl["cg_step"] / (cg_ms * 1e-3) / 1e9
+        traf, traf_src = ncu_traffic()
+        step_traffic = None
+        if world == 1 and all(k in traf for k in ("k_cg_point_pass_tab", "k_cg_camera_pass", "k_cg_camera_step")):
+            step_traffic = traf["k_cg_point_pass_tab"] + traf["k_cg_camera_pass"] + traf["k_cg_camera_step"]
+        km = kernel_models(N, Ml, Kl)
+        lin_ms = kt["linearize_points"] + kt["linearize_cameras"]
+        per_kernel = {
+            "k_cg_point_pass_tab": {"ms": kt["cg_point_pass"], "algorithmic_bytes": km["cg_point_pass"]},
+            "k_cg_camera_pass": {"ms": kt["cg_camera_pass"], "algorithmic_bytes": km["cg_camera_pass"]},
+            "k_linearize_points+k_linearize_cameras": {"ms": lin_ms, "algorithmic_bytes": km["linearize"]},
+            "k_cg_point_pass<2> (back-substitution + trial cost)": {"ms": kt["backsub_cost_points"], "algorithmic_bytes": km["backsub_cost_points"]}}
+        for v in per_kernel.values():
+            v["achieved_gbs"] = v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9
+            v["frac"] = v["achieved_gbs"] / peak
         roof = {"bound": "hbm", "kernel": "one PCG step = k_cg_point_pass_tab + k_cg_camera_pass + k_cg_camera_step (timed back to back, CUDA events on the engine stream)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": step_traffic,
+                "traffic_source": (traf_src + ": dram__bytes_read.sum + dram__bytes_write.sum of the three kernels, per launch") if step_traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": abl["cg_step"], "ms_per_launch": cg_ms,
+                "per_kernel": per_kernel,
                 "share_of_step": CG_STEPS * cg_ms / ms_per_step,
                 "iteration": {"algorithmic_bytes": abl["iteration"], "achieved": abl["iteration"] / (ms_per_step * 1e-3) / 1e9,
                               "frac": abl["iteration"] / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -270,9 +307,11 @@ def main() -> int:
     barrier()
     t0 = time.perf_counter()
     eng2.set_problem_from(prob)
-    r2 = eng2.solve()
+    t1 = time.perf_counter()
+    r2 = eng2.solve()                    # b200ba_solve + b200ba_get_result (device -> host copy of cameras and points)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_solve_s = time.perf_counter() - t1
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -281,7 +320,7 @@ def main() -> int:
     d2h = prob.M * 32 + N * 96
     e2e = {"value": r2.iterations / e2e_s, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d / e2e_steps,
            "d2h_bytes_per_step": d2h / e2e_steps, "seconds_total": e2e_s, "lm_iterations": r2.iterations,
-           "ms_set_problem": r2.ms_h2d, "ms_solve_device": r2.ms_solve, "ms_get_result": r2.ms_d2h,
+           "ms_set_problem": r2.ms_h2d, "ms_solve_device": r2.ms_solve, "ms_solve_and_get_result_wall": e2e_solve_s * 1e3,
            "note": "host arrays -> b200ba_set_problem (marshal, sort, upload) -> b200ba_solve -> b200ba_get_result; bytes amortised over the solve's LM iterations"}
     eng2.close()
 

@@ -832,11 +832,23 @@ int b200ba_begin(b200ba_handle* h)
     h->mean[0] = h->mean[1] = h->mean[2] = 0; h->scale = 1.0;
     std::vector<double> C(3 * (size_t)N);
     for (int i = 0; i < N; ++i) camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i);
+    // Host loops over the points: sequential (the reference's own summation order) up to 200 000 points, where the parity
+    // tests live; above that, contiguous blocks summed by threads and combined in block order (rounding differs at 1e-16).
+    const int T = (M > 200000) ? (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
+    auto blocked_sum = [&](int ncomp, double* out, auto&& term) {
+        std::vector<double> part((size_t)T * ncomp, 0.0);
+        parallel_for(T, [&](int t, int nt) {
+            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
+            double* a = part.data() + (size_t)t * ncomp;
+            for (int j = j0; j < j1; ++j) term(j, a);
+        });
+        for (int t = 0; t < T; ++t) for (int c = 0; c < ncomp; ++c) out[c] += part[(size_t)t * ncomp + c];
+    };
     if (o.normalize) {
         // ScopedBundleExtrinsicNormalizer ctor (v3d_metricbundle.h:327-356); point sums are global over ranks,
         // cameras are replicated and counted once.
         double s[4] = {0, 0, 0, (double)M};
-        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) s[c] += P0[3 * (size_t)j + c];
+        blocked_sum(3, s, [&](int j, double* a) { for (int c = 0; c < 3; ++c) a[c] += P0[3 * (size_t)j + c]; });
         if (int rc = global_sum(h, s, 4)) return rc;
         double cs[3] = {0, 0, 0};
         for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) cs[c] += C[3 * (size_t)i + c];
@@ -844,23 +856,31 @@ int b200ba_begin(b200ba_handle* h)
         double rn = 1.0 / ((double)N + s[3]);
         for (int c = 0; c < 3; ++c) h->mean[c] = (cs[c] + s[c]) * rn;
         double sq[1] = {0};
-        for (int j = 0; j < M; ++j) for (int c = 0; c < 3; ++c) { double v = P0[3 * (size_t)j + c] - h->mean[c]; sq[0] += v * v; }
+        blocked_sum(1, sq, [&](int j, double* a) { for (int c = 0; c < 3; ++c) { double v = P0[3 * (size_t)j + c] - h->mean[c]; a[0] += v * v; } });
         if (int rc = global_sum(h, sq, 1)) return rc;
         double sqc = 0;
         for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) { C[3 * (size_t)i + c] -= h->mean[c]; sqc += C[3 * (size_t)i + c] * C[3 * (size_t)i + c]; }
         h->scale = std::sqrt(sqc + sq[0]);
         double rs = 1.0 / h->scale;
         for (int i = 0; i < N; ++i) { for (int c = 0; c < 3; ++c) C[3 * (size_t)i + c] *= rs; set_camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i); }
-        for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs; }
+        parallel_for(T, [&](int t, int nt) {
+            const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
+            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs; }
+        });
     } else {
-        for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = P0[3 * (size_t)j + c]; }
+        parallel_for(T, [&](int t, int nt) {
+            const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
+            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = P0[3 * (size_t)j + c]; }
+        });
     }
     // cached parameter length (v3d_metricbundle.h:37-45), after normalisation (summed in the caller's point order)
     double L[1] = {0};
-    {
+    if (T == 1) {
         std::vector<int> new_of_orig((size_t)M);
         for (int jn = 0; jn < M; ++jn) new_of_orig[h->orig_of_new[jn]] = jn;
         for (int j = 0; j < M; ++j) { const int jn = new_of_orig[j]; for (int c = 0; c < 3; ++c) L[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; }
+    } else {
+        blocked_sum(1, L, [&](int jn, double* a) { for (int c = 0; c < 3; ++c) a[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; });
     }
     if (int rc = global_sum(h, L, 1)) return rc;
     for (int i = (o.fix_first_camera ? 1 : 0); i < N; ++i) {
@@ -1005,8 +1025,15 @@ int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts)
     if (pts && M) {
         std::vector<double> X4(4 * (size_t)M);
         CU(cudaMemcpy(X4.data(), h->d.X[cur], sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
-        if (h->opt.normalize) for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)jn + c] * h->scale + h->mean[c]; }
-        else for (int jn = 0; jn < M; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = X4[4 * (size_t)jn + c]; }
+        const int T = (M > 200000) ? (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
+        const bool nrm = h->opt.normalize != 0;
+        parallel_for(T, [&](int t, int nt) {
+            const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
+            for (int jn = a; jn < b; ++jn) {
+                const int j = h->orig_of_new[jn];
+                for (int c = 0; c < 3; ++c) pts[3 * (size_t)j + c] = nrm ? X4[4 * (size_t)jn + c] * h->scale + h->mean[c] : X4[4 * (size_t)jn + c];
+            }
+        });
     }
     h->ms_d2h = now_ms() - t0;
     return 0;

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Evidence round: bench line, ncu launch list of the SAME bench command, ncu --set full of every hot kernel.
+# Usage: tools/gpu_profile.sh <tag>
+tag=$1; mkdir -p gpurun_out
+timeout 900 python bench.py --steps 16 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || { echo bench failed; tail -20 gpurun_out/bench_$tag.err; exit 1; }
+tail -c 600 gpurun_out/bench_$tag.json; echo
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$tag.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_$tag.log 2>&1
+wc -l gpurun_out/launches_$tag.csv
+timeout 300 python tools/prof_one.py 0,1,6,8,2,3,11 > gpurun_out/prof_plain_$tag.log 2>&1 || { echo plain failed; cat gpurun_out/prof_plain_$tag.log; exit 1; }
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_linearize|k_schur|k_cg_point_pass|k_cg_camera' -s 2 -c 36 -o gpurun_out/prof_$tag -f \
+    python tools/prof_one.py 0,1,6,8,2,3,11 > gpurun_out/prof_ncu_$tag.log 2>&1
+tail -3 gpurun_out/prof_ncu_$tag.log
