@@ -66,9 +66,9 @@ constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side ker
 constexpr int TRACE_COLS   = 8;
 constexpr int TAB_STRIDE   = 14;    // doubles per camera in the packed table: quaternion 4, T 3, p 6, pad 1 (112 B = 7 x 16 B)
 #ifndef B200BA_TAB_BLOCK
-#define B200BA_TAB_BLOCK 640
+#define B200BA_TAB_BLOCK 608
 #ifndef B200BA_TAB_MAXNREG
-#define B200BA_TAB_MAXNREG 96
+#define B200BA_TAB_MAXNREG 104
 #endif
 #endif
 constexpr int TAB_BLOCK    = B200BA_TAB_BLOCK;   // threads of the persistent shared-memory-table CG point sweep (1 CTA / SM; 640 x 96 registers measured faster than 768 x 80, which spills)
@@ -869,7 +869,11 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
         const int sl = t % CNS;
         const uint32_t bytes = (uint32_t)min(CG, n - t * CG) * REC_BYTES;
         mbar_expect_tx(&bar[sl], bytes);
+#ifdef B200BA_CP_NOHINT
+        bulk_g2s(buf + sl * STAGE_BYTES, src + (size_t)t * STAGE_BYTES, bytes, &bar[sl]);
+#else
         bulk_g2s_hint(buf + sl * STAGE_BYTES, src + (size_t)t * STAGE_BYTES, bytes, &bar[sl], strm);
+#endif
     };
     if (lane == 0) {
 #pragma unroll
@@ -1193,8 +1197,8 @@ __device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double&
     u1 += fma(2.0, o.qw * gy + (o.qx * gz - o.qz * gx), o.h1);
     u2 += fma(2.0, o.qw * gz + (o.qy * gx - o.qx * gy), o.h2);
 }
-constexpr int PR = 3;                                            // rows of the point-order stream staged per warp
-constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * PR * (OREC_BYTES + 8);   // rings + their mbarriers
+constexpr int PR = 4;                                            // rows of the point-order stream staged per warp: 2 stages x 2 rows
+constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * (PR * OREC_BYTES + 2 * 8);   // rings + their two mbarriers per warp
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 #ifdef B200BA_TAB_MAXNREG
@@ -1229,27 +1233,35 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         g = ha.x; g_end = ha.y; src_rows += (size_t)(ha.z >> 5) * OREC_BYTES; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
     }
     // The warp's point-order row records form one contiguous stream (it owns a contiguous range of slices).  The stream
-    // is staged by the TMA into a private ring of PR rows (one bulk copy per row, issued by lane 0, PR rows ahead); a
-    // row's two values are read into registers at the top of its body and the slot is re-armed at the top of the next trip.
+    // is staged by the TMA into a private ring of two stages of two rows (one bulk copy per stage, issued by lane 0 when
+    // the previous occupant of the stage has been consumed); a row's two values are read into registers at the top of
+    // its body.
     // (Prefetching the stream through REGISTERS does not survive ptxas: whatever the source says - rotation, unrolled
     // copies, a phase switch - the loop-carried value is copied, the copy waits for the load it was meant to overlap,
     // and ncu showed 12-25 % of all stall samples on that move.)  All ring addresses are 32-bit shared-window offsets
     // kept in registers; generic pointers made ptxas rebuild them every row.
     const uint32_t tab_bytes = (total + 127u) & ~127u;
     const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (PR * OREC_BYTES);
-    const uint32_t rbar = smem_u32(smem_raw) + tab_bytes + (uint32_t)(TAB_BLOCK / 32) * (PR * OREC_BYTES) + (uint32_t)warp * (PR * 8);
-    auto arm = [&](int slot) {                                   // lane 0 only: next unrequested row -> ring slot
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar + 8u * slot), "r"(OREC_BYTES) : "memory");
+    const uint32_t rbar = smem_u32(smem_raw) + tab_bytes + (uint32_t)(TAB_BLOCK / 32) * (PR * OREC_BYTES) + (uint32_t)warp * 16u;
+    auto arm = [&](int stage) {                                  // lane 0 only: next two unrequested rows -> ring stage
+        const uint32_t bytes = (uint32_t)min(2, n_rows) * OREC_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar + 8u * stage), "r"(bytes) : "memory");
+#ifdef B200BA_PT_NOHINT
         asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(ring + (uint32_t)slot * OREC_BYTES), "l"(src_rows), "r"(OREC_BYTES), "r"(rbar + 8u * slot) : "memory");
-        src_rows += OREC_BYTES; --n_rows;
+                     ::"r"(ring + (uint32_t)stage * (2 * OREC_BYTES)), "l"(src_rows), "r"(bytes), "r"(rbar + 8u * stage) : "memory");
+#else
+        // evict_first: the stream must not push the gathered vectors (X, v: evict_last) out of L2 (by-camera sweep: 43 vs 47.5 us)
+        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(ring + (uint32_t)stage * (2 * OREC_BYTES)), "l"(src_rows), "r"(bytes), "r"(rbar + 8u * stage), "l"(policy_evict_first()) : "memory");
+#endif
+        src_rows += 2 * OREC_BYTES; n_rows -= 2;
     };
     if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < PR; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar + 8u * q), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar + 8u), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
-        for (int q = 0; q < PR - 1 && n_rows > 0; ++q) arm(q);     // the main loop requests row t + PR - 1 at the top of trip t
+        if (n_rows > 0) arm(0);                                  // stage 1 is requested at the top of the first trip
     }
     double X[3] = {0, 0, 0};
     if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
@@ -1287,26 +1299,32 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
             request(Vi, Xn);
             if (!finish(Vi, Xn)) return;
         }
-        // refill the slot consumed by the previous trip (its two reads have been used by that trip's arithmetic, so the
-        // refill cannot overtake them and no proxy fence is needed); the ring therefore runs PR - 1 rows ahead
-        if (lane == 0 && n_rows > 0) arm(slot == 0 ? PR - 1 : slot - 1);
-        {                                                        // wait for the row (compiler-visible loop + reconvergence)
-            uint32_t ok;
+        if ((slot & 1) == 0) {                                   // first row of a stage
+            // the OTHER stage was consumed by the previous two trips (its reads fed their arithmetic, so the refill cannot
+            // overtake them and no proxy fence is needed): request the two rows after this stage into it
+            if (lane == 0 && n_rows > 0) arm((slot >> 1) ^ 1);
+            uint32_t ok;                                         // wait for this stage (compiler-visible loop + reconvergence)
             do {
                 asm volatile("{\n .reg .pred P1;\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }"
-                             : "=r"(ok) : "r"(rbar + 8u * slot), "r"(par) : "memory");
+                             : "=r"(ok) : "r"(rbar + 4u * (uint32_t)slot), "r"(par) : "memory");
             } while (!ok);
             __syncwarp();
         }
         const uint32_t ca = ring + (uint32_t)slot * OREC_BYTES + 4u * lane;
         const int cam = lds_s32(ca);
         const double w = lds_f64(ca + 128u + 4u * lane);
+        if (++slot == PR) { slot = 0; par ^= 1u; }
         const bool last = (--rows_left == 0);                    // warp-uniform
         TabRow o;
-        if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
-        if (++slot == PR) { slot = 0; par ^= 1u; }
+#ifdef B200BA_PT_REQ_EARLY
         double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
         if (last) request(Vi, Xn);
+        if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
+#else
+        if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
+        double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};     // (leaving these uninitialised measured 6 us SLOWER)
+        if (last) request(Vi, Xn);
+#endif
         if (cam >= 0) tab_row_bwd(o, u0, u1, u2);
         if (last && !finish(Vi, Xn)) return;
     }
