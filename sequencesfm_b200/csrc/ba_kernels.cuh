@@ -1351,13 +1351,23 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     const int e = blockIdx.x * STEP_BLOCK + threadIdx.x, n6 = 6 * d.N;
     const bool on = e < n6;
     const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;    // lc: first thread of this camera inside the block
-    double pe = on ? d.p[e] : 0.0;
+    // Every load whose address does not depend on this step's scalars is issued up front (U row, M^-1 row, x, r, segment
+    // range): the kernel is a chain of dependent L2 round trips with almost no parallelism, so overlapping them is what counts.
+    double pe = 0.0, xe0 = 0.0, re0 = 0.0, urow[6] = {0, 0, 0, 0, 0, 0}, mrow[6] = {0, 0, 0, 0, 0, 0};
+    int sg0 = 0, sg1 = 0;
+    if (on) {
+        pe = d.p[e]; xe0 = d.x[e]; re0 = d.r[e];
+        if (sums_ready != 1) { sg0 = d.cam_seg_beg[i]; sg1 = d.cam_seg_beg[i + 1]; }
+        const double* ur = d.U + 36 * (size_t)i + 6 * a; const double* mr = d.Minv + 36 * (size_t)i + 6 * a;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { urow[c] = ur[c]; mrow[c] = mr[c]; }
+    }
     sv[threadIdx.x] = pe;
     __syncthreads();
     double q = 0, s = 0;
     if (on) {
         if (sums_ready == 1) s = d.ar_q[e];
-        else for (int sg = d.cam_seg_beg[i]; sg < d.cam_seg_beg[i + 1]; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + a];
+        else for (int sg = sg0; sg < sg1; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + a];
     }
     unsigned long long coll = 0;
     if (sums_ready == 2) {
@@ -1370,7 +1380,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
         p2p_wait_all(d.p2p, coll);
         if (on) s = p2p_sum(d.p2p, coll, (size_t)e);
     }
-    if (on) q = lam * pe + matvec6_row(d.U + 36 * (size_t)i, sv + lc, a) - s;
+    if (on) q = lam * pe + (urow[0] * sv[lc] + urow[1] * sv[lc + 1] + urow[2] * sv[lc + 2] + urow[3] * sv[lc + 3] + urow[4] * sv[lc + 4] + urow[5] * sv[lc + 5]) - s;
     double bp = block_sum<STEP_BLOCK>(pe * q, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_pq[blockIdx.x] = bp;
     grid.sync();
@@ -1381,11 +1391,11 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     }
     const double alpha = rz / pq;
     double re = 0, xe = 0;
-    if (on) { xe = d.x[e] + alpha * pe; re = d.r[e] - alpha * q; d.x[e] = xe; d.r[e] = re; }
+    if (on) { xe = xe0 + alpha * pe; re = re0 - alpha * q; d.x[e] = xe; d.r[e] = re; }
     __syncthreads();
     sv[threadIdx.x] = re;
     __syncthreads();
-    double z = on ? matvec6_row(d.Minv + 36 * (size_t)i, sv + lc, a) : 0.0;
+    double z = on ? (mrow[0] * sv[lc] + mrow[1] * sv[lc + 1] + mrow[2] * sv[lc + 2] + mrow[3] * sv[lc + 3] + mrow[4] * sv[lc + 4] + mrow[5] * sv[lc + 5]) : 0.0;
     double br = block_sum<STEP_BLOCK>(re * z, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_rz[blockIdx.x] = br;
     grid.sync();
