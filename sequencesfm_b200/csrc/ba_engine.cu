@@ -166,7 +166,7 @@ int allreduce(b200ba_handle* h, double* buf, size_t count, int need = 0)
 int enqueue_linearize(b200ba_handle* h)
 {
     Dev& d = h->d;
-    if (h->use_tab) LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
+    LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
     LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
     LAUNCH(k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
@@ -1087,12 +1087,15 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
     CU(cudaMemcpy(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.p, x, sizeof(double) * n6, cudaMemcpyHostToDevice));
     LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
-    if (h->use_tab) {
-        // exercise the shared-memory-table sweep: scatter x into the packed table's p-slots
+    {
+        // both by-point sweeps read the direction from the packed table: scatter x into its p-slots
+        CU(cudaStreamSynchronize(h->stream));
         std::vector<double> tab((size_t)N * TAB_STRIDE);
         CU(cudaMemcpy(tab.data(), d.ptab, sizeof(double) * tab.size(), cudaMemcpyDeviceToHost));
         for (int i = 0; i < N; ++i) for (int a = 0; a < 6; ++a) tab[(size_t)i * TAB_STRIDE + 7 + a] = x[6 * (size_t)i + a];
         CU(cudaMemcpy(d.ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    }
+    if (h->use_tab && getenv("B200BA_DEBUG_GENERIC") == nullptr) {
         k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d);
         h->launches++;
     } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);

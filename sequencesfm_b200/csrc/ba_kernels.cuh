@@ -741,6 +741,44 @@ __global__ void __launch_bounds__(128) k_precond_invert(Dev d, int precond)
     if (!ok) st->solve_ok = 0;
 }
 
+// one observation of the by-point CG sweep against the packed camera table [quaternion 4 | T 3 | p 6 | pad]
+struct TabRow { double h0, h1, h2, qw, qx, qy, qz; };
+// first half of a row body: forward rotation, projection Jacobian, t = A~ p, h = P~^t t  (table fields die here)
+// GLOBAL = false: the table lives in shared memory (k_cg_point_pass_tab); true: read-only global loads (problems whose
+// camera table does not fit one SM's shared memory: 7 x LDG.128 instead of the 9 of [R|T] + p)
+template <bool GLOBAL>
+__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
+{
+    const double2* t = tab + 7 * cam;
+    double2 a0, a1, a2, a3, a4, a5, a6;
+    if (GLOBAL) { a0 = __ldg(t); a1 = __ldg(t + 1); a2 = __ldg(t + 2); a3 = __ldg(t + 3); a4 = __ldg(t + 4); a5 = __ldg(t + 5); a6 = __ldg(t + 6); }
+    else { a0 = t[0]; a1 = t[1]; a2 = t[2]; a3 = t[3]; a4 = t[4]; a5 = t[5]; a6 = t[6]; }
+    const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
+    // r = R X by the quaternion sandwich  r = X + 2 (qw t + qv x t),  t = qv x X   (no 3x3 matrix in registers)
+    const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];      // t = qv x X
+    const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);                                         // r = X + 2 (qw t + qv x t)
+    const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
+    const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
+    const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
+    const double iz = fast_rcp(z);
+    const double wf = w * in.k00 * iz;
+    const double pa = wf, pb = -wf * x * iz, pc = in.ar * wf, pd = -in.ar * wf * y * iz;
+    // t = A~ p,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x)
+    const double s0 = a3.y + (a5.y * r2 - a6.x * r1);
+    const double s1 = a4.x + (a6.x * r0 - a5.x * r2);
+    const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
+    const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
+    o.h0 = pa * t0; o.h1 = pc * t1; o.h2 = pb * t0 + pd * t1;
+    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz;
+}
+// second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion
+__device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
+{
+    const double gx = o.qz * o.h1 - o.qy * o.h2, gy = o.qx * o.h2 - o.qz * o.h0, gz = o.qy * o.h0 - o.qx * o.h1;   // g = -qv x h
+    u0 += fma(2.0, o.qw * gx + (o.qz * gy - o.qy * gz), o.h0);
+    u1 += fma(2.0, o.qw * gy + (o.qx * gz - o.qz * gx), o.h1);
+    u2 += fma(2.0, o.qw * gz + (o.qy * gx - o.qx * gy), o.h2);
+}
 // ------------------------------------------------------------------------------------------------------
 // K8  cg_point_pass: v_j = (V+lambda I)^-1 u_j with
 //       MODE 0: u_j = sum_k W_k^t p_i(k) = sum_k R^t P~^t P~ (pt + pw x r)     (first half of S p)
@@ -765,8 +803,17 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
         if (MODE != 1) load3p(d.X[cur], j, X);
         if (MODE != 0) load3p(d.gp, j, g);
         int k0, deg; slice_of(d, j, k0, deg);
-        if (MODE != 1) {
-            const double* vec = (MODE == 0) ? d.p : d.x;
+        if (MODE == 0) {                                         // packed table [quat, T, p] from global memory (L2-resident)
+            const double2* tabg = reinterpret_cast<const double2*>(d.ptab);
+            for (int s = 0, k = k0; s < deg; ++s, k += 32) {
+                const int i = __ldg(o_cam_ptr(d, k));
+                if (i < 0) continue;
+                TabRow o; tab_row_fwd<true>(tabg, i, __ldg(o_w_ptr(d, k)), X, d.in, o);
+                tab_row_bwd(o, u[0], u[1], u[2]);
+            }
+        }
+        if (MODE == 2) {
+            const double* vec = d.x;
             const double* rt = d.rt[cur];
             for (int s = 0, k = k0; s < deg; ++s, k += 32) {
                 int i = __ldg(o_cam_ptr(d, k));
@@ -1165,38 +1212,6 @@ __global__ void __launch_bounds__(256) k_fill_rows(Dev d, const int2* __restrict
 //      finished is requested in the middle of the slice's last row body (after the table fields are dead, before the
 //      back-rotation), the next slice's X one slice ahead; the warp's header is one 32-byte record and all start-up
 //      loads are issued BEFORE waiting for the TMA'd camera table.
-struct TabRow { double h0, h1, h2, qw, qx, qy, qz; };
-// first half of a row body: forward rotation, projection Jacobian, t = A~ p, h = P~^t t  (table fields die here)
-__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
-{
-    const double2* t = tab + 7 * cam;
-    const double2 a0 = t[0], a1 = t[1], a2 = t[2], a3 = t[3], a4 = t[4], a5 = t[5], a6 = t[6];
-    const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
-    // r = R X by the quaternion sandwich  r = X + 2 (qw t + qv x t),  t = qv x X   (no 3x3 matrix in registers)
-    const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];      // t = qv x X
-    const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);                                         // r = X + 2 (qw t + qv x t)
-    const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
-    const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
-    const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
-    const double iz = fast_rcp(z);
-    const double wf = w * in.k00 * iz;
-    const double pa = wf, pb = -wf * x * iz, pc = in.ar * wf, pd = -in.ar * wf * y * iz;
-    // t = A~ p,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x)
-    const double s0 = a3.y + (a5.y * r2 - a6.x * r1);
-    const double s1 = a4.x + (a6.x * r0 - a5.x * r2);
-    const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
-    const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
-    o.h0 = pa * t0; o.h1 = pc * t1; o.h2 = pb * t0 + pd * t1;
-    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz;
-}
-// second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion
-__device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
-{
-    const double gx = o.qz * o.h1 - o.qy * o.h2, gy = o.qx * o.h2 - o.qz * o.h0, gz = o.qy * o.h0 - o.qx * o.h1;   // g = -qv x h
-    u0 += fma(2.0, o.qw * gx + (o.qz * gy - o.qy * gz), o.h0);
-    u1 += fma(2.0, o.qw * gy + (o.qx * gz - o.qz * gx), o.h1);
-    u2 += fma(2.0, o.qw * gz + (o.qy * gx - o.qx * gy), o.h2);
-}
 constexpr int PR = 4;                                            // rows of the point-order stream staged per warp: 2 stages x 2 rows
 constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * (PR * OREC_BYTES + 2 * 8);   // rings + their two mbarriers per warp
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -1319,9 +1334,9 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
 #ifdef B200BA_PT_REQ_EARLY
         double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
         if (last) request(Vi, Xn);
-        if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
+        if (cam >= 0) tab_row_fwd<false>(tab, cam, w, X, d.in, o);
 #else
-        if (cam >= 0) tab_row_fwd(tab, cam, w, X, d.in, o);
+        if (cam >= 0) tab_row_fwd<false>(tab, cam, w, X, d.in, o);
         double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};     // (leaving these uninitialised measured 6 us SLOWER)
         if (last) request(Vi, Xn);
 #endif
