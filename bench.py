@@ -335,7 +335,19 @@ def main() -> int:
                 v = q.lm_iterations / q.seconds if q.seconds > 0 else 0.0
                 cpu = {"value": v, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "reference",
                        "sample": f"PBA multicore CPU --double -schur -lmi {lmi} on the same {args.shape} problem: {q.lm_iterations} LM iterations, "
-                                 f"{q.cg_iterations} CG steps in {q.seconds:.2f} s (PBA's own optimisation timer)"}
+                                 f"{q.cg_iterations} CG steps in {q.seconds:.2f} s (PBA's own optimisation timer; PBA stops its PCG after "
+                                 f"{q.cg_iterations // max(1, q.lm_iterations)} steps per iteration, this engine runs {CG_STEPS})"}
+                # the live engine of the reference (SSBA-3.0, single thread, sparse LDL^t) cannot factor a Venice-sized system;
+                # it is timed beside on the largest shape it finishes in seconds, with this engine on the same problem
+                if refs.have_ssba():
+                    small = make_problem("ladybug", args.seed)
+                    t0 = time.perf_counter(); sr = refs.ssba_adjust(small, max_iterations=10, trace=False); dt = time.perf_counter() - t0
+                    with binding.Engine(device=local_rank, max_iterations=10) as es:
+                        es.set_problem_from(small)
+                        t0 = time.perf_counter(); er = es.solve(); de = time.perf_counter() - t0
+                    cpu["ssba_ladybug"] = {"shape": f"ladybug {small.N}/{small.M}/{small.K}", "ssba_lm_iterations_per_s": sr.iterations / (sr.seconds if sr.seconds > 0 else dt),
+                                           "ssba_cores": 1, "this_engine_lm_iterations_per_s": er.iterations / de,
+                                           "note": "SSBA-3.0 minimize() (reference live path, exact sparse LDL^t step) vs b200ba_solve wall time, 10 LM iterations"}
             else:
                 from oracle import oracle as orc
                 t0 = time.perf_counter()

@@ -8,6 +8,7 @@
 #include "../../include/b200ba.h"
 #include "ba_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -104,7 +105,9 @@ struct b200ba_handle {
     Dev d{};
     DBuf<double> rt0, rt1, U, gc, Minv, x, r, z, p, q, ar_lin, ar_q, ar_sd, ar_dec, X0, X1, V, gp, Vinv, v, seg_part, pt_part, trace;
     DBuf<double2> o_meas, c_meas;
-    DBuf<int> o_cam, slice_base, slice_deg, row_j, cam_seg_beg;
+    DBuf<int> o_cam, slice_base, slice_deg, cam_seg_beg, sort_vals, row_tab;
+    DBuf<unsigned long long> sort_keys;
+    DBuf<unsigned char> sort_tmp;
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
     DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
@@ -359,7 +362,7 @@ int b200ba_default_options(b200ba_options* o)
     o->max_iterations = 50; o->min_iterations = 10; o->tau = 1e-3; o->inlier_px = 2.0;
     o->gradient_threshold = 1e-8; o->update_threshold = 1e-8;
     o->round_pixels = 1; o->normalize = 1; o->fix_first_camera = 0; o->discard_converged = 1;
-    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5; o->lane_window = 64;
+    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5; o->lane_window = 32;
     return 0;
 }
 
@@ -415,7 +418,7 @@ void b200ba_destroy(b200ba_handle* h)
     h->z.release(); h->p.release(); h->q.release(); h->ar_lin.release(); h->ar_q.release(); h->ar_sd.release(); h->ar_dec.release();
     h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_rec.release();
     h->seg_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
-    h->row_j.release(); h->row_hdr.release(); h->c_rec.release(); h->cam_seg_beg.release();
+    h->sort_keys.release(); h->sort_vals.release(); h->row_tab.release(); h->sort_tmp.release(); h->row_hdr.release(); h->c_rec.release(); h->cam_seg_beg.release();
     h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->part_pq.release(); h->part_rz.release();
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->arena.base) cudaFree(h->arena.base);
@@ -632,47 +635,33 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
     h->num_sms = n_sm;
-    // camera order: stable counting sort by camera over the NEW point order (parallel: per-thread histograms over
-    // contiguous blocks of slices, exclusive scan over threads, then placement).  Every camera's run is padded to whole
-    // ROWS of 32 observations (point index -1 = padding); see REC_* in ba_kernels.cuh.
-    std::vector<int> row_beg((size_t)N + 1, 0);
-    std::unique_ptr<int[]> row_j;
-    std::unique_ptr<double2[]> c_meas;
+    // camera order.  The host only COUNTS (per-camera histogram -> rows, first sorted position, segments); the row records
+    // themselves are built on the device from the uploaded point-order arrays (radix sort by (camera, point), see k_rows_*):
+    // every camera's run is padded to whole ROWS of 32 observations (point index -1 = padding); see REC_* in ba_kernels.cuh.
+    std::vector<int> row_beg((size_t)N + 1, 0), cam_first((size_t)N + 1, 0);
     int n_rows = 0;
     {
         std::vector<std::vector<int>> cnt((size_t)T, std::vector<int>((size_t)N, 0));
+        parallel_for(T, [&](int t, int nt) {
+            const long long k0 = (long long)K * t / nt, k1 = (long long)K * (t + 1) / nt;
+            std::vector<int>& c = cnt[t];
+            for (long long k = k0; k < k1; ++k) c[obs_cam[k]]++;
+        });
+        for (int i = 0; i < N; ++i) {
+            int c = 0; for (int t = 0; t < T; ++t) c += cnt[t][i];
+            cam_first[i + 1] = cam_first[i] + c;
+            row_beg[i + 1] = row_beg[i] + (c + 31) / 32;
+        }
+        n_rows = row_beg[N];
         auto slice_range = [&](int t, int nt, int& g0, int& g1) { g0 = (int)((long long)n_slices * t / nt); g1 = (int)((long long)n_slices * (t + 1) / nt); };
         parallel_for(T, [&](int t, int nt) {
             int g0, g1; slice_range(t, nt, g0, g1);
-            std::vector<int>& c = cnt[t];
-            for (int jn = 32 * g0; jn < std::min(M, 32 * g1); ++jn) {
-                const int j = h->orig_of_new[jn];
-                for (int k = pstart[j]; k < pstart[j + 1]; ++k) c[obs_cam[k]]++;
-            }
-        });
-        for (int i = 0; i < N; ++i) {
-            int run = 32 * row_beg[i];
-            for (int t = 0; t < T; ++t) { int c = cnt[t][i]; cnt[t][i] = run; run += c; }
-            row_beg[i + 1] = row_beg[i] + (run - 32 * row_beg[i] + 31) / 32;
-        }
-        n_rows = row_beg[N];
-        const size_t ne = 32 * (size_t)std::max(n_rows, 1);
-        row_j.reset(new int[ne]); c_meas.reset(new double2[ne]);
-        parallel_for(T, [&](int t, int nt) {
-            const size_t e0 = ne * t / nt, e1 = ne * (t + 1) / nt;
-            for (size_t e = e0; e < e1; ++e) { row_j[e] = -1; c_meas[e] = make_double2(0.0, 0.0); }
-        });
-        parallel_for(T, [&](int t, int nt) {
-            int g0, g1; slice_range(t, nt, g0, g1);
-            std::vector<int>& fill = cnt[t];
             for (int e = slice_base[g0]; e < slice_base[g1]; ++e) { o_cam_p[e] = -1; o_meas_p[e] = make_double2(0.0, 0.0); }
             for (int jn = 32 * g0; jn < std::min(M, 32 * g1); ++jn) {
                 const int j = h->orig_of_new[jn], g = jn >> 5, l = jn & 31;
                 for (int k = pstart[j], sl = 0; k < pstart[j + 1]; ++k, ++sl) {
                     const int kk = slice_base[g] + 32 * sl + l;
                     o_cam_p[kk] = obs_cam[k]; o_meas_p[kk] = meas[k]; h->entry_of_obs[k] = kk;
-                    const int dst = fill[obs_cam[k]]++;
-                    row_j[dst] = jn; c_meas[dst] = meas[k];
                 }
             }
         });
@@ -695,7 +684,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     }
     int n_pt_blocks = std::max(1, cdiv(M, PT_BLOCK));
 
-    lap("SELL + camera rows build");
+    lap("SELL placement + camera counts");
 
     // ---- device allocation ----
     size_t n6 = 6 * (size_t)N;
@@ -716,7 +705,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->V.take(A, 6 * Mp); h->Vinv.take(A, 6 * Mp); h->gp.take(A, 4 * Mp); h->v.take(A, 4 * Mp);
         h->o_rec.take(A, (Kpp / 32 + 1) * OREC_BYTES); h->o_meas.take(A, Kpp); h->c_meas.take(A, 32 * Rp);
         h->o_cam.take(A, Kpp); h->slice_base.take(A, (size_t)n_slices + 1); h->slice_deg.take(A, (size_t)n_slices);
-        h->c_rec.take(A, Rp * REC_BYTES + 16); h->row_j.take(A, 32 * Rp); h->row_hdr.take(A, Rp);
+        h->c_rec.take(A, Rp * REC_BYTES + 16); h->row_hdr.take(A, Rp);
+        h->sort_keys.take(A, 2 * Kpp); h->sort_vals.take(A, 2 * Kpp); h->row_tab.take(A, 2 * ((size_t)N + 1)); h->sort_tmp.take(A, (size_t)16 << 20);
         h->cam_seg_beg.take(A, (size_t)N + 1);
         h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)n_pt_blocks);
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
@@ -730,11 +720,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     CU(cudaMemsetAsync(h->arena.base, 0, h->arena.cap, s));
     CU(cudaMemcpyAsync(h->o_meas.p, o_meas_p.get(), sizeof(double2) * Kpp, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->o_cam.p, o_cam_p.get(), sizeof(int) * Kpp, cudaMemcpyHostToDevice, s));
-    if (n_rows) {
-        CU(cudaMemcpyAsync(h->c_meas.p, c_meas.get(), sizeof(double2) * 32 * (size_t)n_rows, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->row_j.p, row_j.get(), sizeof(int) * 32 * (size_t)n_rows, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->row_hdr.p, row_hdr.data(), sizeof(int2) * (size_t)n_rows, cudaMemcpyHostToDevice, s));
-    }
+    if (n_rows) CU(cudaMemcpyAsync(h->row_hdr.p, row_hdr.data(), sizeof(int2) * (size_t)n_rows, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->slice_base.p, slice_base.data(), sizeof(int) * ((size_t)n_slices + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->slice_deg.p, slice_deg.data(), sizeof(int) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->cam_seg_beg.p, cam_seg_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
@@ -743,8 +729,23 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         k_fill_orows<<<cdiv(Kp / 32, 8), 256, 0, s>>>(dr, h->o_cam.p, Kp / 32);
     }
     if (n_rows) {
-        Dev dr{}; dr.n_rows = n_rows; dr.c_rec = h->c_rec.p;
-        k_fill_rows<<<cdiv(n_rows, 8), 256, 0, s>>>(dr, h->row_hdr.p, h->row_j.p);
+        // camera-order row records on the device: keys, radix sort by (camera, point), scatter into the rows
+        Dev dr{}; dr.N = N; dr.M = M; dr.K = K; dr.n_rows = n_rows; dr.n_slices = n_slices; dr.c_rec = h->c_rec.p; dr.c_meas = h->c_meas.p;
+        dr.o_meas = h->o_meas.p; dr.slice_base = h->slice_base.p; dr.slice_deg = h->slice_deg.p;
+        CU(cudaMemcpyAsync(h->row_tab.p, cam_first.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->row_tab.p + N + 1, row_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+        k_fill_rows<<<cdiv(n_rows, 8), 256, 0, s>>>(dr, h->row_hdr.p);
+        k_rows_keys<<<cdiv(32 * n_slices, PT_BLOCK), PT_BLOCK, 0, s>>>(dr, h->o_cam.p, h->sort_keys.p, h->sort_vals.p);
+        cub::DoubleBuffer<unsigned long long> kb(h->sort_keys.p, h->sort_keys.p + Kpp);
+        cub::DoubleBuffer<int> vb(h->sort_vals.p, h->sort_vals.p + Kpp);
+        int end_bit = 33; while (end_bit < 64 && ((unsigned long long)N >> (end_bit - 32)) != 0) ++end_bit;
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, Kp, 0, end_bit, s));
+        void* tmp = h->sort_tmp.p; bool own_tmp = false;
+        if (tmp_bytes > ((size_t)16 << 20)) { CU(cudaMalloc(&tmp, tmp_bytes)); own_tmp = true; }
+        CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kb, vb, Kp, 0, end_bit, s));
+        k_rows_fill<<<cdiv(K, 256), 256, 0, s>>>(dr, kb.Current(), vb.Current(), h->row_tab.p, h->row_tab.p + N + 1);
+        if (own_tmp) { CU(cudaStreamSynchronize(s)); cudaFree(tmp); }
     }
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());
@@ -891,7 +892,7 @@ int b200ba_begin(b200ba_handle* h)
     CU(cudaMemcpyAsync(h->rt0.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->rt1.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->X0.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->X1.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->X1.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->X_init.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->rt_init.p, h->rt0.p, sizeof(double) * 12 * (size_t)N, cudaMemcpyDeviceToDevice, s));
     LMState st{};

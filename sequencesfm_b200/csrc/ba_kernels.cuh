@@ -1191,27 +1191,42 @@ __global__ void __launch_bounds__(256) k_fill_orows(Dev d, const int* __restrict
     reinterpret_cast<int*>(d.o_rec + (size_t)r * OREC_BYTES)[lane] = o_cam[32 * (size_t)r + lane];
 }
 
-// one warp per row: scatter the uploaded compact row table (header, 32 point indices) into the row records
-__global__ void __launch_bounds__(256) k_fill_rows(Dev d, const int2* __restrict__ row_hdr, const int* __restrict__ row_j)
+// ---- device-side build of the camera-order row records (set_problem) ----
+// Key of SELL entry e = (camera << 32 | new point index): a radix sort of the keys groups the observations by camera
+// in point order, exactly the order the row records want; padding entries get camera = N and sort to the end.
+__global__ void __launch_bounds__(PT_BLOCK) k_rows_keys(Dev d, const int* __restrict__ o_cam, unsigned long long* __restrict__ keys, int* __restrict__ vals)
+{
+    const int j = blockIdx.x * PT_BLOCK + threadIdx.x;
+    int k0, deg; slice_of(d, j, k0, deg);                        // warp-uniform trip count; lanes past M own only padding entries
+    for (int s = 0, k = k0; s < deg; ++s, k += 32) {
+        const int c = o_cam[k];
+        keys[k] = ((unsigned long long)(unsigned)(c >= 0 ? c : d.N) << 32) | (unsigned)j;
+        vals[k] = k;
+    }
+}
+// one warp per row: header + "no observation" in every lane (the sorted fill below overwrites the real ones)
+__global__ void __launch_bounds__(256) k_fill_rows(Dev d, const int2* __restrict__ row_hdr)
 {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (r >= d.n_rows) return;
     unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
     if (lane == 0) { const int2 h = row_hdr[r]; *reinterpret_cast<int4*>(rec + REC_HDR) = make_int4(h.x, h.y, 0, 0); }
-    reinterpret_cast<int*>(rec + REC_J)[lane] = row_j[32 * (size_t)r + lane];
+    reinterpret_cast<int*>(rec + REC_J)[lane] = -1;
+}
+// sorted position i (< K) -> lane (i - first[cam]) of the camera's rows: point index into the record, measurement beside it
+__global__ void __launch_bounds__(256) k_rows_fill(Dev d, const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                                   const int* __restrict__ cam_first, const int* __restrict__ row_beg)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.K) return;
+    const unsigned long long key = keys[i];
+    const int cam = (int)(key >> 32), jn = (int)(unsigned)key, e = vals[i];
+    const int rank = i - __ldg(cam_first + cam);
+    const int row = __ldg(row_beg + cam) + (rank >> 5), lane = rank & 31;
+    reinterpret_cast<int*>(d.c_rec + (size_t)row * REC_BYTES + REC_J)[lane] = jn;
+    d.c_meas[32 * (size_t)row + lane] = d.o_meas[e];
 }
 
-// K8'  cg_point_pass_tab: persistent (one 768-thread CTA per SM), camera table in shared memory, one thread per point.
-//      Computes v_j = (V+lambda I)^-1 sum_k W_k^t p_i(k)  (MODE 0 of k_cg_point_pass).
-//
-//      Each warp owns a CONTIGUOUS range of slices (balanced by rows on the host), so its o_cam / o_w rows form one
-//      contiguous stream.  THREE rows are always in flight in three fixed register pairs (c0,w0) (c1,w1) (c2,w2) that are
-//      consumed round-robin by a loop unrolled by three: ncu on the previous version (two pairs ROTATED through
-//      registers every row) showed 25 % of all stall samples on the rotation's moves, which have to wait for the
-//      in-flight load they copy - the effective prefetch distance was one row.  (V_j + lambda I)^-1 of the slice being
-//      finished is requested in the middle of the slice's last row body (after the table fields are dead, before the
-//      back-rotation), the next slice's X one slice ahead; the warp's header is one 32-byte record and all start-up
-//      loads are issued BEFORE waiting for the TMA'd camera table.
 constexpr int PR = 4;                                            // rows of the point-order stream staged per warp: 2 stages x 2 rows
 constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * (PR * OREC_BYTES + 2 * 8);   // rings + their two mbarriers per warp
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
