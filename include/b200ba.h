@@ -66,7 +66,7 @@ typedef struct b200ba_options {
     /* --- host interaction --- */
     int32_t poll_every;         /* copy the device status word back every n LM iterations (default 5)     */
     /* --- layout --- */
-    int32_t lane_window;        /* 32: candidate window of the bank-conflict-aware grouping of points into     */
+    int32_t lane_window;        /* 64: candidate window of the bank-conflict-aware grouping of points into     */
                                 /*     quarter-warps for the shared-memory camera table; 0 = keep input order  */
     int32_t reserved[6];
 } b200ba_options;

@@ -112,7 +112,8 @@ struct b200ba_handle {
     DBuf<unsigned char> c_rec, o_rec;
     DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
     DBuf<int> tab_wr;
-    std::vector<int> orig_of_new, entry_of_obs;      // SELL permutation (new point index -> caller's), obs -> padded entry
+    std::vector<int> orig_of_new;                    // SELL permutation (new point index -> caller's)
+    std::unique_ptr<int[]> entry_of_obs;             // obs -> padded SELL entry
     int Kp = 0;                                      // padded SELL entries
     int num_sms = 148, tab_grid = 0, step_grid = 0, cam_grid = 0;
     size_t tab_smem = 0;
@@ -362,7 +363,7 @@ int b200ba_default_options(b200ba_options* o)
     o->max_iterations = 50; o->min_iterations = 10; o->tau = 1e-3; o->inlier_px = 2.0;
     o->gradient_threshold = 1e-8; o->update_threshold = 1e-8;
     o->round_pixels = 1; o->normalize = 1; o->fix_first_camera = 0; o->discard_converged = 1;
-    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5; o->lane_window = 32;
+    o->cg_max_steps = 50; o->cg_rel_tol = 0.0; o->precond = 1; o->poll_every = 5; o->lane_window = 64;
     return 0;
 }
 
@@ -562,7 +563,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     for (int j = 0; j < M; ++j) bucket[maxdeg - (pstart[j + 1] - pstart[j]) + 1]++;
     for (int b = 0; b <= maxdeg; ++b) bucket[b + 1] += bucket[b];
     h->orig_of_new.assign((size_t)M, 0);
-    for (int j = 0; j < M; ++j) h->orig_of_new[bucket[maxdeg - (pstart[j + 1] - pstart[j])]++] = j;
+    std::vector<int> deg_new((size_t)std::max(M, 1));        // track length by NEW point index (sequential reads later on)
+    for (int j = 0; j < M; ++j) { const int dj = pstart[j + 1] - pstart[j]; const int pos = bucket[maxdeg - dj]++; h->orig_of_new[pos] = j; deg_new[pos] = dj; }
     // ---- bank-conflict-aware lane grouping (shared-memory camera table) ----
     // In k_cg_point_pass_tab the 8 lanes of a quarter-warp read the same 16-byte field of 8 different camera records;
     // the bank group of a record is (camera index mod 8), so random cameras collide 2.6-fold on average (ncu: 63 % of the
@@ -572,10 +574,24 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     if (o.lane_window > 0 && K > 0 && getenv("B200BA_NO_LANE_OPT") == nullptr) {
         const int W = std::min(o.lane_window, 1024);
         std::vector<int>& ord = h->orig_of_new;
-        auto degree = [&](int jn) { const int j = ord[jn]; return pstart[j + 1] - pstart[j]; };
+        auto degree = [&](int jn) { return deg_new[jn]; };
+        // one-hot key of a point: bit (8 slot + camera mod 8), slots 0-7 in lo, 8-15 in hi.  A candidate's cost against the
+        // group built so far is the number of slots whose bank group is already taken: popcount(key & used).  The keys are
+        // built in the caller's point order (one streaming pass over obs_cam) and gathered per run: building them per run
+        // meant five dependent cache misses per point and 20 ms.
+        struct Key2 { unsigned long long lo, hi; };
+        std::unique_ptr<Key2[]> pkey(new Key2[(size_t)std::max(M, 1)]);
+        parallel_for(T, [&](int t, int nt) {
+            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
+            for (int j = j0; j < j1; ++j) {
+                Key2 kq = {0ull, 0ull}; const int* oc = obs_cam + pstart[j]; const int ds = std::min(pstart[j + 1] - pstart[j], 16);
+                for (int sl = 0; sl < ds; ++sl) { const unsigned long long bit = 1ull << (8 * (sl & 7) + (oc[sl] & 7)); if (sl < 8) kq.lo |= bit; else kq.hi |= bit; }
+                pkey[j] = kq;
+            }
+        });
         parallel_for(T, [&](int t, int nt) {
             long long a = (long long)(M / 32) * t / nt * 32, b = (t + 1 == nt) ? M : (long long)(M / 32) * (t + 1) / nt * 32;
-            std::vector<int> run, out, pool; std::vector<unsigned long long> key;
+            std::vector<int> run, out, pool; std::vector<Key2> key;
             for (long long r0 = a; r0 < b;) {
                 const int dg = degree((int)r0);
                 long long r1 = r0; while (r1 < b && degree((int)r1) == dg) ++r1;
@@ -583,31 +599,28 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
                 if (n >= 16 && ds > 0) {
                     run.assign(ord.begin() + r0, ord.begin() + r1);
                     key.resize(n);
-                    for (int q = 0; q < n; ++q) { unsigned long long kq = 0; const int j = run[q]; for (int sl = 0; sl < ds; ++sl) kq |= (unsigned long long)(obs_cam[pstart[j] + sl] & 7) << (3 * sl); key[q] = kq; }
+                    for (int q = 0; q < n; ++q) key[q] = pkey[run[q]];
                     out.clear(); out.reserve(n); pool.clear();
                     int next = 0;
                     while (next < n && (int)pool.size() < W) pool.push_back(next++);
-                    unsigned char cnt[16][8]; unsigned char mx[16];
                     int group = (8 - (int)(r0 & 7)) & 7;          // first (partial) group completes the quarter-warp the run starts in
                     if (group == 0) group = 8;
                     for (; !pool.empty(); group = 8) {
-                        memset(cnt, 0, sizeof cnt); memset(mx, 0, sizeof mx);
+                        Key2 used = {0ull, 0ull};
                         for (int g8 = 0; g8 < group && !pool.empty(); ++g8) {
                             int best = 0;
                             if (g8 > 0) {
                                 int best_score = 1 << 30;
-                                for (int c = 0; c < (int)pool.size(); ++c) {
-                                    const unsigned long long kq = key[pool[c]];
-                                    int inc = 0, sum = 0;
-                                    for (int sl = 0; sl < ds; ++sl) { const int c1 = cnt[sl][(kq >> (3 * sl)) & 7] + 1; inc += c1 > mx[sl] ? c1 - mx[sl] : 0; sum += c1; }
-                                    const int score = inc * 256 + sum;
-                                    if (score < best_score) { best_score = score; best = c; if (inc == 0 && sum == ds) break; }
+                                const int np = (int)pool.size();
+                                for (int c = 0; c < np; ++c) {
+                                    const Key2& kq = key[pool[c]];
+                                    const int score = __builtin_popcountll(kq.lo & used.lo) + __builtin_popcountll(kq.hi & used.hi);
+                                    if (score < best_score) { best_score = score; best = c; if (score == 0) break; }
                                 }
                             }
                             const int q = pool[best];
-                            pool.erase(pool.begin() + best);
-                            const unsigned long long kq = key[q];
-                            for (int sl = 0; sl < ds; ++sl) { unsigned char& c = cnt[sl][(kq >> (3 * sl)) & 7]; ++c; if (c > mx[sl]) mx[sl] = c; }
+                            pool[best] = pool.back(); pool.pop_back();
+                            used.lo |= key[q].lo; used.hi |= key[q].hi;
                             out.push_back(run[q]);
                             if (next < n) pool.push_back(next++);
                         }
@@ -623,14 +636,14 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     std::vector<int> slice_base((size_t)n_slices + 1, 0), slice_deg((size_t)n_slices, 0);
     for (int g = 0; g < n_slices; ++g) {
         int j0 = 32 * g;
-        int dg = j0 < M ? pstart[h->orig_of_new[j0] + 1] - pstart[h->orig_of_new[j0]] : 0;
+        int dg = j0 < M ? deg_new[j0] : 0;       // (the grouping permutes only points of equal track length)
         slice_deg[g] = dg; slice_base[g + 1] = slice_base[g] + 32 * dg;
     }
     const int Kp = slice_base[n_slices];
     h->Kp = Kp;
     std::unique_ptr<int[]> o_cam_p(new int[(size_t)std::max(Kp, 1)]);
     std::unique_ptr<double2[]> o_meas_p(new double2[(size_t)std::max(Kp, 1)]);
-    h->entry_of_obs.resize((size_t)K);
+    h->entry_of_obs.reset(new int[(size_t)std::max(K, 1)]);
     int smem_optin = 0, n_sm = 0;
     CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
@@ -828,7 +841,9 @@ int b200ba_begin(b200ba_handle* h)
     CU(cudaSetDevice(h->device));
     const int N = h->N, M = h->M;
     const b200ba_options& o = h->opt;
-    std::vector<double> cam(h->h_cam), X4(4 * (size_t)std::max(M, 1), 0.0);
+    std::vector<double> cam(h->h_cam);
+    std::unique_ptr<double[]> X4(new double[4 * (size_t)std::max(M, 1)]);      // no zero-fill of 32 MB: the pad is written with the point
+    if (M == 0) X4[0] = X4[1] = X4[2] = X4[3] = 0.0;
     const double* P0 = h->h_pts.data();
     h->mean[0] = h->mean[1] = h->mean[2] = 0; h->scale = 1.0;
     std::vector<double> C(3 * (size_t)N);
@@ -866,12 +881,12 @@ int b200ba_begin(b200ba_handle* h)
         for (int i = 0; i < N; ++i) { for (int c = 0; c < 3; ++c) C[3 * (size_t)i + c] *= rs; set_camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i); }
         parallel_for(T, [&](int t, int nt) {
             const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
-            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs; }
+            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs; X4[4 * (size_t)jn + 3] = 0.0; }
         });
     } else {
         parallel_for(T, [&](int t, int nt) {
             const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
-            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = P0[3 * (size_t)j + c]; }
+            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = P0[3 * (size_t)j + c]; X4[4 * (size_t)jn + 3] = 0.0; }
         });
     }
     // cached parameter length (v3d_metricbundle.h:37-45), after normalisation (summed in the caller's point order)
@@ -891,7 +906,7 @@ int b200ba_begin(b200ba_handle* h)
     cudaStream_t s = h->stream;
     CU(cudaMemcpyAsync(h->rt0.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->rt1.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->X0.p, X4.data(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->X0.p, X4.get(), sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->X1.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->X_init.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->rt_init.p, h->rt0.p, sizeof(double) * 12 * (size_t)N, cudaMemcpyDeviceToDevice, s));
@@ -1024,8 +1039,8 @@ int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts)
             }
     }
     if (pts && M) {
-        std::vector<double> X4(4 * (size_t)M);
-        CU(cudaMemcpy(X4.data(), h->d.X[cur], sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
+        std::unique_ptr<double[]> X4(new double[4 * (size_t)M]);
+        CU(cudaMemcpy(X4.get(), h->d.X[cur], sizeof(double) * 4 * (size_t)M, cudaMemcpyDeviceToHost));
         const int T = (M > 200000) ? (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
         const bool nrm = h->opt.normalize != 0;
         parallel_for(T, [&](int t, int nt) {
