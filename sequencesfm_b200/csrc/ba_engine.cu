@@ -554,17 +554,47 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     });
     lap("validate + measurements");
     // ---- by-point layout: SELL-32, points sorted by track length (descending, stable) ----
+    // (threaded: obs_pt is non-decreasing, so pstart is read off the positions where it changes; the stable counting sort
+    // by track length uses per-thread histograms over contiguous point ranges)
     std::vector<int> pstart((size_t)M + 1, 0);
-    for (int k = 0; k < K; ++k) pstart[obs_pt[k] + 1]++;
-    for (int j = 0; j < M; ++j) pstart[j + 1] += pstart[j];
+    pstart[M] = K;
+    parallel_for(T, [&](int t, int nt) {
+        const long long k0 = (long long)K * t / nt, k1 = (long long)K * (t + 1) / nt;
+        for (long long k = k0; k < k1; ++k) {
+            const int ja = (k == 0) ? -1 : obs_pt[k - 1], jb = obs_pt[k];
+            for (int j = ja + 1; j <= jb; ++j) pstart[j] = (int)k;          // points ja+1 .. jb start at k (empty ones included)
+        }
+        if (t + 1 == nt) for (int j = (K ? obs_pt[K - 1] : -1) + 1; j < M; ++j) pstart[j] = K;
+    });
     int maxdeg = 0;
-    for (int j = 0; j < M; ++j) maxdeg = std::max(maxdeg, pstart[j + 1] - pstart[j]);
-    std::vector<int> bucket((size_t)maxdeg + 2, 0);
-    for (int j = 0; j < M; ++j) bucket[maxdeg - (pstart[j + 1] - pstart[j]) + 1]++;
-    for (int b = 0; b <= maxdeg; ++b) bucket[b + 1] += bucket[b];
+    {
+        std::vector<int> mx((size_t)T, 0);
+        parallel_for(T, [&](int t, int nt) {
+            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
+            int m = 0; for (int j = j0; j < j1; ++j) m = std::max(m, pstart[j + 1] - pstart[j]);
+            mx[t] = m;
+        });
+        for (int t = 0; t < T; ++t) maxdeg = std::max(maxdeg, mx[t]);
+    }
     h->orig_of_new.assign((size_t)M, 0);
     std::vector<int> deg_new((size_t)std::max(M, 1));        // track length by NEW point index (sequential reads later on)
-    for (int j = 0; j < M; ++j) { const int dj = pstart[j + 1] - pstart[j]; const int pos = bucket[maxdeg - dj]++; h->orig_of_new[pos] = j; deg_new[pos] = dj; }
+    {
+        const size_t nb = (size_t)maxdeg + 1;
+        std::vector<int> hist((size_t)T * nb, 0);                // hist[t][maxdeg - degree]
+        parallel_for(T, [&](int t, int nt) {
+            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
+            int* hh = hist.data() + (size_t)t * nb;
+            for (int j = j0; j < j1; ++j) hh[maxdeg - (pstart[j + 1] - pstart[j])]++;
+        });
+        int run = 0;
+        for (size_t bk = 0; bk < nb; ++bk) for (int t = 0; t < T; ++t) { int c = hist[(size_t)t * nb + bk]; hist[(size_t)t * nb + bk] = run; run += c; }
+        parallel_for(T, [&](int t, int nt) {
+            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
+            int* hh = hist.data() + (size_t)t * nb;
+            for (int j = j0; j < j1; ++j) { const int dj = pstart[j + 1] - pstart[j]; const int pos = hh[maxdeg - dj]++; h->orig_of_new[pos] = j; deg_new[pos] = dj; }
+        });
+    }
+    lap("point index + track-length sort");
     // ---- bank-conflict-aware lane grouping (shared-memory camera table) ----
     // In k_cg_point_pass_tab the 8 lanes of a quarter-warp read the same 16-byte field of 8 different camera records;
     // the bank group of a record is (camera index mod 8), so random cameras collide 2.6-fold on average (ncu: 63 % of the
