@@ -68,7 +68,12 @@ typedef struct b200ba_options {
     /* --- layout --- */
     int32_t lane_window;        /* 64: candidate window of the bank-conflict-aware grouping of points into     */
                                 /*     quarter-warps for the shared-memory camera table; 0 = keep input order  */
-    int32_t reserved[6];
+    /* --- precision --- */
+    int32_t pcg_fp32;           /* 0: everything fp64 (default).  1: optional mixed-precision mode - the two sweeps that apply  */
+                                /*    W (V + lambda I)^-1 W^t inside the PCG loop run on fp32 copies of the per-observation / */
+                                /*    per-point data; linearisation, preconditioner, PCG vectors and dot products, back-      */
+                                /*    substitution, cost and the LM control stay fp64 (per-iteration cost within 1e-5)        */
+    int32_t reserved[5];
 } b200ba_options;
 
 #define B200BA_TRACE_COLS 8     /* iter, err, lambda, new_err, rho, accepted(1/0/-1), cg_steps, cg_rel_residual */

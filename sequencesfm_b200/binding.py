@@ -35,7 +35,8 @@ class Options(C.Structure):
                 ("gradient_threshold", C.c_double), ("update_threshold", C.c_double),
                 ("round_pixels", C.c_int32), ("normalize", C.c_int32), ("fix_first_camera", C.c_int32),
                 ("discard_converged", C.c_int32), ("cg_max_steps", C.c_int32), ("cg_rel_tol", C.c_double),
-                ("precond", C.c_int32), ("poll_every", C.c_int32), ("lane_window", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("precond", C.c_int32), ("poll_every", C.c_int32), ("lane_window", C.c_int32), ("pcg_fp32", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class Report(C.Structure):

@@ -7,6 +7,7 @@
 // Reference lines replaced by each entry point are cited in include/b200ba.h.
 #include "../../include/b200ba.h"
 #include "ba_kernels.cuh"
+#include "ba_kernels_f32.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
@@ -111,7 +112,9 @@ struct b200ba_handle {
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
     DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
-    DBuf<int> tab_wr;
+    DBuf<int> tab_wr, tab_wr32;
+    DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
+    bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
     std::vector<int> orig_of_new;                    // SELL permutation (new point index -> caller's)
     std::unique_ptr<int[]> entry_of_obs;             // obs -> padded SELL entry
     int Kp = 0;                                      // padded SELL entries
@@ -177,6 +180,12 @@ int enqueue_linearize(b200ba_handle* h)
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
     LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
+    if (h->use_f32) {                                            // fp32 copies for the mixed-precision PCG sweeps
+        LAUNCH(k_f32_points, cdiv(d.M, 256), 256, d, 0);
+        LAUNCH(k_f32_cameras, cdiv(d.N, 128), 128, d);
+        LAUNCH(k_f32_orows, cdiv(h->Kp, 256), 256, d, h->Kp);
+        LAUNCH(k_f32_crows, cdiv(d.n_rows, 8), 256, d);
+    }
     return 0;
 }
 
@@ -184,6 +193,7 @@ int enqueue_precond(b200ba_handle* h)
 {
     Dev& d = h->d;
     LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
+    if (h->use_f32) LAUNCH(k_f32_points, cdiv(d.M, 256), 256, d, 1);
     if (h->opt.precond == 1) {
         LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
         LAUNCH((k_camera_reduce<21, 21>), cdiv((long long)d.N * 21, 256), 256, d, d.ar_sd, 0);
@@ -235,6 +245,15 @@ int launch_camera_step(b200ba_handle* h, int sums_ready)
 int enqueue_cg_step(b200ba_handle* h)
 {
     Dev& d = h->d;
+    if (h->use_f32) {                                            // mixed-precision PCG: both sweeps in fp32, the step kernel as usual
+        k_cg_point_pass_tab32<<<h->tab32_grid, TAB32_BLOCK, h->tab32_smem, h->stream>>>(d);
+        k_cg_camera_pass32<<<h->cam_grid, CW * 32, CAMPASS32_SMEM, h->stream>>>(d);
+        h->launches += 2;
+        if (h->world <= 1) return launch_camera_step(h, 0);
+        if (h->p2p_ready) return launch_camera_step(h, 2);
+        if (int rc = enqueue_camera_sums(h)) return rc;
+        return launch_camera_step(h, 1);
+    }
     if (h->use_tab) {
         k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d);
         h->launches++;
@@ -755,7 +774,12 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
         h->ptab.take(A, (size_t)N * TAB_STRIDE);
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
-        h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8); h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
+        h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
+        if (o.pcg_fp32) {
+            h->tab_wr32.take(A, (size_t)(n_sm > 0 ? n_sm : 148) * (TAB32_BLOCK / 32) * 8 + 8);
+            h->o_rec32.take(A, (Kpp / 32 + 1) * OREC32_BYTES); h->c_rec32.take(A, Rp * REC32_BYTES + 16);
+            h->X32.take(A, Mp); h->v32.take(A, Mp); h->Vinv32.take(A, 8 * Mp); h->ptab32.take(A, (size_t)N * TAB32_STRIDE + 8); h->rt32.take(A, 12 * (size_t)N);
+        } h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
         if (pass == 0) { A.cap = A.off; CU(cudaMalloc((void**)&A.base, A.cap)); }
     }
     lap("cudaMalloc");
@@ -805,23 +829,40 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
     // one 32-byte header per warp: {first slice, end slice, first entry, end entry, deg(first), deg(first+1), 0, 0}
     int tab_warps = std::max(1, h->tab_grid) * (TAB_BLOCK / 32);
-    {
-        std::vector<int> wr((size_t)tab_warps + 1, n_slices);
+    auto warp_headers = [&](int nwarps, int* dst) -> int {
+        std::vector<int> wr((size_t)nwarps + 1, n_slices);
         long long total = 0; for (int g = 0; g < n_slices; ++g) total += slice_deg[g] + 1;
         long long acc = 0; int w = 0; wr[0] = 0;
-        for (int g = 0; g < n_slices && w + 1 < tab_warps; ++g) {
+        for (int g = 0; g < n_slices && w + 1 < nwarps; ++g) {
             acc += slice_deg[g] + 1;
-            while (w + 1 < tab_warps && acc * tab_warps >= total * (long long)(w + 1)) wr[++w] = g + 1;
+            while (w + 1 < nwarps && acc * nwarps >= total * (long long)(w + 1)) wr[++w] = g + 1;
         }
-        for (int q = w + 1; q <= tab_warps; ++q) wr[q] = n_slices;
-        std::vector<int> hdr((size_t)tab_warps * 8, 0);
-        for (int q = 0; q < tab_warps; ++q) {
+        for (int q = w + 1; q <= nwarps; ++q) wr[q] = n_slices;
+        std::vector<int> hdr((size_t)nwarps * 8, 0);
+        for (int q = 0; q < nwarps; ++q) {
             const int g0 = wr[q], g1 = wr[q + 1];
             int* o = hdr.data() + 8 * (size_t)q;
             o[0] = g0; o[1] = g1; o[2] = slice_base[g0]; o[3] = slice_base[g1];
             o[4] = g0 < n_slices ? slice_deg[g0] : 0; o[5] = g0 + 1 < g1 ? slice_deg[g0 + 1] : 0;
         }
-        CU(cudaMemcpy(h->tab_wr.p, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dst, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (int rc = warp_headers(tab_warps, h->tab_wr.p)) return rc;
+    // ---- optional mixed-precision PCG (options.pcg_fp32): needs the fp32 camera table in shared memory ----
+    h->use_f32 = false;
+    int tab_warps32 = 0;
+    if (o.pcg_fp32) {
+        const size_t t32 = (((size_t)N * TAB32_STRIDE * sizeof(float)) + 127) & ~(size_t)127;
+        h->tab32_smem = t32 + TAB32_RING_BYTES;
+        if (h->tab32_smem + 256 > (size_t)smem_optin || (size_t)CAMPASS32_SMEM > (size_t)smem_optin)
+            return fail(h, B200BA_E_INVALID, "options.pcg_fp32 needs the fp32 camera table (%d cameras x 80 bytes) to fit one SM's shared memory", N);
+        CU(cudaFuncSetAttribute(k_cg_point_pass_tab32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab32_smem));
+        CU(cudaFuncSetAttribute(k_cg_camera_pass32, cudaFuncAttributeMaxDynamicSharedMemorySize, CAMPASS32_SMEM));
+        h->tab32_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB32_BLOCK / 32)));
+        tab_warps32 = h->tab32_grid * (TAB32_BLOCK / 32);
+        if (int rc = warp_headers(tab_warps32, h->tab_wr32.p)) return rc;
+        h->use_f32 = true;
     }
     if ((size_t)CAMPASS_SMEM > (size_t)smem_optin) return fail(h, B200BA_E_CUDA, "device offers %d bytes of shared memory per block, the by-camera sweep needs %d", smem_optin, CAMPASS_SMEM);
     CU(cudaFuncSetAttribute(k_cg_camera_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CAMPASS_SMEM));
@@ -858,6 +899,13 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
     d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
+    if (h->use_f32) {
+        d.o_rec32 = h->o_rec32.p; d.c_rec32 = h->c_rec32.p; d.X32 = h->X32.p; d.v32 = h->v32.p; d.Vinv32 = h->Vinv32.p;
+        d.ptab32 = h->ptab32.p; d.rt32 = h->rt32.p; d.tab_wr32 = h->tab_wr32.p; d.tab_warps32 = tab_warps32;
+        k_f32_indices<<<cdiv(std::max(Kp / 32, n_rows), 8), 256, 0, h->stream>>>(d, Kp / 32);
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+    }
     lap("plan");
     h->have_problem = true; h->begun = false; h->finished = false;
     h->ms_h2d = now_ms() - t0;
@@ -1163,7 +1211,7 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
 static const char* kKernelNames[] = {"linearize_points", "linearize_cameras", "cg_point_pass", "cg_camera_pass",
                                      "camera_reduce6", "cg_update", "schur_diag_cameras", "point_vinv",
                                      "backsub_cost_points", "precond_invert", "cg_point_pass_generic", "cg_camera_step_fused", "cg_step",
-                                     "cg_camera_pass_generic"};
+                                     "cg_camera_pass_generic", "cg_point_pass_f32", "cg_camera_pass_f32"};
 const char* b200ba_kernel_name(int32_t which)
 {
     return (which >= 0 && which < (int)(sizeof kKernelNames / sizeof *kKernelNames)) ? kKernelNames[which] : nullptr;
@@ -1193,6 +1241,8 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
                  CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 3: if (int rc = enqueue_camera_half(h, 0)) return rc; break;
         case 13: if (int rc = enqueue_camera_half(h, 0)) return rc; break;
+        case 14: if (h->use_f32) { k_cg_point_pass_tab32<<<h->tab32_grid, TAB32_BLOCK, h->tab32_smem, h->stream>>>(d); h->launches++; } break;
+        case 15: if (h->use_f32) { k_cg_camera_pass32<<<h->cam_grid, CW * 32, CAMPASS32_SMEM, h->stream>>>(d); h->launches++; } break;
         case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0); break;
         case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;

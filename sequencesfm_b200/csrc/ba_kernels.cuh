@@ -133,6 +133,8 @@ struct Dev {
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
+    // optional fp32 copies for the mixed-precision PCG (ba_kernels_f32.cuh); all null when options.pcg_fp32 = 0
+    unsigned char *o_rec32, *c_rec32; float4 *X32, *v32; float *Vinv32, *ptab32, *rt32; int* tab_wr32; int tab_warps32;
     int* tab_wr;                  // [tab_warps + 1] contiguous slice ranges of the persistent CG point sweep's warps (balanced by rows)
     int tab_warps;
     int* cam_seg_beg;     // N + 1: segments of camera i
@@ -1101,6 +1103,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_init(Dev d)
         int i = e / 6, a = e - 6 * i;
         double z = matvec6_row(d.Minv + 36 * (size_t)i, d.r + 6 * (size_t)i, a);
         d.z[e] = z; d.p[e] = z; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = z; rz += d.r[e] * z;
+        if (d.ptab32) d.ptab32[(size_t)i * 20 + 8 + a] = (float)z;
     }
     rz = block_sum<ONE_CTA>(rz, sm);
     if (threadIdx.x == 0) {
@@ -1146,6 +1149,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
         for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
             double pn = d.z[e] + beta * d.p[e];
             d.p[e] = pn; d.ptab[(size_t)(e / 6) * TAB_STRIDE + 7 + (e % 6)] = pn;
+            if (d.ptab32) d.ptab32[(size_t)(e / 6) * 20 + 8 + (e % 6)] = (float)pn;
         }
     }
     if (threadIdx.x == 0) {
@@ -1435,6 +1439,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     if (!stop && on) {
         double pn = z + (rzn / rz) * pe;
         d.p[e] = pn; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = pn;
+        if (d.ptab32) d.ptab32[(size_t)i * 20 + 8 + a] = (float)pn;
     }
     if (e == 0) {
         st->cg_steps = steps + 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;

@@ -147,6 +147,26 @@ def test_alternative_execution_plans_agree(env, monkeypatch):
     assert kk >= 8 and rel_cost_diff(alt.trace, c.trace, 8).max() < COST_RTOL
 
 
+@pytest.mark.parametrize("shape,seed", [("ladybug", 2), ("trafalgar", 1)])
+def test_fp32_pcg_mode(shape, seed):
+    """Optional mixed-precision mode (options.pcg_fp32): the two PCG sweeps in fp32, everything else fp64.  North star:
+    per-iteration cost within 1e-5 relative of the fp64 path."""
+    p = make_problem(shape, seed, outlier_frac=0.01)
+    a = _solve(p, max_iterations=12)
+    b = _solve(p, max_iterations=12, pcg_fp32=1)
+    k = parity_window(b.trace, a.trace)
+    assert k >= 8
+    d = rel_cost_diff(b.trace, a.trace, k)
+    assert d.max() < 1e-5, d
+    assert d.max() > 0                                                  # it really is a different arithmetic
+    assert abs(b.mean_px[1] - a.mean_px[1]) < 1e-3 * a.mean_px[1]       # final reprojection error: the north star's 1e-3
+    x = np.random.default_rng(3).normal(size=(p.N, 6))
+    with binding.Engine(pcg_fp32=1) as eng:                             # the fp64 stage-level entry points are unaffected
+        eng.set_problem_from(p); eng.begin(); g = eng.debug_linearize()
+        o = oracle.linearize(p, x=x.reshape(-1), lam=g["lambda0"])
+        assert rel(eng.debug_schur_matvec(g["lambda0"], x), o["Sx"]) < 1e-11
+
+
 def test_status_and_discard_convention():
     p = make_problem("tiny", 9)
     r = _solve(p, max_iterations=1)
