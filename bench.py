@@ -180,6 +180,7 @@ def main() -> int:
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--ref-lm-iterations", type=int, default=3)
     ap.add_argument("--steps-ref", type=int, default=1)
     ap.add_argument("--warmup-ref", type=int, default=0)
@@ -298,6 +299,24 @@ def main() -> int:
         eng.finish()
     eng.close()
 
+    # ---------------- optional mixed-precision PCG (options.pcg_fp32), reported beside; the headline stays fp64 ----------------
+    f32 = None
+    if world == 1 and not args.no_fp32:
+        try:
+            optf = binding.default_options(device=local_rank, max_iterations=max(W, 8) + 2, min_iterations=10 ** 6,
+                                           gradient_threshold=0.0, cg_max_steps=CG_STEPS, cg_rel_tol=0.0, poll_every=64, pcg_fp32=1)
+            ef = binding.Engine(optf)
+            ef.set_problem_from(prob); ef.begin(); ef.iterate(W); ef.restart()
+            ef.iterate(8); msf = ef.last_iterate_ms() / 8
+            rf = ef.finish()
+            nn = min(len(rf.trace), len(trace), 8)
+            dmax = float(np.max(np.abs(rf.trace[:nn, 1] - trace[:nn, 1]) / trace[:nn, 1]))
+            f32 = {"ms_per_step": msf, "value": 1e3 / msf, "unit": "LM iterations/s", "dtype": "f64 with both PCG sweeps in f32 (options.pcg_fp32 = 1)",
+                   "max_rel_cost_diff_vs_f64_first_iterations": dmax, "tolerance": 1e-5}
+            ef.close()
+        except Exception as ex:  # pragma: no cover
+            f32 = {"error": str(ex)}
+
     # ---------------- end-to-end through the public entry: `e2e` ----------------
     e2e_steps = K_steps
     opt2 = binding.default_options(device=local_rank, max_iterations=e2e_steps, min_iterations=10 ** 6, gradient_threshold=0.0,
@@ -380,7 +399,7 @@ def main() -> int:
                 "observations_per_s": value * K, "cg_steps_per_s": value * CG_STEPS,
                 "wall_ms_per_step": wall_ms / K_steps,
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_iter * K_steps)),
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "pcg_fp32": f32,
                 "final_mean_px": res.mean_px[1], "initial_mean_px": res.mean_px[0]}
         print(json.dumps(line))
     if world > 1:

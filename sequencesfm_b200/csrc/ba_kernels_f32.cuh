@@ -24,7 +24,10 @@ constexpr int REC32_R1     = REC32_R0 + 128;
 constexpr int REC32_R2     = REC32_R1 + 128;
 constexpr int REC32_BYTES  = REC32_R2 + 128;     // 656 = 41 x 16
 constexpr int TAB32_STRIDE = 20;                 // floats per camera
-constexpr int TAB32_BLOCK  = 768;
+#ifndef B200BA_TAB32_BLOCK
+#define B200BA_TAB32_BLOCK 1024
+#endif
+constexpr int TAB32_BLOCK  = B200BA_TAB32_BLOCK;
 constexpr int PR32         = 4;                  // ring rows per warp (2 stages x 2 rows)
 constexpr int TAB32_RING_BYTES = (TAB32_BLOCK / 32) * (PR32 * OREC32_BYTES + 2 * 8);
 constexpr int STAGE32_BYTES  = CG * REC32_BYTES;
