@@ -21,10 +21,10 @@ rows = [r for r in csv.reader(open(os.path.join(G, f"launches_{tag}.csv"))) if l
 with open(os.path.join(P, f"launches_{name}.csv"), "w", newline="") as f:
     w = csv.writer(f); w.writerow(["id", "kernel", "block", "grid", "ns"])
     for r in rows:
-        w.writerow([r[0], r[4], r[7], r[8], r[-1]])
+        w.writerow([r[0], r[4].replace("b200ba::", ""), r[7], r[8], r[-1]])
 agg = collections.OrderedDict()
 for r in rows:
-    k = r[4].split("(")[0]
+    k = r[4].split("(")[0].replace("b200ba::", "")
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += float(r[-1])
 tot = sum(a[1] for a in agg.values())
 summ = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
@@ -33,7 +33,7 @@ summ = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c
         "kernels": {k: {"launches": a[0], "mean_us": a[1] / a[0] / 1e3, "share": a[1] / tot} for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}}
 # one full LM iteration = the launches between two consecutive k_lm_decide (the list also holds set-up and bench.py's
 # per-kernel timing section, so the share that has to agree with bench.py's `share_of_step` is taken inside an iteration)
-names = [r[4].split("(")[0] for r in rows]
+names = [r[4].split("(")[0].replace("b200ba::", "") for r in rows]
 ends = [i for i, n in enumerate(names) if n == "k_lm_decide"]
 cg = None
 if len(ends) >= 3:
@@ -47,11 +47,17 @@ if len(ends) >= 3:
                                 "kernels": {k: {"launches": x[0], "mean_us": x[1] / x[0] / 1e3, "share": x[1] / it_tot} for k, x in sorted(it.items(), key=lambda kv: -kv[1][1])}}
 json.dump(summ, open(os.path.join(P, f"launches_{name}_summary.json"), "w"), indent=1)
 
-# ncu --set full digest
-tmp = os.path.join("/tmp", f"ncu_{tag}.json")
-subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_digest.py"), os.path.join(G, f"prof_{tag}.ncu-rep"), "4", "--json", tmp], stdout=subprocess.DEVNULL)
+# ncu --set full digests (one report, or the two the evidence script writes to stay under gpurun's 64 MiB limit)
+reps = [os.path.join(G, f"prof_{tag}{suf}.ncu-rep") for suf in ("", "_sweeps", "_rest")]
+allrows = []
+for rep in reps:
+    if not os.path.exists(rep):
+        continue
+    tmp = os.path.join("/tmp", os.path.basename(rep) + ".json")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_digest.py"), rep, "4", "--json", tmp], stdout=subprocess.DEVNULL)
+    allrows += json.load(open(tmp))
 last = collections.OrderedDict()
-for d in json.load(open(tmp)):
+for d in allrows:
     last[d["Kernel Name"]] = d
 out = []
 for k, d in last.items():
@@ -63,6 +69,6 @@ for k, d in last.items():
     d["dram_traffic_bytes_per_launch"] = rd * scale + wr * wscale
     out.append(d)
 json.dump(out, open(os.path.join(P, f"ncu_{name}_summary.json"), "w"), indent=1)
-print("pcg step share of the launch list:", round(cg, 3))
+print("pcg step share inside one LM iteration of the launch list:", cg)
 for d in out:
     print(d["Kernel Name"][:40].ljust(40), d["gpu__time_duration.sum"], round(d["dram_traffic_bytes_per_launch"] / 1e6, 1), "MB")
