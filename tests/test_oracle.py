@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle, refs
-from tests.util import COST_RTOL, golden_names, golden_problem, load_golden, parity_window, rel_cost_diff
+from tests.util import COST_RTOL, golden_names, golden_problem, load_golden, parity_window, pose_agreement, rel_cost_diff
 
 FAST = [n for n in golden_names() if "trafalgar" not in n]
 
@@ -109,6 +109,23 @@ def test_pba_reference_reaches_same_optimum():
     r = oracle.solve(p, solver=1, inlier_px=0.0, round_pixels=0, fix_first_camera=1)
     ours_mse = r.trace[-1, 1] * p.K5[0] ** 2 / p.K if np.isnan(r.trace[-1, 3]) else r.trace[-1, 3] * p.K5[0] ** 2 / p.K
     assert abs(ours_mse - q.final_mse) < 2e-3 * q.final_mse
+
+
+def test_poses_match_reference_pba_after_similarity_alignment():
+    """North star: "final reprojection RMS and camera poses within a stated tolerance of the reference PBA run".  The PBA
+    personality (camera 0 constant, no robustifier, sub-pixel measurements) of this algorithm against the cameras the
+    reference PBA (--double -schur, its own LM variant and fp32 I/O) ends with, stored in the fixture: after the 7-dof
+    similarity that PBA's internal rescaling leaves free, centres within 1e-3 x scene scale (measured 3.5e-6) and rotations
+    within 1e-3 rad (measured 3.1e-4); final RMS within 1e-3 relative."""
+    fx = load_golden("ssba_ladybug_s1")
+    p = golden_problem(fx)
+    o = oracle.solve(p, fix_first_camera=1, inlier_px=0.0, round_pixels=0, max_iterations=50)
+    cerr, ang = pose_agreement(o.cam_RT, np.array(fx["pba_double_schur"]["cam_RT_all"]))
+    assert cerr < 1e-3 and ang < 1e-3, (cerr, ang)
+    acc = o.trace[o.trace[:, 5] == 1]
+    mse = acc[-1, 3] * p.K5[0] ** 2 / p.K
+    g = fx["pba_double_schur"]["final_mse"]
+    assert abs(np.sqrt(mse) - np.sqrt(g)) < 1e-3 * np.sqrt(g)
 
 
 def test_edge_cases_oracle():

@@ -64,3 +64,29 @@ def rel_cost_diff(ours: np.ndarray, ref: np.ndarray, k: int) -> np.ndarray:
 def rel(a, b) -> float:
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def pose_agreement(cam_a: np.ndarray, cam_b: np.ndarray) -> tuple[float, float]:
+    """(max camera-centre error / scene scale, max rotation difference in rad) between two sets of [R|T] cameras after the
+    7-dof similarity (Umeyama) that best maps the centres of `a` onto those of `b`.  The north star's "camera poses within a
+    stated tolerance of the reference PBA run": SURVEY.md section 8d proposes 1e-3 x scene scale and 1e-3 rad."""
+    def centres(cam):
+        P = np.asarray(cam, dtype=np.float64).reshape(-1, 3, 4)
+        return -np.einsum("nji,nj->ni", P[:, :, :3], P[:, :, 3]), P[:, :, :3]
+    Ca, Ra = centres(cam_a); Cb, Rb = centres(cam_b)
+    ma, mb = Ca.mean(0), Cb.mean(0)
+    Ac, Bc = Ca - ma, Cb - mb
+    U, S, Vt = np.linalg.svd(Bc.T @ Ac / len(Ca))
+    D = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        D[2, 2] = -1
+    R = U @ D @ Vt
+    s = np.trace(np.diag(S) @ D) / (Ac ** 2).sum() * len(Ca)
+    t = mb - s * R @ ma
+    scale = np.sqrt(((Cb - mb) ** 2).sum(1).mean())
+    cerr = np.linalg.norm((s * (R @ Ca.T)).T + t - Cb, axis=1).max() / scale
+    ang = 0.0
+    for i in range(len(Ra)):
+        Rrel = Rb[i] @ (Ra[i] @ R.T).T
+        ang = max(ang, float(np.arccos(np.clip((np.trace(Rrel) - 1) / 2, -1, 1))))
+    return float(cerr), ang

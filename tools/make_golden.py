@@ -27,9 +27,25 @@ def checksum(p):
         h.update(np.ascontiguousarray(a).tobytes())
     return h.hexdigest()
 
+def add_pba_poses(out_dir):
+    """python tools/make_golden.py --pba-poses : add PBA's adjusted cameras to the existing fixtures (no SSBA re-run)."""
+    for shape in ("ladybug", "trafalgar"):
+        path = os.path.join(out_dir, f"ssba_{shape}_s1.json")
+        fx = json.load(open(path))
+        p = make_problem(shape, 1, **fx["kwargs"])
+        assert checksum(p) == fx["input_sha256"]
+        q = refs.pba_adjust(p, double=True, args=("-schur", "-v", "0"))
+        assert abs(q.final_mse - fx["pba_double_schur"]["final_mse"]) < 1e-6 * q.final_mse
+        fx["pba_double_schur"]["cam_RT_all"] = q.cam_RT.tolist()
+        json.dump(fx, open(path, "w"), indent=1)
+        print(shape, "PBA cameras stored", q.cam_RT.shape, flush=True)
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--pba-poses" in sys.argv:
+        return add_pba_poses(out_dir)
     only = sys.argv[1:] 
     for shape, seed, kw in CASES:
         name = f"ssba_{shape}_s{seed}"
@@ -53,6 +69,8 @@ def main():
                     "initial_mse": q.initial_mse, "final_mse": q.final_mse, "lm_iterations": q.lm_iterations,
                     "cg_iterations": q.cg_iterations, "return_code": q.return_code, "seconds": q.seconds,
                     "cam_RT_head": q.cam_RT[:3].tolist(), "pts_head": q.pts[:5].tolist()}
+                if dbl:      # every adjusted camera: the pose-agreement test aligns them with a 7-dof similarity
+                    fx["pba_double_schur"]["cam_RT_all"] = q.cam_RT.tolist()
         json.dump(fx, open(os.path.join(out_dir, name + ".json"), "w"), indent=1)
         print(name, "status", r.status, "its", r.iterations, "px", r.mean_px, f"{time.time()-t:.1f}s", flush=True)
 
