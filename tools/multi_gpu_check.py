@@ -18,7 +18,8 @@ shard = p.slice_points(j0, j1)
 def mark(m):
     print(f"[rank {rank}] {m}", flush=True)
 mark("process group up")
-eng = binding.Engine(device=lr, max_iterations=iters)
+F32 = int(os.environ.get("B200BA_TEST_FP32", "0"))       # 1: mixed-precision PCG on the multi-rank side (tolerance 1e-5)
+eng = binding.Engine(device=lr, max_iterations=iters, pcg_fp32=F32)
 eng.comm_setup_torch(rank, world, p.N)          # NCCL id + NVLink peer windows (B200BA_NO_P2P=1: NCCL only)
 mark("comm set up, peer windows " + ("off" if os.environ.get("B200BA_NO_P2P") else "on"))
 eng.set_problem_from(shard)
@@ -50,7 +51,9 @@ if rank == 0:
     # ("parity window"): 1e-9 on the first 8 iterations, 1e-7 overall, same accept history, same optimum.
     out["max_rel_cost_diff_first8"] = float(rel[:8].max())
     print(json.dumps(out))
-    assert out["max_rel_cost_diff_first8"] < 1e-9 and out["max_rel_cost_diff"] < 1e-7 and out["accept_equal"], out
+    tol8, tol = (1e-5, 1e-5) if F32 else (1e-9, 1e-7)
+    out["pcg_fp32"] = bool(F32)
+    assert out["max_rel_cost_diff_first8"] < tol8 and out["max_rel_cost_diff"] < tol and out["accept_equal"], out
     assert abs(r.mean_px[1] - s.mean_px[1]) < 1e-6 * s.mean_px[1] and out["cam_diff"] < 1e-3 and out["pts_diff"] < 1e-3, out
 eng.close()
 dist.barrier(); dist.destroy_process_group()
