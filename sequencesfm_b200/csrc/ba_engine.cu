@@ -250,7 +250,7 @@ int enqueue_cg_step(b200ba_handle* h)
         k_cg_camera_pass32<<<h->cam_grid, CW * 32, CAMPASS32_SMEM, h->stream>>>(d);
         h->launches += 2;
         if (h->world <= 1) return launch_camera_step(h, 0);
-        if (h->p2p_ready) return launch_camera_step(h, 2);
+        if (h->p2p_ready && h->step_grid <= P2P_MAX_BLOCKS) return launch_camera_step(h, 2);
         if (int rc = enqueue_camera_sums(h)) return rc;
         return launch_camera_step(h, 1);
     }
@@ -260,7 +260,7 @@ int enqueue_cg_step(b200ba_handle* h)
     } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
     if (h->use_coop && h->world <= 1) return launch_camera_step(h, 0);
-    if (h->use_coop && h->p2p_ready) return launch_camera_step(h, 2);      // all-reduce fused into the step kernel (NVLink peer loads)
+    if (h->use_coop && h->p2p_ready && h->step_grid <= P2P_MAX_BLOCKS) return launch_camera_step(h, 2);   // all-reduce fused into the step kernel (NVLink peer memory)
     if (int rc = enqueue_camera_sums(h)) return rc;
     if (h->use_coop) return launch_camera_step(h, 1);
     LAUNCH(k_cg_update, 1, ONE_CTA, d);

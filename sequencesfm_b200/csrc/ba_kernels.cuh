@@ -106,7 +106,8 @@ struct LMState {
 // measured 16 us per PCG step at 2 GPUs.)  Half c & 1 is rewritten at collective c + 2, which a rank only starts after it
 // has seen every flag of c + 1, i.e. after every peer has finished reading c.
 constexpr int P2P_MAX_WORLD = 8;
-constexpr int P2P_HDR_BYTES = 2 * P2P_MAX_WORLD * 64;
+constexpr int P2P_MAX_BLOCKS = 511;                              // per-block flags of the fused PCG-step exchange (6 N <= 511 x 192)
+constexpr int P2P_HDR_BYTES = 2 * P2P_MAX_WORLD * (P2P_MAX_BLOCKS + 1) * 8;
 struct P2P {
     int on, world, rank, pad;
     unsigned long long cap;                  // doubles per slot
@@ -1010,9 +1011,12 @@ __device__ __forceinline__ double* p2p_data(const P2P& x, int dst, unsigned long
 {
     return reinterpret_cast<double*>(x.win[dst] + P2P_HDR_BYTES) + ((c & 1ull) * x.world + src) * x.cap;
 }
-__device__ __forceinline__ unsigned long long* p2p_flag(const P2P& x, int dst, unsigned long long c, int src)
+// flag of (half, source rank, slot): slot 0 = "the whole contribution is there" (two-kernel collectives), slot 1 + b =
+// "the elements of block b are there" (fused PCG-step exchange: block b of every rank handles the same elements, so a
+// receiver block only waits for its own slot and no grid-wide sync is needed before the flags)
+__device__ __forceinline__ unsigned long long* p2p_flag(const P2P& x, int dst, unsigned long long c, int src, int slot = 0)
 {
-    return reinterpret_cast<unsigned long long*>(x.win[dst] + 64 * ((c & 1ull) * P2P_MAX_WORLD + src));
+    return reinterpret_cast<unsigned long long*>(x.win[dst]) + (((c & 1ull) * P2P_MAX_WORLD + src) * (P2P_MAX_BLOCKS + 1) + slot);
 }
 // element e of this rank's contribution -> every window
 __device__ __forceinline__ void p2p_push(const P2P& x, unsigned long long c, size_t e, double v)
@@ -1021,21 +1025,21 @@ __device__ __forceinline__ void p2p_push(const P2P& x, unsigned long long c, siz
 }
 // Threads 0 .. world-1 of ONE block, after every push of the grid has been ordered before them (grid sync / kernel
 // boundary): raise this rank's flag in every window.
-__device__ __forceinline__ void p2p_raise_flags(const P2P& x, unsigned long long c)
+__device__ __forceinline__ void p2p_raise_flags(const P2P& x, unsigned long long c, int slot = 0)
 {
     const int r = threadIdx.x;
     if (r < x.world) {
         __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p2p_flag(x, r, c, x.rank)), "l"(c + 1ull) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p2p_flag(x, r, c, x.rank, slot)), "l"(c + 1ull) : "memory");
     }
 }
 // threads 0 .. world-1 of a block each wait for one source's flag IN THE OWN WINDOW; bounded spin (about a second) so that a
 // dead peer cannot hang the GPU
-__device__ __forceinline__ void p2p_wait_all(const P2P& x, unsigned long long c)
+__device__ __forceinline__ void p2p_wait_all(const P2P& x, unsigned long long c, int slot = 0)
 {
     const int r = threadIdx.x;
     if (r < x.world) {
-        const unsigned long long* f = p2p_flag(x, x.rank, c, r);
+        const unsigned long long* f = p2p_flag(x, x.rank, c, r, slot);
         unsigned long long v = 0; unsigned int spins = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
@@ -1406,12 +1410,12 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     unsigned long long coll = 0;
     if (sums_ready == 2) {
         // multi-rank: the all-reduce of the 6N camera sums happens HERE, over NVLink peer memory, between the second-level
-        // sum and the q = S p assembly - push into every window, grid sync, raise the flags, poll the own window, sum its slots
+        // sum and the q = S p assembly - push into every window, raise this block's flags, poll the own window, sum its slots
         coll = *d.p2p.seq;
         if (on) p2p_push(d.p2p, coll, (size_t)e, s);
-        grid.sync();
-        if (blockIdx.x == 0) p2p_raise_flags(d.p2p, coll);
-        p2p_wait_all(d.p2p, coll);
+        __syncthreads();                                         // this block's pushes are ordered before its flags (CTA barrier + release)
+        p2p_raise_flags(d.p2p, coll, 1 + (int)blockIdx.x);
+        p2p_wait_all(d.p2p, coll, 1 + (int)blockIdx.x);           // block b of every rank pushes exactly the elements block b reads
         if (on) s = p2p_sum(d.p2p, coll, (size_t)e);
     }
     if (on) q = lam * pe + (urow[0] * sv[lc] + urow[1] * sv[lc + 1] + urow[2] * sv[lc + 2] + urow[3] * sv[lc + 3] + urow[4] * sv[lc + 4] + urow[5] * sv[lc + 5]) - s;
