@@ -228,22 +228,6 @@ __device__ __forceinline__ void load3p_256(const double* __restrict__ base, int 
 // evict_first / no L1 allocation; gathered arrays are loaded and stored evict_last.
 __device__ __forceinline__ uint64_t policy_evict_last()  { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
-__device__ __forceinline__ int ldg_stream(const int* p)
-{
-    int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
-}
-__device__ __forceinline__ double ldg_stream(const double* p)
-{
-    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
-}
-__device__ __forceinline__ int ldg_stream(const int* p, uint64_t pol)
-{
-    int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
-}
-__device__ __forceinline__ double ldg_stream(const double* p, uint64_t pol)
-{
-    double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
-}
 __device__ __forceinline__ void load3p_256_keep(const double* __restrict__ base, int j, double X[3], uint64_t pol)
 {
     double pad;
@@ -919,11 +903,7 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
         const int sl = t % CNS;
         const uint32_t bytes = (uint32_t)min(CG, n - t * CG) * REC_BYTES;
         mbar_expect_tx(&bar[sl], bytes);
-#ifdef B200BA_CP_NOHINT
-        bulk_g2s(buf + sl * STAGE_BYTES, src + (size_t)t * STAGE_BYTES, bytes, &bar[sl]);
-#else
-        bulk_g2s_hint(buf + sl * STAGE_BYTES, src + (size_t)t * STAGE_BYTES, bytes, &bar[sl], strm);
-#endif
+        bulk_g2s_hint(buf + sl * STAGE_BYTES, src + (size_t)t * STAGE_BYTES, bytes, &bar[sl], strm);      // evict_first: 43 vs 47.5 us without the hint
     };
     if (lane == 0) {
 #pragma unroll
@@ -1284,14 +1264,9 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
     auto arm = [&](int stage) {                                  // lane 0 only: next two unrequested rows -> ring stage
         const uint32_t bytes = (uint32_t)min(2, n_rows) * OREC_BYTES;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar + 8u * stage), "r"(bytes) : "memory");
-#ifdef B200BA_PT_NOHINT
-        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(ring + (uint32_t)stage * (2 * OREC_BYTES)), "l"(src_rows), "r"(bytes), "r"(rbar + 8u * stage) : "memory");
-#else
         // evict_first: the stream must not push the gathered vectors (X, v: evict_last) out of L2 (by-camera sweep: 43 vs 47.5 us)
         asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                      ::"r"(ring + (uint32_t)stage * (2 * OREC_BYTES)), "l"(src_rows), "r"(bytes), "r"(rbar + 8u * stage), "l"(policy_evict_first()) : "memory");
-#endif
         src_rows += 2 * OREC_BYTES; n_rows -= 2;
     };
     if (lane == 0) {
@@ -1354,15 +1329,9 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         if (++slot == PR) { slot = 0; par ^= 1u; }
         const bool last = (--rows_left == 0);                    // warp-uniform
         TabRow o;
-#ifdef B200BA_PT_REQ_EARLY
-        double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
-        if (last) request(Vi, Xn);
         if (cam >= 0) tab_row_fwd<false>(tab, cam, w, X, d.in, o);
-#else
-        if (cam >= 0) tab_row_fwd<false>(tab, cam, w, X, d.in, o);
-        double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};     // (leaving these uninitialised measured 6 us SLOWER)
-        if (last) request(Vi, Xn);
-#endif
+        double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};     // (leaving these uninitialised measured 6 us SLOWER; requesting
+        if (last) request(Vi, Xn);                                //  before the forward half 2 us slower)
         if (cam >= 0) tab_row_bwd(o, u0, u1, u2);
         if (last && !finish(Vi, Xn)) return;
     }
