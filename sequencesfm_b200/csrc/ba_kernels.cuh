@@ -733,8 +733,10 @@ struct TabRow { double h0, h1, h2, qw, qx, qy, qz; };
 // first half of a row body: forward rotation, projection Jacobian, t = A~ p, h = P~^t t  (table fields die here)
 // GLOBAL = false: the table lives in shared memory (k_cg_point_pass_tab); true: read-only global loads (problems whose
 // camera table does not fit one SM's shared memory: 7 x LDG.128 instead of the 9 of [R|T] + p)
+// pad: the entry is SELL padding - the caller passes camera 0 and weight 0 and the depth is replaced by 1, so the row body
+// runs without a divergent branch and contributes exact zeros
 template <bool GLOBAL>
-__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
+__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o, bool pad = false)
 {
     const double2* t = tab + 7 * cam;
     double2 a0, a1, a2, a3, a4, a5, a6;
@@ -746,7 +748,7 @@ __device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int
     const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);                                         // r = X + 2 (qw t + qv x t)
     const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
     const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
-    const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
+    const double x = r0 + a2.x, y = r1 + a2.y, z = pad ? 1.0 : r2 + a3.x;
     const double iz = fast_rcp(z);
     const double wf = w * in.k00 * iz;
     const double pa = wf, pb = -wf * x * iz, pc = in.ar * wf, pd = -in.ar * wf * y * iz;
@@ -1329,10 +1331,11 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         if (++slot == PR) { slot = 0; par ^= 1u; }
         const bool last = (--rows_left == 0);                    // warp-uniform
         TabRow o;
-        if (cam >= 0) tab_row_fwd<false>(tab, cam, w, X, d.in, o);
+        const bool pad = cam < 0;                                // padding entries run the body on camera 0 with weight 0: no divergence
+        tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
         double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};     // (leaving these uninitialised measured 6 us SLOWER; requesting
         if (last) request(Vi, Xn);                                //  before the forward half 2 us slower)
-        if (cam >= 0) tab_row_bwd(o, u0, u1, u2);
+        tab_row_bwd(o, u0, u1, u2);
         if (last && !finish(Vi, Xn)) return;
     }
 }

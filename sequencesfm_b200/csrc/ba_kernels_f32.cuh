@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) k_f32_indices(Dev d, int n_orows)
 
 // ---- by-point sweep, fp32 ----
 struct TabRow32 { float h0, h1, h2, qw, qx, qy, qz; };
-__device__ __forceinline__ void tab32_fwd(const float4* __restrict__ tab, int cam, float w, const float X[3], float f, float ar, TabRow32& o)
+__device__ __forceinline__ float rcp_fast(float z) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z)); return r; }   // 1 ulp, no slow path
+__device__ __forceinline__ void tab32_fwd(const float4* __restrict__ tab, int cam, float w, const float X[3], float f, float ar, TabRow32& o, bool pad)
 {
     const float4* t = tab + 5 * cam;
     const float4 q = t[0], T = t[1], pa4 = t[2], pb4 = t[3];
@@ -115,8 +116,8 @@ __device__ __forceinline__ void tab32_fwd(const float4* __restrict__ tab, int ca
     const float r0 = fmaf(2.f, q.x * tx + (q.z * tz - q.w * ty), X[0]);
     const float r1 = fmaf(2.f, q.x * ty + (q.w * tx - q.y * tz), X[1]);
     const float r2 = fmaf(2.f, q.x * tz + (q.y * ty - q.z * tx), X[2]);
-    const float x = r0 + T.x, y = r1 + T.y, z = r2 + T.z;
-    const float iz = __frcp_rn(z);
+    const float x = r0 + T.x, y = r1 + T.y, z = pad ? 1.f : r2 + T.z;
+    const float iz = rcp_fast(z);
     const float wf = w * f * iz;
     const float pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
     const float s0 = pa4.x + (pb4.x * r2 - pb4.y * r1);          // p = (pa4.x pa4.y pa4.z | pa4.w pb4.x pb4.y)
@@ -218,10 +219,11 @@ __global__ void __launch_bounds__(TAB32_BLOCK, 1) k_cg_point_pass_tab32(Dev d)
         if (++slot == PR32) { slot = 0; par ^= 1u; }
         const bool last = (--rows_left == 0);
         TabRow32 o;
-        if (cam >= 0) tab32_fwd(tab, cam, w, X, f, ar, o);
+        const bool pad = cam < 0;                                // padding entries: camera 0, weight 0, depth 1 - no divergent branch
+        tab32_fwd(tab, pad ? 0 : cam, pad ? 0.f : w, X, f, ar, o, pad);
         float4 Va = make_float4(0, 0, 0, 0), Vb = Va, Xn = Va;
         if (last) request(Va, Vb, Xn);
-        if (cam >= 0) tab32_bwd(o, u0, u1, u2);
+        tab32_bwd(o, u0, u1, u2);
         if (last && !finish(Va, Vb, Xn)) return;
     }
 }
@@ -231,7 +233,7 @@ struct Cam32 { float R[9], T[3]; };
 __device__ __forceinline__ void cam32_one(const Cam32& cm, float f, float ar, bool ok, float r0, float r1, float r2, const float4& v, float w, float acc[6])
 {
     const float x = r0 + cm.T[0], y = r1 + cm.T[1], z = ok ? r2 + cm.T[2] : 1.f;
-    const float iz = __frcp_rn(z);
+    const float iz = rcp_fast(z);
     const float wf = w * f * iz;
     const float pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
     const float g0 = cm.R[0] * v.x + cm.R[1] * v.y + cm.R[2] * v.z;
