@@ -200,7 +200,7 @@ int enqueue_linearize(b200ba_handle* h)
     Dev& d = h->d;
     LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
     LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
-    LAUNCH(k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
+    k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++;
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
@@ -758,7 +758,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         });
     }
     // virtual warps (equal row ranges) and segments (runs of one camera inside one virtual warp's range)
-    const int n_vwarps = std::max(1, n_sm) * CW;
+    const int n_vwarps = std::max(1, n_sm) * CW * VSPLIT;
     std::vector<int2> row_hdr((size_t)std::max(n_rows, 1), make_int2(0, 0));
     std::vector<int> cam_seg_beg((size_t)N + 1, 0);
     int n_segs = 0;
@@ -895,7 +895,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     }
     if ((size_t)CAMPASS_SMEM > (size_t)smem_optin) return fail(h, B200BA_E_CUDA, "device offers %d bytes of shared memory per block, the by-camera sweep needs %d", smem_optin, CAMPASS_SMEM);
     CU(cudaFuncSetAttribute(k_cg_camera_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, CAMPASS_SMEM));
-    h->cam_grid = cdiv(n_vwarps, CW);
+    CU(cudaFuncSetAttribute(k_linearize_cameras, cudaFuncAttributeMaxDynamicSharedMemorySize, LINCAM_SMEM));
+    h->cam_grid = cdiv(n_vwarps, CW * VSPLIT);
     h->step_grid = cdiv((long long)N * 6, STEP_BLOCK);
     {
         int per_sm = 0, coop = 0;
@@ -1263,7 +1264,7 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
     auto one = [&]() {
         switch (which) {
         case 0: LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d); break;
-        case 1: LAUNCH(k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;
+        case 1: k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++; break;
         case 2: if (h->use_tab) { k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d); h->launches++; }
                 else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
                 break;

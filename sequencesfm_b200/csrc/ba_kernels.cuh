@@ -56,7 +56,13 @@ constexpr int OREC_BYTES   = 128 + 256;         // point-order row record: 32 x 
 #ifndef B200BA_CNS
 #define B200BA_CNS 4
 #endif
-constexpr int CW  = B200BA_CW;      // warps per CTA of the persistent CG by-camera sweep = virtual warps per SM
+constexpr int CW  = B200BA_CW;      // warps per CTA of the persistent CG by-camera sweep
+#ifndef B200BA_VSPLIT
+#define B200BA_VSPLIT 1
+#endif
+constexpr int VSPLIT = B200BA_VSPLIT;   // virtual warps per sweep warp.  2 (finer units for the once-per-iteration by-camera kernels: 2.67 waves of
+                                        // fat warps instead of 1.33) took linearize_cameras from 156 to 136 us but the extra segments cost the
+                                        // camera-side step as much over 50 PCG steps: 1 stays
 constexpr int CG  = B200BA_CG;      // rows per stage = rows whose arithmetic is interleaved (ILP) = gathers per register set
 constexpr int CNS = B200BA_CNS;     // stages staged in shared memory per warp (TMA ring, one mbarrier each)
 static_assert(CNS >= 3, "two stages are in use (gather front, arithmetic) while a third is being refilled");
@@ -446,63 +452,107 @@ template <int NACC> __device__ __forceinline__ void seg_flush(const Dev& d, int 
 
 // K2  linearize_cameras: U_i += A~^t A~ (21 unique), g_c,i += A~^t (-w e)   (v3d_optimization.cpp:530-541, 600-614); the
 //     weight is recomputed from the residual and written, with the lever arm R X, into the row record for the CG sweeps.
+//     One warp per virtual warp (4 per CTA, 3 CTAs per SM at ~156 registers).  Same staging as the CG by-camera sweep: a
+//     ring of LC_NS stages of CG rows per warp, each stage = the row records + the rows' measurements, filled by two TMA
+//     bulk copies; the X_j gathers of stage t+1 are in flight while stage t is computed.  (The version that loaded two
+//     rows at a time through registers was latency-bound at 12 warps per SM: 166 us.)
+constexpr int LC_NS = 3;
+constexpr int LC_STAGE_BYTES = CG * (REC_BYTES + 512);           // CG row records, then CG x 32 double2 measurements
+constexpr int LINCAM_SMEM = (CH_BLOCK / 32) * LC_NS * (LC_STAGE_BYTES + 8);
 __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
-    const int lane = threadIdx.x & 31, wpb = CH_BLOCK / 32, nw = gridDim.x * wpb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vw = blockIdx.x * (CH_BLOCK / 32) + warp;
+    if (vw >= d.n_vwarps) return;                                // warps are independent: no CTA-wide barrier below
+    const int rb = vrow(d, vw), n = vrow(d, vw + 1) - rb;
+    if (n <= 0) return;
+    const int nst = (n + CG - 1) / CG;
+    unsigned char* buf = smem_raw + (size_t)warp * LC_NS * LC_STAGE_BYTES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)(CH_BLOCK / 32) * LC_NS * LC_STAGE_BYTES) + warp * LC_NS;
+    unsigned char* grec = d.c_rec + (size_t)rb * REC_BYTES;
+    const double2* gmeas = d.c_meas + 32 * (size_t)rb;
+    const uint64_t strm = policy_evict_first();
+    auto arm = [&](int t) {
+        const int sl = t % LC_NS;
+        const uint32_t rows = (uint32_t)min(CG, n - t * CG);
+        mbar_expect_tx(&bar[sl], rows * (REC_BYTES + 512));
+        bulk_g2s_hint(buf + sl * LC_STAGE_BYTES, grec + (size_t)t * CG * REC_BYTES, rows * REC_BYTES, &bar[sl], strm);
+        bulk_g2s_hint(buf + sl * LC_STAGE_BYTES + CG * REC_BYTES, gmeas + 32 * (size_t)t * CG, rows * 512, &bar[sl], strm);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LC_NS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        for (int t = 0; t < LC_NS && t < nst; ++t) arm(t);
+    }
+    __syncwarp();
     const int cur = st->cur;
     const double* Xb = d.X[cur];
     const double* rt = d.rt[cur];
-    for (int vw = blockIdx.x * wpb + (threadIdx.x >> 5); vw < d.n_vwarps; vw += nw) {
-        const int rb = vrow(d, vw), re = vrow(d, vw + 1);
-        int seg = -1, cam = 0;
-        Cam cm;
-        double acc[27];
+    int seg = -1, cam = 0;
+    Cam cm;
+    double acc[27];
 #pragma unroll
-        for (int q = 0; q < 27; ++q) acc[q] = 0;
-        // one row: segment bookkeeping, geometry, write-back of weight / lever arm, accumulation
-        auto do_row = [&](unsigned char* rec, int2 h, int j, double2 m, const double X[3]) {
-            if (h.y != seg) {
-                if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
-                seg = h.y; cam = h.x; load_cam(rt, cam, cm);
-            }
-            if (j >= 0 && cam >= d.first_free) {
-                Obs o; obs_full(cm, X, m, d.in, o);
-                reinterpret_cast<double*>(rec + REC_W)[lane] = o.w;
-                reinterpret_cast<double*>(rec + REC_R0)[lane] = o.r0;
-                reinterpret_cast<double*>(rec + REC_R1)[lane] = o.r1;
-                reinterpret_cast<double*>(rec + REC_R2)[lane] = o.r2;
-                double A0[6], A1[6]; jac_rows_A(o, A0, A1);
-                const double we0 = -o.w * o.e0, we1 = -o.w * o.e1;
-                int q = 0;
+    for (int q = 0; q < 27; ++q) acc[q] = 0;
+    auto issue = [&](int t, int (&jj)[CG], double (&XX)[CG][3]) {
+        const int sl = t % LC_NS;
+        mbar_wait(&bar[sl], (uint32_t)(t / LC_NS) & 1u);
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int b = a; b < 6; ++b) acc[q++] += A0[a] * A0[b] + A1[a] * A1[b];
-#pragma unroll
-                for (int a = 0; a < 6; ++a) acc[21 + a] += A0[a] * we0 + A1[a] * we1;
-            }
-        };
-        // two rows per trip: both rows' index / measurement loads and both X gathers are issued before any arithmetic
-        for (int r = rb; r < re; r += 2) {
-            unsigned char* rec0 = d.c_rec + (size_t)r * REC_BYTES;
-            unsigned char* rec1 = rec0 + REC_BYTES;
-            const bool two = r + 1 < re;
-            const int2 h0 = __ldg(reinterpret_cast<const int2*>(rec0 + REC_HDR));
-            const int j0 = __ldg(reinterpret_cast<const int*>(rec0 + REC_J) + lane);
-            const int2 h1 = two ? __ldg(reinterpret_cast<const int2*>(rec1 + REC_HDR)) : h0;
-            const int j1 = two ? __ldg(reinterpret_cast<const int*>(rec1 + REC_J) + lane) : -1;
-            const double2 m0 = __ldg(d.c_meas + 32 * (size_t)r + lane);
-            const double2 m1 = two ? __ldg(d.c_meas + 32 * (size_t)(r + 1) + lane) : m0;
-            double X0[3] = {0, 0, 1}, X1[3] = {0, 0, 1};
-            if (j0 >= 0) load3p_256(Xb, j0, X0);
-            if (j1 >= 0) load3p_256(Xb, j1, X1);
-            do_row(rec0, h0, j0, m0, X0);
-            if (two) do_row(rec1, h1, j1, m1, X1);
+        for (int g = 0; g < CG; ++g) {
+            jj[g] = (t * CG + g < n) ? reinterpret_cast<const int*>(buf + sl * LC_STAGE_BYTES + g * REC_BYTES + REC_J)[lane] : -1;
+            XX[g][0] = 0.0; XX[g][1] = 0.0; XX[g][2] = 1.0;
+            if (jj[g] >= 0) load3p_256(Xb, jj[g], XX[g]);
         }
-        if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
+    };
+    auto compute = [&](int t, const int (&jj)[CG], const double (&XX)[CG][3]) {
+        const int sl = t % LC_NS;
+        const unsigned char* sb = buf + sl * LC_STAGE_BYTES;
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+            if (t * CG + g < n) {                                // warp-uniform
+                const int2 h = *reinterpret_cast<const int2*>(sb + g * REC_BYTES + REC_HDR);
+                if (h.y != seg) {
+                    if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
+                    seg = h.y; cam = h.x; load_cam(rt, cam, cm);
+                }
+                if (jj[g] >= 0 && cam >= d.first_free) {
+                    const double2 m = reinterpret_cast<const double2*>(sb + CG * REC_BYTES + g * 512)[lane];
+                    Obs o; obs_full(cm, XX[g], m, d.in, o);
+                    unsigned char* rec = grec + (size_t)(t * CG + g) * REC_BYTES;          // write-back goes to the record in HBM
+                    reinterpret_cast<double*>(rec + REC_W)[lane] = o.w;
+                    reinterpret_cast<double*>(rec + REC_R0)[lane] = o.r0;
+                    reinterpret_cast<double*>(rec + REC_R1)[lane] = o.r1;
+                    reinterpret_cast<double*>(rec + REC_R2)[lane] = o.r2;
+                    double A0[6], A1[6]; jac_rows_A(o, A0, A1);
+                    const double we0 = -o.w * o.e0, we1 = -o.w * o.e1;
+                    int q = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int b = a; b < 6; ++b) acc[q++] += A0[a] * A0[b] + A1[a] * A1[b];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) acc[21 + a] += A0[a] * we0 + A1[a] * we1;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && t + LC_NS < nst) { fence_proxy_async(); arm(t + LC_NS); }
+    };
+    int jA[CG], jB[CG]; double XA[CG][3], XB[CG][3];
+    issue(0, jA, XA);
+    for (int t = 0; t < nst; t += 2) {
+        if (t + 1 < nst) issue(t + 1, jB, XB);
+        compute(t, jA, XA);
+        if (t + 1 < nst) {
+            if (t + 2 < nst) issue(t + 2, jA, XA);
+            compute(t + 1, jB, XB);
+        }
     }
+    if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
 }
 
 // second level of every by-camera reduction: fixed-order sum of a camera's segment partials
@@ -891,9 +941,9 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
     if (st->done) return;
     if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int vw = blockIdx.x * CW + warp;
+    const int vw = (blockIdx.x * CW + warp) * VSPLIT;  // this warp's VSPLIT consecutive virtual warps = one contiguous row range
     if (vw >= d.n_vwarps) return;                       // no CTA-wide barrier below: warps are independent
-    const int rb = vrow(d, vw), n = vrow(d, vw + 1) - rb;
+    const int rb = vrow(d, vw), n = vrow(d, min(vw + VSPLIT, d.n_vwarps)) - rb;
     if (n <= 0) return;
     const int nst = (n + CG - 1) / CG;                  // stages of this warp's range
     unsigned char* buf = smem_raw + (size_t)warp * CNS * STAGE_BYTES;

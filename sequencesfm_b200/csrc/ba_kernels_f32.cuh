@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass32(Dev d)
     const LMState* st = d.st;
     if (st->done || !st->cg_active) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int vw = blockIdx.x * CW + warp;
+    const int vw = (blockIdx.x * CW + warp) * VSPLIT;
     if (vw >= d.n_vwarps) return;
-    const int rb = vrow(d, vw), n = vrow(d, vw + 1) - rb;
+    const int rb = vrow(d, vw), n = vrow(d, min(vw + VSPLIT, d.n_vwarps)) - rb;
     if (n <= 0) return;
     const int nst = (n + CG - 1) / CG;
     unsigned char* buf = smem_raw + (size_t)warp * CNS * STAGE32_BYTES;
