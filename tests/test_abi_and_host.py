@@ -152,3 +152,20 @@ def test_python_mirror_with_oracle_as_engine(monkeypatch):
     # pba entry point always returns 0 (src/sfm_ba_pba.cpp:173)
     cloud3, Kmat3, imgpts3, Pmats3 = _tracker_containers(p)
     assert ba.adjustBundle_pba(cloud3, Kmat3, np.zeros(4), imgpts3, Pmats3) == 0
+
+
+def test_bench_byte_model_is_the_surveys():
+    """bench.py's algorithmic bytes are SURVEY.md section 8(d)'s model: fp64 Venice shape 216 MB linearisation, 335.5 MB per
+    PCG step, 17.34 GB per LM iteration; the per-kernel split of a PCG step adds up to the step."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, M, K = 1778, 993923, 5001946
+    ab = bench.algorithmic_bytes(N, M, K)
+    assert abs(ab["lin"] - 216.06e6) < 0.1e6
+    assert abs(ab["cg_step"] - 335.51e6) < 0.1e6
+    assert abs(ab["iteration"] - 17.342e9) < 0.01e9
+    km = bench.kernel_models(N, M, K)
+    assert km["cg_point_pass"] + km["cg_camera_pass"] == ab["cg_step"]
+    assert km["linearize"] == ab["lin"]
