@@ -371,6 +371,13 @@ def main() -> int:
                        "sample": f"PBA multicore CPU --double -schur -lmi {lmi} on the same {args.shape} problem: {q.lm_iterations} LM iterations, "
                                  f"{q.cg_iterations} CG steps in {q.seconds:.2f} s (PBA's own optimisation timer; PBA stops its PCG after "
                                  f"{q.cg_iterations // max(1, q.lm_iterations)} steps per iteration, this engine runs {CG_STEPS})"}
+                # PBA's default arithmetic (fp32 arrays and scalars), same problem, same bounded sample
+                try:
+                    qf = refs.pba_adjust(full, double=False, args=("-schur", "-lmi", str(lmi), "-v", "0"))
+                    cpu["pba_float_schur"] = {"value": qf.lm_iterations / qf.seconds if qf.seconds > 0 else None, "unit": "LM iterations/s",
+                                              "lm_iterations": qf.lm_iterations, "cg_steps": qf.cg_iterations, "seconds": qf.seconds}
+                except Exception as ex:  # pragma: no cover
+                    cpu["pba_float_schur"] = {"error": str(ex)}
                 # the live engine of the reference (SSBA-3.0, single thread, sparse LDL^t) cannot factor a Venice-sized system;
                 # it is timed beside on the largest shape it finishes in seconds, with this engine on the same problem
                 if refs.have_ssba():
