@@ -274,6 +274,11 @@ int enqueue_cg_step(b200ba_handle* h)
         k_cg_point_pass_tab32<<<h->tab32_grid, TAB32_BLOCK, h->tab32_smem, h->stream>>>(d);
         k_cg_camera_pass32<<<h->cam_grid, CW * 32, CAMPASS32_SMEM, h->stream>>>(d);
         h->launches += 2;
+        if (!h->use_coop) {                                      // no cooperative launch: second-level sums + single-CTA step
+            if (int rc = enqueue_camera_sums(h)) return rc;
+            LAUNCH(k_cg_update, 1, ONE_CTA, d);
+            return 0;
+        }
         if (h->world <= 1) return launch_camera_step(h, 0);
         if (h->p2p_ready && h->step_grid <= P2P_MAX_BLOCKS) return launch_camera_step(h, 2);
         if (int rc = enqueue_camera_sums(h)) return rc;

@@ -162,12 +162,14 @@ def test_alternative_execution_plans_agree(env, monkeypatch):
     assert kk >= 8 and rel_cost_diff(alt.trace, c.trace, 8).max() < COST_RTOL
 
 
-@pytest.mark.parametrize("shape,seed", [("ladybug", 2), ("trafalgar", 1)])
-def test_fp32_pcg_mode(shape, seed):
+@pytest.mark.parametrize("shape,seed,env", [("ladybug", 2, None), ("trafalgar", 1, None), ("ladybug", 4, "B200BA_NO_COOP"), ("ladybug", 5, "B200BA_NO_GRAPH")])
+def test_fp32_pcg_mode(shape, seed, env, monkeypatch):
     """Optional mixed-precision mode (options.pcg_fp32): the two PCG sweeps in fp32, everything else fp64.  North star:
     per-iteration cost within 1e-5 relative of the fp64 path."""
     p = make_problem(shape, seed, outlier_frac=0.01)
     a = _solve(p, max_iterations=12)
+    if env:
+        monkeypatch.setenv(env, "1")                                    # the fp32 sweeps with the single-CTA step / without graph replay
     b = _solve(p, max_iterations=12, pcg_fp32=1)
     k = parity_window(b.trace, a.trace)
     assert k >= 8
