@@ -176,3 +176,42 @@ def partition_points(obs_pt: np.ndarray, M: int, world: int) -> list[tuple[int, 
         cuts.append(min(max(j, cuts[-1]), M))
     cuts.append(M)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+# ---- post-BA ground-plane stage -------------------------------------------------------
+def make_ground_scene(seed: int, M: int, *, extent: float = 30.0, noise: float = 0.3, outlier_frac: float = 0.1,
+                      tilt: float = 0.4, n_cams: int = 8, on_plane_frac: float = 0.0):
+    """A map as the tracker hands it to ``PointsPlaneFit_RANSAC`` (``src/sfm_tracker.cpp:884``): M points scattered about a
+    tilted, shifted ground plane with Gaussian height noise, a fraction of outliers well above it (buildings, trees), and
+    cameras flying over it looking down.  ``on_plane_frac`` puts that fraction of points EXACTLY on a coordinate-aligned
+    plane before the tilt is applied with tilt = 0 (ties in the distance median).  Returns (pts M x 3, cam_RT n_cams x 12).
+    """
+    rng = np.random.default_rng(seed)
+    pts = np.c_[rng.uniform(-extent, extent, M), rng.uniform(-extent, extent, M), noise * rng.standard_normal(M)]
+    n_out = int(outlier_frac * M)
+    pts[:n_out, 2] += rng.uniform(2.0, 15.0, n_out)
+    n_on = int(on_plane_frac * M)
+    if n_on:
+        pts[n_out:n_out + n_on, 2] = 0.0
+    cams = np.zeros((n_cams, 3, 4))
+    centres = np.c_[rng.uniform(-extent, extent, n_cams), rng.uniform(-extent, extent, n_cams), rng.uniform(40, 60, n_cams)]
+    for i in range(n_cams):
+        yaw = rng.uniform(-np.pi, np.pi)
+        Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+        Rc = np.diag([1.0, -1.0, -1.0]) @ Rz            # looking down -z of the world
+        cams[i, :, :3] = Rc
+        cams[i, :, 3] = -Rc @ centres[i]
+    if tilt > 0:
+        w = rng.normal(0, tilt, 3)
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t = rng.normal(0, 5, 3)
+        pts = pts @ R.T + t
+        for i in range(n_cams):                          # x_cam = Rc (R^t (X' - t)) + tc
+            Rc, tc = cams[i, :, :3].copy(), cams[i, :, 3].copy()
+            cams[i, :, :3] = Rc @ R.T
+            cams[i, :, 3] = tc - Rc @ R.T @ t
+    pts = np.ascontiguousarray(pts[rng.permutation(M)])
+    return pts, np.ascontiguousarray(cams.reshape(n_cams, 12))

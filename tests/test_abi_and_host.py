@@ -13,10 +13,10 @@ from sequencesfm_b200.synth import SHAPES, make_problem, mean_reprojection_error
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "b200ba.h")).read()
+def _declared_symbols(header="b200ba.h", prefix="b200ba_"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200ba_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,6 +26,14 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), f"libb200ba.so does not export {sym}"
     assert sorted(binding.ABI_SYMBOLS) == declared
+    # the post-BA stage header
+    from sequencesfm_b200 import post
+    declared_post = _declared_symbols("b200ba_post.h", "b200post_")
+    assert len(declared_post) >= 9
+    for sym in declared_post:
+        assert hasattr(lib, sym), f"libb200ba.so does not export {sym}"
+    assert sorted(post.ABI_SYMBOLS) == declared_post
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["b200ba.h", "b200ba_post.h"]
 
 
 def test_options_struct_layout_and_defaults():

@@ -1,0 +1,58 @@
+"""Timing of the post-BA ground-plane stage (b200post_*) beside the reference's own CPU functions on the same map.
+    python tools/post_bench.py [M ...]      -> one JSON object on stdout
+"""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sequencesfm_b200 import post as ppost
+from sequencesfm_b200.synth import make_ground_scene
+from oracle import post as opost
+
+
+def one(stage, M, H=100, cpu=True):
+    pts, cams = make_ground_scene(7, M)
+    stream = opost.rand_stream(7, 4 * H + 64)
+    tri, _ = opost.oracle_draw_triples(M, H, stream)
+    stage.ground_stage(pts, cams, tri)                       # warm-up: allocations, module load
+    best = None
+    for _ in range(3):
+        t = time.perf_counter()
+        fit, p2, c2, axes = stage.ground_stage(pts, cams, tri)
+        wall = (time.perf_counter() - t) * 1e3
+        if best is None or wall < best["wall_ms"]:
+            best = {"wall_ms": wall, "ms_device": fit.ms_device, "ms_kernels": fit.ms_kernels, "gpu_launches": fit.gpu_launches}
+    fit = stage.plane_fit(pts, tri)
+    kern = {ppost.KERNELS[w]: stage.time_kernel(w, 10) for w in range(4)}
+    pairs = M * H
+    out = {"M": M, "n_ransac": H, "n_kept": fit.n_kept, "n_inliers": fit.n_inliers, "select_fallback": fit.select_fallback,
+           **best, "kernels_ms": kern,
+           "pair_evaluations_per_s": {k: pairs / (v * 1e-3) for k, v in kern.items() if "mask" not in k},
+           "points_bytes": 24 * M}
+    if cpu:
+        t = time.perf_counter()
+        if opost.have_ref():
+            r, _ = opost.ref_plane_fit(pts, stream, H, 2.0)
+            a = opost.ref_ground_axes(cams[0], r.plane, r.plane_se3)
+            opost.ref_transform(a, pts[r.keep != 0], cams)
+            kind = "reference"
+        else:
+            r = opost.oracle_plane_fit(pts, tri, 2.0)
+            a = opost.oracle_ground_axes(cams[0], r.plane, r.plane_se3)
+            opost.oracle_transform(a, pts[r.keep != 0], cams)
+            kind = "port"
+        out["cpu"] = {"kind": kind, "cores": 1, "ms": (time.perf_counter() - t) * 1e3,
+                      "what": "PointsPlaneFit_RANSAC + CalcCameraGround_axes + TransCloudPoint + TransCamera (src/sfm_utils.cpp), single thread like the reference"}
+        out["cpFilter_identical_to_cpu"] = bool(np.array_equal(r.keep, fit.keep))
+        out["speedup_wall"] = out["cpu"]["ms"] / best["wall_ms"]
+    return out
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [100000, 993923]
+    with ppost.PostStage(device=0) as stage:
+        print(json.dumps({"post_stage": [one(stage, M) for M in sizes]}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
