@@ -16,6 +16,14 @@ struct Matx34d {
     double& operator()(int r, int c) { return val[4 * r + c]; }
     const double& operator()(int r, int c) const { return val[4 * r + c]; }
 };
+struct Vec4d {
+    double val[4];
+    Vec4d() { std::memset(val, 0, sizeof val); }
+    double& operator[](int i) { return val[i]; }
+    const double& operator[](int i) const { return val[i]; }
+    double& operator()(int i) { return val[i]; }
+    const double& operator()(int i) const { return val[i]; }
+};
 // CV_64F matrix, row-major, only what the BA boundary touches: at<double>(r,c), at<double>(i), clone()
 class Mat {
 public:

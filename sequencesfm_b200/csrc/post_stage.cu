@@ -40,7 +40,19 @@
 
 namespace {
 
-constexpr int kHG = 8;                 // hypotheses per CTA
+// Compile-time knobs of the sweeps, A/B-timed on a B200 at 993 923 points x 100 hypotheses (tools/build_post_variants.sh;
+// kernels of one call, ms): HG/PPT/MINB = 8/1/2 1.02, 8/2/2 1.10, 8/2/1 1.11, 8/1/1 1.36, 8/4/1 0.98, 4/4/2 0.96, 4/2/3 0.92.
+#ifndef POST_HG
+#define POST_HG 4
+#endif
+#ifndef POST_PPT
+#define POST_PPT 2
+#endif
+#ifndef POST_MINB
+#define POST_MINB 3
+#endif
+constexpr int kHG = POST_HG;           // hypotheses per CTA
+constexpr int kPPT = POST_PPT;         // points per thread and loop iteration (all loads issued before the FP64 chains)
 constexpr int kBits = 11;
 constexpr int kBins = 1 << kBits;
 constexpr int kSweepThreads = 256;
@@ -66,7 +78,11 @@ __global__ void k_post_init(SelState* st, unsigned* cand_n, const double* hyp, i
 }
 
 // One radix pass for all hypotheses.  grid = (point slices, hypothesis groups); dynamic smem = kHG * kBins counters.
-__global__ void __launch_bounds__(kSweepThreads, 2)
+// AGG: warp-aggregate equal bins before the shared atomic (the exponent pass puts a whole warp into 2-3 bins); the later
+// passes scatter over 2048 mantissa bins and use plain shared atomics (MATCH.ANY costs one round per distinct value).
+// Two points per thread and iteration: both loads are in flight before the 2 x kHG dependent FP64 chains start.
+template <bool AGG>
+__global__ void __launch_bounds__(kSweepThreads, POST_MINB)
 k_post_hist(const double* __restrict__ pts, int M, int H, const double* __restrict__ hyp, const SelState* __restrict__ st,
             int shift, int hi_shift, unsigned mask, unsigned* __restrict__ hist, double* res, int check_finite)
 {
@@ -85,20 +101,34 @@ k_post_hist(const double* __restrict__ pts, int M, int H, const double* __restri
     }
     __syncthreads();
     bool bad = false;
-    for (int base = blockIdx.x * kSweepThreads; base < M; base += gridDim.x * kSweepThreads) {
-        const int i = base + tid;
-        const bool in = i < M;
-        double x = 0, y = 0, z = 0;
-        if (in) { x = pts[3 * (size_t)i]; y = pts[3 * (size_t)i + 1]; z = pts[3 * (size_t)i + 2]; }
-        if (check_finite && in && !(isfinite(x) && isfinite(y) && isfinite(z))) bad = true;
+    for (int base = blockIdx.x * kPPT * kSweepThreads; base < M; base += gridDim.x * kPPT * kSweepThreads) {   // uniform per CTA
+        double x[kPPT], y[kPPT], z[kPPT];
+        bool in[kPPT];
+#pragma unroll
+        for (int u = 0; u < kPPT; ++u) {
+            const int i = base + u * kSweepThreads + tid;
+            in[u] = i < M;
+            x[u] = in[u] ? pts[3 * (size_t)i] : 0.0; y[u] = in[u] ? pts[3 * (size_t)i + 1] : 0.0; z[u] = in[u] ? pts[3 * (size_t)i + 2] : 0.0;
+        }
+        if (check_finite) {
+#pragma unroll
+            for (int u = 0; u < kPPT; ++u) if (in[u] && !(isfinite(x[u]) && isfinite(y[u]) && isfinite(z[u]))) bad = true;
+        }
 #pragma unroll
         for (int g = 0; g < kHG; ++g) {
             if (!s_valid[g]) continue;                                    // uniform over the CTA
-            const unsigned long long key = (unsigned long long)__double_as_longlong(plane_dist(x, y, z, s_hyp[g]));
-            const bool pass = in && (key >> hi_shift) == s_prefix[g];
-            const unsigned bin = (unsigned)(key >> shift) & mask;
-            const unsigned peers = __match_any_sync(0xffffffffu, pass ? bin : (0x80000000u | (unsigned)lane));
-            if (pass && lane == __ffs(peers) - 1) atomicAdd(&s_hist[g * kBins + bin], (unsigned)__popc(peers));
+#pragma unroll
+            for (int u = 0; u < kPPT; ++u) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(plane_dist(x[u], y[u], z[u], s_hyp[g]));
+                const bool pass = in[u] && (key >> hi_shift) == s_prefix[g];
+                const unsigned bin = (unsigned)(key >> shift) & mask;
+                if (AGG) {
+                    const unsigned peers = __match_any_sync(0xffffffffu, pass ? bin : 0xffffffffu);
+                    if (pass && lane == __ffs(peers) - 1) atomicAdd(&s_hist[g * kBins + bin], (unsigned)__popc(peers));
+                } else if (pass) {
+                    atomicAdd(&s_hist[g * kBins + bin], 1u);
+                }
+            }
         }
     }
     __syncthreads();
@@ -145,7 +175,7 @@ k_post_scan(unsigned* __restrict__ hist, SelState* __restrict__ st, int bits)
 }
 
 // Append the keys that survived the first passes (key >> hi_shift == prefix) to each hypothesis' candidate buffer.
-__global__ void __launch_bounds__(kSweepThreads, 2)
+__global__ void __launch_bounds__(kSweepThreads, POST_MINB)
 k_post_gather(const double* __restrict__ pts, int M, int H, const double* __restrict__ hyp, const SelState* __restrict__ st,
               int hi_shift, unsigned long long* __restrict__ cand, unsigned* __restrict__ cand_n, int cap)
 {
@@ -161,15 +191,25 @@ k_post_gather(const double* __restrict__ pts, int M, int H, const double* __rest
         for (int k = 0; k < 6; ++k) s_hyp[tid][k] = v ? hyp[h * kHypStride + k] : 0.0;
     }
     __syncthreads();
-    for (int i = blockIdx.x * kSweepThreads + tid; i < M; i += gridDim.x * kSweepThreads) {
-        const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+    for (int base = blockIdx.x * kPPT * kSweepThreads + tid; base < M; base += gridDim.x * kPPT * kSweepThreads) {
+        double x[kPPT], y[kPPT], z[kPPT];
+        bool in[kPPT];
+#pragma unroll
+        for (int u = 0; u < kPPT; ++u) {
+            const int i = base + u * kSweepThreads;
+            in[u] = i < M;
+            x[u] = in[u] ? pts[3 * (size_t)i] : 0.0; y[u] = in[u] ? pts[3 * (size_t)i + 1] : 0.0; z[u] = in[u] ? pts[3 * (size_t)i + 2] : 0.0;
+        }
 #pragma unroll
         for (int g = 0; g < kHG; ++g) {
             if (!s_valid[g]) continue;
-            const unsigned long long key = (unsigned long long)__double_as_longlong(plane_dist(x, y, z, s_hyp[g]));
-            if ((key >> hi_shift) == s_prefix[g]) {
-                const unsigned slot = atomicAdd(&cand_n[h0 + g], 1u);
-                if (slot < (unsigned)cap) cand[(size_t)(h0 + g) * cap + slot] = key;
+#pragma unroll
+            for (int u = 0; u < kPPT; ++u) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(plane_dist(x[u], y[u], z[u], s_hyp[g]));
+                if (in[u] && (key >> hi_shift) == s_prefix[g]) {
+                    const unsigned slot = atomicAdd(&cand_n[h0 + g], 1u);
+                    if (slot < (unsigned)cap) cand[(size_t)(h0 + g) * cap + slot] = key;
+                }
             }
         }
     }
@@ -215,7 +255,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Truncated sums: partial[(h, slice)] = sum over this CTA's points of min(err, sigma2).
-__global__ void __launch_bounds__(kSweepThreads, 2)
+__global__ void __launch_bounds__(kSweepThreads, POST_MINB)
 k_post_score(const double* __restrict__ pts, int M, int H, const double* __restrict__ hyp, double* __restrict__ partial)
 {
     __shared__ double s_hyp[kHG][7];
@@ -232,12 +272,23 @@ k_post_score(const double* __restrict__ pts, int M, int H, const double* __restr
     double acc[kHG];
 #pragma unroll
     for (int g = 0; g < kHG; ++g) acc[g] = 0.0;
-    for (int i = blockIdx.x * kSweepThreads + tid; i < M; i += gridDim.x * kSweepThreads) {
-        const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+    for (int base = blockIdx.x * kPPT * kSweepThreads + tid; base < M; base += gridDim.x * kPPT * kSweepThreads) {
+        double x[kPPT], y[kPPT], z[kPPT];
+        bool in[kPPT];
+#pragma unroll
+        for (int u = 0; u < kPPT; ++u) {
+            const int i = base + u * kSweepThreads;
+            in[u] = i < M;
+            x[u] = in[u] ? pts[3 * (size_t)i] : 0.0; y[u] = in[u] ? pts[3 * (size_t)i + 1] : 0.0; z[u] = in[u] ? pts[3 * (size_t)i + 2] : 0.0;
+        }
 #pragma unroll
         for (int g = 0; g < kHG; ++g) {
-            const double e = plane_dist(x, y, z, s_hyp[g]), s2 = s_hyp[g][6];
-            acc[g] += e > s2 ? s2 : e;
+            const double s2 = s_hyp[g][6];
+#pragma unroll
+            for (int u = 0; u < kPPT; ++u) {        // same order as before for u = 0, 1, ...: fixed, run-to-run reproducible
+                const double e = plane_dist(x[u], y[u], z[u], s_hyp[g]);
+                acc[g] += in[u] ? (e > s2 ? s2 : e) : 0.0;
+            }
         }
     }
 #pragma unroll
@@ -251,19 +302,22 @@ k_post_score(const double* __restrict__ pts, int M, int H, const double* __restr
 }
 
 // Sum the slices in order, then the reference's `if (dSumError < dBestDistSquared)` scan from 9e99: first minimum wins.
+// dynamic smem: H doubles.
 __global__ void __launch_bounds__(256)
 k_post_pick(const double* __restrict__ partial, int nx, int H, const double* __restrict__ hyp, double* __restrict__ score, double* res)
 {
+    extern __shared__ double s_score[];
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
         double v = 0.0;
         for (int k = 0; k < nx; ++k) v += partial[(size_t)h * nx + k];
         score[h] = v;
+        s_score[h] = hyp[h * kHypStride + 7] != 0.0 ? v : INFINITY;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         double best = 9e99; int bi = -1;
         for (int h = 0; h < H; ++h)
-            if (hyp[h * kHypStride + 7] != 0.0 && score[h] < best) { best = score[h]; bi = h; }
+            if (s_score[h] < best) { best = s_score[h]; bi = h; }
         res[R_BEST] = (double)bi; res[R_SCORE] = best;
         if (bi >= 0) {
             res[R_SIGMA2] = hyp[bi * kHypStride + 6];
@@ -288,7 +342,7 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out 
 }
 
 // Distances to the winning plane: cpFilter (err < k sigma2), inliers (err < sigma2): count and coordinate sums.
-__global__ void __launch_bounds__(kSweepThreads, 2)
+__global__ void __launch_bounds__(kSweepThreads, POST_MINB)
 k_post_mask(const double* __restrict__ pts, int M, const double* __restrict__ res, double k_threshold,
             int* __restrict__ keep, double* __restrict__ partial /* 5 per CTA: cnt, kept, sx, sy, sz */)
 {
@@ -309,20 +363,30 @@ k_post_mask(const double* __restrict__ pts, int M, const double* __restrict__ re
     block_reduce_store<5>(v, partial);
 }
 
-__global__ void k_post_mean(const double* __restrict__ partial, int nx, double* res)
+// Second-level sums: warp k adds the nx per-CTA partials of quantity k (lane-strided, then a fixed shuffle tree).
+template <int NV>
+__device__ __forceinline__ double second_level_sum(const double* __restrict__ partial, int nx)
+{
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = 0.0;
+    if (k < NV) for (int b = lane; b < nx; b += 32) v += partial[(size_t)b * NV + k];
+    return warp_sum(v);
+}
+
+__global__ void __launch_bounds__(32 * 5) k_post_mean(const double* __restrict__ partial, int nx, double* res)
 {
     __shared__ double s[5];
-    const int k = threadIdx.x;
-    double v = 0.0;
-    if (k < 5) { for (int b = 0; b < nx; ++b) v += partial[(size_t)b * 5 + k]; s[k] = v; }
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double v = second_level_sum<5>(partial, nx);
+    if (lane == 0) s[k] = v;
     __syncthreads();
-    if (k == 0) res[R_CNT] = v;
-    if (k == 1) res[R_KEPT] = v;
-    if (k >= 2 && k < 5) res[R_IMEAN + k - 2] = __ddiv_rn(v, s[0]);       // v3MeanOfInliers / vv3Inliers.size()
+    if (threadIdx.x == 0) res[R_CNT] = s[0];
+    if (threadIdx.x == 1) res[R_KEPT] = s[1];
+    if (threadIdx.x >= 2 && threadIdx.x < 5) res[R_IMEAN + threadIdx.x - 2] = __ddiv_rn(s[threadIdx.x], s[0]);   // v3MeanOfInliers / size
 }
 
 // Scatter matrix of the inliers about their mean (6 unique entries), src/sfm_utils.cpp:911-916.
-__global__ void __launch_bounds__(kSweepThreads, 2)
+__global__ void __launch_bounds__(kSweepThreads, POST_MINB)
 k_post_scatter(const double* __restrict__ pts, int M, const double* __restrict__ res, double* __restrict__ partial /* 6 per CTA */)
 {
     __shared__ double s_b[10];
@@ -342,14 +406,10 @@ k_post_scatter(const double* __restrict__ pts, int M, const double* __restrict__
     block_reduce_store<6>(v, partial);
 }
 
-__global__ void k_post_scatter_final(const double* __restrict__ partial, int nx, double* res)
+__global__ void __launch_bounds__(32 * 6) k_post_scatter_final(const double* __restrict__ partial, int nx, double* res)
 {
-    const int k = threadIdx.x;
-    if (k < 6) {
-        double v = 0.0;
-        for (int b = 0; b < nx; ++b) v += partial[(size_t)b * 6 + k];
-        res[R_SCATTER + k] = v;
-    }
+    const double v = second_level_sum<6>(partial, nx);
+    if ((threadIdx.x & 31) == 0) res[R_SCATTER + (threadIdx.x >> 5)] = v;
 }
 
 // TransCloudPoint (Matrix4d * [p; 1], accumulated left to right, src/sfm_utils.cpp:1148-1179); pos == NULL: in place,
@@ -588,7 +648,7 @@ Grid grid_for(const b200post_handle* h, int H)
     Grid g;
     g.groups = (H + kHG - 1) / kHG;
     g.nx = std::max(1, (2 * h->sms + g.groups - 1) / g.groups);   // >= 2 CTAs per SM over the whole grid
-    g.nx1 = 4 * h->sms;                                            // single-hypothesis sweeps
+    g.nx1 = 2 * h->sms;                                            // single-hypothesis sweeps
     return g;
 }
 
@@ -604,8 +664,14 @@ void launch_hist(b200post_handle* h, const Grid& g, int pass, int check_finite)
 {
     static const int shifts[6] = {52, 41, 30, 19, 8, 0};
     const int shift = shifts[pass], bits = pass == 5 ? 8 : kBits;
-    k_post_hist<<<dim3(g.nx, g.groups), kSweepThreads, kHG * kBins * sizeof(unsigned), h->stream>>>(
-        h->d_pts, h->M, h->H, h->d_hyp, h->d_st, shift, shift + bits, (1u << bits) - 1u, h->d_hist, h->d_res, check_finite);
+    const dim3 grid(g.nx, g.groups);
+    const size_t smem = kHG * kBins * sizeof(unsigned);
+    if (pass == 0)
+        k_post_hist<true><<<grid, kSweepThreads, smem, h->stream>>>(h->d_pts, h->M, h->H, h->d_hyp, h->d_st, shift, shift + bits,
+                                                                   (1u << bits) - 1u, h->d_hist, h->d_res, check_finite);
+    else
+        k_post_hist<false><<<grid, kSweepThreads, smem, h->stream>>>(h->d_pts, h->M, h->H, h->d_hyp, h->d_st, shift, shift + bits,
+                                                                    (1u << bits) - 1u, h->d_hist, h->d_res, check_finite);
 }
 
 // Median of every hypothesis' distances -> sigma2 in d_hyp.  radix_only: all six passes.
@@ -639,15 +705,15 @@ int run_score_and_moments(b200post_handle* h, const Grid& g)
     int rc;
     k_post_score<<<dim3(g.nx, g.groups), kSweepThreads, 0, h->stream>>>(h->d_pts, h->M, h->H, h->d_hyp, h->d_partial);
     if ((rc = launch_check(h, "k_post_score"))) return rc;
-    k_post_pick<<<1, 256, 0, h->stream>>>(h->d_partial, g.nx, h->H, h->d_hyp, h->d_score, h->d_res);
+    k_post_pick<<<1, 256, (size_t)h->H * sizeof(double), h->stream>>>(h->d_partial, g.nx, h->H, h->d_hyp, h->d_score, h->d_res);
     if ((rc = launch_check(h, "k_post_pick"))) return rc;
     k_post_mask<<<g.nx1, kSweepThreads, 0, h->stream>>>(h->d_pts, h->M, h->d_res, h->k_threshold, h->d_keep, h->d_partial);
     if ((rc = launch_check(h, "k_post_mask"))) return rc;
-    k_post_mean<<<1, 32, 0, h->stream>>>(h->d_partial, g.nx1, h->d_res);
+    k_post_mean<<<1, 32 * 5, 0, h->stream>>>(h->d_partial, g.nx1, h->d_res);
     if ((rc = launch_check(h, "k_post_mean"))) return rc;
     k_post_scatter<<<g.nx1, kSweepThreads, 0, h->stream>>>(h->d_pts, h->M, h->d_res, h->d_partial);
     if ((rc = launch_check(h, "k_post_scatter"))) return rc;
-    k_post_scatter_final<<<1, 32, 0, h->stream>>>(h->d_partial, g.nx1, h->d_res);
+    k_post_scatter_final<<<1, 32 * 6, 0, h->stream>>>(h->d_partial, g.nx1, h->d_res);
     return launch_check(h, "k_post_scatter_final");
 }
 
@@ -768,7 +834,8 @@ int b200post_create(int32_t device, int32_t select_cap, b200post_handle** out)
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_res, kResDoubles * sizeof(double)) == cudaSuccess;
     ok = ok && cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_post_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kHG * kBins * sizeof(unsigned))) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_post_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kHG * kBins * sizeof(unsigned))) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_post_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kHG * kBins * sizeof(unsigned))) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_post_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 6000 * (int)sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) {
         g_post_create_error = std::string("b200post_create: ") + cudaGetErrorString(cudaGetLastError());

@@ -49,9 +49,10 @@ def one(stage, M, H=100, cpu=True):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [100000, 993923]
+    cpu = "--no-cpu" not in sys.argv
+    sizes = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [100000, 993923]
     with ppost.PostStage(device=0) as stage:
-        print(json.dumps({"post_stage": [one(stage, M) for M in sizes]}, indent=1))
+        print(json.dumps({"post_stage": [one(stage, M, cpu=cpu) for M in sizes]}, indent=1))
 
 
 if __name__ == "__main__":
