@@ -186,6 +186,7 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--no-post", action="store_true", help="skip the post-BA ground-plane stage (SURVEY.md 8(f) rank 1) reported beside")
     ap.add_argument("--ref-lm-iterations", type=int, default=0)
     ap.add_argument("--steps-ref", type=int, default=1)
     ap.add_argument("--warmup-ref", type=int, default=0)
@@ -399,6 +400,22 @@ def main() -> int:
         except Exception as ex:  # pragma: no cover
             cpu = {"value": None, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
 
+    # ---------------- post-BA ground-plane stage, reported beside; not part of `value` ----------------
+    post = None
+    if rank == 0 and world == 1 and not args.no_post:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("post_bench", os.path.join(ROOT, "tools", "post_bench.py"))
+            pb = importlib.util.module_from_spec(spec); spec.loader.exec_module(pb)
+            from sequencesfm_b200 import post as ppost
+            with ppost.PostStage(device=local_rank) as st:
+                post = pb.one(st, M, 100, cpu=not args.no_cpu_baseline)
+            post["what"] = ("what SfM_Tracker::bundleAdjustFrames runs after every BA (src/sfm_tracker.cpp:876-908) on a map of this BA problem's "
+                            "point count: RANSAC plane fit over 100 hypotheses (exact median of the distances per hypothesis), outlier mask, "
+                            "ground axes, re-axis + compaction; host arrays in, host arrays out (b200post_ground_stage)")
+        except Exception as ex:  # pragma: no cover
+            post = {"error": str(ex)}
+
     if rank == 0:
         line = {"metric": "lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": K_steps,
                 "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -411,7 +428,7 @@ def main() -> int:
                 "observations_per_s": value * K, "cg_steps_per_s": value * CG_STEPS,
                 "wall_ms_per_step": wall_ms / K_steps,
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_iter * K_steps)),
-                "roofline": roof, "cpu_baseline": cpu, "pcg_fp32": f32,
+                "roofline": roof, "cpu_baseline": cpu, "pcg_fp32": f32, "post_stage": post,
                 "final_mean_px": res.mean_px[1], "initial_mean_px": res.mean_px[0]}
         print(json.dumps(line))
     if world > 1:

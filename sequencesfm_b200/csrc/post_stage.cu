@@ -647,7 +647,9 @@ Grid grid_for(const b200post_handle* h, int H)
 {
     Grid g;
     g.groups = (H + kHG - 1) / kHG;
-    g.nx = std::max(1, (2 * h->sms + g.groups - 1) / g.groups);   // >= 2 CTAs per SM over the whole grid
+    // one wave that fills (not overfills) the POST_MINB resident CTAs per SM: the sweeps are grid-stride, a few CTAs too
+    // many would cost a whole second wave.  (ncu, 2 CTAs / SM: 31-41 % of the stall samples waited for the point loads.)
+    g.nx = std::max(1, (POST_MINB * h->sms) / g.groups);
     g.nx1 = 2 * h->sms;                                            // single-hypothesis sweeps
     return g;
 }
