@@ -133,6 +133,14 @@ int b200ba_finish(b200ba_handle* h, b200ba_report* report);
  * "discarded" (report.ret == -1) the inputs are returned unchanged, like the reference. */
 int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts);
 
+/* The same with the points left on the device (state stays resident between the stages that
+ * follow a BA): cam_RT (host, N x 12, may be NULL) as above; d_pts = DEVICE memory on the handle's device, M x 3 doubles in
+ * the caller's point order, bit-identical to what b200ba_get_result writes.  b200post_ground_stage_ba (b200ba_post.h)
+ * chains the post-BA stage onto it.  The reference has no counterpart (its BA result lives in host containers). */
+int b200ba_get_result_device(b200ba_handle* h, double* cam_RT, double* d_pts);
+/* Sizes of the uploaded problem (any pointer may be NULL). */
+int b200ba_problem_size(const b200ba_handle* h, int32_t* N, int32_t* M, int32_t* K);
+
 /* ---- multi-GPU: one handle per rank, problem partitioned by point ---- */
 #define B200BA_COMM_ID_BYTES 128
 int b200ba_comm_unique_id(void* id_bytes);    /* rank 0 creates, the launcher broadcasts (e.g. torch.distributed) */

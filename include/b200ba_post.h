@@ -87,6 +87,17 @@ int b200post_ground_stage(b200post_handle* h, int32_t M, double* pts, int32_t N,
                           int32_t n_ransac, const int32_t* triples, double k_threshold,
                           b200post_plane* out, int32_t* keep, int32_t* m_out, double* axes_se3);
 
+/* The same chained onto a finished bundle adjustment WITHOUT the points leaving the device:
+ * the adjusted points are taken from `ba` through b200ba_get_result_device (caller order, de-normalised, bit-identical to
+ * b200ba_get_result), fitted, masked, re-axed and compacted; only the kept points come back.  `ba` must have returned from
+ * b200ba_solve / b200ba_finish and live on the same CUDA device as `h`.  pts_out: room for M x 3 doubles (M = the BA
+ * problem's point count), the first *m_out rows are written; cam_RT: N x 12, receives the adjusted AND re-axed cameras;
+ * keep: M (may be NULL).  Replaces the sequence adjustBundle_* -> write-back -> PointsPlaneFit_RANSAC -> ... -> TransCamera
+ * of src/sfm_tracker.cpp:862-904 with one upload (the BA problem) and one download (the kept points). */
+int b200post_ground_stage_ba(b200post_handle* h, b200ba_handle* ba, int32_t n_ransac, const int32_t* triples,
+                             double k_threshold, b200post_plane* out, int32_t* keep, int32_t* m_out, double* pts_out,
+                             double* cam_RT, double* axes_se3);
+
 /* Time `reps` launches of one kernel of the last b200post_plane_fit problem (still resident) with CUDA events.
  * which: 0 radix histogram sweep, 1 candidate gather sweep, 2 score sweep, 3 mask + moments sweep. */
 int b200post_debug_time_kernel(b200post_handle* h, int32_t which, int32_t reps, double* ms_per_launch);

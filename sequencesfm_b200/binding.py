@@ -24,6 +24,7 @@ STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 ABI_SYMBOLS = [
     "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
+    "b200ba_get_result_device", "b200ba_problem_size",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
     "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
 ]
@@ -215,6 +216,12 @@ class Engine:
         return SolveResult(rep.ret, rep.status, rep.iterations, tr[: rep.n_trace].copy(), (rep.mean_px[0], rep.mean_px[1]),
                            cam, pts, rep.total_cg_steps, rep.gpu_launches, rep.ms_solve, rep.ms_h2d, rep.ms_d2h,
                            rep.initial_cost, rep.final_cost)
+
+    def get_result(self):
+        """``b200ba_get_result``: (cam_RT N x 12, pts M x 3) as new host arrays."""
+        cam = np.empty((self.N, 12)); pts = np.empty((self.M, 3))
+        self._check(self.lib.b200ba_get_result(self.h, _dp(cam), _dp(pts)))
+        return cam, pts
 
     def solve(self) -> SolveResult:
         rep, tr = self._report()

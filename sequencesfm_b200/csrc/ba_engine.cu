@@ -1172,6 +1172,57 @@ int b200ba_get_result(b200ba_handle* h, double* cam_RT, double* pts)
     return 0;
 }
 
+int b200ba_problem_size(const b200ba_handle* h, int32_t* N, int32_t* M, int32_t* K)
+{
+    if (!h || !h->have_problem) return B200BA_E_STATE;
+    if (N) *N = h->N;
+    if (M) *M = h->M;
+    if (K) *K = h->K;
+    return 0;
+}
+
+// Point half of b200ba_get_result without leaving the device: caller order restored and the normaliser undone by a kernel
+// (X * scale + mean evaluated as a rounded product and a rounded sum, like the host loop above: identical bits).
+__global__ void k_export_points(const double* __restrict__ X4, const int* __restrict__ orig_of_new, int M, int nrm,
+                                double scale, double m0, double m1, double m2, double* __restrict__ out)
+{
+    const int jn = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jn >= M) return;
+    const size_t j = (size_t)orig_of_new[jn];
+    const double x = X4[4 * (size_t)jn], y = X4[4 * (size_t)jn + 1], z = X4[4 * (size_t)jn + 2];
+    out[3 * j] = nrm ? __dadd_rn(__dmul_rn(x, scale), m0) : x;
+    out[3 * j + 1] = nrm ? __dadd_rn(__dmul_rn(y, scale), m1) : y;
+    out[3 * j + 2] = nrm ? __dadd_rn(__dmul_rn(z, scale), m2) : z;
+}
+
+int b200ba_get_result_device(b200ba_handle* h, double* cam_RT, double* d_pts)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->finished) return fail(h, B200BA_E_STATE, "b200ba_get_result_device before b200ba_solve / b200ba_finish");
+    if (int rc = b200ba_get_result(h, cam_RT, nullptr)) return rc;
+    const int M = h->M;
+    if (!d_pts || !M) return 0;
+    CU(cudaSetDevice(h->device));
+    const bool discard = h->opt.discard_converged && h->h_st.status == B200BA_STATUS_CONVERGED;
+    if (discard) {                                               // results discarded: the inputs, unchanged
+        CU(cudaMemcpy(d_pts, h->h_pts.data(), sizeof(double) * 3 * (size_t)M, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int* d_perm = nullptr;
+    CU(cudaMalloc((void**)&d_perm, sizeof(int) * (size_t)M));
+    cudaError_t e = cudaMemcpyAsync(d_perm, h->orig_of_new.data(), sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_export_points<<<cdiv(M, 256), 256, 0, h->stream>>>(h->d.X[h->h_st.cur], d_perm, M, h->opt.normalize != 0, h->scale,
+                                                             h->mean[0], h->mean[1], h->mean[2], d_pts);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_perm);
+    if (e != cudaSuccess) return fail(h, B200BA_E_CUDA, "b200ba_get_result_device: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // stage-level access
 // ---------------------------------------------------------------------------------------------------------

@@ -77,6 +77,39 @@ __global__ void k_post_init(SelState* st, unsigned* cand_n, const double* hyp, i
     if (h < kResDoubles) res[h] = 0.0;
 }
 
+// 3 points -> (mean, unit normal) per hypothesis, src/sfm_utils.cpp:847-854, in the reference's operation order with IEEE
+// division / square root and no FMA: ((A + B) + C) / 3, n = (C - A) x (B - A), skipped when |n.n| < 1e-9 (valid = 0),
+// n / sqrt(nx^2 + (ny^2 + nz^2)).  One thread per hypothesis; the points are gathered from the resident cloud.
+__global__ void k_post_hypotheses(const double* __restrict__ pts, const int* __restrict__ triples, int H, double* __restrict__ hyp,
+                                  unsigned* __restrict__ n_degenerate)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const double* A = pts + 3 * (size_t)triples[3 * h];
+    const double* B = pts + 3 * (size_t)triples[3 * h + 1];
+    const double* C = pts + 3 * (size_t)triples[3 * h + 2];
+    double mean[3], ca[3], ba[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        mean[k] = __ddiv_rn(__dadd_rn(__dadd_rn(A[k], B[k]), C[k]), 3.0);
+        ca[k] = __dsub_rn(C[k], A[k]);
+        ba[k] = __dsub_rn(B[k], A[k]);
+    }
+    double n[3];
+    n[0] = __dsub_rn(__dmul_rn(ca[1], ba[2]), __dmul_rn(ca[2], ba[1]));
+    n[1] = __dsub_rn(__dmul_rn(ca[2], ba[0]), __dmul_rn(ca[0], ba[2]));
+    n[2] = __dsub_rn(__dmul_rn(ca[0], ba[1]), __dmul_rn(ca[1], ba[0]));
+    const double nn = __dadd_rn(__dmul_rn(n[0], n[0]), __dadd_rn(__dmul_rn(n[1], n[1]), __dmul_rn(n[2], n[2])));
+    double* q = hyp + (size_t)h * kHypStride;
+    const bool ok = fabs(nn) >= 1e-9;                      // NaN counts as degenerate
+    const double len = __dsqrt_rn(nn);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { q[k] = mean[k]; q[3 + k] = ok ? __ddiv_rn(n[k], len) : 0.0; }
+    q[6] = 0.0;
+    q[7] = ok ? 1.0 : 0.0;
+    if (!ok) atomicAdd(n_degenerate, 1u);
+}
+
 // One radix pass for all hypotheses.  grid = (point slices, hypothesis groups); dynamic smem = kHG * kBins counters.
 // AGG: warp-aggregate equal bins before the shared atomic (the exponent pass puts a whole warp into 2-3 bins); the later
 // passes scatter over 2048 mantissa bins and use plain shared atomics (MATCH.ANY costs one round per distinct value).
@@ -584,7 +617,7 @@ struct b200post_handle {
     double* d_pts = nullptr; double* d_out = nullptr; int* d_keep = nullptr; int* d_pos = nullptr; size_t cap_pts = 0;
     double* d_hyp = nullptr; unsigned* d_hist = nullptr; SelState* d_st = nullptr; SelState* d_st_b = nullptr;
     unsigned long long* d_cand = nullptr; unsigned* d_cand_n = nullptr; unsigned long long* d_med = nullptr;
-    double* d_score = nullptr; size_t cap_hyp = 0;
+    double* d_score = nullptr; int* d_tri = nullptr; unsigned* d_ndeg = nullptr; size_t cap_hyp = 0;
     double* d_partial = nullptr; size_t cap_partial = 0;
     double* d_res = nullptr;
     double* d_cams = nullptr; size_t cap_cams = 0;
@@ -625,7 +658,8 @@ int reserve_hyp(b200post_handle* h, size_t H)
     const size_t n = ((H + kHG - 1) / kHG) * kHG + 64;
     int rc;
     if ((rc = grow(h, h->d_hyp, n * kHypStride)) || (rc = grow(h, h->d_hist, n * kBins)) || (rc = grow(h, h->d_st, n)) ||
-        (rc = grow(h, h->d_st_b, n)) || (rc = grow(h, h->d_cand_n, n)) || (rc = grow(h, h->d_med, n)) || (rc = grow(h, h->d_score, n))) return rc;
+        (rc = grow(h, h->d_st_b, n)) || (rc = grow(h, h->d_cand_n, n)) || (rc = grow(h, h->d_med, n)) || (rc = grow(h, h->d_score, n)) || (rc = grow(h, h->d_tri, 3 * n)) ||
+        (rc = grow(h, h->d_ndeg, (size_t)1))) return rc;
     if (h->cap > 0 && (rc = grow(h, h->d_cand, n * (size_t)h->cap))) return rc;
     POST_CUDA(cudaMemsetAsync(h->d_hist, 0, n * kBins * sizeof(unsigned), h->stream));
     POST_CUDA(cudaMemsetAsync(h->d_hyp, 0, n * kHypStride * sizeof(double), h->stream));
@@ -719,31 +753,18 @@ int run_score_and_moments(b200post_handle* h, const Grid& g)
     return launch_check(h, "k_post_scatter_final");
 }
 
-// Upload, fit, leave points / mask resident.  keep_host may be NULL.
+// Fit on the points in d_pts (uploaded from `pts` first unless pts == NULL: already resident, b200post_ground_stage_ba);
+// points and mask stay resident.  keep_host may be NULL.
 int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ransac, const int32_t* triples,
-                 double k_threshold, b200post_plane* out, int32_t* keep_host)
+                 double k_threshold, b200post_plane* out, int32_t* keep_host, bool resident = false)
 {
     if (!h) return B200BA_E_INVALID;
-    if (!pts || !triples || !out || n_ransac <= 0) { h->err = "b200post_plane_fit: null argument or n_ransac <= 0"; return B200BA_E_INVALID; }
+    if ((!pts && !resident) || !triples || !out || n_ransac <= 0) { h->err = "b200post_plane_fit: null argument or n_ransac <= 0"; return B200BA_E_INVALID; }
     if (M < 10) { h->err = "b200post_plane_fit: fewer than 10 points (the reference returns -1, src/sfm_utils.cpp:826-829)"; return B200BA_E_INVALID; }
     POST_CUDA(cudaSetDevice(h->device));
-    h->launches = 0;
-    // hypotheses: 3 points -> (mean, unit normal), src/sfm_utils.cpp:847-854
-    std::vector<double> hyp((size_t)n_ransac * kHypStride, 0.0);
-    int degenerate = 0;
-    for (int i = 0; i < n_ransac; ++i) {
-        const int32_t a = triples[3 * i], b = triples[3 * i + 1], c = triples[3 * i + 2];
-        if (a < 0 || b < 0 || c < 0 || a >= M || b >= M || c >= M) { h->err = "b200post_plane_fit: hypothesis index out of range"; return B200BA_E_INVALID; }
-        const double *A = pts + 3 * (size_t)a, *B = pts + 3 * (size_t)b, *C = pts + 3 * (size_t)c;
-        double* q = &hyp[(size_t)i * kHypStride];
-        double ca[3], ba[3], n[3];
-        for (int k = 0; k < 3; ++k) { q[k] = ((A[k] + B[k]) + C[k]) / 3.0; ca[k] = C[k] - A[k]; ba[k] = B[k] - A[k]; }
-        cross3(ca, ba, n);
-        if (!(std::fabs(dot3_pairwise(n, n)) >= 1e-9)) { ++degenerate; continue; }      // `continue` of :853 (NaN counts as degenerate)
-        unit3(n);
-        q[3] = n[0]; q[4] = n[1]; q[5] = n[2]; q[7] = 1.0;
-    }
-    if (degenerate == n_ransac) { h->err = "b200post_plane_fit: every hypothesis is degenerate"; return B200BA_E_INVALID; }
+    if (!resident) h->launches = 0;
+    for (int i = 0; i < 3 * n_ransac; ++i)
+        if (triples[i] < 0 || triples[i] >= M) { h->err = "b200post_plane_fit: hypothesis index out of range"; return B200BA_E_INVALID; }
 
     int rc;
     if ((rc = reserve_points(h, (size_t)M)) || (rc = reserve_hyp(h, (size_t)n_ransac))) return rc;
@@ -752,9 +773,14 @@ int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ran
     if ((rc = reserve_partial(h, std::max((size_t)g.nx * (size_t)(g.groups * kHG), (size_t)g.nx1 * 6)))) return rc;
 
     POST_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    POST_CUDA(cudaMemcpyAsync(h->d_pts, pts, (size_t)M * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    POST_CUDA(cudaMemcpyAsync(h->d_hyp, hyp.data(), hyp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!resident) POST_CUDA(cudaMemcpyAsync(h->d_pts, pts, (size_t)M * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    POST_CUDA(cudaMemcpyAsync(h->d_tri, triples, (size_t)n_ransac * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    POST_CUDA(cudaMemsetAsync(h->d_ndeg, 0, sizeof(unsigned), h->stream));
     POST_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    k_post_hypotheses<<<(n_ransac + 127) / 128, 128, 0, h->stream>>>(h->d_pts, h->d_tri, n_ransac, h->d_hyp, h->d_ndeg);
+    if ((rc = launch_check(h, "k_post_hypotheses"))) return rc;
+    unsigned degenerate_u = 0;
+    POST_CUDA(cudaMemcpyAsync(&degenerate_u, h->d_ndeg, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     const bool radix_only = h->cap <= 0;
     if ((rc = run_select(h, g, radix_only)) || (rc = run_score_and_moments(h, g))) return rc;
     POST_CUDA(cudaEventRecord(h->ev[2], h->stream));
@@ -774,7 +800,9 @@ int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ran
     if (keep_host) POST_CUDA(cudaMemcpyAsync(keep_host, h->d_keep, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     POST_CUDA(cudaEventRecord(h->ev[3], h->stream));
     POST_CUDA(cudaStreamSynchronize(h->stream));
+    const int degenerate = (int)degenerate_u;
     if (flags & 1ull) { h->err = "b200post_plane_fit: non-finite point coordinate"; return B200BA_E_INVALID; }
+    if (degenerate == n_ransac) { h->err = "b200post_plane_fit: every hypothesis is degenerate"; return B200BA_E_INVALID; }
     if (res[R_BEST] < 0) { h->err = "b200post_plane_fit: no hypothesis scored below 9e99"; return B200BA_E_INVALID; }
     if (res[R_CNT] < 1) { h->err = "b200post_plane_fit: no inliers"; return B200BA_E_INVALID; }
 
@@ -854,7 +882,7 @@ void b200post_destroy(b200post_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_pts, h->d_out, h->d_keep, h->d_pos, h->d_hyp, h->d_hist, h->d_st, h->d_st_b, h->d_cand, h->d_cand_n,
-                    h->d_med, h->d_score, h->d_partial, h->d_res, h->d_cams, h->d_scan_tmp};
+                    h->d_med, h->d_score, h->d_tri, h->d_ndeg, h->d_partial, h->d_res, h->d_cams, h->d_scan_tmp};
     for (void* p : bufs) if (p) cudaFree(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -927,14 +955,11 @@ int b200post_transform(b200post_handle* h, const double* axes, int32_t M, double
     return B200BA_OK;
 }
 
-int b200post_ground_stage(b200post_handle* h, int32_t M, double* pts, int32_t N, double* cam_RT,
-                          int32_t n_ransac, const int32_t* triples, double k_threshold,
-                          b200post_plane* out, int32_t* keep, int32_t* m_out, double* axes_out)
+// Tail shared by the two ground-stage entry points: the fit is done, points and mask are resident.
+static int ground_stage_tail(b200post_handle* h, int32_t M, double* pts_out, int32_t N, double* cam_RT,
+                             b200post_plane* out, int32_t* m_out, double* axes_out)
 {
-    if (!h) return B200BA_E_INVALID;
-    if (!cam_RT || N < 1 || !m_out) { h->err = "b200post_ground_stage: needs at least one camera and m_out"; return B200BA_E_INVALID; }
-    int rc = fit_resident(h, M, pts, n_ransac, triples, k_threshold, out, keep);
-    if (rc) return rc;
+    int rc;
     double axes[12];
     if ((rc = b200post_ground_axes(cam_RT, out->plane, out->plane_se3, axes))) return rc;
     for (double v : axes) if (!std::isfinite(v)) { h->err = "b200post_ground_stage: ground axes are not finite (plane through the camera axis?)"; return B200BA_E_INVALID; }
@@ -949,9 +974,10 @@ int b200post_ground_stage(b200post_handle* h, int32_t M, double* pts, int32_t N,
         h->cap_scan_tmp = need;
     }
     POST_CUDA(cub::DeviceScan::ExclusiveSum(h->d_scan_tmp, need, h->d_keep, h->d_pos, M, h->stream));
+    h->launches += 2;                                        // cub: DeviceScanInitKernel + DeviceScanKernel
     k_post_reaxis_points<<<(M + 255) / 256, 256, 0, h->stream>>>(h->d_pts, M, to_se3(axes), h->d_keep, h->d_pos, h->d_out);
     if ((rc = launch_check(h, "k_post_reaxis_points"))) return rc;
-    POST_CUDA(cudaMemcpyAsync(pts, h->d_out, (size_t)out->n_kept * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    POST_CUDA(cudaMemcpyAsync(pts_out, h->d_out, (size_t)out->n_kept * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if ((rc = reaxis_cameras(h, axes, N, cam_RT))) return rc;
     POST_CUDA(cudaEventRecord(h->ev[1], h->stream));
     POST_CUDA(cudaStreamSynchronize(h->stream));
@@ -961,6 +987,40 @@ int b200post_ground_stage(b200post_handle* h, int32_t M, double* pts, int32_t N,
     out->gpu_launches = h->launches;
     *m_out = out->n_kept;
     return B200BA_OK;
+}
+
+int b200post_ground_stage(b200post_handle* h, int32_t M, double* pts, int32_t N, double* cam_RT,
+                          int32_t n_ransac, const int32_t* triples, double k_threshold,
+                          b200post_plane* out, int32_t* keep, int32_t* m_out, double* axes_out)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!cam_RT || N < 1 || !m_out) { h->err = "b200post_ground_stage: needs at least one camera and m_out"; return B200BA_E_INVALID; }
+    int rc = fit_resident(h, M, pts, n_ransac, triples, k_threshold, out, keep);
+    if (rc) return rc;
+    return ground_stage_tail(h, M, pts, N, cam_RT, out, m_out, axes_out);
+}
+
+int b200post_ground_stage_ba(b200post_handle* h, b200ba_handle* ba, int32_t n_ransac, const int32_t* triples, double k_threshold,
+                             b200post_plane* out, int32_t* keep, int32_t* m_out, double* pts_out, double* cam_RT,
+                             double* axes_out)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!ba || !pts_out || !cam_RT || !m_out) { h->err = "b200post_ground_stage_ba: null argument"; return B200BA_E_INVALID; }
+    int32_t N = 0, M = 0;
+    if (b200ba_problem_size(ba, &N, &M, nullptr) != B200BA_OK || N < 1) { h->err = "b200post_ground_stage_ba: the BA handle holds no problem"; return B200BA_E_STATE; }
+    if (M < 10) { h->err = "b200post_plane_fit: fewer than 10 points (the reference returns -1, src/sfm_utils.cpp:826-829)"; return B200BA_E_INVALID; }
+    POST_CUDA(cudaSetDevice(h->device));
+    h->launches = 0;
+    int rc;
+    if ((rc = reserve_points(h, (size_t)M))) return rc;          // before the export: growing frees the old buffer
+    POST_CUDA(cudaStreamSynchronize(h->stream));
+    if (b200ba_get_result_device(ba, cam_RT, h->d_pts) != B200BA_OK) {   // must live on the same device as this handle
+        h->err = std::string("b200post_ground_stage_ba: ") + b200ba_last_error(ba);
+        return B200BA_E_STATE;
+    }
+    ++h->launches;                                               // k_export_points
+    if ((rc = fit_resident(h, M, nullptr, n_ransac, triples, k_threshold, out, keep, true))) return rc;
+    return ground_stage_tail(h, M, pts_out, N, cam_RT, out, m_out, axes_out);
 }
 
 int b200post_debug_time_kernel(b200post_handle* h, int32_t which, int32_t reps, double* ms_per_launch)

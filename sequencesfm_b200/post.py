@@ -17,7 +17,7 @@ from .binding import B200BAError, load
 # every symbol include/b200ba_post.h declares
 ABI_SYMBOLS = [
     "b200post_create", "b200post_destroy", "b200post_last_error", "b200post_draw_triples", "b200post_plane_fit",
-    "b200post_ground_axes", "b200post_transform", "b200post_ground_stage", "b200post_debug_time_kernel",
+    "b200post_ground_axes", "b200post_transform", "b200post_ground_stage", "b200post_ground_stage_ba", "b200post_debug_time_kernel",
 ]
 KERNELS = {0: "k_post_hist (exponent pass)", 1: "k_post_gather", 2: "k_post_score", 3: "k_post_mask"}
 
@@ -67,6 +67,8 @@ def _lib():
         lib.b200post_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         lib.b200post_ground_stage.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                               C.c_double, C.POINTER(Plane), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+        lib.b200post_ground_stage_ba.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.POINTER(Plane), C.c_void_p,
+                                                 C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200post_debug_time_kernel.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         lib._post_ready = True
     return lib
@@ -157,6 +159,20 @@ class PostStage:
         pl = Plane()
         self._check(self._lib.b200post_ground_stage(self._h, len(p), _vp(p), len(c), _vp(c), len(tri), _vp(tri), k_threshold,
                                                     C.byref(pl), _vp(keep), C.byref(m_out), _vp(axes)))
+        return self._result(pl, keep), p[:m_out.value].copy(), c, axes.reshape(3, 4)
+
+    def ground_stage_ba(self, engine, triples: np.ndarray, k_threshold: float = 2.0):
+        """The stage chained onto a finished ``binding.Engine`` without the points leaving the device
+        (``b200post_ground_stage_ba``); returns (fit, kept transformed points, adjusted + re-axed cameras, axes)."""
+        tri = np.ascontiguousarray(triples, np.int32)
+        p = np.zeros((engine.M, 3))
+        c = np.zeros((engine.N, 12))
+        keep = np.zeros(engine.M, np.int32)
+        axes = np.zeros(12)
+        m_out = C.c_int32(0)
+        pl = Plane()
+        self._check(self._lib.b200post_ground_stage_ba(self._h, engine.h, len(tri), _vp(tri), k_threshold, C.byref(pl), _vp(keep),
+                                                       C.byref(m_out), _vp(p), _vp(c), _vp(axes)))
         return self._result(pl, keep), p[:m_out.value].copy(), c, axes.reshape(3, 4)
 
     def time_kernel(self, which: int, reps: int = 10) -> float:

@@ -213,3 +213,31 @@ def test_cpp_adapter_runs_the_tracker_sequence(tmp_path, mode):
     po, co = opost.oracle_transform(axes, pts[o.keep != 0], cams)      # from the adapter's own axes: bit-exact
     assert _same_bits(p_out, po) and _same_bits(cam_out, co)
     np.testing.assert_allclose(axes, opost.oracle_ground_axes(cams[0], o.plane, o.plane_se3), rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("discard", [0, 1])
+def test_stage_chained_onto_a_bundle_adjustment_on_the_device(stage, discard):
+    """b200post_ground_stage_ba: the adjusted points go from the BA engine to the plane fit without leaving the device
+    (b200ba_get_result_device) - same bits as downloading them with b200ba_get_result and running the stage on the host
+    arrays.  discard = 1: gradient-converged result discarded like src/sfm_ba_ssba.cpp:221 -> the inputs flow through."""
+    from sequencesfm_b200 import binding
+    from sequencesfm_b200.synth import make_problem
+    p = make_problem("ladybug", 3)
+    kw = dict(device=0, max_iterations=6) if not discard else dict(device=0, max_iterations=50, gradient_threshold=1e30, discard_converged=1)
+    with binding.Engine(**kw) as eng:
+        eng.set_problem_from(p)
+        res = eng.solve()
+        assert (res.ret == -1) == bool(discard)
+        tri = _triples(91, p.M, 100)
+        fit_d, pts_d, cams_d, axes_d = stage.ground_stage_ba(eng, tri)
+        assert eng.N == p.N and eng.M == p.M
+    if discard:
+        assert np.array_equal(res.pts, p.pts)
+    fit_h, pts_h, cams_h, axes_h = stage.ground_stage(res.pts, res.cam_RT, tri)
+    assert np.array_equal(fit_d.keep, fit_h.keep) and fit_d.sigma2 == fit_h.sigma2 and fit_d.best_hypothesis == fit_h.best_hypothesis
+    assert _same_bits(fit_d.plane_se3, fit_h.plane_se3) and _same_bits(axes_d, axes_h)
+    assert _same_bits(pts_d, pts_h) and _same_bits(cams_d, cams_h)
+    o = opost.oracle_plane_fit(res.pts, tri, 2.0)                     # and the checker on the downloaded BA result
+    assert np.array_equal(fit_d.keep, o.keep) and fit_d.sigma2 == o.sigma2
+    po, co = opost.oracle_transform(axes_d, res.pts[o.keep != 0], res.cam_RT)
+    assert _same_bits(pts_d, po) and _same_bits(cams_d, co)

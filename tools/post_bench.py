@@ -48,11 +48,38 @@ def one(stage, M, H=100, cpu=True):
     return out
 
 
+def chained(stage, shape="venice"):
+    """After a BA: download + host-array stage (what the reference's call sequence implies) vs b200post_ground_stage_ba."""
+    from sequencesfm_b200 import binding
+    from sequencesfm_b200.synth import make_problem
+    p = make_problem(shape, 1)
+    tri, _ = opost.oracle_draw_triples(p.M, 100, opost.rand_stream(7, 464))
+    with binding.Engine(device=0, max_iterations=2) as eng:
+        eng.set_problem_from(p)
+        res = eng.solve()                                    # includes get_result (the reference's write-back)
+        best = {}
+        for _ in range(3):
+            t = time.perf_counter(); r2 = eng.get_result() if hasattr(eng, "get_result") else None; t_get = (time.perf_counter() - t) * 1e3
+            pts = res.pts if r2 is None else r2[1]
+            cams = res.cam_RT if r2 is None else r2[0]
+            t = time.perf_counter(); fit_h, ph, ch, _ = stage.ground_stage(pts, cams, tri); t_host = (time.perf_counter() - t) * 1e3
+            t = time.perf_counter(); fit_d, pd, cd, _ = stage.ground_stage_ba(eng, tri); t_dev = (time.perf_counter() - t) * 1e3
+            if not best or t_dev < best["chained_wall_ms"]:
+                best = {"get_result_wall_ms": t_get, "host_array_stage_wall_ms": t_host, "chained_wall_ms": t_dev,
+                        "chained_ms_device": fit_d.ms_device, "host_array_ms_device": fit_h.ms_device}
+        best["identical"] = bool(np.array_equal(pd, ph) and np.array_equal(cd, ch) and np.array_equal(fit_d.keep, fit_h.keep))
+        best["shape"] = f"{shape} {p.N}/{p.M}/{p.K}"
+    return best
+
+
 def main():
     cpu = "--no-cpu" not in sys.argv
     sizes = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [100000, 993923]
     with ppost.PostStage(device=0) as stage:
-        print(json.dumps({"post_stage": [one(stage, M, cpu=cpu) for M in sizes]}, indent=1))
+        out = {"post_stage": [one(stage, M, cpu=cpu) for M in sizes]}
+        if "--chained" in sys.argv:
+            out["after_ba"] = chained(stage)
+        print(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
