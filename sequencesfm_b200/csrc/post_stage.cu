@@ -23,6 +23,7 @@
 // Distances are evaluated exactly like the reference's Eigen expression |(p - mean) . n| = |d0 n0 + (d1 n1 + d2 n2)|
 // with __dsub_rn / __dmul_rn / __dadd_rn so that no FMA is contracted: medians, sigma^2 and the mask are bit-exact.
 #include "../../include/b200ba_post.h"
+#include "pinned_pool.h"
 
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
@@ -36,6 +37,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -753,6 +755,23 @@ int run_score_and_moments(b200post_handle* h, const Grid& g)
     return launch_check(h, "k_post_scatter_final");
 }
 
+// Large host<->device copies go through the library's pinned staging pool (pinned_pool.h): a few host threads move the
+// caller's pageable array into / out of page-locked memory, the DMA then runs at PCIe speed instead of the ~12 GB/s of a
+// pageable cudaMemcpy.
+void threaded_copy(void* dst, const void* src, size_t bytes)
+{
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = bytes >= ((size_t)4 << 20) ? (int)std::max(1u, std::min(8u, hw)) : 1;
+    if (T == 1) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) {
+        const size_t a = bytes * t / T, b = bytes * (t + 1) / T;
+        th.emplace_back([=] { std::memcpy((char*)dst + a, (const char*)src + a, b - a); });
+    }
+    std::memcpy(dst, src, bytes / T);
+    for (auto& x : th) x.join();
+}
+
 // Fit on the points in d_pts (uploaded from `pts` first unless pts == NULL: already resident, b200post_ground_stage_ba);
 // points and mask stay resident.  keep_host may be NULL.
 int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ransac, const int32_t* triples,
@@ -772,8 +791,15 @@ int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ran
     const Grid g = grid_for(h, n_ransac);
     if ((rc = reserve_partial(h, std::max((size_t)g.nx * (size_t)(g.groups * kHG), (size_t)g.nx1 * 6)))) return rc;
 
+    const size_t pts_bytes = (size_t)M * 3 * sizeof(double), keep_bytes = (size_t)M * sizeof(int);
+    b200ba::PinnedPool::Lease stage;                           // held until this call returns (all copies synchronised by then)
+    b200ba::g_pinned.lease(stage, (resident ? 0 : pts_bytes) + keep_bytes);
+    char* stage_keep = stage.p + (resident ? 0 : pts_bytes);
     POST_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    if (!resident) POST_CUDA(cudaMemcpyAsync(h->d_pts, pts, (size_t)M * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!resident) {
+        threaded_copy(stage.p, pts, pts_bytes);
+        POST_CUDA(cudaMemcpyAsync(h->d_pts, stage.p, pts_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     POST_CUDA(cudaMemcpyAsync(h->d_tri, triples, (size_t)n_ransac * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     POST_CUDA(cudaMemsetAsync(h->d_ndeg, 0, sizeof(unsigned), h->stream));
     POST_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -797,9 +823,10 @@ int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ran
         POST_CUDA(cudaStreamSynchronize(h->stream));
         std::memcpy(&flags, &res[R_FLAGS], sizeof(flags));
     }
-    if (keep_host) POST_CUDA(cudaMemcpyAsync(keep_host, h->d_keep, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (keep_host) POST_CUDA(cudaMemcpyAsync(stage_keep, h->d_keep, keep_bytes, cudaMemcpyDeviceToHost, h->stream));
     POST_CUDA(cudaEventRecord(h->ev[3], h->stream));
     POST_CUDA(cudaStreamSynchronize(h->stream));
+    if (keep_host) threaded_copy(keep_host, stage_keep, keep_bytes);
     const int degenerate = (int)degenerate_u;
     if (flags & 1ull) { h->err = "b200post_plane_fit: non-finite point coordinate"; return B200BA_E_INVALID; }
     if (degenerate == n_ransac) { h->err = "b200post_plane_fit: every hypothesis is degenerate"; return B200BA_E_INVALID; }
@@ -944,11 +971,17 @@ int b200post_transform(b200post_handle* h, const double* axes, int32_t M, double
     int rc;
     if (M > 0 && pts) {
         if ((rc = reserve_points(h, (size_t)M))) return rc;
-        POST_CUDA(cudaMemcpyAsync(h->d_pts, pts, (size_t)M * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const size_t bytes = (size_t)M * 3 * sizeof(double);
+        b200ba::PinnedPool::Lease stage;
+        b200ba::g_pinned.lease(stage, bytes);
+        threaded_copy(stage.p, pts, bytes);
+        POST_CUDA(cudaMemcpyAsync(h->d_pts, stage.p, bytes, cudaMemcpyHostToDevice, h->stream));
         k_post_reaxis_points<<<(M + 255) / 256, 256, 0, h->stream>>>(h->d_pts, M, to_se3(axes), nullptr, nullptr, h->d_out);
         if ((rc = launch_check(h, "k_post_reaxis_points"))) return rc;
-        POST_CUDA(cudaMemcpyAsync(pts, h->d_out, (size_t)M * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        POST_CUDA(cudaMemcpyAsync(stage.p, h->d_out, bytes, cudaMemcpyDeviceToHost, h->stream));
         h->M = 0;                                           // d_pts no longer holds a fitted problem
+        POST_CUDA(cudaStreamSynchronize(h->stream));
+        threaded_copy(pts, stage.p, bytes);
     }
     if ((rc = reaxis_cameras(h, axes, N, cam_RT))) return rc;
     POST_CUDA(cudaStreamSynchronize(h->stream));
@@ -977,10 +1010,14 @@ static int ground_stage_tail(b200post_handle* h, int32_t M, double* pts_out, int
     h->launches += 2;                                        // cub: DeviceScanInitKernel + DeviceScanKernel
     k_post_reaxis_points<<<(M + 255) / 256, 256, 0, h->stream>>>(h->d_pts, M, to_se3(axes), h->d_keep, h->d_pos, h->d_out);
     if ((rc = launch_check(h, "k_post_reaxis_points"))) return rc;
-    POST_CUDA(cudaMemcpyAsync(pts_out, h->d_out, (size_t)out->n_kept * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const size_t out_bytes = (size_t)out->n_kept * 3 * sizeof(double);
+    b200ba::PinnedPool::Lease stage;
+    b200ba::g_pinned.lease(stage, out_bytes);
+    POST_CUDA(cudaMemcpyAsync(stage.p, h->d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     if ((rc = reaxis_cameras(h, axes, N, cam_RT))) return rc;
     POST_CUDA(cudaEventRecord(h->ev[1], h->stream));
     POST_CUDA(cudaStreamSynchronize(h->stream));
+    threaded_copy(pts_out, stage.p, out_bytes);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     out->ms_device += ms;
