@@ -123,3 +123,34 @@ def pba_adjust(p, *, double: bool = True, args: tuple[str, ...] = (), threads: i
     code = int(stats[5])
     return PbaResult(float(stats[0]), float(stats[1]), int(stats[2]), int(stats[3]), float(stats[4]),
                      chr(code) if code > 0 else "", int(stats[6]), cam, pts)
+
+
+# ---- the reference's model-file readers / writers (oracle/io_ref_harness.cpp -> oracle/_ref/libio_ref.so) -------------
+def have_io() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libio_ref.so"))
+
+
+def io_load(path: str) -> dict:
+    """LoadModelFile of Thirdparty/pba/pba/pba_util.h:392-411 (float storage widened to float64 arrays)."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libio_ref.so"))
+    N, M, K = C.c_int(0), C.c_int(0), C.c_int(0)
+    if lib.io_ref_load(str(path).encode(), C.byref(N), C.byref(M), C.byref(K)) != 0:
+        raise RuntimeError(f"reference LoadModelFile failed on {path}")
+    N, M, K = N.value, M.value, K.value
+    out = {"cam_RT": np.zeros((N, 12)), "focal": np.zeros(N), "radial": np.zeros(N), "distortion_type": np.zeros(N, np.int32),
+           "pts": np.zeros((M, 3)), "pt_rgb": np.zeros((M, 3), np.int32), "obs_xy": np.zeros((K, 2)),
+           "obs_cam": np.zeros(K, np.int32), "obs_pt": np.zeros(K, np.int32)}
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.io_ref_copy(vp(out["cam_RT"]), vp(out["focal"]), vp(out["radial"]), vp(out["distortion_type"]), vp(out["pts"]), vp(out["pt_rgb"]),
+                    vp(out["obs_xy"]), vp(out["obs_cam"]), vp(out["obs_pt"]))
+    return out
+
+
+def io_save(path: str, kind: int, m) -> None:
+    """SaveBundlerModel (kind 0) / SaveNVM (1) / SaveBundlerOut (2) of pba_util.h on the arrays of a sequencesfm_b200.io.Model."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libio_ref.so"))
+    vp = lambda a, dt: np.ascontiguousarray(a, dt).ctypes.data_as(C.c_void_p)
+    keep = [np.ascontiguousarray(m.cam_RT, np.float64), np.ascontiguousarray(m.focal, np.float64), np.ascontiguousarray(m.radial, np.float64),
+            np.ascontiguousarray(m.distortion_type, np.int32), np.ascontiguousarray(m.pts, np.float64), np.ascontiguousarray(m.pt_rgb, np.int32),
+            np.ascontiguousarray(m.obs_xy, np.float64), np.ascontiguousarray(m.obs_cam, np.int32), np.ascontiguousarray(m.obs_pt, np.int32)]
+    lib.io_ref_save(str(path).encode(), kind, len(m.cam_RT), len(m.pts), len(m.obs_cam), *[a.ctypes.data_as(C.c_void_p) for a in keep])

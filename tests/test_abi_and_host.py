@@ -33,7 +33,12 @@ def test_library_exports_every_declared_symbol():
     for sym in declared_post:
         assert hasattr(lib, sym), f"libb200ba.so does not export {sym}"
     assert sorted(post.ABI_SYMBOLS) == declared_post
-    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["b200ba.h", "b200ba_post.h"]
+    from sequencesfm_b200 import io as bio
+    declared_io = _declared_symbols("b200ba_io.h", "b200io_")
+    for sym in declared_io:
+        assert hasattr(lib, sym), f"libb200ba.so does not export {sym}"
+    assert sorted(bio.ABI_SYMBOLS) == declared_io
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["b200ba.h", "b200ba_io.h", "b200ba_post.h"]
 
 
 def test_options_struct_layout_and_defaults():
