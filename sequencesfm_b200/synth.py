@@ -215,3 +215,35 @@ def make_ground_scene(seed: int, M: int, *, extent: float = 30.0, noise: float =
             cams[i, :, 3] = tc - Rc @ R.T @ t
     pts = np.ascontiguousarray(pts[rng.permutation(M)])
     return pts, np.ascontiguousarray(cams.reshape(n_cams, 12))
+
+
+# ---- two-view triangulation -----------------------------------------------------------
+def make_two_view(seed: int, n: int, *, baseline: float = 1.0, noise_px: float = 0.5, dist=None, f: float = 800.0,
+                  pp=(640.0, 360.0)):
+    """Two cameras `baseline` apart looking at n points 5-15 units ahead, pixel measurements with Gaussian noise (stored
+    as float32 like cv::KeyPoint::pt) and, optionally, lens distortion applied to the ideal pixels.
+    Returns (pt1, pt2, K, P, P1, X_true)."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[f, 0, pp[0]], [0, f * 1.01, pp[1]], [0, 0, 1.0]])
+    X = np.c_[rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.uniform(5, 15, n)]
+    P = np.hstack([np.eye(3), np.zeros((3, 1))])
+    w = rng.normal(0, 0.05, 3); th = np.linalg.norm(w); k = w / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    t = np.array([-baseline, 0.05 * baseline, 0.1 * baseline])
+    P1 = np.hstack([R, t[:, None]])
+
+    def project(Pm):
+        xc = X @ Pm[:, :3].T + Pm[:, 3]
+        x, y = xc[:, 0] / xc[:, 2], xc[:, 1] / xc[:, 2]
+        if dist is not None:
+            kk = np.zeros(8); kk[:len(dist)] = dist
+            r2 = x * x + y * y
+            rad = (1 + ((kk[4] * r2 + kk[1]) * r2 + kk[0]) * r2) / (1 + ((kk[7] * r2 + kk[6]) * r2 + kk[5]) * r2)
+            xd = x * rad + 2 * kk[2] * x * y + kk[3] * (r2 + 2 * x * x)
+            yd = y * rad + kk[2] * (r2 + 2 * y * y) + 2 * kk[3] * x * y
+            x, y = xd, yd
+        px = np.c_[x * K[0, 0] + K[0, 2], y * K[1, 1] + K[1, 2]] + rng.normal(0, noise_px, (n, 2))
+        return px.astype(np.float32)
+
+    return project(P), project(P1), K, P, P1, X

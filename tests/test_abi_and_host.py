@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared_io:
         assert hasattr(lib, sym), f"libb200ba.so does not export {sym}"
     assert sorted(bio.ABI_SYMBOLS) == declared_io
-    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["b200ba.h", "b200ba_io.h", "b200ba_post.h"]
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["b200ba.h", "b200ba_io.h", "b200ba_post.h", "b200ba_tri.h"]
 
 
 def test_options_struct_layout_and_defaults():
