@@ -33,6 +33,7 @@ public:
     template <class T> T& at(int r, int c) { return d[(size_t)r * cols + c]; }
     template <class T> const T& at(int r, int c) const { return d[(size_t)r * cols + c]; }
     template <class T> T& at(int i) { return d[i]; }
+    template <class T> const T& at(int i) const { return d[i]; }
     Mat clone() const { return *this; }
 };
 }
