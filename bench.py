@@ -416,6 +416,18 @@ def main() -> int:
         except Exception as ex:  # pragma: no cover
             post = {"error": str(ex)}
 
+    # ---------------- two-view triangulation feeding the BA, reported beside ----------------
+    tri_line = None
+    if rank == 0 and world == 1 and not args.no_post:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("tri_bench", os.path.join(ROOT, "tools", "tri_bench.py"))
+            tb = importlib.util.module_from_spec(spec); spec.loader.exec_module(tb)
+            tri_line = tb.run(1_000_000, cpu=not args.no_cpu_baseline, device=local_rank)
+            tri_line["what"] = "TriangulatePoints (src/sfm_triangulation.cpp:95-202) on 1 M matches, host arrays in / out (b200tri_triangulate)"
+        except Exception as ex:  # pragma: no cover
+            tri_line = {"error": str(ex)}
+
     if rank == 0:
         line = {"metric": "lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": K_steps,
                 "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -428,7 +440,7 @@ def main() -> int:
                 "observations_per_s": value * K, "cg_steps_per_s": value * CG_STEPS,
                 "wall_ms_per_step": wall_ms / K_steps,
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_iter * K_steps)),
-                "roofline": roof, "cpu_baseline": cpu, "pcg_fp32": f32, "post_stage": post,
+                "roofline": roof, "cpu_baseline": cpu, "pcg_fp32": f32, "post_stage": post, "triangulation": tri_line,
                 "final_mean_px": res.mean_px[1], "initial_mean_px": res.mean_px[0]}
         print(json.dumps(line))
     if world > 1:

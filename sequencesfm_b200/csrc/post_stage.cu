@@ -755,22 +755,7 @@ int run_score_and_moments(b200post_handle* h, const Grid& g)
     return launch_check(h, "k_post_scatter_final");
 }
 
-// Large host<->device copies go through the library's pinned staging pool (pinned_pool.h): a few host threads move the
-// caller's pageable array into / out of page-locked memory, the DMA then runs at PCIe speed instead of the ~12 GB/s of a
-// pageable cudaMemcpy.
-void threaded_copy(void* dst, const void* src, size_t bytes)
-{
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int T = bytes >= ((size_t)4 << 20) ? (int)std::max(1u, std::min(8u, hw)) : 1;
-    if (T == 1) { std::memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) {
-        const size_t a = bytes * t / T, b = bytes * (t + 1) / T;
-        th.emplace_back([=] { std::memcpy((char*)dst + a, (const char*)src + a, b - a); });
-    }
-    std::memcpy(dst, src, bytes / T);
-    for (auto& x : th) x.join();
-}
+using b200ba::threaded_copy;                              // pinned_pool.h
 
 // Fit on the points in d_pts (uploaded from `pts` first unless pts == NULL: already resident, b200post_ground_stage_ba);
 // points and mask stay resident.  keep_host may be NULL.

@@ -6,6 +6,7 @@
 // One thread per match, everything in registers; the matches are independent, so the kernel streams 16 B in and 44 B out
 // per match and is bound by its FP64 arithmetic (up to 10 Householder QR solves of a 4x3 system).
 #include "../../include/b200ba_tri.h"
+#include "pinned_pool.h"
 
 #include <cuda_runtime.h>
 
@@ -248,9 +249,13 @@ int b200tri_triangulate(b200tri_handle* h, int32_t n, const float* pt1, const fl
         h->cap = total + total / 4;
     }
     char* d = h->d_buf;
+    // host <-> device through the library's pinned staging pool (pinned_pool.h): [pt1 | pt2 | pts | err | pt1_out]
+    b200ba::PinnedPool::Lease stage;
+    b200ba::g_pinned.lease(stage, o_part);
     TRI_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    TRI_CUDA(cudaMemcpyAsync(d + o_pt1, pt1, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-    TRI_CUDA(cudaMemcpyAsync(d + o_pt2, pt2, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    b200ba::threaded_copy(stage.p + o_pt1, pt1, (size_t)n * 8);
+    b200ba::threaded_copy(stage.p + o_pt2, pt2, (size_t)n * 8);
+    TRI_CUDA(cudaMemcpyAsync(d + o_pt1, stage.p + o_pt1, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
     TRI_CUDA(cudaMemsetAsync(d + o_sc, 0, 16, h->stream));
     TRI_CUDA(cudaEventRecord(h->ev[1], h->stream));
     k_tri_points<<<nb, 128, 0, h->stream>>>((const float2*)(d + o_pt1), (const float2*)(d + o_pt2), n, t, (double*)(d + o_pts),
@@ -258,13 +263,16 @@ int b200tri_triangulate(b200tri_handle* h, int32_t n, const float* pt1, const fl
     k_tri_mean<<<1, 256, 0, h->stream>>>((const double*)(d + o_part), nb, (double*)(d + o_sc));
     TRI_CUDA(cudaGetLastError());
     TRI_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    if (pts) TRI_CUDA(cudaMemcpyAsync(pts, d + o_pts, (size_t)n * 24, cudaMemcpyDeviceToHost, h->stream));
-    if (reproj_err) TRI_CUDA(cudaMemcpyAsync(reproj_err, d + o_err, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (pt1_undistorted) TRI_CUDA(cudaMemcpyAsync(pt1_undistorted, d + o_out, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (pts || reproj_err || pt1_undistorted)
+        TRI_CUDA(cudaMemcpyAsync(stage.p + o_pts, d + o_pts, o_part - o_pts, cudaMemcpyDeviceToHost, h->stream));
     double sc[2];
     TRI_CUDA(cudaMemcpyAsync(sc, d + o_sc, 16, cudaMemcpyDeviceToHost, h->stream));
-    TRI_CUDA(cudaEventRecord(h->ev[3], h->stream));
     TRI_CUDA(cudaStreamSynchronize(h->stream));
+    if (pts) b200ba::threaded_copy(pts, stage.p + o_pts, (size_t)n * 24);
+    if (reproj_err) b200ba::threaded_copy(reproj_err, stage.p + o_err, (size_t)n * 8);
+    if (pt1_undistorted) b200ba::threaded_copy(pt1_undistorted, stage.p + o_out, (size_t)n * 8);
+    TRI_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    TRI_CUDA(cudaEventSynchronize(h->ev[3]));
     unsigned ndeg; std::memcpy(&ndeg, &sc[1], sizeof(ndeg));
     report->mean_reproj_error = sc[0] / (double)n;
     report->n_degenerate = (int32_t)ndeg;
