@@ -43,7 +43,9 @@
 namespace {
 
 // Compile-time knobs of the sweeps, A/B-timed on a B200 at 993 923 points x 100 hypotheses (tools/build_post_variants.sh;
-// kernels of one call, ms): HG/PPT/MINB = 8/1/2 1.02, 8/2/2 1.10, 8/2/1 1.11, 8/1/1 1.36, 8/4/1 0.98, 4/4/2 0.96, 4/2/3 0.92.
+// kernels of one call, ms): HG/PPT/MINB = 8/1/2 1.02, 8/2/2 1.10, 8/2/1 1.11, 8/1/1 1.36, 8/4/1 0.98, 4/4/2 0.96, 4/2/3 0.92;
+// with the grid filling exactly MINB CTAs per SM: 4/2/3 0.72, 4/1/4 0.83; + register prefetch of the next points
+// (POST_PREFETCH): 4/2/2 0.68, 4/2/3 0.95 (spills), 4/1/3 0.74, 4/1/4 0.96.
 #ifndef POST_HG
 #define POST_HG 4
 #endif
@@ -51,7 +53,10 @@ namespace {
 #define POST_PPT 2
 #endif
 #ifndef POST_MINB
-#define POST_MINB 3
+#define POST_MINB 2
+#endif
+#ifndef POST_PREFETCH
+#define POST_PREFETCH 1
 #endif
 constexpr int kHG = POST_HG;           // hypotheses per CTA
 constexpr int kPPT = POST_PPT;         // points per thread and loop iteration (all loads issued before the FP64 chains)
@@ -71,6 +76,35 @@ __device__ __forceinline__ double plane_dist(double x, double y, double z, const
     const double d0 = __dsub_rn(x, hp[0]), d1 = __dsub_rn(y, hp[1]), d2 = __dsub_rn(z, hp[2]);
     return fabs(__dadd_rn(__dmul_rn(d0, hp[3]), __dadd_rn(__dmul_rn(d1, hp[4]), __dmul_rn(d2, hp[5]))));
 }
+
+// kPPT points of one thread and loop iteration: point u is element first + u * kSweepThreads of the cloud.
+struct PtBatch { double x[kPPT], y[kPPT], z[kPPT]; bool in[kPPT]; };
+__device__ __forceinline__ void load_batch(const double* __restrict__ pts, int M, int first, PtBatch& b)
+{
+#pragma unroll
+    for (int u = 0; u < kPPT; ++u) {
+        const int i = first + u * kSweepThreads;
+        b.in[u] = i < M;
+        b.x[u] = b.in[u] ? pts[3 * (size_t)i] : 0.0; b.y[u] = b.in[u] ? pts[3 * (size_t)i + 1] : 0.0; b.z[u] = b.in[u] ? pts[3 * (size_t)i + 2] : 0.0;
+    }
+}
+// POST_PREFETCH: the next iteration's points are requested before the current ones are used (register double buffer).
+#if POST_PREFETCH
+#define SWEEP_LOOP(first_expr, cond_expr)                                                                     \
+    const int sweep_stride = gridDim.x * kPPT * kSweepThreads;                                                \
+    int sweep_first = (first_expr);                                                                           \
+    PtBatch cur; load_batch(pts, M, sweep_first, cur);                                                        \
+    for (int base = blockIdx.x * kPPT * kSweepThreads; (cond_expr); base += sweep_stride, sweep_first += sweep_stride)
+#define SWEEP_NEXT() PtBatch nxt; load_batch(pts, M, sweep_first + sweep_stride, nxt)
+#define SWEEP_ADVANCE() cur = nxt
+#else
+#define SWEEP_LOOP(first_expr, cond_expr)                                                                     \
+    const int sweep_stride = gridDim.x * kPPT * kSweepThreads;                                                \
+    int sweep_first = (first_expr);                                                                           \
+    for (int base = blockIdx.x * kPPT * kSweepThreads; (cond_expr); base += sweep_stride, sweep_first += sweep_stride)
+#define SWEEP_NEXT() PtBatch cur; load_batch(pts, M, sweep_first, cur)
+#define SWEEP_ADVANCE() ((void)0)
+#endif
 
 __global__ void k_post_init(SelState* st, unsigned* cand_n, const double* hyp, int H, unsigned rank, unsigned M, double* res)
 {
@@ -136,15 +170,9 @@ k_post_hist(const double* __restrict__ pts, int M, int H, const double* __restri
     }
     __syncthreads();
     bool bad = false;
-    for (int base = blockIdx.x * kPPT * kSweepThreads; base < M; base += gridDim.x * kPPT * kSweepThreads) {   // uniform per CTA
-        double x[kPPT], y[kPPT], z[kPPT];
-        bool in[kPPT];
-#pragma unroll
-        for (int u = 0; u < kPPT; ++u) {
-            const int i = base + u * kSweepThreads + tid;
-            in[u] = i < M;
-            x[u] = in[u] ? pts[3 * (size_t)i] : 0.0; y[u] = in[u] ? pts[3 * (size_t)i + 1] : 0.0; z[u] = in[u] ? pts[3 * (size_t)i + 2] : 0.0;
-        }
+    SWEEP_LOOP(blockIdx.x * kPPT * kSweepThreads + tid, base < M) {                                   // trip count uniform per CTA
+        SWEEP_NEXT();
+        const double (&x)[kPPT] = cur.x; const double (&y)[kPPT] = cur.y; const double (&z)[kPPT] = cur.z; const bool (&in)[kPPT] = cur.in;
         if (check_finite) {
 #pragma unroll
             for (int u = 0; u < kPPT; ++u) if (in[u] && !(isfinite(x[u]) && isfinite(y[u]) && isfinite(z[u]))) bad = true;
@@ -165,6 +193,7 @@ k_post_hist(const double* __restrict__ pts, int M, int H, const double* __restri
                 }
             }
         }
+        SWEEP_ADVANCE();
     }
     __syncthreads();
     for (int i = tid; i < kHG * kBins; i += kSweepThreads) {
@@ -226,15 +255,9 @@ k_post_gather(const double* __restrict__ pts, int M, int H, const double* __rest
         for (int k = 0; k < 6; ++k) s_hyp[tid][k] = v ? hyp[h * kHypStride + k] : 0.0;
     }
     __syncthreads();
-    for (int base = blockIdx.x * kPPT * kSweepThreads + tid; base < M; base += gridDim.x * kPPT * kSweepThreads) {
-        double x[kPPT], y[kPPT], z[kPPT];
-        bool in[kPPT];
-#pragma unroll
-        for (int u = 0; u < kPPT; ++u) {
-            const int i = base + u * kSweepThreads;
-            in[u] = i < M;
-            x[u] = in[u] ? pts[3 * (size_t)i] : 0.0; y[u] = in[u] ? pts[3 * (size_t)i + 1] : 0.0; z[u] = in[u] ? pts[3 * (size_t)i + 2] : 0.0;
-        }
+    SWEEP_LOOP(blockIdx.x * kPPT * kSweepThreads + tid, base + tid < M) {
+        SWEEP_NEXT();
+        const double (&x)[kPPT] = cur.x; const double (&y)[kPPT] = cur.y; const double (&z)[kPPT] = cur.z; const bool (&in)[kPPT] = cur.in;
 #pragma unroll
         for (int g = 0; g < kHG; ++g) {
             if (!s_valid[g]) continue;
@@ -247,6 +270,7 @@ k_post_gather(const double* __restrict__ pts, int M, int H, const double* __rest
                 }
             }
         }
+        SWEEP_ADVANCE();
     }
 }
 
@@ -307,24 +331,19 @@ k_post_score(const double* __restrict__ pts, int M, int H, const double* __restr
     double acc[kHG];
 #pragma unroll
     for (int g = 0; g < kHG; ++g) acc[g] = 0.0;
-    for (int base = blockIdx.x * kPPT * kSweepThreads + tid; base < M; base += gridDim.x * kPPT * kSweepThreads) {
-        double x[kPPT], y[kPPT], z[kPPT];
-        bool in[kPPT];
-#pragma unroll
-        for (int u = 0; u < kPPT; ++u) {
-            const int i = base + u * kSweepThreads;
-            in[u] = i < M;
-            x[u] = in[u] ? pts[3 * (size_t)i] : 0.0; y[u] = in[u] ? pts[3 * (size_t)i + 1] : 0.0; z[u] = in[u] ? pts[3 * (size_t)i + 2] : 0.0;
-        }
+    SWEEP_LOOP(blockIdx.x * kPPT * kSweepThreads + tid, base + tid < M) {
+        SWEEP_NEXT();
+        const double (&x)[kPPT] = cur.x; const double (&y)[kPPT] = cur.y; const double (&z)[kPPT] = cur.z; const bool (&in)[kPPT] = cur.in;
 #pragma unroll
         for (int g = 0; g < kHG; ++g) {
             const double s2 = s_hyp[g][6];
 #pragma unroll
-            for (int u = 0; u < kPPT; ++u) {        // same order as before for u = 0, 1, ...: fixed, run-to-run reproducible
+            for (int u = 0; u < kPPT; ++u) {        // fixed order u = 0, 1, ...: run-to-run reproducible
                 const double e = plane_dist(x[u], y[u], z[u], s_hyp[g]);
                 acc[g] += in[u] ? (e > s2 ? s2 : e) : 0.0;
             }
         }
+        SWEEP_ADVANCE();
     }
 #pragma unroll
     for (int g = 0; g < kHG; ++g) { const double v = warp_sum(acc[g]); if (lane == 0) s_red[w][g] = v; }
