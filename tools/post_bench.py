@@ -7,13 +7,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sequencesfm_b200 import post as ppost
 from sequencesfm_b200.synth import make_ground_scene
-from oracle import post as opost
+# oracle/ (the CPU checker / the reference's own functions) is imported only inside the CPU leg below
+
+
+def draw(M, H, seed=7):
+    """Hypotheses through the product's own draw (glibc rand(), src/sfm_utils.cpp:837-845) after srand(seed); also returns
+    the rand() values so that the reference can be handed the very same stream."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.srand(seed)
+    stream = np.array([libc.rand() for _ in range(4 * H + 64)], np.int32)
+    libc.srand(seed)
+    return ppost.draw_triples(M, H), stream
 
 
 def one(stage, M, H=100, cpu=True):
     pts, cams = make_ground_scene(7, M)
-    stream = opost.rand_stream(7, 4 * H + 64)
-    tri, _ = opost.oracle_draw_triples(M, H, stream)
+    tri, stream = draw(M, H)
     stage.ground_stage(pts, cams, tri)                       # warm-up: allocations, module load
     best = None
     for _ in range(3):
@@ -30,6 +40,7 @@ def one(stage, M, H=100, cpu=True):
            "pair_evaluations_per_s": {k: pairs / (v * 1e-3) for k, v in kern.items() if "mask" not in k},
            "points_bytes": 24 * M}
     if cpu:
+        from oracle import post as opost
         t = time.perf_counter()
         if opost.have_ref():
             r, _ = opost.ref_plane_fit(pts, stream, H, 2.0)
@@ -53,7 +64,7 @@ def chained(stage, shape="venice"):
     from sequencesfm_b200 import binding
     from sequencesfm_b200.synth import make_problem
     p = make_problem(shape, 1)
-    tri, _ = opost.oracle_draw_triples(p.M, 100, opost.rand_stream(7, 464))
+    tri, _ = draw(p.M, 100)
     with binding.Engine(device=0, max_iterations=2) as eng:
         eng.set_problem_from(p)
         res = eng.solve()                                    # includes get_result (the reference's write-back)

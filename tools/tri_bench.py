@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sequencesfm_b200 import tri
 from sequencesfm_b200.synth import make_two_view
-from oracle import tri_oracle
+# oracle/ is imported only inside the CPU leg below
 
 
 def run(n=1_000_000, cpu=True, device=0):
@@ -23,6 +23,7 @@ def run(n=1_000_000, cpu=True, device=0):
            "bytes_per_match": {"in": 16, "out": 40}, "kernel_gbs": n * 56 / (best["ms_kernels"] * 1e-3) / 1e9}
     if not cpu:
         return out
+    from oracle import tri_oracle
     m = min(n, 200000)
     t = time.perf_counter(); Xo, eo, _, mo = tri_oracle.triangulate(pt1[:m], pt2[:m], K, P, P1); dt = time.perf_counter() - t
     out["cpu_numpy_checker"] = {"sample": m, "ms": dt * 1e3, "matches_per_s": m / dt, "cores": "numpy / LAPACK batched SVD",
