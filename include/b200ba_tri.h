@@ -58,6 +58,23 @@ int b200tri_triangulate(b200tri_handle* h, int32_t n, const float* pt1, const fl
                         const double* Kinv9, const double* dist, int32_t n_dist, const double* P, const double* P1,
                         double* pts, double* reproj_err, float* pt1_undistorted, b200tri_report* report);
 
+/* The gating the tracker applies to a fresh triangulation (SfM_Tracker::triangulateTwoFrames, src/sfm_tracker.cpp:718-771;
+ * TestTriangulation, src/sfm_cameraMatrices.cpp:180-204), on the results of the LAST b200tri_triangulate call, which are
+ * still resident on the device: points in front of P and of P1 (z > 0, at least 75 % each), cut-off = 2.4 x the
+ * sorted error at index 4 n / 5 (an exact order statistic: the errors are radix-sorted on the device), keep[i] = in front
+ * of P1 and error < cut-off (the reference's status vector is overwritten by its second TestTriangulation call, :725-726).
+ * status: 0 ok, -1 fewer than 10 points, -2 fewer than 75 % in front of a camera, -3 at most 10 points survive -
+ * the reference's return codes.  keep: n bytes (may be NULL). */
+typedef struct b200tri_gate_report {
+    int32_t status;
+    int32_t n_front_P, n_front_P1, n_kept;
+    double  cutoff;
+    int32_t gpu_launches;
+    double  ms_device;
+    int32_t reserved[4];
+} b200tri_gate_report;
+int b200tri_gate(b200tri_handle* h, uint8_t* keep, b200tri_gate_report* report);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,3 +86,23 @@ def triangulate(pt1, pt2, K, P, P1, dist=None, Kinv=None):
     d = proj - k2                                                   # Point2f arithmetic
     err = np.sqrt(d[:, 0].astype(np.float64) ** 2 + d[:, 1].astype(np.float64) ** 2)
     return X, err, k1, float(err.mean()) if len(err) else 0.0
+
+
+def gate(pts, err, P, P1):
+    """The tracker's gating of a fresh triangulation (``src/sfm_tracker.cpp:718-771`` with ``TestTriangulation``,
+    ``src/sfm_cameraMatrices.cpp:180-204``): returns (status, keep uint8, cutoff, n_front_P, n_front_P1)."""
+    pts, err = np.asarray(pts, np.float64), np.asarray(err, np.float64)
+    P, P1 = np.asarray(P, np.float64).reshape(3, 4), np.asarray(P1, np.float64).reshape(3, 4)
+    n = len(pts)
+    if n < 10:
+        return -1, np.zeros(n, np.uint8), 0.0, 0, 0
+    f0 = pts @ P[2, :3] + P[2, 3] > 0
+    f1 = pts @ P1[2, :3] + P1[2, 3] > 0
+    cutoff = np.sort(err)[4 * n // 5] * 2.4
+    keep = (f1 & (err < cutoff)).astype(np.uint8)          # the status vector holds the SECOND TestTriangulation's result
+    status = 0
+    if f0.sum() / n < 0.75 or f1.sum() / n < 0.75:
+        status = -2
+    elif keep.sum() <= 10:
+        status = -3
+    return status, keep, float(cutoff), int(f0.sum()), int(f1.sum())

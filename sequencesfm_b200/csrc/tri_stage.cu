@@ -9,6 +9,7 @@
 #include "pinned_pool.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -163,6 +164,37 @@ __global__ void __launch_bounds__(256) k_tri_mean(const double* __restrict__ par
     if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < 8; ++k) t += s[k]; out[0] = t; }
 }
 
+// TestTriangulation (src/sfm_cameraMatrices.cpp:180-204): cv::perspectiveTransform with [P; 0 0 0 1] leaves w = 1, so the
+// test is the sign of the third row of P applied to the point.  counts[0] / [1]: points in front of P / P1.
+__global__ void __launch_bounds__(256)
+k_tri_front(const double* __restrict__ pts, int n, TriParams t, unsigned char* __restrict__ front1, unsigned* __restrict__ counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool f0 = false, f1 = false;
+    if (i < n) {
+        const double x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+        f0 = t.P[8] * x + t.P[9] * y + t.P[10] * z + t.P[11] > 0;
+        f1 = t.P1[8] * x + t.P1[9] * y + t.P1[10] * z + t.P1[11] > 0;
+        front1[i] = f1 ? 1 : 0;
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+    if ((threadIdx.x & 31) == 0) { if (b0) atomicAdd(&counts[0], (unsigned)__popc(b0)); if (b1) atomicAdd(&counts[1], (unsigned)__popc(b1)); }
+}
+
+// keep[i] = in front of P1 and error < 2.4 x sorted_err[4 n / 5]  (src/sfm_tracker.cpp:736-761)
+__global__ void __launch_bounds__(256)
+k_tri_keep(const double* __restrict__ err, const double* __restrict__ sorted, int n, const unsigned char* __restrict__ front1,
+           unsigned char* __restrict__ keep, unsigned* __restrict__ counts, double* __restrict__ cutoff_out)
+{
+    const double cutoff = __dmul_rn(sorted[4 * (size_t)n / 5], 2.4);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool k = false;
+    if (i < n) { k = front1[i] && err[i] < cutoff; keep[i] = k ? 1 : 0; }
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&counts[2], (unsigned)__popc(b));
+    if (i == 0) cutoff_out[0] = cutoff;
+}
+
 std::string g_tri_create_error;
 
 }  // namespace
@@ -173,6 +205,8 @@ struct b200tri_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     char* d_buf = nullptr; size_t cap = 0;            // one grow-only arena: pt1 | pt2 | pts | err | pt1_out | partial | scalars
+    char* d_gate = nullptr; size_t cap_gate = 0;      // gating scratch: sorted errors | front flags | keep | counters | cub temp
+    int n_last = 0; size_t o_pts_last = 0, o_err_last = 0; TriParams params_last;   // resident results of the last call
 };
 
 #define TRI_CUDA(call)                                                                                          \
@@ -209,6 +243,7 @@ void b200tri_destroy(b200tri_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->d_buf) cudaFree(h->d_buf);
+    if (h->d_gate) cudaFree(h->d_gate);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -224,6 +259,7 @@ int b200tri_triangulate(b200tri_handle* h, int32_t n, const float* pt1, const fl
     if (n < 0 || (n > 0 && (!pt1 || !pt2)) || !K9 || !Kinv9 || !P || !P1 || !report) { h->err = "b200tri_triangulate: null argument"; return B200BA_E_INVALID; }
     if (!(n_dist == 0 || n_dist == 4 || n_dist == 5 || n_dist == 8) || (n_dist > 0 && !dist)) { h->err = "b200tri_triangulate: n_dist must be 0, 4, 5 or 8"; return B200BA_E_INVALID; }
     std::memset(report, 0, sizeof(*report));
+    h->n_last = 0;
     if (n == 0) return B200BA_OK;                                 // cv::mean of an empty vector is 0
     TRI_CUDA(cudaSetDevice(h->device));
     TriParams t;
@@ -273,6 +309,7 @@ int b200tri_triangulate(b200tri_handle* h, int32_t n, const float* pt1, const fl
     if (pt1_undistorted) b200ba::threaded_copy(pt1_undistorted, stage.p + o_out, (size_t)n * 8);
     TRI_CUDA(cudaEventRecord(h->ev[3], h->stream));
     TRI_CUDA(cudaEventSynchronize(h->ev[3]));
+    h->n_last = n; h->o_pts_last = o_pts; h->o_err_last = o_err; h->params_last = t;
     unsigned ndeg; std::memcpy(&ndeg, &sc[1], sizeof(ndeg));
     report->mean_reproj_error = sc[0] / (double)n;
     report->n_degenerate = (int32_t)ndeg;
@@ -280,6 +317,51 @@ int b200tri_triangulate(b200tri_handle* h, int32_t n, const float* pt1, const fl
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); report->ms_device = ms;
     cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); report->ms_kernels = ms;
+    return B200BA_OK;
+}
+
+int b200tri_gate(b200tri_handle* h, uint8_t* keep, b200tri_gate_report* report)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!report) { h->err = "b200tri_gate: null report"; return B200BA_E_INVALID; }
+    std::memset(report, 0, sizeof(*report));
+    const int n = h->n_last;
+    if (n < 10) { report->status = -1; return B200BA_OK; }        // "triangulated point is too few" (:718-721); also: nothing resident
+    TRI_CUDA(cudaSetDevice(h->device));
+    const double* d_pts = (const double*)(h->d_buf + h->o_pts_last);
+    const double* d_err = (const double*)(h->d_buf + h->o_err_last);
+    size_t tmp_bytes = 0;
+    TRI_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_err, (double*)nullptr, n, 0, 64, h->stream));
+    const size_t o_sorted = 0, o_front = o_sorted + (size_t)n * 8, o_keep = o_front + (((size_t)n + 15) & ~(size_t)15),
+                 o_cnt = o_keep + (((size_t)n + 15) & ~(size_t)15), o_tmp = o_cnt + 32, total = o_tmp + tmp_bytes;
+    if (total > h->cap_gate) {
+        if (h->d_gate) cudaFree(h->d_gate);
+        h->d_gate = nullptr; h->cap_gate = 0;
+        TRI_CUDA(cudaMalloc((void**)&h->d_gate, total + total / 4));
+        h->cap_gate = total + total / 4;
+    }
+    char* g = h->d_gate;
+    unsigned* d_cnt = (unsigned*)(g + o_cnt);
+    TRI_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    TRI_CUDA(cudaMemsetAsync(g + o_cnt, 0, 32, h->stream));
+    k_tri_front<<<(n + 255) / 256, 256, 0, h->stream>>>(d_pts, n, h->params_last, (unsigned char*)(g + o_front), d_cnt);
+    TRI_CUDA(cub::DeviceRadixSort::SortKeys(g + o_tmp, tmp_bytes, d_err, (double*)(g + o_sorted), n, 0, 64, h->stream));
+    k_tri_keep<<<(n + 255) / 256, 256, 0, h->stream>>>(d_err, (const double*)(g + o_sorted), n, (const unsigned char*)(g + o_front),
+                                                      (unsigned char*)(g + o_keep), d_cnt, (double*)(g + o_cnt + 16));
+    TRI_CUDA(cudaGetLastError());
+    unsigned char cnt_host[32];
+    TRI_CUDA(cudaMemcpyAsync(cnt_host, g + o_cnt, 32, cudaMemcpyDeviceToHost, h->stream));
+    if (keep) TRI_CUDA(cudaMemcpyAsync(keep, g + o_keep, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    TRI_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    TRI_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned c[3]; std::memcpy(c, cnt_host, sizeof(c));
+    std::memcpy(&report->cutoff, cnt_host + 16, sizeof(double));
+    report->n_front_P = (int32_t)c[0]; report->n_front_P1 = (int32_t)c[1]; report->n_kept = (int32_t)c[2];
+    report->gpu_launches = 2 + 3;                                  // + cub's radix sort passes (>= 3 kernels for 64-bit keys)
+    float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); report->ms_device = ms;
+    // TestTriangulation on P, then on P1 (short-circuit ||, :725-729): less than 75 % in front of either -> -2
+    if ((double)c[0] / (double)n < 0.75 || (double)c[1] / (double)n < 0.75) report->status = -2;
+    else if (c[2] <= 10) report->status = -3;                      // "Filted points are too few" (:765-768)
     return B200BA_OK;
 }
 

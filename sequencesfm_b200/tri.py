@@ -9,12 +9,28 @@ import numpy as np
 
 from .binding import B200BAError, load
 
-ABI_SYMBOLS = ["b200tri_create", "b200tri_destroy", "b200tri_last_error", "b200tri_triangulate"]
+ABI_SYMBOLS = ["b200tri_create", "b200tri_destroy", "b200tri_last_error", "b200tri_triangulate", "b200tri_gate"]
 
 
 class Report(C.Structure):
     _fields_ = [("mean_reproj_error", C.c_double), ("n_degenerate", C.c_int32), ("gpu_launches", C.c_int32),
                 ("ms_device", C.c_double), ("ms_kernels", C.c_double), ("reserved", C.c_int32 * 4)]
+
+
+class GateReport(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_front_P", C.c_int32), ("n_front_P1", C.c_int32), ("n_kept", C.c_int32),
+                ("cutoff", C.c_double), ("gpu_launches", C.c_int32), ("ms_device", C.c_double), ("reserved", C.c_int32 * 4)]
+
+
+@dataclass
+class Gate:
+    status: int            # 0 ok, -1 / -2 / -3: the return codes of SfM_Tracker::triangulateTwoFrames
+    keep: np.ndarray       # uint8 n
+    cutoff: float
+    n_front_P: int
+    n_front_P1: int
+    n_kept: int
+    ms_device: float
 
 
 @dataclass
@@ -42,6 +58,8 @@ class Triangulator:
         self._lib.b200tri_destroy.argtypes = [C.c_void_p]
         self._lib.b200tri_destroy.restype = None
         self._lib.b200tri_triangulate.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] + [C.c_void_p] * 5 + [C.POINTER(Report)]
+        self._lib.b200tri_gate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(GateReport)]
+        self._n_last = 0
         self._h = C.c_void_p()
         rc = self._lib.b200tri_create(device, C.byref(self._h))
         if rc != 0:
@@ -81,4 +99,14 @@ class Triangulator:
                                            _vp(P), _vp(P1), _vp(pts), _vp(err), _vp(out), C.byref(rep))
         if rc != 0:
             raise B200BAError(rc, (self._lib.b200tri_last_error(self._h) or b"").decode())
+        self._n_last = n
         return Triangulation(pts, err, out, rep.mean_reproj_error, rep.n_degenerate, rep.gpu_launches, rep.ms_device, rep.ms_kernels)
+
+    def gate(self) -> Gate:
+        """The tracker's gating of the LAST triangulation (``src/sfm_tracker.cpp:718-771``), on the device-resident results."""
+        keep = np.zeros(self._n_last, np.uint8)
+        rep = GateReport()
+        rc = self._lib.b200tri_gate(self._h, _vp(keep) if self._n_last else None, C.byref(rep))
+        if rc != 0:
+            raise B200BAError(rc, (self._lib.b200tri_last_error(self._h) or b"").decode())
+        return Gate(rep.status, keep, rep.cutoff, rep.n_front_P, rep.n_front_P1, rep.n_kept, rep.ms_device)

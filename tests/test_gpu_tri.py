@@ -32,6 +32,25 @@ def test_matches_opencv_golden(eng, path):
     assert np.abs(r.pts - fx["X"]).max() <= tol * np.abs(fx["X"]).max()
     assert np.abs(r.reproj_err - fx["err"]).max() < 1e-4
     assert abs(r.mean_reproj_error - float(fx["mean"])) < 1e-6
+    g = eng.gate()                                                 # on OUR device-resident points / errors
+    st, keep, cutoff, n0, n1 = tri_oracle.gate(r.pts, r.reproj_err, fx["P"], fx["P1"])
+    assert (g.status, g.cutoff, g.n_front_P, g.n_front_P1) == (st, cutoff, n0, n1) and np.array_equal(g.keep, keep)
+    assert g.n_kept == int(keep.sum())
+    assert (g.keep != fx["gate_keep"]).sum() <= 2                  # vs the fixture's own errors: only threshold ties may differ
+    assert abs(g.cutoff - float(fx["gate_cutoff"])) < 1e-4
+
+
+def test_gate_return_codes_and_sizes(eng):
+    pt1, pt2, K, P, P1, _ = make_two_view(41, 200000)
+    r = eng.triangulate(pt1, pt2, K, P, P1)
+    g = eng.gate()
+    st, keep, cutoff, n0, n1 = tri_oracle.gate(r.pts, r.reproj_err, P, P1)
+    assert g.status == 0 and g.cutoff == cutoff and np.array_equal(g.keep, keep) and 0.75 * len(pt1) < g.n_kept < len(pt1)
+    eng.triangulate(pt1[:9], pt2[:9], K, P, P1)
+    assert eng.gate().status == -1                                  # "triangulated point is too few"
+    Pb = P.copy(); Pb[2] *= -1.0; P1b = P1.copy(); P1b[2] *= -1.0   # cameras looking the other way: points behind them
+    eng.triangulate(pt1[:500], pt2[:500], K, Pb, P1b)
+    assert eng.gate().status == -2
 
 
 @pytest.mark.parametrize("seed,n,kw", [(11, 1, {}), (12, 127, {}), (13, 129, {"baseline": 2.0}), (14, 100000, {}),

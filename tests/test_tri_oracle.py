@@ -36,6 +36,20 @@ def test_oracle_matches_opencv_golden(path):
     assert np.abs(X - fx["X"]).max() <= X_RTOL * scale.max()
     assert np.abs(err - fx["err"]).max() < 1e-4          # the pixel error is computed from float32-rounded projections
     assert abs(mean - float(fx["mean"])) < 1e-6
+    # the tracker's gating on the FIXTURE's points / errors: same cut-off bits, same mask
+    status, keep, cutoff, n0, n1 = tri_oracle.gate(fx["X"], fx["err"], fx["P"], fx["P1"])
+    assert status == 0 and cutoff == float(fx["gate_cutoff"]) and np.array_equal(keep, fx["gate_keep"])
+    assert [n0, n1] == fx["gate_front"].tolist()
+
+
+def test_gate_return_codes():
+    pt1, pt2, K, P, P1, X = make_two_view(8, 50, noise_px=0.1)
+    pts, err, _, _ = tri_oracle.triangulate(pt1, pt2, K, P, P1)
+    assert tri_oracle.gate(pts[:9], err[:9], P, P1)[0] == -1                       # fewer than 10 points
+    assert tri_oracle.gate(-pts, err, P, P1)[0] == -2                              # behind the cameras
+    few = pts[:12].copy(); few[:3] *= -1.0                                         # 9 of 12 in front: exactly 75 %, not below
+    st, keep, cutoff, n0, n1 = tri_oracle.gate(few, np.ones(12), P, P1)
+    assert st == -3 and keep.sum() == 9 and cutoff == 2.4 and (n0, n1) == (9, 9)   # at most 10 survive
 
 
 def test_oracle_pieces_against_cv2_live():

@@ -52,7 +52,11 @@ def main():
     for name, seed, n, kw in CASES:
         pt1, pt2, K, P, P1, Xt = make_two_view(seed, n, **kw)
         X, err, k1, mean = reference_loop(pt1, pt2, K, P, P1, kw.get("dist"))
-        np.savez_compressed(os.path.join(out, f"tri_{name}.npz"), seed=seed, n=n, kwargs=repr(kw), pt1=pt1, pt2=pt2, K=K, P=P, P1=P1,
+        # the gating of src/sfm_tracker.cpp:718-771, literally: std::sort, index 4 n / 5, x 2.4, status of the SECOND front test
+        srt = sorted(err.tolist()); cutoff = srt[4 * len(srt) // 5] * 2.4
+        front0 = [(P[2, :3] @ x + P[2, 3]) > 0 for x in X]; front1 = [(P1[2, :3] @ x + P1[2, 3]) > 0 for x in X]
+        keep = np.array([1 if (front1[i] and err[i] < cutoff) else 0 for i in range(len(err))], np.uint8)
+        np.savez_compressed(os.path.join(out, f"tri_{name}.npz"), gate_cutoff=cutoff, gate_keep=keep, gate_front=np.array([sum(front0), sum(front1)]), seed=seed, n=n, kwargs=repr(kw), pt1=pt1, pt2=pt2, K=K, P=P, P1=P1,
                             dist=np.asarray(kw.get("dist", []), np.float64), X=X, err=err, pt1_undistorted=k1, mean=mean,
                             cv2_version=cv2.__version__)
         print(name, "mean reprojection error", mean, "max |X - truth|", np.abs(X - Xt).max())
