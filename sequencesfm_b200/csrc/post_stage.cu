@@ -667,6 +667,8 @@ int reserve_points(b200post_handle* h, size_t M)
 {
     if (M <= h->cap_pts) return 0;
     const size_t n = M + M / 8 + 1024;
+    h->cap_pts = 0;                                    // a failed growth must not leave a stale capacity behind
+    h->M = 0;
     int rc;
     if ((rc = grow(h, h->d_pts, 3 * n)) || (rc = grow(h, h->d_out, 3 * n)) || (rc = grow(h, h->d_keep, n)) || (rc = grow(h, h->d_pos, n))) return rc;
     h->cap_pts = n;
@@ -677,6 +679,7 @@ int reserve_hyp(b200post_handle* h, size_t H)
 {
     if (H <= h->cap_hyp) return 0;
     const size_t n = ((H + kHG - 1) / kHG) * kHG + 64;
+    h->cap_hyp = 0;
     int rc;
     if ((rc = grow(h, h->d_hyp, n * kHypStride)) || (rc = grow(h, h->d_hist, n * kBins)) || (rc = grow(h, h->d_st, n)) ||
         (rc = grow(h, h->d_st_b, n)) || (rc = grow(h, h->d_cand_n, n)) || (rc = grow(h, h->d_med, n)) || (rc = grow(h, h->d_score, n)) || (rc = grow(h, h->d_tri, 3 * n)) ||
@@ -691,6 +694,7 @@ int reserve_hyp(b200post_handle* h, size_t H)
 int reserve_partial(b200post_handle* h, size_t n)
 {
     if (n <= h->cap_partial) return 0;
+    h->cap_partial = 0;
     int rc = grow(h, h->d_partial, n);
     if (rc) return rc;
     h->cap_partial = n;
@@ -862,7 +866,7 @@ Se3 to_se3(const double* a) { Se3 t; std::memcpy(t.a, a, sizeof(t.a)); return t;
 int reaxis_cameras(b200post_handle* h, const double* axes, int32_t N, double* cam_RT)
 {
     if (N <= 0 || !cam_RT) return 0;
-    if ((size_t)N > h->cap_cams) { int rc = grow(h, h->d_cams, (size_t)N * 12); if (rc) return rc; h->cap_cams = (size_t)N; }
+    if ((size_t)N > h->cap_cams) { h->cap_cams = 0; int rc = grow(h, h->d_cams, (size_t)N * 12); if (rc) return rc; h->cap_cams = (size_t)N; }
     POST_CUDA(cudaMemcpyAsync(h->d_cams, cam_RT, (size_t)N * 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     k_post_reaxis_cameras<<<(N + 127) / 128, 128, 0, h->stream>>>(h->d_cams, N, to_se3(axes));
     int rc = launch_check(h, "k_post_reaxis_cameras");

@@ -1,5 +1,5 @@
-"""Small run of every kernel of the post-BA stage and the triangulation for compute-sanitizer:
-    compute-sanitizer --tool memcheck python tools/sanitize_new_stages.py"""
+"""Small, ragged-size run of every kernel of the post-BA stage and the triangulation (written as the driver of a
+`compute-sanitizer --tool memcheck` pass; the sanitizer is closed on this GPU pool, so it only runs plainly here)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
