@@ -649,7 +649,7 @@ struct b200post_handle {
 };
 
 namespace {
-std::string g_post_create_error;
+thread_local std::string g_post_create_error;
 
 #define POST_CUDA(call)                                                                                         \
     do { cudaError_t e_ = (call);                                                                               \

@@ -195,7 +195,7 @@ k_tri_keep(const double* __restrict__ err, const double* __restrict__ sorted, in
     if (i == 0) cutoff_out[0] = cutoff;
 }
 
-std::string g_tri_create_error;
+thread_local std::string g_tri_create_error;
 
 }  // namespace
 
