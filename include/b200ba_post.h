@@ -68,7 +68,7 @@ const char* b200post_last_error(const b200post_handle* h);
 int b200post_draw_triples(int32_t M, int32_t n_ransac, int32_t* triples);
 
 /* PointsPlaneFit_RANSAC on pts (M x 3) with the given hypotheses.  keep (M, may be NULL) receives cpFilter.
- * B200BA_E_INVALID when M < 10 (the reference returns -1 there), when an index is out of range, when a coordinate is not
+ * n_ransac <= 4096.  B200BA_E_INVALID when M < 10 (the reference returns -1 there), when an index is out of range, when a coordinate is not
  * finite, or when every hypothesis is degenerate (the reference reads uninitialised memory in that case). */
 int b200post_plane_fit(b200post_handle* h, int32_t M, const double* pts, int32_t n_ransac, const int32_t* triples,
                        double k_threshold, b200post_plane* out, int32_t* keep);

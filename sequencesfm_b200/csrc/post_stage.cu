@@ -788,6 +788,7 @@ int fit_resident(b200post_handle* h, int32_t M, const double* pts, int32_t n_ran
     if (!h) return B200BA_E_INVALID;
     if ((!pts && !resident) || !triples || !out || n_ransac <= 0) { h->err = "b200post_plane_fit: null argument or n_ransac <= 0"; return B200BA_E_INVALID; }
     if (M < 10) { h->err = "b200post_plane_fit: fewer than 10 points (the reference returns -1, src/sfm_utils.cpp:826-829)"; return B200BA_E_INVALID; }
+    if (n_ransac > 4096) { h->err = "b200post_plane_fit: at most 4096 hypotheses per call (the reference's default is 100)"; return B200BA_E_INVALID; }
     POST_CUDA(cudaSetDevice(h->device));
     if (!resident) h->launches = 0;
     for (int i = 0; i < 3 * n_ransac; ++i)

@@ -113,6 +113,8 @@ def test_error_behaviour(stage):
         stage.plane_fit(pts, tri + 490)
     with pytest.raises(B200BAError, match="degenerate"):
         stage.plane_fit(pts, np.zeros((5, 3), np.int32))
+    with pytest.raises(B200BAError, match="4096 hypotheses"):
+        stage.plane_fit(pts, np.tile(tri, (300, 1)))
     bad = pts.copy(); bad[77, 1] = np.nan
     with pytest.raises(B200BAError, match="non-finite"):
         stage.plane_fit(bad, tri)
