@@ -86,6 +86,18 @@ def test_oracle_matches_live_reference(seed, M, kw):
     assert _same_bits(pr, po) and _same_bits(cr, co)
 
 
+@pytest.mark.skipif(not opost.have_ref(), reason="oracle/_ref/libpost_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("n_ransac,k_thr", [(1, 2.0), (7, 3.0), (250, 0.5)])
+def test_oracle_matches_live_reference_other_settings(n_ransac, k_thr):
+    """nRansacs and kThreshold away from their defaults (src/sfm_utils.h:90-91)."""
+    pts, cams = make_ground_scene(40 + n_ransac, 3001, outlier_frac=0.25)
+    stream = opost.rand_stream(n_ransac, 4 * n_ransac + 64)
+    r, used = opost.ref_plane_fit(pts, stream, n_ransac, k_thr)
+    tri, used2 = opost.oracle_draw_triples(len(pts), n_ransac, stream)
+    o = opost.oracle_plane_fit(pts, tri, k_thr)
+    assert used == used2 and np.array_equal(o.keep, r.keep) and _same_bits(o.plane, r.plane) and _same_bits(o.plane_se3, r.plane_se3)
+
+
 def test_oracle_rejects_what_the_reference_rejects():
     pts, _ = make_ground_scene(1, 9)
     with pytest.raises(RuntimeError, match="rc=-1"):      # nPoints < 10 -> -1, src/sfm_utils.cpp:826-829
