@@ -11,6 +11,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -52,6 +53,75 @@ struct Tokens {
     }
     char peek() { return p < end ? *p : 0; }
 };
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+
+template <class F> void io_parallel(int T, F&& fn)
+{
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back([&fn, t, T] { fn(t, T); });
+    fn(0, T);
+    for (auto& x : th) x.join();
+}
+int io_threads(size_t bytes) { return bytes < ((size_t)8 << 20) ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())); }
+
+// A purely numeric file (BAL text) as one flat array of doubles: the buffer is cut at whitespace into one chunk per thread,
+// tokens are counted, then converted in place (strtod) - the reference reads the same file through ifstream >> double.
+bool parse_all_numbers(const char* p, const char* end, std::vector<double>& out)
+{
+    const size_t bytes = (size_t)(end - p);
+    const int T = io_threads(bytes);
+    std::vector<const char*> cut((size_t)T + 1);
+    cut[0] = p; cut[T] = end;
+    for (int t = 1; t < T; ++t) {
+        const char* c = p + bytes * t / T;
+        while (c < end && !is_ws(*c)) ++c;                     // never inside a token
+        cut[t] = c;
+    }
+    std::vector<size_t> count((size_t)T + 1, 0);
+    io_parallel(T, [&](int t, int) {
+        size_t n = 0;
+        for (const char* c = cut[t]; c < cut[t + 1];) {
+            while (c < cut[t + 1] && is_ws(*c)) ++c;
+            if (c >= cut[t + 1]) break;
+            ++n;
+            while (c < end && !is_ws(*c)) ++c;                 // a token that starts in this chunk belongs to it
+        }
+        count[t + 1] = n;
+    });
+    for (int t = 0; t < T; ++t) count[t + 1] += count[t];
+    out.resize(count[T]);
+    std::vector<char> bad((size_t)T, 0);
+    io_parallel(T, [&](int t, int) {
+        size_t k = count[t];
+        for (const char* c = cut[t]; c < cut[t + 1];) {
+            while (c < cut[t + 1] && is_ws(*c)) ++c;
+            if (c >= cut[t + 1]) break;
+            char* q = nullptr;
+            out[k++] = strtod(c, &q);                          // the buffer is NUL-terminated
+            if (q == c || (q < end && !is_ws(*q))) { bad[t] = 1; return; }
+            c = q;
+        }
+    });
+    for (char b : bad) if (b) return false;
+    return true;
+}
+
+// Formats rows [0, n) with `row(i, buf)` (returns the characters written, at most 160) on several threads and writes the pieces in order.
+template <class F> bool write_rows_parallel(FILE* f, size_t n, F&& row)
+{
+    const int T = n < 100000 ? 1 : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::string> piece((size_t)T);
+    io_parallel(T, [&](int t, int nt) {
+        const size_t a = n * t / nt, b = n * (t + 1) / nt;
+        std::string& s = piece[t];
+        s.reserve((b - a) * 64);
+        char buf[192];
+        for (size_t i = a; i < b; ++i) s.append(buf, (size_t)row(i, buf));
+    });
+    for (const std::string& s : piece) if (!s.empty() && fwrite(s.data(), 1, s.size(), f) != s.size()) return false;
+    return true;
+}
 
 bool ends_with(const char* s, const char* suffix) { return strstr(s, suffix) != nullptr; }   // like LoadModelFile's strstr
 
@@ -127,28 +197,33 @@ bool check_indices(const b200io_model* m, std::string& why)
 // ---- BAL / bundler model: pba_util.h:309-362 ----
 int load_bal(Tokens& in, b200io_model** out)
 {
-    long long ncam, npt, nproj;
-    if (!in.integer(ncam) || !in.integer(npt) || !in.integer(nproj) || ncam < 0 || npt < 0 || nproj < 0)
+    std::vector<double> v;
+    if (!parse_all_numbers(in.p, in.end, v)) return io_fail(B200BA_E_INVALID, "BAL: not a number where one was expected");
+    if (v.size() < 3 || v[0] < 0 || v[1] < 0 || v[2] < 0 || v[0] > 2e9 || v[1] > 2e9 || v[2] > 2e9)
         return io_fail(B200BA_E_INVALID, "BAL: bad header (expected: cameras points projections)");
+    const long long ncam = (long long)v[0], npt = (long long)v[1], nproj = (long long)v[2];
+    const size_t o_obs = 3, o_cam = o_obs + 4 * (size_t)nproj, o_pt = o_cam + 9 * (size_t)ncam, need = o_pt + 3 * (size_t)npt;
+    if (v.size() < o_cam) return io_fail(B200BA_E_INVALID, "BAL: truncated observation list");
+    if (v.size() < o_pt) return io_fail(B200BA_E_INVALID, "BAL: truncated camera block");
+    if (v.size() < need) return io_fail(B200BA_E_INVALID, "BAL: truncated point block");
     b200io_model* m = nullptr;
     if (int rc = b200io_alloc((int32_t)ncam, (int32_t)npt, (int32_t)nproj, 0, &m)) return rc;
-    for (long long i = 0; i < nproj; ++i) {
-        long long c, p; double x, y;
-        if (!in.integer(c) || !in.integer(p) || !in.number(x) || !in.number(y)) { b200io_free(m); return io_fail(B200BA_E_INVALID, "BAL: truncated observation list"); }
-        m->obs_cam[i] = (int32_t)c; m->obs_pt[i] = (int32_t)p;
-        m->obs_xy[2 * i] = x; m->obs_xy[2 * i + 1] = -y;               // measurements[i].SetPoint2D(x, -y)
-    }
+    io_parallel(io_threads((size_t)nproj * 32), [&](int t, int nt) {
+        for (long long i = nproj * t / nt, e = nproj * (t + 1) / nt; i < e; ++i) {
+            const double* o = &v[o_obs + 4 * (size_t)i];
+            m->obs_cam[i] = (int32_t)o[0]; m->obs_pt[i] = (int32_t)o[1];
+            m->obs_xy[2 * i] = o[2]; m->obs_xy[2 * i + 1] = -o[3];       // measurements[i].SetPoint2D(x, -y)
+        }
+    });
     for (long long i = 0; i < ncam; ++i) {
-        double p[9];
-        for (int j = 0; j < 9; ++j) if (!in.number(p[j])) { b200io_free(m); return io_fail(B200BA_E_INVALID, "BAL: truncated camera block"); }
+        const double* p = &v[o_cam + 9 * (size_t)i];
         double R[9];
         rodrigues_to_matrix(p, R);
         set_camera_inverted(m, (int)i, R, p + 3);                       // SetInvertedRT(p, p + 3)
         m->focal[i] = p[6];
         m->radial[i] = p[7]; m->distortion_type[i] = 1;                 // SetProjectionDistortion(p[7]); p[8] is not read
     }
-    for (long long i = 0; i < npt; ++i)
-        for (int j = 0; j < 3; ++j) if (!in.number(m->pts[3 * i + j])) { b200io_free(m); return io_fail(B200BA_E_INVALID, "BAL: truncated point block"); }
+    std::memcpy(m->pts, &v[o_pt], 3 * (size_t)npt * sizeof(double));
     *out = m;
     return 0;
 }
@@ -156,7 +231,9 @@ int load_bal(Tokens& in, b200io_model** out)
 int save_bal(FILE* f, const b200io_model* m)                             // pba_util.h:364-390
 {
     fprintf(f, "%d %d %d\n", m->N, m->M, m->K);
-    for (int k = 0; k < m->K; ++k) fprintf(f, "%d %d %.17g %.17g\n", m->obs_cam[k], m->obs_pt[k], m->obs_xy[2 * k], -m->obs_xy[2 * k + 1]);
+    bool ok = write_rows_parallel(f, (size_t)m->K, [&](size_t k, char* buf) {
+        return snprintf(buf, 160, "%d %d %.17g %.17g\n", m->obs_cam[k], m->obs_pt[k], m->obs_xy[2 * k], -m->obs_xy[2 * k + 1]);
+    });
     for (int i = 0; i < m->N; ++i) {
         double R[9], T[3], r[3];
         get_camera_inverted(m, i, R, T);                                 // GetInvertedRT
@@ -164,8 +241,10 @@ int save_bal(FILE* f, const b200io_model* m)                             // pba_
         fprintf(f, "%.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g 0\n", r[0], r[1], r[2], T[0], T[1], T[2], m->focal[i],
                 m->distortion_type[i] == 1 ? m->radial[i] : 0.0);
     }
-    for (int j = 0; j < m->M; ++j) fprintf(f, "%.17g %.17g %.17g\n", m->pts[3 * j], m->pts[3 * j + 1], m->pts[3 * j + 2]);
-    return 0;
+    ok = ok && write_rows_parallel(f, (size_t)m->M, [&](size_t j, char* buf) {
+        return snprintf(buf, 160, "%.17g %.17g %.17g\n", m->pts[3 * j], m->pts[3 * j + 1], m->pts[3 * j + 2]);
+    });
+    return ok ? 0 : io_fail(B200BA_E_INVALID, "save: write failed");
 }
 
 // Points with their observation lists, shared by NVM and .out: "x y z r g b n [cam feat x y]*n"
