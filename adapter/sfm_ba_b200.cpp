@@ -97,6 +97,8 @@ int adjustBundle_ssba(std::vector<CloudPoint>& pointcloud, cv::Mat& camIntrinsic
 int adjustBundle_pba(std::vector<CloudPoint>& pointcloud, cv::Mat& camIntrinsic, cv::Mat& camDistortion,
                      std::map<int, std::vector<cv::KeyPoint> >& imgpts, std::map<int, cv::Matx34d>& Pmats)
 {
+#ifdef USE_PBA
+    // Built with USE_PBA the reference runs the PBA personality and always returns 0 (src/sfm_ba_pba.cpp:49-166,173).
     (void)camDistortion;                   // read but unused by the reference too (src/sfm_ba_pba.cpp:64-65,87,136)
     b200ba_options opt;
     b200ba_pba_preset(&opt);               // camera 0 constant, no robustifier, sub-pixel measurements
@@ -105,4 +107,15 @@ int adjustBundle_pba(std::vector<CloudPoint>& pointcloud, cv::Mat& camIntrinsic,
     Kp.at<double>(0, 0) = f; Kp.at<double>(1, 1) = f; Kp.at<double>(0, 1) = 0.0;
     run(opt, "adjustBundle_pba", pointcloud, Kp, imgpts, Pmats);
     return 0;                              // src/sfm_ba_pba.cpp:173
+#else
+    // The SHIPPED build leaves USE_PBA undefined: the function forwards to the SSBA path and returns ITS value
+    // (src/sfm_ba_pba.cpp:167-171) - integer-rounded pixels, Huber weights, all cameras free, -1 on CONVERGED.  This is the
+    // call the tracker makes for every BA with >= 5 keyframes (src/sfm_tracker.cpp:863-866).
+    (void)camDistortion;
+    int K = 0;                             // the reference prints its own banner first (src/sfm_ba_pba.cpp:43-48)
+    for (size_t j = 0; j < pointcloud.size(); ++j) K += (int)pointcloud[j].img_kp.size();
+    printf("\nadjustBundle_pba: \n");
+    printf("  N (cams) = %d, M (points) = %d, K (measurements) = %d\n", (int)Pmats.size(), (int)pointcloud.size(), K);
+    return adjustBundle_ssba(pointcloud, camIntrinsic, imgpts, Pmats);
+#endif
 }

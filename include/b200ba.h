@@ -141,6 +141,30 @@ int b200ba_get_result_device(b200ba_handle* h, double* cam_RT, double* d_pts);
 /* Sizes of the uploaded problem (any pointer may be NULL). */
 int b200ba_problem_size(const b200ba_handle* h, int32_t* N, int32_t* M, int32_t* K);
 
+/* Execution plan b200ba_set_problem chose for the uploaded problem (the reference has no counterpart: SSBA / PBA have one
+ * code path).  Tests use it to make sure a given plan is the one a parity case exercised. */
+enum {
+    B200BA_TABLE_GLOBAL  = 0,   /* packed camera table [quaternion | T | p] read through L2 by every observation        */
+    B200BA_TABLE_SHARED  = 1,   /* whole table staged into one SM's shared memory by TMA bulk copies (<= 2075 cameras)  */
+    B200BA_TABLE_CLUSTER = 2    /* table sharded over the distributed shared memory of a thread-block cluster           */
+};
+typedef struct b200ba_plan {
+    int32_t struct_size;
+    int32_t camera_table;             /* B200BA_TABLE_*                                                              */
+    int32_t cluster_size;             /* CTAs per cluster of the by-point sweeps (1 unless camera_table == CLUSTER)   */
+    int32_t cooperative_step;         /* camera-side PCG step as one cooperative kernel                               */
+    int32_t cuda_graph;               /* one LM iteration replayed as a CUDA graph                                    */
+    int32_t peer_windows;             /* NVLink peer-memory collectives mapped                                        */
+    int32_t world, rank;
+    int32_t launches_per_iteration;   /* kernels of one LM iteration (0 until the first iteration has been enqueued)  */
+    int32_t n_slices, padded_entries; /* SELL-32 slices / entries of the point-order layout                           */
+    int32_t n_rows, n_segments;       /* camera-order rows of 32 / partial-sum segments                               */
+    int32_t fp32_pcg;
+    int64_t device_bytes;             /* size of the problem's device arena                                           */
+    int32_t reserved[8];
+} b200ba_plan;
+int b200ba_get_plan(const b200ba_handle* h, b200ba_plan* plan);
+
 /* ---- multi-GPU: one handle per rank, problem partitioned by point ---- */
 #define B200BA_COMM_ID_BYTES 128
 int b200ba_comm_unique_id(void* id_bytes);    /* rank 0 creates, the launcher broadcasts (e.g. torch.distributed) */

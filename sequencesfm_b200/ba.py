@@ -93,16 +93,31 @@ def adjustBundle_ssba(pointcloud: List[CloudPoint], camIntrinsic: np.ndarray,
     return _run("ssba", pointcloud, camIntrinsic, imgpts, Pmats, options, report)
 
 
+# Build-time switch of the reference (``#ifdef USE_PBA``, ``src/sfm_ba_pba.cpp:14,49``).  The shipped build leaves it
+# undefined, so ``adjustBundle_pba`` is a forwarder to ``adjustBundle_ssba``; set it to True (or pass ``use_pba=True``)
+# for the behaviour of a ``-DUSE_PBA`` build.
+USE_PBA = False
+
+
 def adjustBundle_pba(pointcloud: List[CloudPoint], camIntrinsic: np.ndarray, camDistortion: np.ndarray,
                      imgpts: Dict[int, Sequence[Sequence[float]]], Pmats: Dict[int, np.ndarray],
-                     *, options: dict | None = None, report: dict | None = None) -> int:
+                     *, options: dict | None = None, report: dict | None = None, use_pba: bool | None = None) -> int:
     """Drop-in for ``adjustBundle_pba`` (``src/sfm_ba_pba.cpp:33-174``).
+
+    Shipped build (``USE_PBA`` undefined, the default here): prints its banner and **forwards to adjustBundle_ssba,
+    returning its value** (``src/sfm_ba_pba.cpp:167-171``) - integer-rounded pixels, Huber weights, all cameras free,
+    -1 when the optimizer ended CONVERGED.  This is what the tracker calls for every BA with >= 5 keyframes
+    (``src/sfm_tracker.cpp:863-866``).
 
     With ``USE_PBA`` the reference pins camera 0, keeps sub-pixel float measurements, uses f = (fx+fy)/2 with the
     principal point subtracted and no robustifier, and always returns 0.  ``camDistortion`` is read by the
     reference only to fill a field that ``SetFixedIntrinsics(true)`` + no ``EnableRadialDistortion`` leaves unused
     (``src/sfm_ba_pba.cpp:64-65,87,136``); it is accepted and ignored here as well.
     """
+    if not (USE_PBA if use_pba is None else use_pba):
+        K = sum(len(cp.img_kp) for cp in pointcloud)        # Count2DMeasurements_pba, src/sfm_ba_pba.cpp:21-30
+        print(f"\nadjustBundle_pba: \n  N (cams) = {len(Pmats)}, M (points) = {len(pointcloud)}, K (measurements) = {K}")
+        return adjustBundle_ssba(pointcloud, camIntrinsic, imgpts, Pmats, options=options, report=report)
     Kmat = np.array(camIntrinsic, dtype=np.float64)
     f = (Kmat[0, 0] + Kmat[1, 1]) / 2.0                      # src/sfm_ba_pba.cpp:60
     Kp = np.array([[f, 0.0, Kmat[0, 2]], [0.0, f, Kmat[1, 2]], [0.0, 0.0, 1.0]])

@@ -24,7 +24,7 @@ STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 ABI_SYMBOLS = [
     "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
-    "b200ba_get_result_device", "b200ba_problem_size",
+    "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
     "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
 ]
@@ -46,6 +46,17 @@ class Report(C.Structure):
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("ms_solve", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("trace", C.POINTER(C.c_double)),
                 ("trace_cap", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("camera_table", C.c_int32), ("cluster_size", C.c_int32),
+                ("cooperative_step", C.c_int32), ("cuda_graph", C.c_int32), ("peer_windows", C.c_int32),
+                ("world", C.c_int32), ("rank", C.c_int32), ("launches_per_iteration", C.c_int32),
+                ("n_slices", C.c_int32), ("padded_entries", C.c_int32), ("n_rows", C.c_int32), ("n_segments", C.c_int32),
+                ("fp32_pcg", C.c_int32), ("device_bytes", C.c_int64), ("reserved", C.c_int32 * 8)]
+
+
+TABLE_NAMES = {0: "global", 1: "shared", 2: "cluster"}
 
 
 class B200BAError(RuntimeError):
@@ -248,6 +259,14 @@ class Engine:
         rep, tr = self._report()
         self._check(self.lib.b200ba_finish(self.h, C.byref(rep)))
         return self._result(rep, tr)
+
+    def plan(self) -> dict:
+        """``b200ba_get_plan``: the execution plan chosen by set_problem, as a dict (camera_table as a name)."""
+        pl = Plan()
+        self._check(self.lib.b200ba_get_plan(self.h, C.byref(pl)))
+        out = {k: getattr(pl, k) for k, _ in Plan._fields_ if k not in ("reserved", "struct_size")}
+        out["camera_table"] = TABLE_NAMES.get(pl.camera_table, str(pl.camera_table))
+        return out
 
     # -- stage-level ----------------------------------------------------------------------------------
     def debug_linearize(self) -> dict:

@@ -556,6 +556,10 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     double tm = t0;
     auto lap = [&](const char* what) { if (verbose) { double t = now_ms(); fprintf(stderr, "[b200ba] set_problem %-28s %8.2f ms\n", what, t - tm); tm = t; } };
     CU(cudaSetDevice(h->device));
+    // A failed call must not leave a half-replaced problem behind: from here on the handle has NO problem until the very
+    // end of this function (begin / solve / get_result then fail with B200BA_E_STATE instead of touching freed buffers).
+    h->have_problem = false; h->begun = false; h->finished = false;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     h->N = N; h->M = M; h->K = K;
     h->h_cam.assign(cam_RT, cam_RT + 12 * (size_t)N);
     h->h_pts.assign(pts, pts + 3 * (size_t)M);
@@ -705,6 +709,9 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     PinnedPool::Lease stage;
     const size_t stage_meas = sizeof(double2) * (size_t)std::max(Kp, 1);
     g_pinned.lease(stage, stage_meas + sizeof(int) * (size_t)std::max(Kp, 1));
+    // Declared after the lease, so it runs BEFORE the lease is released on every exit path (the CU() early returns
+    // included): no asynchronous upload may still be reading the staging memory when another handle gets it.
+    struct SyncOnExit { cudaStream_t s; ~SyncOnExit() { cudaStreamSynchronize(s); } } sync_on_exit{h->stream};
     double2* o_meas_p = reinterpret_cast<double2*>(stage.p);
     int* o_cam_p = reinterpret_cast<int*>(stage.p + stage_meas);
     h->entry_of_obs.reset(new int[(size_t)std::max(K, 1)]);
@@ -936,10 +943,6 @@ int b200ba_begin(b200ba_handle* h)
     const int N = h->N, M = h->M;
     const b200ba_options& o = h->opt;
     std::vector<double> cam(h->h_cam);
-    PinnedPool::Lease stage;                                      // released when this call returns (after the stream sync below)
-    g_pinned.lease(stage, sizeof(double) * 4 * (size_t)std::max(M, 1));
-    double* X4 = reinterpret_cast<double*>(stage.p);             // no zero-fill of 32 MB: the pad is written with the point
-    if (M == 0) X4[0] = X4[1] = X4[2] = X4[3] = 0.0;
     const double* P0 = h->h_pts.data();
     h->mean[0] = h->mean[1] = h->mean[2] = 0; h->scale = 1.0;
     std::vector<double> C(3 * (size_t)N);
@@ -956,53 +959,64 @@ int b200ba_begin(b200ba_handle* h)
         });
         for (int t = 0; t < T; ++t) for (int c = 0; c < ncomp; ++c) out[c] += part[(size_t)t * ncomp + c];
     };
+    double rs = 1.0;
     if (o.normalize) {
         // ScopedBundleExtrinsicNormalizer ctor (v3d_metricbundle.h:327-356); point sums are global over ranks,
-        // cameras are replicated and counted once.
-        double s[4] = {0, 0, 0, (double)M};
-        blocked_sum(3, s, [&](int j, double* a) { for (int c = 0; c < 3; ++c) a[c] += P0[3 * (size_t)j + c]; });
-        if (int rc = global_sum(h, s, 4)) return rc;
+        // cameras are replicated and counted once.  (The cross-rank sums run BEFORE the pinned staging pool is leased:
+        // the pool is a process-wide mutex, and a rank that lives as a thread of the same process must be able to reach
+        // its side of the collective.)
+        double sm4[4] = {0, 0, 0, (double)M};
+        blocked_sum(3, sm4, [&](int j, double* a) { for (int c = 0; c < 3; ++c) a[c] += P0[3 * (size_t)j + c]; });
+        if (int rc = global_sum(h, sm4, 4)) return rc;
         double cs[3] = {0, 0, 0};
         for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) cs[c] += C[3 * (size_t)i + c];
         // reference adds camera centres first, then points
-        double rn = 1.0 / ((double)N + s[3]);
-        for (int c = 0; c < 3; ++c) h->mean[c] = (cs[c] + s[c]) * rn;
+        double rn = 1.0 / ((double)N + sm4[3]);
+        for (int c = 0; c < 3; ++c) h->mean[c] = (cs[c] + sm4[c]) * rn;
         double sq[1] = {0};
         blocked_sum(1, sq, [&](int j, double* a) { for (int c = 0; c < 3; ++c) { double v = P0[3 * (size_t)j + c] - h->mean[c]; a[0] += v * v; } });
         if (int rc = global_sum(h, sq, 1)) return rc;
         double sqc = 0;
         for (int i = 0; i < N; ++i) for (int c = 0; c < 3; ++c) { C[3 * (size_t)i + c] -= h->mean[c]; sqc += C[3 * (size_t)i + c] * C[3 * (size_t)i + c]; }
         h->scale = std::sqrt(sqc + sq[0]);
-        double rs = 1.0 / h->scale;
+        rs = 1.0 / h->scale;
         for (int i = 0; i < N; ++i) { for (int c = 0; c < 3; ++c) C[3 * (size_t)i + c] *= rs; set_camera_centre(cam.data() + 12 * (size_t)i, C.data() + 3 * (size_t)i); }
-        parallel_for(T, [&](int t, int nt) {
-            const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
-            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = (P0[3 * (size_t)j + c] - h->mean[c]) * rs; X4[4 * (size_t)jn + 3] = 0.0; }
-        });
-    } else {
-        parallel_for(T, [&](int t, int nt) {
-            const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
-            for (int jn = a; jn < b; ++jn) { const int j = h->orig_of_new[jn]; for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = P0[3 * (size_t)j + c]; X4[4 * (size_t)jn + 3] = 0.0; }
-        });
     }
-    // cached parameter length (v3d_metricbundle.h:37-45), after normalisation (summed in the caller's point order)
     double L[1] = {0};
-    if (T == 1) {
-        std::vector<int> new_of_orig((size_t)M);
-        for (int jn = 0; jn < M; ++jn) new_of_orig[h->orig_of_new[jn]] = jn;
-        for (int j = 0; j < M; ++j) { const int jn = new_of_orig[j]; for (int c = 0; c < 3; ++c) L[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; }
-    } else {
-        blocked_sum(1, L, [&](int jn, double* a) { for (int c = 0; c < 3; ++c) a[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; });
+    cudaStream_t s = h->stream;
+    {
+        PinnedPool::Lease stage;                                  // scoped: staging of the point block and its upload only
+        g_pinned.lease(stage, sizeof(double) * 4 * (size_t)std::max(M, 1));
+        struct SyncOnExit { cudaStream_t s; ~SyncOnExit() { cudaStreamSynchronize(s); } } sync_on_exit{s};   // before the lease goes
+        double* X4 = reinterpret_cast<double*>(stage.p);         // no zero-fill of 32 MB: the pad is written with the point
+        if (M == 0) X4[0] = X4[1] = X4[2] = X4[3] = 0.0;
+        const bool nrm = o.normalize != 0;
+        parallel_for(T, [&](int t, int nt) {
+            const int a = (int)((long long)M * t / nt), b = (int)((long long)M * (t + 1) / nt);
+            for (int jn = a; jn < b; ++jn) {
+                const int j = h->orig_of_new[jn];
+                for (int c = 0; c < 3; ++c) X4[4 * (size_t)jn + c] = nrm ? (P0[3 * (size_t)j + c] - h->mean[c]) * rs : P0[3 * (size_t)j + c];
+                X4[4 * (size_t)jn + 3] = 0.0;
+            }
+        });
+        // cached parameter length (v3d_metricbundle.h:37-45), after normalisation (summed in the caller's point order)
+        if (T == 1) {
+            std::vector<int> new_of_orig((size_t)M);
+            for (int jn = 0; jn < M; ++jn) new_of_orig[h->orig_of_new[jn]] = jn;
+            for (int j = 0; j < M; ++j) { const int jn = new_of_orig[j]; for (int c = 0; c < 3; ++c) L[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; }
+        } else {
+            blocked_sum(1, L, [&](int jn, double* a) { for (int c = 0; c < 3; ++c) a[0] += X4[4 * (size_t)jn + c] * X4[4 * (size_t)jn + c]; });
+        }
+        CU(cudaMemcpyAsync(h->X0.p, X4, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
     }
     if (int rc = global_sum(h, L, 1)) return rc;
     for (int i = (o.fix_first_camera ? 1 : 0); i < N; ++i) {
         const double* P = cam.data() + 12 * (size_t)i;
         L[0] += P[3] * P[3] + P[7] * P[7] + P[11] * P[11] + 3.0;
     }
-    cudaStream_t s = h->stream;
     CU(cudaMemcpyAsync(h->rt0.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->rt1.p, cam.data(), sizeof(double) * 12 * (size_t)N, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(h->X0.p, X4, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->X1.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->X_init.p, h->X0.p, sizeof(double) * 4 * (size_t)std::max(M, 1), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->rt_init.p, h->rt0.p, sizeof(double) * 12 * (size_t)N, cudaMemcpyDeviceToDevice, s));
@@ -1159,6 +1173,26 @@ int b200ba_problem_size(const b200ba_handle* h, int32_t* N, int32_t* M, int32_t*
     if (N) *N = h->N;
     if (M) *M = h->M;
     if (K) *K = h->K;
+    return 0;
+}
+
+int b200ba_get_plan(const b200ba_handle* h, b200ba_plan* plan)
+{
+    if (!h || !plan) return B200BA_E_INVALID;
+    if (!h->have_problem) return B200BA_E_STATE;
+    memset(plan, 0, sizeof *plan);
+    plan->struct_size = (int32_t)sizeof *plan;
+    plan->camera_table = h->use_tab ? B200BA_TABLE_SHARED : B200BA_TABLE_GLOBAL;
+    plan->cluster_size = 1;
+    plan->cooperative_step = h->use_coop ? 1 : 0;
+    plan->cuda_graph = (h->use_graph && !(h->opt.cg_rel_tol > 0)) ? 1 : 0;
+    plan->peer_windows = h->p2p_ready ? 1 : 0;
+    plan->world = h->world; plan->rank = h->rank;
+    plan->launches_per_iteration = (int32_t)h->launches_per_graph;
+    plan->n_slices = h->d.n_slices; plan->padded_entries = h->Kp;
+    plan->n_rows = h->d.n_rows; plan->n_segments = h->d.n_segs;
+    plan->fp32_pcg = h->use_f32 ? 1 : 0;
+    plan->device_bytes = (int64_t)h->arena.cap;
     return 0;
 }
 

@@ -24,6 +24,24 @@ SHAPES = {
     "final": (13682, 4456117, 28987644),
 }
 
+# Big cases with a committed oracle trace (tests/golden/trace50_<case>_s<seed>.json, tools/make_golden_big.py):
+# case -> (shape, seed, LM iterations stored).  "camheavy" has Final's camera count (the execution plan for camera tables that
+# do not fit one SM's shared memory) with the point count cut down so that the CPU oracle finishes in seconds.
+BIG_CASES = {
+    "venice": ("venice", 1, 6),
+    "final": ("final", 1, 3),
+    "camheavy": ((13682, 250000, 1250000), 1, 4),
+}
+
+
+def input_checksum(p: "Problem") -> str:
+    """sha256 over the arrays a problem hands to b200ba_set_problem (pins the generator for the committed fixtures)."""
+    import hashlib
+    h = hashlib.sha256()
+    for a in (p.K5, p.cam_RT, p.pts, p.obs_xy, p.obs_cam, p.obs_pt):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
 
 @dataclass
 class Problem:

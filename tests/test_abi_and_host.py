@@ -144,7 +144,9 @@ def test_python_mirror_with_oracle_as_engine(monkeypatch):
                              round_pixels=self.opt.round_pixels, fix_first_camera=self.opt.fix_first_camera,
                              gradient_threshold=self.opt.gradient_threshold, solver=1)
             ret = -1 if (self.opt.discard_converged and r.status == 2) else 0
-            return SolveResult(ret, r.status, r.iterations, r.trace, r.mean_px, r.cam_RT, r.pts, 0, 0, 0, 0, 0, 0, 0)
+            out = SolveResult(ret, r.status, r.iterations, r.trace, r.mean_px, r.cam_RT, r.pts, 0, 0, 0, 0, 0, 0, 0)
+            out.opt_seen = self.opt
+            return out
 
     monkeypatch.setattr(binding, "Engine", FakeEngine)
     p = make_problem("tiny", 6)
@@ -162,9 +164,21 @@ def test_python_mirror_with_oracle_as_engine(monkeypatch):
     assert ba.adjustBundle_ssba(cloud2, Kmat2, imgpts2, Pmats2, options={"gradient_threshold": 1e30}) == -1
     assert all(np.array_equal(snap[k], Pmats2[k]) for k in snap)
     assert np.array_equal(cloud2[0].pt, p.pts[0])
-    # pba entry point always returns 0 (src/sfm_ba_pba.cpp:173)
+    # Shipped build (USE_PBA undefined): adjustBundle_pba forwards to adjustBundle_ssba and returns ITS value
+    # (src/sfm_ba_pba.cpp:167-171): same results, and -1 with untouched inputs on a gradient-converged outcome
     cloud3, Kmat3, imgpts3, Pmats3 = _tracker_containers(p)
-    assert ba.adjustBundle_pba(cloud3, Kmat3, np.zeros(4), imgpts3, Pmats3) == 0
+    rep3 = {}
+    assert ba.adjustBundle_pba(cloud3, Kmat3, np.zeros(4), imgpts3, Pmats3, report=rep3) == 0
+    assert rep3["result"].opt_seen.round_pixels == 1 and rep3["result"].opt_seen.fix_first_camera == 0
+    assert all(np.array_equal(Pmats[k], Pmats3[k]) for k in Pmats) and np.array_equal(cloud[5].pt, cloud3[5].pt)
+    cloud4, Kmat4, imgpts4, Pmats4 = _tracker_containers(p)
+    assert ba.adjustBundle_pba(cloud4, Kmat4, np.zeros(4), imgpts4, Pmats4, options={"gradient_threshold": 1e30}) == -1
+    assert all(np.array_equal(snap[k], Pmats4[k]) for k in snap)
+    # a -DUSE_PBA build: PBA personality (camera 0 constant, sub-pixel, no robustifier), always 0 (src/sfm_ba_pba.cpp:173)
+    cloud5, Kmat5, imgpts5, Pmats5 = _tracker_containers(p)
+    rep5 = {}
+    assert ba.adjustBundle_pba(cloud5, Kmat5, np.zeros(4), imgpts5, Pmats5, options={"gradient_threshold": 1e30}, report=rep5, use_pba=True) == 0
+    assert rep5["result"].opt_seen.round_pixels == 0 and rep5["result"].opt_seen.fix_first_camera == 1
 
 
 def test_bench_byte_model_is_the_surveys():

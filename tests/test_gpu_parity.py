@@ -297,6 +297,94 @@ def test_python_mirror_and_cpp_adapter_agree(tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# the benchmark's big shapes against the oracle (stage level + fifty-step LM iterations)
+# ---------------------------------------------------------------------------------------------------------
+def _stage_and_trace_vs_oracle(p, iters, fx=None, n_live=2):
+    """Linearisation blocks and one Schur product against oracle/ba_oracle.c run live on the same inputs, then `iters` full
+    LM iterations of the throughput mode (fixed 50-step PCG, no early stop: bench.py's timed workload) against the oracle -
+    live for the first n_live iterations, and against the committed oracle trace (tests/golden/trace50_*.json) for all."""
+    o = oracle.linearize(p)
+    x = np.random.default_rng(11).normal(size=(p.N, 6))
+    kw = dict(max_iterations=iters, min_iterations=10 ** 6, gradient_threshold=0.0, cg_max_steps=50, cg_rel_tol=0.0)
+    with binding.Engine(**kw) as eng:
+        eng.set_problem_from(p)
+        eng.begin()
+        g = eng.debug_linearize()
+        lam = o["lambda0"]
+        Sx = eng.debug_schur_matvec(lam, x)
+        r = eng.solve()
+        plan = eng.plan()
+    oS = oracle.linearize(p, x=x.reshape(-1), lam=lam)["Sx"]
+    assert abs(g["cost"] - o["cost"]) < 1e-12 * o["cost"]
+    assert abs(g["lambda0"] - o["lambda0"]) < 1e-12 * o["lambda0"]
+    assert np.array_equal(g["w"] == 1.0, o["w"] == 1.0)
+    for k in ("w", "gc", "gp", "U", "V"):
+        assert rel(g[k], o[k]) < 1e-11, k
+    assert rel(Sx, oS) < 1e-10
+    c = oracle.solve(p, solver=0, **{**kw, "max_iterations": n_live})
+    assert np.array_equal(r.trace[:n_live, 5], c.trace[:n_live, 5])
+    assert rel_cost_diff(r.trace, c.trace, n_live).max() < COST_RTOL
+    assert np.abs(r.trace[:n_live, 3] - c.trace[:n_live, 3]).max() < COST_RTOL * c.trace[0, 1]      # trial costs too
+    if fx is not None:
+        ref = fx["trace"]
+        n = min(iters, len(ref))
+        assert np.array_equal(r.trace[:n, 5], ref[:n, 5])
+        assert rel_cost_diff(r.trace, ref, n).max() < COST_RTOL, rel_cost_diff(r.trace, ref, n)
+        assert np.allclose(r.trace[:n, 2], ref[:n, 2], rtol=1e-9)
+    return r, plan
+
+
+def test_venice_shape_matches_oracle():
+    """The configuration the headline metric is quoted on (1778 / 993 923 / 5 001 946): shared-memory camera table plan."""
+    from sequencesfm_b200.synth import BIG_CASES, input_checksum
+    fx = load_golden("trace50_venice_s1")
+    shape, seed, _ = BIG_CASES["venice"]
+    p = make_problem(shape, seed)
+    assert input_checksum(p) == fx["input_sha256"]
+    r, plan = _stage_and_trace_vs_oracle(p, 4, fx)
+    assert plan["camera_table"] == "shared"
+    assert r.gpu_launches > 0
+
+
+def test_final_camera_count_matches_oracle():
+    """13 682 cameras (Final's camera count; points cut to 250 000 so that the oracle runs in seconds): the camera table does
+    not fit one SM's shared memory, so this exercises the large-camera-count plan at scale."""
+    from sequencesfm_b200.synth import BIG_CASES, input_checksum
+    fx = load_golden("trace50_camheavy_s1")
+    shape, seed, _ = BIG_CASES["camheavy"]
+    p = make_problem(tuple(shape), seed)
+    assert input_checksum(p) == fx["input_sha256"]
+    r, plan = _stage_and_trace_vs_oracle(p, 4, fx)
+    assert plan["camera_table"] != "shared"
+
+
+def test_final_shape_against_committed_oracle_trace():
+    """Final shape (13 682 / 4 456 117 / 28 987 644) on one GPU against the oracle trace committed by tools/make_golden_big.py
+    (the oracle needs ~70 s per LM iteration at this size, so it is not run live)."""
+    from sequencesfm_b200.synth import BIG_CASES, input_checksum
+    fx = load_golden("trace50_final_s1")
+    shape, seed, _ = BIG_CASES["final"]
+    p = make_problem(shape, seed)
+    assert input_checksum(p) == fx["input_sha256"]
+    kw = dict(max_iterations=3, min_iterations=10 ** 6, gradient_threshold=0.0, cg_max_steps=50, cg_rel_tol=0.0)
+    with binding.Engine(**kw) as eng:
+        eng.set_problem_from(p)
+        eng.begin()
+        g = eng.debug_linearize()
+        r = eng.solve()
+    L = fx["lin"]
+    assert abs(g["cost"] - L["cost"]) < 1e-12 * L["cost"] and abs(g["lambda0"] - L["lambda0"]) < 1e-12 * L["lambda0"]
+    assert abs(np.abs(g["gc"]).sum() - L["gc_abs_sum"]) < 1e-10 * L["gc_abs_sum"]
+    assert abs(np.abs(g["gp"]).sum() - L["gp_abs_sum"]) < 1e-10 * L["gp_abs_sum"]
+    assert abs(np.einsum("nii->", g["U"]) - L["U_trace_sum"]) < 1e-11 * L["U_trace_sum"]
+    assert abs(np.einsum("nii->", g["V"]) - L["V_trace_sum"]) < 1e-11 * L["V_trace_sum"]
+    assert int((g["w"] != 1.0).sum()) == L["outliers"]
+    n = min(3, len(fx["trace"]))
+    assert np.array_equal(r.trace[:n, 5], fx["trace"][:n, 5])
+    assert rel_cost_diff(r.trace, fx["trace"], n).max() < COST_RTOL
+
+
+# ---------------------------------------------------------------------------------------------------------
 # the benchmark's full size: properties that do not need the oracle
 # ---------------------------------------------------------------------------------------------------------
 def test_venice_shape_properties():
