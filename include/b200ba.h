@@ -91,7 +91,9 @@ typedef struct b200ba_report {
     double  ms_h2d, ms_d2h;     /* upload (set_problem) / download (get_result) wall time                 */
     double* trace;              /* optional caller buffer, trace_cap rows x B200BA_TRACE_COLS; may be NULL */
     int32_t trace_cap;
-    int32_t reserved[5];
+    int32_t iterations_total;   /* LM iterations / accepted steps summed over every b200ba_restart since b200ba_begin  */
+    int32_t accepted_total;     /* (iterations counts the last run only)                                              */
+    int32_t reserved[3];
 } b200ba_report;
 
 typedef struct b200ba_handle b200ba_handle;
@@ -127,6 +129,8 @@ int b200ba_iterate(b200ba_handle* h, int32_t n, int32_t* done);
 int b200ba_restart(b200ba_handle* h);
 /* Device time (CUDA events on the engine's stream) of the last b200ba_iterate call, in milliseconds. */
 int b200ba_last_iterate_ms(b200ba_handle* h, double* ms);
+/* Device time of the last b200ba_restart (its device-to-device copies), in milliseconds. */
+int b200ba_last_restart_ms(b200ba_handle* h, double* ms);
 int b200ba_finish(b200ba_handle* h, b200ba_report* report);
 
 /* Download the adjusted cameras / points (what src/sfm_ba_ssba.cpp:250-271 writes back).  When the outcome is

@@ -23,7 +23,7 @@ STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 # every symbol include/b200ba.h declares (tests check that the library exports each of them)
 ABI_SYMBOLS = [
     "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
-    "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_finish", "b200ba_get_result",
+    "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_last_restart_ms", "b200ba_finish", "b200ba_get_result",
     "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
     "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
@@ -45,7 +45,7 @@ class Report(C.Structure):
                 ("total_cg_steps", C.c_int32), ("gpu_launches", C.c_int32), ("mean_px", C.c_double * 2),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("ms_solve", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("trace", C.POINTER(C.c_double)),
-                ("trace_cap", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("trace_cap", C.c_int32), ("iterations_total", C.c_int32), ("accepted_total", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Plan(C.Structure):
@@ -226,7 +226,7 @@ class Engine:
         rep2 = Report()
         return SolveResult(rep.ret, rep.status, rep.iterations, tr[: rep.n_trace].copy(), (rep.mean_px[0], rep.mean_px[1]),
                            cam, pts, rep.total_cg_steps, rep.gpu_launches, rep.ms_solve, rep.ms_h2d, rep.ms_d2h,
-                           rep.initial_cost, rep.final_cost)
+                           rep.initial_cost, rep.final_cost, {"iterations_total": rep.iterations_total, "accepted_total": rep.accepted_total})
 
     def get_result(self):
         """``b200ba_get_result``: (cam_RT N x 12, pts M x 3) as new host arrays."""
@@ -253,6 +253,11 @@ class Engine:
     def last_iterate_ms(self) -> float:
         ms = C.c_double(0)
         self._check(self.lib.b200ba_last_iterate_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def last_restart_ms(self) -> float:
+        ms = C.c_double(0)
+        self._check(self.lib.b200ba_last_restart_ms(self.h, C.byref(ms)))
         return ms.value
 
     def finish(self) -> SolveResult:

@@ -134,7 +134,8 @@ struct b200ba_handle {
     Arena arena;
     LMState h_st{}, h_st_init{};
     long long launches = 0;
-    double ms_h2d = 0, ms_d2h = 0, ms_solve = 0, ms_last_iterate = 0;
+    double ms_h2d = 0, ms_d2h = 0, ms_solve = 0, ms_last_iterate = 0, ms_last_restart = 0;
+    long long iters_before_restart = 0, accepts_before_restart = 0;   // totals of the runs ended by b200ba_restart
     double mean_px[2] = {0, 0};
     double initial_cost = 0;
     int trace_cap = 0;
@@ -1029,7 +1030,7 @@ int b200ba_begin(b200ba_handle* h)
     h->h_st = st; h->h_st_init = st;
     CU(cudaMemcpyAsync(h->st.p, &h->h_st, sizeof st, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));
-    h->launches = 0; h->ms_solve = 0;
+    h->launches = 0; h->ms_solve = 0; h->iters_before_restart = 0; h->accepts_before_restart = 0;
     if (int rc = mean_reproj(h, 0, &h->mean_px[0])) return rc;
     h->begun = true; h->finished = false;
     return 0;
@@ -1042,14 +1043,30 @@ int b200ba_restart(b200ba_handle* h)
     CU(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const size_t xb = sizeof(double) * 4 * (size_t)std::max(h->M, 1), rb = sizeof(double) * 12 * (size_t)h->N;
+    {   // keep the totals of the run that ends here (reported by b200ba_finish)
+        LMState cur; CU(cudaMemcpyAsync(&cur, h->st.p, sizeof cur, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        h->iters_before_restart += cur.iter; h->accepts_before_restart += cur.n_accept;
+    }
+    CU(cudaEventRecord(h->ev0, s));
     CU(cudaMemcpyAsync(h->X0.p, h->X_init.p, xb, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->X1.p, h->X_init.p, xb, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->rt0.p, h->rt_init.p, rb, cudaMemcpyDeviceToDevice, s));
     CU(cudaMemcpyAsync(h->rt1.p, h->rt_init.p, rb, cudaMemcpyDeviceToDevice, s));
     LMState st = h->h_st_init;
     CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(h->ev1, s));
     CU(cudaStreamSynchronize(s));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ms_last_restart = ms;
     h->finished = false;
+    return 0;
+}
+
+int b200ba_last_restart_ms(b200ba_handle* h, double* ms)
+{
+    if (!h || !ms) return B200BA_E_INVALID;
+    *ms = h->ms_last_restart;
     return 0;
 }
 
@@ -1102,6 +1119,8 @@ int b200ba_finish(b200ba_handle* h, b200ba_report* rep)
         rep->status = h->h_st.status; rep->iterations = h->h_st.iter;
         rep->ret = (h->opt.discard_converged && h->h_st.status == B200BA_STATUS_CONVERGED) ? -1 : 0;
         rep->total_cg_steps = h->h_st.total_cg;
+        rep->iterations_total = (int32_t)(h->iters_before_restart + h->h_st.iter);
+        rep->accepted_total = (int32_t)(h->accepts_before_restart + h->h_st.n_accept);
         rep->gpu_launches = (int32_t)std::min<long long>(h->launches, 2147483647LL);
         rep->mean_px[0] = h->mean_px[0]; rep->mean_px[1] = h->mean_px[1];
         rep->ms_solve = h->ms_solve; rep->ms_h2d = h->ms_h2d; rep->ms_d2h = h->ms_d2h;

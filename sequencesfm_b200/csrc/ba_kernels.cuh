@@ -99,6 +99,7 @@ struct LMState {
     int iter, status, done, compute, cur, first;
     int cg_active, cg_steps, solve_ok, total_cg;
     int max_iter, min_iter, n_trace, trace_cap;
+    int n_accept;                                 // accepted LM steps since b200ba_begin / b200ba_restart
 };
 
 // NVLink peer-memory exchange window (multi-rank), PUSH design.  Every rank owns one window
@@ -1544,7 +1545,7 @@ __global__ void k_lm_decide(Dev d)
         accept = rho > 0;
         if (tr) { tr[3] = new_err; tr[4] = rho; tr[5] = accept ? 1 : 0; }
     }
-    if (accept) { st->lambda = fmax(1e-10, st->lambda * 0.1); st->compute = 1; st->cur ^= 1; }
+    if (accept) { st->lambda = fmax(1e-10, st->lambda * 0.1); st->compute = 1; st->cur ^= 1; st->n_accept += 1; }
     else        { st->lambda *= 10.0; st->compute = 0; }
     st->iter = it + 1;
     if (it + 1 >= st->max_iter) st->done = 1;
