@@ -118,6 +118,7 @@ struct b200ba_handle {
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
     DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
+    DBuf<unsigned long long> stamps;
     DBuf<int> tab_wr, tab_wr32;
     DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
     bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
@@ -798,6 +799,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->ptab.take(A, (size_t)N * TAB_STRIDE);
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
+        h->stamps.take(A, 512 * 40);
         if (o.pcg_fp32) {
             h->tab_wr32.take(A, (size_t)(n_sm > 0 ? n_sm : 148) * (TAB32_BLOCK / 32) * 8 + 8);
             h->o_rec32.take(A, (Kpp / 32 + 1) * OREC32_BYTES); h->c_rec32.take(A, Rp * REC32_BYTES + 16);
@@ -922,7 +924,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
-    d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p;
+    d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p; d.stamps = h->stamps.p;
     if (h->use_f32) {
         d.o_rec32 = h->o_rec32.p; d.c_rec32 = h->c_rec32.p; d.X32 = h->X32.p; d.v32 = h->v32.p; d.Vinv32 = h->Vinv32.p;
         d.ptab32 = h->ptab32.p; d.rt32 = h->rt32.p; d.tab_wr32 = h->tab_wr32.p; d.tab_warps32 = tab_warps32;
@@ -1331,6 +1333,16 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
     CU(cudaMemcpy(h->st.p, &sv, sizeof sv, cudaMemcpyHostToDevice));
     return 0;
 }
+
+#ifdef B200BA_STAMPS
+// profiling builds only (not part of include/b200ba.h): the clock stamps written by the last launches of the two PCG sweeps
+int b200ba_debug_stamps(b200ba_handle* h, unsigned long long* out, int32_t cap)
+{
+    if (!h || !out) return B200BA_E_INVALID;
+    CU(cudaMemcpy(out, h->stamps.p, sizeof(unsigned long long) * (size_t)std::min<int>(cap, 512 * 40), cudaMemcpyDeviceToHost));
+    return 0;
+}
+#endif
 
 static const char* kKernelNames[] = {"linearize_points", "linearize_cameras", "cg_point_pass", "cg_camera_pass",
                                      "camera_reduce6", "cg_update", "schur_diag_cameras", "point_vinv",

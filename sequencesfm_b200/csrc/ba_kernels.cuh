@@ -149,6 +149,7 @@ struct Dev {
     double* seg_part;     // n_segs x PART_STRIDE
     double* pt_part;      // n_pt_blocks x 4
     double* trace;
+    unsigned long long* stamps;   // profiling builds only (-DB200BA_STAMPS): per-CTA / per-warp clock stamps of the two PCG sweeps
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -287,6 +288,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     __syncwarp();
 }
 
+#ifdef B200BA_STAMPS
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr int STAMP_STRIDE = 40;   // per CTA: [0] entry (globaltimer) [1] table ready [2] entry clock64 [3] ready clock64 [8 + w] end clock64 of warp w
+#endif
 // SELL-32 addressing: first entry and (warp-uniform) trip count of point j
 __device__ __forceinline__ void slice_of(const Dev& d, int j, int& k0, int& deg)
 {
@@ -942,6 +947,11 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
     if (st->done) return;
     if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200BA_STAMPS
+    unsigned long long* stp = d.stamps + (size_t)(256 + blockIdx.x) * STAMP_STRIDE;
+    if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
+    struct EndStamp { unsigned long long* p; int lane; __device__ ~EndStamp() { if (lane == 0) *p = clock64(); } } end_stamp{stp + 8 + warp, lane};
+#endif
     const int vw = (blockIdx.x * CW + warp) * VSPLIT;  // this warp's VSPLIT consecutive virtual warps = one contiguous row range
     if (vw >= d.n_vwarps) return;                       // no CTA-wide barrier below: warps are independent
     const int rb = vrow(d, vw), n = vrow(d, min(vw + VSPLIT, d.n_vwarps)) - rb;
@@ -1284,14 +1294,29 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
     if (st->done || !st->cg_active) return;
     const double2* tab = reinterpret_cast<const double2*>(smem_raw);
     const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+#ifdef B200BA_STAMPS
+    unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
+    if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
+#endif
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, total);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
+#ifdef B200BA_TAB_STAGGER
+        // every CTA asks for the same 199 KB at the same moment: start each one at a different chunk so that the requests
+        // spread over the L2 slices instead of all hitting the first lines together
+        const uint32_t nch = (total + B200BA_TAB_STAGGER - 1) / B200BA_TAB_STAGGER;
+        for (uint32_t c = 0; c < nch; ++c) {
+            const uint32_t off = ((c + blockIdx.x) % nch) * B200BA_TAB_STAGGER;
+            const uint32_t n = total - off < (uint32_t)B200BA_TAB_STAGGER ? total - off : (uint32_t)B200BA_TAB_STAGGER;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+#else
         for (uint32_t off = 0; off < total; off += 32768u) {
             uint32_t n = total - off < 32768u ? total - off : 32768u;
             bulk_g2s(smem_raw + off, src + off, n, &bar);
         }
+#endif
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* Xb = d.X[st->cur];
@@ -1333,6 +1358,10 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
     if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
     __syncthreads();
     mbar_wait(&bar, 0);
+#ifdef B200BA_STAMPS
+    if (threadIdx.x == 0) { stp[1] = gtime(); stp[3] = clock64(); }
+    struct EndStamp { unsigned long long* p; int lane; __device__ ~EndStamp() { if (lane == 0) *p = clock64(); } } end_stamp{stp + 8 + warp, lane};
+#endif
     if (g >= g_end) return;
     double u0 = 0, u1 = 0, u2 = 0;
     // Requests what the END of slice g needs: its inverse block and the next slice's X.  Called in the middle of the

@@ -80,6 +80,15 @@ class Problem:
                        self.obs_cam[k0:k1].copy(), (self.obs_pt[k0:k1] - j0).astype(np.int32), self.name, self.seed)
 
 
+def load_problem_npz(path: str, name: str = "") -> Problem:
+    """A captured BA problem stored as .npz (K5, cam_RT, pts, obs_xy float32 pixels, obs_cam, obs_pt [, frame_ids]) -
+    the demo-sequence fixtures written by tools/make_demo_problem.py (BASELINE.json configs[0])."""
+    z = np.load(path)
+    return Problem(z["K5"].astype(np.float64), np.ascontiguousarray(z["cam_RT"], dtype=np.float64), np.ascontiguousarray(z["pts"], dtype=np.float64),
+                   np.ascontiguousarray(z["obs_xy"].astype(np.float32).astype(np.float64)), z["obs_cam"].astype(np.int32), z["obs_pt"].astype(np.int32),
+                   name or "fixture", 0)
+
+
 def rodrigues(w: np.ndarray) -> np.ndarray:
     """Batch Rodrigues: (n,3) rotation vectors -> (n,3,3) rotation matrices."""
     w = np.asarray(w, dtype=np.float64).reshape(-1, 3)

@@ -32,6 +32,19 @@ def golden_problem(fx: dict):
     return make_problem(fx["shape"], fx["seed"], **kw)
 
 
+def demo_names() -> list[str]:
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "demo_kf*.json")))
+
+
+def load_demo(name: str):
+    """(fixture dict with the reference SSBA run, Problem, frame ids) of a captured demo-sequence BA call
+    (tools/make_demo_problem.py; BASELINE.json configs[0])."""
+    from sequencesfm_b200.synth import load_problem_npz
+    fx = load_golden(name)
+    p = load_problem_npz(os.path.join(GOLDEN_DIR, name + ".npz"), name)
+    return fx, p, [int(v) for v in np.load(os.path.join(GOLDEN_DIR, name + ".npz"))["frame_ids"]]
+
+
 def parity_window(ours: np.ndarray, ref: np.ndarray, lambda_floor_rel: float = 2e-9) -> int:
     """Number of leading LM iterations over which two traces are comparable at 1e-9.
 
