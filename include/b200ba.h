@@ -195,6 +195,12 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
 /* Time `reps` launches of one kernel group with CUDA events; which: see b200ba_kernel_name. */
 int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, double* ms_per_launch);
 const char* b200ba_kernel_name(int32_t which);   /* NULL past the last kernel */
+/* Host-only, needs no device: conflict factor of the point-order layout b200ba_set_problem builds for these observations
+ * (expected shared-memory wavefronts of one 16-byte camera-table read per quarter-warp phase; 1.0 = conflict-free).
+ * out[4] = {factor with options.lane_window grouping + slot assignment, factor of the plain track-length order,
+ * milliseconds of the layout build, padded SELL entries / K}.  B200BA_E_STATE if the slot assignment is not a permutation. */
+int b200ba_debug_layout_stats(int32_t N, int32_t M, int32_t K, const int32_t* obs_cam, const int32_t* obs_pt,
+                              int32_t lane_window, double* out);
 int b200ba_version(void);
 
 #ifdef __cplusplus

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_last_restart_ms", "b200ba_finish", "b200ba_get_result",
     "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
-    "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version",
+    "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version", "b200ba_debug_layout_stats",
 ]
 
 
@@ -124,6 +124,16 @@ class SolveResult:
     initial_cost: float
     final_cost: float
     extra: dict = field(default_factory=dict)
+
+
+def layout_stats(p, lane_window: int = 64) -> dict:
+    """``b200ba_debug_layout_stats`` (host only, no device needed): conflict factor of the point-order layout."""
+    out = np.zeros(4)
+    oc = np.ascontiguousarray(p.obs_cam, dtype=np.int32); op = np.ascontiguousarray(p.obs_pt, dtype=np.int32)
+    rc = load().b200ba_debug_layout_stats(C.c_int32(p.N), C.c_int32(p.M), C.c_int32(p.K), _ip(oc), _ip(op), C.c_int32(lane_window), _dp(out))
+    if rc:
+        raise B200BAError(rc, "b200ba_debug_layout_stats")
+    return {"conflict_factor": out[0], "conflict_factor_plain": out[1], "ms": out[2], "padding": out[3]}
 
 
 class Engine:

@@ -9,6 +9,7 @@
 #include "ba_kernels.cuh"
 #include "ba_kernels_f32.cuh"
 #include "pinned_pool.h"
+#include "layout_host.h"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
@@ -30,6 +31,14 @@
 using namespace b200ba;
 
 namespace b200ba { PinnedPool g_pinned; }
+
+#ifndef B200BA_TAB_ILP_DEFAULT
+#define B200BA_TAB_ILP_DEFAULT 3
+#endif
+#ifndef B200BA_SLICE_W_NUM
+#define B200BA_SLICE_W_NUM 2
+#endif
+constexpr int SLICE_W_NUM = B200BA_SLICE_W_NUM, SLICE_W_DEN = 3;   // epilogue of a slice, in row bodies
 
 namespace {
 
@@ -128,6 +137,7 @@ struct b200ba_handle {
     int num_sms = 148, tab_grid = 0, step_grid = 0, cam_grid = 0;
     size_t tab_smem = 0;
     bool use_tab = false, use_coop = false, use_graph = false;
+    int tab_ilp = 1, tab_block = TAB_BLOCK;          // rows of a slice in flight per trip of the shared-memory-table sweep (1 or 2)
     cudaGraphExec_t graph_exec = nullptr;
     long long launches_per_graph = 0;
     DBuf<LMState> st;
@@ -177,6 +187,15 @@ int allreduce(b200ba_handle* h, double* buf, size_t count, int need = 0)
 
 // ---- kernel launch sequences ---------------------------------------------------------------------------
 #define LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+
+// by-point PCG sweep against the shared-memory camera table (one or two rows in flight per trip)
+void launch_point_tab(b200ba_handle* h)
+{
+    if (h->tab_ilp == 3) k_cg_point_pass_tabc<<<h->tab_grid, TABC_BLOCK, h->tab_smem, h->stream>>>(h->d);
+    else if (h->tab_ilp == 2) k_cg_point_pass_tab2<<<h->tab_grid, TAB2_BLOCK, h->tab_smem, h->stream>>>(h->d);
+    else k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(h->d);
+    h->launches++;
+}
 
 int enqueue_linearize(b200ba_handle* h)
 {
@@ -267,10 +286,8 @@ int enqueue_cg_step(b200ba_handle* h)
         if (int rc = enqueue_camera_sums(h)) return rc;
         return launch_camera_step(h, 1);
     }
-    if (h->use_tab) {
-        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d);
-        h->launches++;
-    } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    if (h->use_tab) launch_point_tab(h);
+    else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
     if (h->use_coop && h->world <= 1) return launch_camera_step(h, 0);
     if (h->use_coop && h->p2p_ready && h->step_grid <= P2P_MAX_BLOCKS) return launch_camera_step(h, 2);   // all-reduce fused into the step kernel (NVLink peer memory)
@@ -589,115 +606,15 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         }
     });
     lap("validate + measurements");
-    // ---- by-point layout: SELL-32, points sorted by track length (descending, stable) ----
-    // (threaded: obs_pt is non-decreasing, so pstart is read off the positions where it changes; the stable counting sort
-    // by track length uses per-thread histograms over contiguous point ranges)
-    std::vector<int> pstart((size_t)M + 1, 0);
-    pstart[M] = K;
-    parallel_for(T, [&](int t, int nt) {
-        const long long k0 = (long long)K * t / nt, k1 = (long long)K * (t + 1) / nt;
-        for (long long k = k0; k < k1; ++k) {
-            const int ja = (k == 0) ? -1 : obs_pt[k - 1], jb = obs_pt[k];
-            for (int j = ja + 1; j <= jb; ++j) pstart[j] = (int)k;          // points ja+1 .. jb start at k (empty ones included)
-        }
-        if (t + 1 == nt) for (int j = (K ? obs_pt[K - 1] : -1) + 1; j < M; ++j) pstart[j] = K;
-    });
-    int maxdeg = 0;
-    {
-        std::vector<int> mx((size_t)T, 0);
-        parallel_for(T, [&](int t, int nt) {
-            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
-            int m = 0; for (int j = j0; j < j1; ++j) m = std::max(m, pstart[j + 1] - pstart[j]);
-            mx[t] = m;
-        });
-        for (int t = 0; t < T; ++t) maxdeg = std::max(maxdeg, mx[t]);
-    }
-    h->orig_of_new.assign((size_t)M, 0);
-    std::vector<int> deg_new((size_t)std::max(M, 1));        // track length by NEW point index (sequential reads later on)
-    {
-        const size_t nb = (size_t)maxdeg + 1;
-        std::vector<int> hist((size_t)T * nb, 0);                // hist[t][maxdeg - degree]
-        parallel_for(T, [&](int t, int nt) {
-            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
-            int* hh = hist.data() + (size_t)t * nb;
-            for (int j = j0; j < j1; ++j) hh[maxdeg - (pstart[j + 1] - pstart[j])]++;
-        });
-        int run = 0;
-        for (size_t bk = 0; bk < nb; ++bk) for (int t = 0; t < T; ++t) { int c = hist[(size_t)t * nb + bk]; hist[(size_t)t * nb + bk] = run; run += c; }
-        parallel_for(T, [&](int t, int nt) {
-            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
-            int* hh = hist.data() + (size_t)t * nb;
-            for (int j = j0; j < j1; ++j) { const int dj = pstart[j + 1] - pstart[j]; const int pos = hh[maxdeg - dj]++; h->orig_of_new[pos] = j; deg_new[pos] = dj; }
-        });
-    }
-    lap("point index + track-length sort");
-    // ---- bank-conflict-aware lane grouping (shared-memory camera table) ----
-    // In k_cg_point_pass_tab the 8 lanes of a quarter-warp read the same 16-byte field of 8 different camera records;
-    // the bank group of a record is (camera index mod 8), so random cameras collide 2.6-fold on average (ncu: 63 % of the
-    // sweep's shared-memory wavefronts were conflicts).  Points of equal track length are interchangeable, so they are
-    // regrouped greedily (candidate window lane_window) such that the cameras met by a quarter-warp in each slot have
-    // distinct residues mod 8 as far as possible (measured 2.6 -> ~1.7).  Only the point permutation changes.
-    if (o.lane_window > 0 && K > 0 && getenv("B200BA_NO_LANE_OPT") == nullptr) {
-        const int W = std::min(o.lane_window, 1024);
-        std::vector<int>& ord = h->orig_of_new;
-        auto degree = [&](int jn) { return deg_new[jn]; };
-        // one-hot key of a point: bit (8 slot + camera mod 8), slots 0-7 in lo, 8-15 in hi.  A candidate's cost against the
-        // group built so far is the number of slots whose bank group is already taken: popcount(key & used).  The keys are
-        // built in the caller's point order (one streaming pass over obs_cam) and gathered per run: building them per run
-        // meant five dependent cache misses per point and 20 ms.
-        struct Key2 { unsigned long long lo, hi; };
-        std::unique_ptr<Key2[]> pkey(new Key2[(size_t)std::max(M, 1)]);
-        parallel_for(T, [&](int t, int nt) {
-            const int j0 = (int)((long long)M * t / nt), j1 = (int)((long long)M * (t + 1) / nt);
-            for (int j = j0; j < j1; ++j) {
-                Key2 kq = {0ull, 0ull}; const int* oc = obs_cam + pstart[j]; const int ds = std::min(pstart[j + 1] - pstart[j], 16);
-                for (int sl = 0; sl < ds; ++sl) { const unsigned long long bit = 1ull << (8 * (sl & 7) + (oc[sl] & 7)); if (sl < 8) kq.lo |= bit; else kq.hi |= bit; }
-                pkey[j] = kq;
-            }
-        });
-        parallel_for(T, [&](int t, int nt) {
-            long long a = (long long)(M / 32) * t / nt * 32, b = (t + 1 == nt) ? M : (long long)(M / 32) * (t + 1) / nt * 32;
-            std::vector<int> run, out, pool; std::vector<Key2> key;
-            for (long long r0 = a; r0 < b;) {
-                const int dg = degree((int)r0);
-                long long r1 = r0; while (r1 < b && degree((int)r1) == dg) ++r1;
-                const int n = (int)(r1 - r0), ds = std::min(dg, 16);
-                if (n >= 16 && ds > 0) {
-                    run.assign(ord.begin() + r0, ord.begin() + r1);
-                    key.resize(n);
-                    for (int q = 0; q < n; ++q) key[q] = pkey[run[q]];
-                    out.clear(); out.reserve(n); pool.clear();
-                    int next = 0;
-                    while (next < n && (int)pool.size() < W) pool.push_back(next++);
-                    int group = (8 - (int)(r0 & 7)) & 7;          // first (partial) group completes the quarter-warp the run starts in
-                    if (group == 0) group = 8;
-                    for (; !pool.empty(); group = 8) {
-                        Key2 used = {0ull, 0ull};
-                        for (int g8 = 0; g8 < group && !pool.empty(); ++g8) {
-                            int best = 0;
-                            if (g8 > 0) {
-                                int best_score = 1 << 30;
-                                const int np = (int)pool.size();
-                                for (int c = 0; c < np; ++c) {
-                                    const Key2& kq = key[pool[c]];
-                                    const int score = __builtin_popcountll(kq.lo & used.lo) + __builtin_popcountll(kq.hi & used.hi);
-                                    if (score < best_score) { best_score = score; best = c; if (score == 0) break; }
-                                }
-                            }
-                            const int q = pool[best];
-                            pool[best] = pool.back(); pool.pop_back();
-                            used.lo |= key[q].lo; used.hi |= key[q].hi;
-                            out.push_back(run[q]);
-                            if (next < n) pool.push_back(next++);
-                        }
-                    }
-                    std::copy(out.begin(), out.end(), ord.begin() + r0);
-                }
-                r0 = r1;
-            }
-        });
-        lap("lane grouping");
-    }
+    // ---- by-point layout: SELL-32, points sorted by track length (descending, stable), quarter-warps grouped and slots
+    //      assigned for conflict-free reads of the shared-memory camera table (layout_host.h) ----
+    PointLayout lay;
+    build_point_layout(M, K, obs_cam, obs_pt, getenv("B200BA_NO_LANE_OPT") ? 0 : o.lane_window, T, lay);
+    h->orig_of_new.swap(lay.orig_of_new);
+    const std::vector<int>& pstart = lay.pstart;
+    const std::vector<int>& deg_new = lay.deg_new;
+    const std::vector<int>& slot_obs = lay.slot_obs;
+    lap("point order + lane grouping + slots");
     const int n_slices = cdiv(std::max(M, 1), 32);
     std::vector<int> slice_base((size_t)n_slices + 1, 0), slice_deg((size_t)n_slices, 0);
     for (int g = 0; g < n_slices; ++g) {
@@ -745,8 +662,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             for (int e = slice_base[g0]; e < slice_base[g1]; ++e) { o_cam_p[e] = -1; o_meas_p[e] = make_double2(0.0, 0.0); }
             for (int jn = 32 * g0; jn < std::min(M, 32 * g1); ++jn) {
                 const int j = h->orig_of_new[jn], g = jn >> 5, l = jn & 31;
-                for (int k = pstart[j], sl = 0; k < pstart[j + 1]; ++k, ++sl) {
-                    const int kk = slice_base[g] + 32 * sl + l;
+                for (int q = pstart[j], sl = 0; q < pstart[j + 1]; ++q, ++sl) {
+                    const int k = slot_obs[q], kk = slice_base[g] + 32 * sl + l;      // observation k sits in slot sl of its point
                     o_cam_p[kk] = obs_cam[k]; o_meas_p[kk] = meas[k]; h->entry_of_obs[k] = kk;
                 }
             }
@@ -778,7 +695,7 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     h->trace_cap = o.max_iterations + 2;
     const size_t Mp = (size_t)std::max(M, 1), Kpp = (size_t)std::max(Kp, 1), Rp = (size_t)std::max(n_rows, 1);
     if (h->arena.base) { cudaFree(h->arena.base); h->arena = Arena(); }
-    int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (TAB_BLOCK / 32);
+    int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (std::max(std::max(TAB_BLOCK, TAB2_BLOCK), TABC_BLOCK) / 32);
     const int step_grid = cdiv((long long)N * 6, STEP_BLOCK);
     for (int pass = 0; pass < 2; ++pass) {
         Arena& A = h->arena;
@@ -845,21 +762,29 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     lap("upload");
     // ---- execution plan: shared-memory camera table, cooperative camera-side step, CUDA graph ----
     const size_t tab_bytes = (size_t)N * TAB_STRIDE * sizeof(double);
-    h->tab_smem = ((tab_bytes + 127) & ~(size_t)127) + TAB_RING_BYTES;       // camera table + per-warp stream rings
+    { const char* e = getenv("B200BA_TAB_ILP"); h->tab_ilp = (e && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : B200BA_TAB_ILP_DEFAULT; }
+    h->tab_block = h->tab_ilp == 3 ? TABC_BLOCK : h->tab_ilp == 2 ? TAB2_BLOCK : TAB_BLOCK;
+    h->tab_smem = ((tab_bytes + 127) & ~(size_t)127) + (h->tab_ilp == 3 ? TABC_RING_BYTES : h->tab_ilp == 2 ? TAB2_RING_BYTES : TAB_RING_BYTES);   // camera table + per-warp stream rings
     h->use_tab = h->tab_smem + 256 <= (size_t)smem_optin && getenv("B200BA_NO_TAB") == nullptr;
     if (h->use_tab) {
-        if (cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem) != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
-        h->tab_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB_BLOCK / 32)));
+        cudaError_t ea = h->tab_ilp == 3 ? cudaFuncSetAttribute(k_cg_point_pass_tabc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem)
+                       : h->tab_ilp == 2 ? cudaFuncSetAttribute(k_cg_point_pass_tab2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem)
+                                         : cudaFuncSetAttribute(k_cg_point_pass_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem);
+        if (ea != cudaSuccess) { cudaGetLastError(); h->use_tab = false; }
+        h->tab_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, h->tab_block / 32)));
     }
     // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
     // one 32-byte header per warp: {first slice, end slice, first entry, end entry, deg(first), deg(first+1), 0, 0}
-    int tab_warps = std::max(1, h->tab_grid) * (TAB_BLOCK / 32);
+    int tab_warps = std::max(1, h->tab_grid) * (h->tab_block / 32);
     auto warp_headers = [&](int nwarps, int* dst) -> int {
         std::vector<int> wr((size_t)nwarps + 1, n_slices);
-        long long total = 0; for (int g = 0; g < n_slices; ++g) total += slice_deg[g] + 1;
+        // cost of a slice = SLICE_W_NUM / SLICE_W_DEN row bodies for its epilogue + one per row (clock stamps of the sweep's
+        // warps at Venice shape: a slice end costs 0.6-0.7 of a row body; weighting it as a whole row left the CTAs that own
+        // the long tracks 10 % behind those with the two-observation points)
+        long long total = 0; for (int g = 0; g < n_slices; ++g) total += (long long)SLICE_W_DEN * slice_deg[g] + SLICE_W_NUM;
         long long acc = 0; int w = 0; wr[0] = 0;
         for (int g = 0; g < n_slices && w + 1 < nwarps; ++g) {
-            acc += slice_deg[g] + 1;
+            acc += (long long)SLICE_W_DEN * slice_deg[g] + SLICE_W_NUM;
             while (w + 1 < nwarps && acc * nwarps >= total * (long long)(w + 1)) wr[++w] = g + 1;
         }
         for (int q = w + 1; q <= nwarps; ++q) wr[q] = n_slices;
@@ -1315,10 +1240,8 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
         for (int i = 0; i < N; ++i) for (int a = 0; a < 6; ++a) tab[(size_t)i * TAB_STRIDE + 7 + a] = x[6 * (size_t)i + a];
         CU(cudaMemcpy(d.ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
-    if (h->use_tab && getenv("B200BA_DEBUG_GENERIC") == nullptr) {
-        k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d);
-        h->launches++;
-    } else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    if (h->use_tab && getenv("B200BA_DEBUG_GENERIC") == nullptr) launch_point_tab(h);
+    else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
     if (int rc = enqueue_camera_sums(h)) return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -1331,6 +1254,30 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
         Sx[6 * (size_t)i + a] = v - wv[6 * (size_t)i + a];
     }
     CU(cudaMemcpy(h->st.p, &sv, sizeof sv, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Host-only (works without a CUDA device): the conflict factor of the point-order layout b200ba_set_problem would build -
+// expected shared-memory wavefronts of one 16-byte camera-table read per quarter-warp phase (1.0 = conflict-free).
+// out[0] = factor with the grouping / slot assignment, out[1] = factor of the plain track-length order, out[2] = milliseconds
+// the layout build took, out[3] = padded SELL entries / K.
+int b200ba_debug_layout_stats(int32_t N, int32_t M, int32_t K, const int32_t* obs_cam, const int32_t* obs_pt, int32_t lane_window, double* out)
+{
+    if (N <= 0 || M <= 0 || K <= 0 || !obs_cam || !obs_pt || !out) return B200BA_E_INVALID;
+    for (int k = 0; k < K; ++k) if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M || (k && obs_pt[k] < obs_pt[k - 1])) return B200BA_E_INVALID;
+    const int T = (K > 200000) ? (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
+    PointLayout a, b;
+    const double t0 = now_ms();
+    build_point_layout(M, K, obs_cam, obs_pt, lane_window, T, a);
+    out[2] = now_ms() - t0;
+    build_point_layout(M, K, obs_cam, obs_pt, 0, T, b);
+    out[0] = layout_conflict_factor(M, obs_cam, a);
+    out[1] = layout_conflict_factor(M, obs_cam, b);
+    long long kp = 0; for (int g = 0; 32 * g < M; ++g) kp += 32ll * a.deg_new[(size_t)32 * g];
+    out[3] = (double)kp / (double)K;
+    // every observation must appear in exactly one slot of its point
+    std::vector<unsigned char> seen((size_t)K, 0);
+    for (int j = 0; j < M; ++j) for (int q = a.pstart[j]; q < a.pstart[j + 1]; ++q) { const int k = a.slot_obs[q]; if (k < a.pstart[j] || k >= a.pstart[j + 1] || seen[k]) return B200BA_E_STATE; seen[k] = 1; }
     return 0;
 }
 
@@ -1367,7 +1314,7 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
         switch (which) {
         case 0: LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d); break;
         case 1: k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++; break;
-        case 2: if (h->use_tab) { k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(d); h->launches++; }
+        case 2: if (h->use_tab) launch_point_tab(h);
                 else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
                 break;
         case 10: LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d); break;

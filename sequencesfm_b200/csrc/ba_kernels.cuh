@@ -143,8 +143,9 @@ struct Dev {
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
     // optional fp32 copies for the mixed-precision PCG (ba_kernels_f32.cuh); all null when options.pcg_fp32 = 0
     unsigned char *o_rec32, *c_rec32; float4 *X32, *v32; float *Vinv32, *ptab32, *rt32; int* tab_wr32; int tab_warps32;
-    int* tab_wr;                  // [tab_warps + 1] contiguous slice ranges of the persistent CG point sweep's warps (balanced by rows)
+    int* tab_wr;                  // tab_warps 32-byte headers: contiguous slice ranges of the persistent CG point sweep (one per warp, or per chunk)
     int tab_warps;
+
     int* cam_seg_beg;     // N + 1: segments of camera i
     double* seg_part;     // n_segs x PART_STRIDE
     double* pt_part;      // n_pt_blocks x 4
@@ -1279,6 +1280,15 @@ __global__ void __launch_bounds__(256) k_rows_fill(Dev d, const unsigned long lo
 }
 
 constexpr int PR = 4;                                            // rows of the point-order stream staged per warp: 2 stages x 2 rows
+// The ring is only two stages deep (the camera table leaves 28 KB of shared memory for all the warps' rings), so a warp has
+// ONE bulk copy in flight while it consumes the other stage: with the copy coming from DRAM (~1.2 us under load) every warp
+// ran at "two rows per DRAM latency" whatever its instruction-level parallelism (one row or two rows in flight: the same
+// 1200 cycles per row per warp, clock stamps + ncu round 2).  The stream is therefore pulled into L2 TAB_PF rows ahead of the
+// ring by bulk L2 prefetches issued with each re-arm, which turns the ring's copies into L2 hits.
+#ifndef B200BA_TAB_PF
+#define B200BA_TAB_PF 12
+#endif
+constexpr int TAB_PF = B200BA_TAB_PF;
 constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * (PR * OREC_BYTES + 2 * 8);   // rings + their two mbarriers per warp
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
@@ -1345,6 +1355,7 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         // evict_first: the stream must not push the gathered vectors (X, v: evict_last) out of L2 (by-camera sweep: 43 vs 47.5 us)
         asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                      ::"r"(ring + (uint32_t)stage * (2 * OREC_BYTES)), "l"(src_rows), "r"(bytes), "r"(rbar + 8u * stage), "l"(policy_evict_first()) : "memory");
+        if (TAB_PF > 0 && n_rows > TAB_PF) prefetch_l2_bulk(src_rows + (size_t)TAB_PF * OREC_BYTES, (uint32_t)min(2, n_rows - TAB_PF) * OREC_BYTES);
         src_rows += 2 * OREC_BYTES; n_rows -= 2;
     };
     if (lane == 0) {
@@ -1352,6 +1363,7 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar + 8u), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
+        if (TAB_PF > 0 && n_rows > 2) prefetch_l2_bulk(src_rows + 2 * OREC_BYTES, (uint32_t)min(TAB_PF, n_rows - 2) * OREC_BYTES);
         if (n_rows > 0) arm(0);                                  // stage 1 is requested at the top of the first trip
     }
     double X[3] = {0, 0, 0};
@@ -1417,6 +1429,290 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         if (last) request(Vi, Xn);                                //  before the forward half 2 us slower)
         tab_row_bwd(o, u0, u1, u2);
         if (last && !finish(Vi, Xn)) return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K8'' cg_point_pass_tab2: the same sweep with TWO rows of a slice in flight per trip (B200BA_TAB_ILP=2).
+//      The clock stamps of the one-row sweep (tools/stamps.py) showed it latency-bound per warp: the scheduler with 4 of the
+//      CTA's 19 warps finished 10 % ahead of the three with 5 - 25 % more work per scheduler cost 10 % more time, i.e. the
+//      dependent FP64 chain of a row (LDS camera index -> LDS table -> ~25 dependent DFMA) is what a warp waits on, and
+//      more independent chains per scheduler is what helps.  Registers allow no more warps (96 x 608), so the chains come
+//      from instruction-level parallelism: when the current slice has >= 2 rows left, both run in one basic block (their
+//      table reads, rotations and projections are independent; only the final u += differs).  Fewer, fatter warps
+//      (TAB2_BLOCK threads at <= 128 registers), same ring (2 stages x 2 rows, one bulk copy per stage), same headers.
+// ------------------------------------------------------------------------------------------------------
+#ifndef B200BA_TAB2_BLOCK
+#define B200BA_TAB2_BLOCK 512
+#endif
+constexpr int TAB2_BLOCK = B200BA_TAB2_BLOCK;
+constexpr int TAB2_RING_BYTES = (TAB2_BLOCK / 32) * (PR * OREC_BYTES + 2 * 8);
+__global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;
+    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
+    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+#ifdef B200BA_STAMPS
+    unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
+    if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
+#endif
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* Xb = d.X[st->cur];
+    const int wid = blockIdx.x * (TAB2_BLOCK / 32) + warp;
+    const bool active = wid < d.tab_warps;
+    int g = 0, g_end = 0, n_rows = 0, rows_left = 0, deg_next = 0;
+    const unsigned char* src_rows = d.o_rec;
+    if (active) {
+        const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
+        g = ha.x; g_end = ha.y; src_rows += (size_t)(ha.z >> 5) * OREC_BYTES; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
+    }
+    const uint32_t tab_bytes = (total + 127u) & ~127u;
+    const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (PR * OREC_BYTES);
+    const uint32_t rbar = smem_u32(smem_raw) + tab_bytes + (uint32_t)(TAB2_BLOCK / 32) * (PR * OREC_BYTES) + (uint32_t)warp * 16u;
+    auto arm = [&](int stage) {                                  // lane 0 only: next two unrequested rows -> ring stage
+        const uint32_t bytes = (uint32_t)min(2, n_rows) * OREC_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar + 8u * stage), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(ring + (uint32_t)stage * (2 * OREC_BYTES)), "l"(src_rows), "r"(bytes), "r"(rbar + 8u * stage), "l"(policy_evict_first()) : "memory");
+        if (TAB_PF > 0 && n_rows > TAB_PF) prefetch_l2_bulk(src_rows + (size_t)TAB_PF * OREC_BYTES, (uint32_t)min(2, n_rows - TAB_PF) * OREC_BYTES);
+        src_rows += 2 * OREC_BYTES; n_rows -= 2;
+    };
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rbar + 8u), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        if (TAB_PF > 0 && n_rows > 4) prefetch_l2_bulk(src_rows + 4 * OREC_BYTES, (uint32_t)min(TAB_PF, n_rows - 4) * OREC_BYTES);
+        if (n_rows > 0) arm(0);
+        if (n_rows > 0) arm(1);
+    }
+    double X[3] = {0, 0, 0};
+    if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
+    __syncthreads();
+    mbar_wait(&bar, 0);
+#ifdef B200BA_STAMPS
+    if (threadIdx.x == 0) { stp[1] = gtime(); stp[3] = clock64(); }
+    struct EndStamp { unsigned long long* p; int lane; __device__ ~EndStamp() { if (lane == 0) *p = clock64(); } } end_stamp{stp + 8 + warp, lane};
+#endif
+    if (g >= g_end) return;
+    double u0 = 0, u1 = 0, u2 = 0;
+    auto request = [&](double Vi[6], double Xn[3]) {
+        if (32 * g + lane < d.M) load6(d.Vinv, 32 * g + lane, Vi);
+        if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, policy_evict_last());
+    };
+    auto finish = [&](const double Vi[6], const double Xn[3]) -> bool {
+        const int j = 32 * g + lane;
+        if (j < d.M)
+            store4_keep(d.v + 4 * (size_t)j, Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2,
+                        Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0, policy_evict_last());
+        if (++g >= g_end) return false;
+        rows_left = deg_next; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; u0 = u1 = u2 = 0;
+        if (g + 1 < g_end) {
+            deg_next = __ldg(d.slice_deg + g + 1);
+            if (lane == 0) {
+                const int nj = min(32, d.M - 32 * (g + 1));
+                if (nj > 0) { prefetch_l2_bulk(d.Vinv + 6 * (size_t)(32 * (g + 1)), (uint32_t)nj * 48u); prefetch_l2_bulk(Xb + 4 * (size_t)(32 * (g + 1)), (uint32_t)nj * 32u); }
+            }
+        }
+        return true;
+    };
+    // r: rows of the stream consumed so far; row r sits in ring slot r & 3, its pair r >> 1 in stage (r >> 1) & 1 with
+    // mbarrier parity (r >> 2) & 1.  arrived: pairs known to have landed.  rearm: stage whose two rows the PREVIOUS trip finished
+    // reading (it is handed back to the TMA at the top of the next trip, when those reads have long fed their arithmetic).
+    int r = 0, arrived = 0, rearm = -1;
+    auto need_pair = [&](int pr) {
+        if (pr >= arrived) {
+            uint32_t ok;
+            do {
+                asm volatile("{\n .reg .pred P1;\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }"
+                             : "=r"(ok) : "r"(rbar + 8u * (uint32_t)(pr & 1)), "r"((uint32_t)(pr >> 1) & 1u) : "memory");
+            } while (!ok);
+            __syncwarp();
+            arrived = pr + 1;
+        }
+    };
+    for (;;) {
+        while (rows_left == 0) {
+            double Vi[6], Xn[3];
+            request(Vi, Xn);
+            if (!finish(Vi, Xn)) return;
+        }
+        if (rearm >= 0) { if (lane == 0 && n_rows > 0) arm(rearm); rearm = -1; }
+        const bool two = rows_left >= 2;                          // warp-uniform
+        need_pair(r >> 1);
+        if (two) need_pair((r + 1) >> 1);
+        const uint32_t ca = ring + (uint32_t)(r & 3) * OREC_BYTES + 4u * lane;
+        const int camA = lds_s32(ca);
+        const double wA = lds_f64(ca + 128u + 4u * lane);
+        if (two) {
+            const uint32_t cb = ring + (uint32_t)((r + 1) & 3) * OREC_BYTES + 4u * lane;
+            const int camB = lds_s32(cb);
+            const double wB = lds_f64(cb + 128u + 4u * lane);
+            if (r & 1) rearm = (r >> 1) & 1; else rearm = ((r + 1) >> 1) & 1;      // exactly one pair completes: the one whose odd row is r or r + 1
+            r += 2; rows_left -= 2;
+            const bool last = rows_left == 0;
+            TabRow oA, oB;
+            const bool padA = camA < 0, padB = camB < 0;
+            tab_row_fwd<false>(tab, padA ? 0 : camA, padA ? 0.0 : wA, X, d.in, oA, padA);
+            tab_row_fwd<false>(tab, padB ? 0 : camB, padB ? 0.0 : wB, X, d.in, oB, padB);
+            double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+            if (last) request(Vi, Xn);
+            tab_row_bwd(oA, u0, u1, u2);
+            tab_row_bwd(oB, u0, u1, u2);
+            if (last && !finish(Vi, Xn)) return;
+        } else {
+            if (r & 1) rearm = (r >> 1) & 1;
+            r += 1; rows_left = 0;
+            TabRow oA;
+            const bool padA = camA < 0;
+            tab_row_fwd<false>(tab, padA ? 0 : camA, padA ? 0.0 : wA, X, d.in, oA, padA);
+            double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+            request(Vi, Xn);
+            tab_row_bwd(oA, u0, u1, u2);
+            if (!finish(Vi, Xn)) return;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K8c cg_point_pass_tabc: the same sweep with the row stream staged by per-lane cp.async (LDGSTS) instead of TMA bulk copies
+//      (B200BA_TAB_ILP=3).  A lane only ever reads ITS OWN camera index and weight of a row, so every lane copies exactly what it
+//      will read (4 + 8 bytes per row, coalesced across the warp) into a private ring of TABC_ROWS rows and waits with
+//      cp.async.wait_group: no mbarrier, no elected lane, no bulk-copy issue per stage, rows in flight = TABC_ROWS - 1.
+//      Measured (Venice, round 2): 51.4 us (TMA ring, one row) / 49.4 (TMA ring, two rows) -> 47.4 (this, 608 threads) ->
+//      46.9 (640 threads = 5 warps on every scheduler).  The SASS of the row body is ~155 instructions of which ~71 are FP64
+//      (2 issue cycles each): 5 warps x 57 rows x ~226 issue cycles is what a scheduler spends, i.e. the sweep is bound by
+//      instruction issue, and what helped was fewer instructions per row.  A device-wide chunk queue (guided self-scheduling,
+//      claims by atomicAdd) evened out the warps' finish times (spread 16 % -> 5 %) but cost more than it gained (51-55 us):
+//      every chunk switch drains and refills the ring.
+// ------------------------------------------------------------------------------------------------------
+#ifndef B200BA_TABC_BLOCK
+#define B200BA_TABC_BLOCK 640
+#endif
+#ifndef B200BA_TABC_ROWS
+#define B200BA_TABC_ROWS 4
+#endif
+constexpr int TABC_BLOCK = B200BA_TABC_BLOCK, TABC_ROWS = B200BA_TABC_ROWS;
+constexpr int TABC_RING_BYTES = (TABC_BLOCK / 32) * (TABC_ROWS * OREC_BYTES);
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;
+    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
+    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+#ifdef B200BA_STAMPS
+    unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
+    if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
+#endif
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* Xb = d.X[st->cur];
+    const int wid = blockIdx.x * (TABC_BLOCK / 32) + warp;
+    const bool active = wid < d.tab_warps;
+    int g = 0, g_end = 0, n_rows = 0, rows_left = 0, deg_next = 0;
+    const unsigned char* src_rows = d.o_rec;
+    if (active) {
+        const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
+        g = ha.x; g_end = ha.y; src_rows += (size_t)(ha.z >> 5) * OREC_BYTES; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
+    }
+    const uint32_t tab_bytes = (total + 127u) & ~127u;
+    const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (TABC_ROWS * OREC_BYTES);
+    // every lane: its two words of the next unrequested row -> ring slot; one commit group per row (empty past the end, so that
+    // the group arithmetic of wait_group stays uniform)
+    const unsigned char* src_lane = src_rows + 4 * lane;          // camera index of this lane in the row; weight at + 128 + 4 lane more
+    int fetched = 0;                                              // rows requested so far
+    auto fetch = [&]() {
+        if (fetched < n_rows) {
+            const uint32_t dst = ring + (uint32_t)(fetched % TABC_ROWS) * OREC_BYTES + 4u * lane;
+            cp_async4(dst, src_lane);
+            cp_async8(dst + 128u + 4u * lane, src_lane + 128 + 4 * lane);
+            src_lane += OREC_BYTES;
+        }
+        ++fetched;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < TABC_ROWS - 1; ++i) fetch();
+    double X[3] = {0, 0, 0};
+    if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
+    __syncthreads();
+    mbar_wait(&bar, 0);
+#ifdef B200BA_STAMPS
+    if (threadIdx.x == 0) { stp[1] = gtime(); stp[3] = clock64(); }
+    struct EndStamp { unsigned long long* p; int lane; __device__ ~EndStamp() { if (lane == 0) *p = clock64(); } } end_stamp{stp + 8 + warp, lane};
+#endif
+    if (g >= g_end) return;
+    double u0 = 0, u1 = 0, u2 = 0;
+    auto request = [&](double Vi[6], double Xn[3]) {
+        if (32 * g + lane < d.M) load6(d.Vinv, 32 * g + lane, Vi);
+        if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, policy_evict_last());
+    };
+    auto finish = [&](const double Vi[6], const double Xn[3]) -> bool {
+        const int j = 32 * g + lane;
+        if (j < d.M)
+            store4_keep(d.v + 4 * (size_t)j, Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2,
+                        Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0, policy_evict_last());
+        if (++g >= g_end) return false;
+        rows_left = deg_next; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; u0 = u1 = u2 = 0;
+        if (g + 1 < g_end) {
+            deg_next = __ldg(d.slice_deg + g + 1);
+            if (lane == 0) {
+                const int nj = min(32, d.M - 32 * (g + 1));
+                if (nj > 0) { prefetch_l2_bulk(d.Vinv + 6 * (size_t)(32 * (g + 1)), (uint32_t)nj * 48u); prefetch_l2_bulk(Xb + 4 * (size_t)(32 * (g + 1)), (uint32_t)nj * 32u); }
+            }
+        }
+        return true;
+    };
+    int r = 0;                                                    // rows consumed
+    for (;;) {
+        while (rows_left == 0) {
+            double Vi[6], Xn[3];
+            request(Vi, Xn);
+            if (!finish(Vi, Xn)) return;
+        }
+        fetch();                                                  // row r + TABC_ROWS - 1 into the slot row r - 1 has left
+        cp_async_wait<TABC_ROWS - 1>();                           // all but the newest TABC_ROWS - 1 groups have landed: row r is there
+        const uint32_t ca = ring + (uint32_t)(r % TABC_ROWS) * OREC_BYTES + 4u * lane;
+        const int cam = lds_s32(ca);
+        const double w = lds_f64(ca + 128u + 4u * lane);
+        ++r;
+        TabRow o;
+        const bool pad = cam < 0;
+        tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
+        if (--rows_left != 0) {                                   // warp-uniform; the common path carries no slice-end state
+            tab_row_bwd(o, u0, u1, u2);
+        } else {
+            double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+            request(Vi, Xn);                                      // what the END of the slice needs, in flight during the back-rotation
+            tab_row_bwd(o, u0, u1, u2);
+            if (!finish(Vi, Xn)) return;
+        }
     }
 }
 

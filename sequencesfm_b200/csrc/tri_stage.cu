@@ -9,7 +9,6 @@
 #include "pinned_pool.h"
 
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -181,12 +180,56 @@ k_tri_front(const double* __restrict__ pts, int n, TriParams t, unsigned char* _
     if ((threadIdx.x & 31) == 0) { if (b0) atomicAdd(&counts[0], (unsigned)__popc(b0)); if (b1) atomicAdd(&counts[1], (unsigned)__popc(b1)); }
 }
 
+// ---- exact order statistic by radix selection (the tracker std::sorts all errors to read ONE of them, :738-742) ----
+// Order-preserving key of a double (negative values and NaNs included): what a sort of the values would compare.
+__device__ __forceinline__ unsigned long long sel_key(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+constexpr int SEL_BITS = 11, SEL_BINS = 1 << SEL_BITS;
+// state[0] = key prefix found so far, state[1] = rank still to find among the elements that share the prefix
+// one pass: histogram of the next SEL_BITS key bits over those elements (integer counters: exact, order-independent)
+__global__ void __launch_bounds__(256)
+k_sel_hist(const double* __restrict__ v, int n, int shift, int bits, const unsigned long long* __restrict__ state, unsigned* __restrict__ hist)
+{
+    __shared__ unsigned sh[SEL_BINS];
+    for (int b = threadIdx.x; b < SEL_BINS; b += 256) sh[b] = 0;
+    __syncthreads();
+    const int top = shift + bits;
+    const unsigned bin_mask = (1u << bits) - 1u;
+    const unsigned long long mask = top >= 64 ? 0ull : (~0ull << top), prefix = state[0] & mask;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const unsigned long long k = sel_key(v[i]);
+        if ((k & mask) == prefix) atomicAdd(&sh[(unsigned)(k >> shift) & bin_mask], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < SEL_BINS; b += 256) if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+// narrow to the bin that holds the wanted rank; clears the histogram for the next pass; the last pass writes the value
+__global__ void __launch_bounds__(32) k_sel_pick(int shift, unsigned long long* __restrict__ state, unsigned* __restrict__ hist, double* __restrict__ value_out)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long rank = state[1], cum = 0;
+        int b = 0;
+        for (; b < SEL_BINS - 1; ++b) { if (cum + hist[b] > rank) break; cum += hist[b]; }
+        state[0] |= (unsigned long long)b << shift;
+        state[1] = rank - cum;
+        if (shift == 0) {
+            const unsigned long long k = state[0], bits = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+            *value_out = __longlong_as_double((long long)bits);
+        }
+    }
+    __syncwarp();
+    for (int b = threadIdx.x; b < SEL_BINS; b += 32) hist[b] = 0;
+}
+
 // keep[i] = in front of P1 and error < 2.4 x sorted_err[4 n / 5]  (src/sfm_tracker.cpp:736-761)
 __global__ void __launch_bounds__(256)
-k_tri_keep(const double* __restrict__ err, const double* __restrict__ sorted, int n, const unsigned char* __restrict__ front1,
+k_tri_keep(const double* __restrict__ err, const double* __restrict__ pct80, int n, const unsigned char* __restrict__ front1,
            unsigned char* __restrict__ keep, unsigned* __restrict__ counts, double* __restrict__ cutoff_out)
 {
-    const double cutoff = __dmul_rn(sorted[4 * (size_t)n / 5], 2.4);
+    const double cutoff = __dmul_rn(pct80[0], 2.4);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool k = false;
     if (i < n) { k = front1[i] && err[i] < cutoff; keep[i] = k ? 1 : 0; }
@@ -205,7 +248,7 @@ struct b200tri_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     char* d_buf = nullptr; size_t cap = 0;            // one grow-only arena: pt1 | pt2 | pts | err | pt1_out | partial | scalars
-    char* d_gate = nullptr; size_t cap_gate = 0;      // gating scratch: sorted errors | front flags | keep | counters | cub temp
+    char* d_gate = nullptr; size_t cap_gate = 0;      // gating scratch: selected value | select state | histogram | front flags | keep | counters
     int n_last = 0; size_t o_pts_last = 0, o_err_last = 0; TriParams params_last;   // resident results of the last call
 };
 
@@ -330,10 +373,9 @@ int b200tri_gate(b200tri_handle* h, uint8_t* keep, b200tri_gate_report* report)
     TRI_CUDA(cudaSetDevice(h->device));
     const double* d_pts = (const double*)(h->d_buf + h->o_pts_last);
     const double* d_err = (const double*)(h->d_buf + h->o_err_last);
-    size_t tmp_bytes = 0;
-    TRI_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_err, (double*)nullptr, n, 0, 64, h->stream));
-    const size_t o_sorted = 0, o_front = o_sorted + (size_t)n * 8, o_keep = o_front + (((size_t)n + 15) & ~(size_t)15),
-                 o_cnt = o_keep + (((size_t)n + 15) & ~(size_t)15), o_tmp = o_cnt + 32, total = o_tmp + tmp_bytes;
+    // scratch: [selected value | select state (prefix, rank) | histogram | front flags | keep | counters]
+    const size_t o_sel = 0, o_state = 16, o_hist = 32, o_front = o_hist + SEL_BINS * 4, o_keep = o_front + (((size_t)n + 15) & ~(size_t)15),
+                 o_cnt = o_keep + (((size_t)n + 15) & ~(size_t)15), total = o_cnt + 32;
     if (total > h->cap_gate) {
         if (h->d_gate) cudaFree(h->d_gate);
         h->d_gate = nullptr; h->cap_gate = 0;
@@ -345,8 +387,21 @@ int b200tri_gate(b200tri_handle* h, uint8_t* keep, b200tri_gate_report* report)
     TRI_CUDA(cudaEventRecord(h->ev[0], h->stream));
     TRI_CUDA(cudaMemsetAsync(g + o_cnt, 0, 32, h->stream));
     k_tri_front<<<(n + 255) / 256, 256, 0, h->stream>>>(d_pts, n, h->params_last, (unsigned char*)(g + o_front), d_cnt);
-    TRI_CUDA(cub::DeviceRadixSort::SortKeys(g + o_tmp, tmp_bytes, d_err, (double*)(g + o_sorted), n, 0, 64, h->stream));
-    k_tri_keep<<<(n + 255) / 256, 256, 0, h->stream>>>(d_err, (const double*)(g + o_sorted), n, (const unsigned char*)(g + o_front),
+    // 80th percentile = element 4 n / 5 of the sorted errors (:742), found by radix selection on the key bits, most
+    // significant first: 5 passes of 11 bits + one of 9 (exactly the value std::sort would put there)
+    const unsigned long long st0[2] = {0ull, (unsigned long long)(4 * (size_t)n / 5)};
+    TRI_CUDA(cudaMemsetAsync(g + o_hist, 0, SEL_BINS * 4, h->stream));
+    TRI_CUDA(cudaMemcpyAsync(g + o_state, st0, 16, cudaMemcpyHostToDevice, h->stream));
+    const int sel_grid = std::max(1, std::min(592, (n + 1023) / 1024));
+    int n_sel = 0;
+    for (int shift = 64 - SEL_BITS; ; shift = shift >= SEL_BITS ? shift - SEL_BITS : 0) {
+        const int bits = shift == 0 ? 64 - 5 * SEL_BITS : SEL_BITS;   // 53, 42, 31, 20, 9 (11 bits each), then the last 9 bits
+        k_sel_hist<<<sel_grid, 256, 0, h->stream>>>(d_err, n, shift, bits, (const unsigned long long*)(g + o_state), (unsigned*)(g + o_hist));
+        k_sel_pick<<<1, 32, 0, h->stream>>>(shift, (unsigned long long*)(g + o_state), (unsigned*)(g + o_hist), (double*)(g + o_sel));
+        n_sel += 2;
+        if (shift == 0) break;
+    }
+    k_tri_keep<<<(n + 255) / 256, 256, 0, h->stream>>>(d_err, (const double*)(g + o_sel), n, (const unsigned char*)(g + o_front),
                                                       (unsigned char*)(g + o_keep), d_cnt, (double*)(g + o_cnt + 16));
     TRI_CUDA(cudaGetLastError());
     unsigned char cnt_host[32];
@@ -357,7 +412,7 @@ int b200tri_gate(b200tri_handle* h, uint8_t* keep, b200tri_gate_report* report)
     unsigned c[3]; std::memcpy(c, cnt_host, sizeof(c));
     std::memcpy(&report->cutoff, cnt_host + 16, sizeof(double));
     report->n_front_P = (int32_t)c[0]; report->n_front_P1 = (int32_t)c[1]; report->n_kept = (int32_t)c[2];
-    report->gpu_launches = 2 + 3;                                  // + cub's radix sort passes (>= 3 kernels for 64-bit keys)
+    report->gpu_launches = 2 + n_sel;                              // front test, keep + the selection passes
     float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); report->ms_device = ms;
     // TestTriangulation on P, then on P1 (short-circuit ||, :725-729): less than 75 % in front of either -> -2
     if ((double)c[0] / (double)n < 0.75 || (double)c[1] / (double)n < 0.75) report->status = -2;

@@ -11,7 +11,7 @@ import pytest
 from oracle import oracle
 from sequencesfm_b200 import ba, binding
 from sequencesfm_b200.synth import make_problem
-from tests.util import COST_RTOL, golden_problem, load_golden, parity_window, pose_agreement, rel, rel_cost_diff
+from tests.util import COST_RTOL, demo_names, golden_problem, load_demo, load_golden, parity_window, pose_agreement, rel, rel_cost_diff
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -294,6 +294,54 @@ def test_python_mirror_and_cpp_adapter_agree(tmp_path):
     cam = arr[: 12 * p.N].reshape(p.N, 12); pts = arr[12 * p.N:].reshape(p.M, 3)
     assert np.allclose(cam, direct.cam_RT, rtol=0, atol=1e-13) and np.allclose(pts, direct.pts, rtol=0, atol=1e-13)
     assert np.allclose(np.array([Pmats[k].reshape(12) for k in sorted(Pmats)]), direct.cam_RT, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: the repo's demo sequence (BA calls captured by tools/make_demo_problem.py)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", demo_names())
+def test_demo_sequence_matches_reference_ssba(name):
+    """Same captured inputs -> reference SSBA (golden) vs the CUDA engine: per-iteration cost <= 1e-9 in the exact-step
+    mode over the parity window, same damping schedule, final mean reprojection error; and the throughput mode (fixed
+    50-step PCG) ends at the same error."""
+    fx, p, ids = load_demo(name)
+    ref = fx["trace"]
+    r = _solve(p, cg_max_steps=4000, cg_rel_tol=1e-13)
+    k = parity_window(r.trace, ref)
+    assert k >= min(8, len(ref) - 1), (k, len(ref))
+    assert rel_cost_diff(r.trace, ref, k).max() < COST_RTOL
+    assert np.allclose(r.trace[:k, 2], ref[:k, 2], rtol=1e-9)
+    assert abs(r.mean_px[0] - fx["mean_px"][0]) < 1e-9 * fx["mean_px"][0]
+    assert abs(r.mean_px[1] - fx["mean_px"][1]) < 1e-4 * fx["mean_px"][1]
+    if k == len(ref) and r.iterations == fx["iterations"]:
+        assert (r.status, r.ret) == (fx["status"], fx["ret"])
+        assert np.allclose(r.cam_RT[:3], np.array(fx["cam_RT_head"]), atol=1e-6)
+    t = _solve(p)                                                        # throughput mode
+    assert abs(t.mean_px[1] - fx["mean_px"][1]) < 2e-3 * fx["mean_px"][1]
+    o = oracle.solve(p)                                                  # the same fifty-step algorithm on the CPU
+    kk = parity_window(t.trace, o.trace)
+    assert kk >= min(6, len(o.trace) - 1) and rel_cost_diff(t.trace, o.trace, min(kk, 8)).max() < 1e-7
+
+
+def test_demo_sequence_through_the_tracker_entry_points():
+    """The call the tracker makes (src/sfm_tracker.cpp:858-866): containers keyed by sparse frame ids, adjustBundle_pba for
+    >= 5 keyframes - which, in the shipped build, IS the SSBA path (src/sfm_ba_pba.cpp:167-171)."""
+    fx, p, ids = load_demo(demo_names()[1])
+    cloud = [ba.CloudPoint(pt=p.pts[j].copy()) for j in range(p.M)]
+    imgpts = {f: [] for f in ids}
+    for k in range(p.K):
+        f = ids[p.obs_cam[k]]
+        cloud[p.obs_pt[k]].img_kp[f] = len(imgpts[f]); imgpts[f].append((p.obs_xy[k, 0], p.obs_xy[k, 1]))
+    Pmats = {f: p.cam_RT[i].reshape(3, 4).copy() for i, f in enumerate(ids)}
+    Kmat = np.array([[p.K5[0], p.K5[1], p.K5[2]], [0, p.K5[3], p.K5[4]], [0, 0, 1.0]])
+    rep = {}
+    ret = ba.adjustBundle_pba(cloud, Kmat, np.zeros(5), imgpts, Pmats, report=rep, options={"cg_max_steps": 4000, "cg_rel_tol": 1e-13})
+    r = rep["result"]
+    assert ret == fx["ret"] == r.ret
+    k = parity_window(r.trace, fx["trace"])
+    assert k >= 8 and rel_cost_diff(r.trace, fx["trace"], k).max() < COST_RTOL
+    if ret == 0:
+        assert np.array_equal(Pmats[ids[2]].reshape(12), r.cam_RT[2]) and np.array_equal(cloud[7].pt, r.pts[7])
 
 
 # ---------------------------------------------------------------------------------------------------------

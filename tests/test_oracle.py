@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle, refs
-from tests.util import COST_RTOL, golden_names, golden_problem, load_golden, parity_window, pose_agreement, rel_cost_diff
+from tests.util import COST_RTOL, demo_names, golden_names, golden_problem, load_demo, load_golden, parity_window, pose_agreement, rel_cost_diff
 
 FAST = [n for n in golden_names() if "trafalgar" not in n]
 
@@ -137,3 +137,33 @@ def test_edge_cases_oracle():
     # max_iterations = 1 -> TIMEOUT after one loop iteration
     r1 = oracle.solve(p, solver=1, max_iterations=1)
     assert r1.status == 0 and r1.iterations == 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: BA calls captured on the repo's demo sequence (tools/make_demo_problem.py)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", demo_names())
+def test_demo_sequence_oracle_matches_reference_ssba(name):
+    """Real images (data/img_sfm_1s), real track structure (a camera sees its neighbours' points), gross outliers under the
+    Huber weights: the exact-step oracle against the reference SSBA run stored with the captured inputs."""
+    from sequencesfm_b200.synth import input_checksum
+    fx, p, ids = load_demo(name)
+    assert (p.N, p.M, p.K) == (fx["N"], fx["M"], fx["K"]) and input_checksum(p) == fx["input_sha256"]
+    assert ids == sorted(ids) and len(ids) == p.N
+    r = oracle.solve(p, solver=1)
+    ref = fx["trace"]
+    k = parity_window(r.trace, ref)
+    assert k >= min(8, len(ref) - 1), (k, len(ref))
+    assert rel_cost_diff(r.trace, ref, k).max() < COST_RTOL
+    assert np.allclose(r.trace[:k, 2], ref[:k, 2], rtol=1e-9)
+    assert abs(r.mean_px[0] - fx["mean_px"][0]) < 1e-9 * fx["mean_px"][0]
+    assert abs(r.mean_px[1] - fx["mean_px"][1]) < 1e-4 * fx["mean_px"][1]
+
+
+@pytest.mark.skipif(not refs.have_ssba(), reason="oracle/_ref not built (needs /root/reference)")
+def test_demo_fixture_is_the_live_reference_run():
+    fx, p, _ = load_demo(demo_names()[0])
+    ref = refs.ssba_adjust(p)
+    n = min(len(ref.trace), len(fx["trace"]))
+    assert n == len(fx["trace"]) and np.allclose(ref.trace[:n, 1], fx["trace"][:n, 1], rtol=1e-12)
+    assert (ref.status, ref.iterations) == (fx["status"], fx["iterations"])

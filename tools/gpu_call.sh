@@ -8,6 +8,10 @@ pytest)
   ( timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 2>&1 | tail -30 ) > gpurun_out/pytest_$tag.log; tail -12 gpurun_out/pytest_$tag.log ;;
 variants)
   bash tools/gpu_variants.sh $tag ;;
+ilp2test)
+  ( B200BA_TAB_ILP=2 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "linearisation or venice_shape_matches or ragged or fifty or symmetric" 2>&1 | tail -5 ) > gpurun_out/pytest_ilp2_$tag.log; tail -3 gpurun_out/pytest_ilp2_$tag.log ;;
+stamps2)
+  B200BA_LIB=$PWD/sequencesfm_b200/variants/lib_stamps2.so timeout 300 python tools/stamps.py venice > gpurun_out/stamps2_$tag.log 2>&1; cat gpurun_out/stamps2_$tag.log; cp gpurun_out/stamps_venice.npy gpurun_out/stamps2_venice.npy ;;
 stamps)
   B200BA_LIB=$PWD/sequencesfm_b200/variants/lib_stamps.so timeout 300 python tools/stamps.py venice > gpurun_out/stamps_$tag.log 2>&1; cat gpurun_out/stamps_$tag.log ;;
 bench)

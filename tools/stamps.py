@@ -18,7 +18,7 @@ st = buf.reshape(512, 40).astype(np.int64)
 os.makedirs('gpurun_out', exist_ok=True)
 np.save(os.path.join('gpurun_out', f'stamps_{shape}.npy'), st)
 def q(a): a = np.asarray(a, dtype=np.float64); return f"min {a.min():.0f} med {np.median(a):.0f} p90 {np.percentile(a, 90):.0f} max {a.max():.0f}"
-for name, base, nw in (("point_pass_tab", 0, 19), ("camera_pass", 256, 16)):
+for name, base, nw in (("point_pass_tab", 0, int(os.environ.get("TABW", "19"))), ("camera_pass", 256, 16)):
     rows = st[base:base + 148]
     rows = rows[rows[:, 0] > 0]
     if not len(rows):
