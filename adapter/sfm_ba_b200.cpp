@@ -12,6 +12,7 @@
 // "discard a gradient-converged result" rule (:221) are applied inside the engine (options.round_pixels,
 // options.discard_converged), not here.
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -52,25 +53,44 @@ void marshal(const std::vector<CloudPoint>& pointcloud, const cv::Mat& K,
     }
 }
 
+// ONE engine handle per option set lives as long as the process (the tracker calls the BA once per keyframe from a single
+// worker thread, src/utils_gui.cpp:825): stream, events, pinned staging pool and the grow-only device arena are created once
+// instead of on every keyframe (src/sfm_ba_ssba.cpp builds and tears down its whole optimizer per call).  The map between two
+// calls is not a pure extension - the post-BA stage drops outliers and re-axes everything (src/sfm_tracker.cpp:876-908) - so
+// the problem is uploaded with b200ba_set_problem each time; b200ba_append / b200ba_set_state (include/b200ba.h) serve callers
+// whose map only grows.  b200ba_adapter_release() frees the handle (optional, e.g. at shutdown).
+b200ba_handle* g_handle = 0;
+b200ba_options g_handle_opt;
+
+b200ba_handle* persistent_handle(const b200ba_options& opt, const char* name)
+{
+    if (g_handle && memcmp(&g_handle_opt, &opt, sizeof opt) != 0) { b200ba_destroy(g_handle); g_handle = 0; }
+    if (!g_handle) {
+        if (b200ba_create(&opt, &g_handle) != B200BA_OK) { fprintf(stderr, "%s: %s\n", name, b200ba_last_error(0)); g_handle = 0; return 0; }
+        g_handle_opt = opt;
+    }
+    return g_handle;
+}
+
 int run(const b200ba_options& opt, const char* name, std::vector<CloudPoint>& pointcloud, const cv::Mat& K,
         std::map<int, std::vector<cv::KeyPoint> >& imgpts, std::map<int, cv::Matx34d>& Pmats)
 {
     Flat f; marshal(pointcloud, K, imgpts, Pmats, f);
     const int N = (int)f.cam_ids.size(), M = (int)pointcloud.size(), Kobs = (int)f.oc.size();
     printf("\n%s: \n  N (cams) = %d, M (points) = %d, K (measurements) = %d\n", name, N, M, Kobs);
-    b200ba_handle* h = 0;
-    if (b200ba_create(&opt, &h) != B200BA_OK) { fprintf(stderr, "%s: %s\n", name, b200ba_last_error(0)); return -1; }
+    b200ba_handle* h = persistent_handle(opt, name);
+    if (!h) return -1;
     b200ba_report rep = b200ba_report();
     int rc = b200ba_set_problem(h, N, M, Kobs, f.cam.data(), f.K5, f.pts.data(), f.xy.data(), f.oc.data(), f.op.data());
     if (rc == B200BA_OK) rc = b200ba_solve(h, &rep);
-    if (rc != B200BA_OK) { fprintf(stderr, "%s: %s\n", name, b200ba_last_error(h)); b200ba_destroy(h); return -1; }
+    if (rc != B200BA_OK) { fprintf(stderr, "%s: %s\n", name, b200ba_last_error(h)); return -1; }
     printf("mean reprojection error (in pixels): %g\n", rep.mean_px[0]);
     printf("optimizer status = %d\n", rep.status);
     printf("mean reprojection error (in pixels): %g\n", rep.mean_px[1]);
     int ret = rep.ret;
     if (ret == 0) {
         rc = b200ba_get_result(h, f.cam.data(), f.pts.data());
-        if (rc != B200BA_OK) { fprintf(stderr, "%s: %s\n", name, b200ba_last_error(h)); b200ba_destroy(h); return -1; }
+        if (rc != B200BA_OK) { fprintf(stderr, "%s: %s\n", name, b200ba_last_error(h)); return -1; }
         for (size_t j = 0; j < pointcloud.size(); ++j) {
             pointcloud[j].pt.x = f.pts[3 * j]; pointcloud[j].pt.y = f.pts[3 * j + 1]; pointcloud[j].pt.z = f.pts[3 * j + 2];
         }
@@ -80,11 +100,12 @@ int run(const b200ba_options& opt, const char* name, std::vector<CloudPoint>& po
             Pmats[f.cam_ids[i]] = P;
         }
     }
-    b200ba_destroy(h);
     return ret;
 }
 
 } // namespace
+
+extern "C" void b200ba_adapter_release(void) { if (g_handle) { b200ba_destroy(g_handle); g_handle = 0; } }
 
 int adjustBundle_ssba(std::vector<CloudPoint>& pointcloud, cv::Mat& camIntrinsic,
                       std::map<int, std::vector<cv::KeyPoint> >& imgpts, std::map<int, cv::Matx34d>& Pmats)

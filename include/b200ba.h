@@ -73,7 +73,10 @@ typedef struct b200ba_options {
                                 /*    W (V + lambda I)^-1 W^t inside the PCG loop run on fp32 copies of the per-observation / */
                                 /*    per-point data; linearisation, preconditioner, PCG vectors and dot products, back-      */
                                 /*    substitution, cost and the LM control stay fp64 (per-iteration cost within 1e-5)        */
-    int32_t reserved[5];
+    /* --- persistent handles --- */
+    int32_t keep_problem;       /* 0 (default).  1: the handle keeps the marshalled observations so that b200ba_append can extend  */
+                                /*    the problem by what a new keyframe adds                     */
+    int32_t reserved[4];
 } b200ba_options;
 
 #define B200BA_TRACE_COLS 8     /* iter, err, lambda, new_err, rho, accepted(1/0/-1), cg_steps, cg_rel_residual */
@@ -115,6 +118,19 @@ const char* b200ba_last_error(const b200ba_handle* h);   /* h may be NULL: error
 int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
                        const double* cam_RT, const double* K5, const double* pts,
                        const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt);
+
+/* ---- persistent state across keyframes (the reference re-marshals the whole map through std::map
+ * look-ups on every keyframe, src/sfm_ba_ssba.cpp:124-182, src/sfm_tracker.cpp:192-195,389-399) ----
+ * A handle may be reused: b200ba_set_problem on a handle that already holds a problem keeps the stream, the pinned staging pool
+ * and the device arena (grow-only, 25 % headroom when it has to grow).  With options.keep_problem = 1 the problem can also be
+ * EXTENDED: b200ba_append adds n_cam cameras (indices N .. N + n_cam - 1), n_pts points (M .. M + n_pts - 1) and n_obs
+ * observations whose indices refer to the extended numbering (obs_pt non-decreasing; observations of old points are merged behind
+ * the stored ones of the same point, i.e. the new frames have the largest ids).  The result is bit-identical to
+ * b200ba_set_problem on the full arrays.  b200ba_set_state replaces the parameter values (either pointer may be NULL) without
+ * touching the observation layout. */
+int b200ba_append(b200ba_handle* h, int32_t n_cam, const double* cam_RT, int32_t n_pts, const double* pts,
+                  int32_t n_obs, const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt);
+int b200ba_set_state(b200ba_handle* h, const double* cam_RT, const double* pts);
 
 /* Whole BA: normalise, run LM until a stop criterion, de-normalise.  Equivalent of opt.minimize() inside the
  * normaliser scope of src/sfm_ba_ssba.cpp:200-222. */

@@ -24,7 +24,7 @@ STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
 ABI_SYMBOLS = [
     "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_last_restart_ms", "b200ba_finish", "b200ba_get_result",
-    "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan",
+    "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan", "b200ba_append", "b200ba_set_state",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
     "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version", "b200ba_debug_layout_stats",
 ]
@@ -37,7 +37,7 @@ class Options(C.Structure):
                 ("round_pixels", C.c_int32), ("normalize", C.c_int32), ("fix_first_camera", C.c_int32),
                 ("discard_converged", C.c_int32), ("cg_max_steps", C.c_int32), ("cg_rel_tol", C.c_double),
                 ("precond", C.c_int32), ("poll_every", C.c_int32), ("lane_window", C.c_int32), ("pcg_fp32", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("keep_problem", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Report(C.Structure):
@@ -220,6 +220,22 @@ class Engine:
 
     def set_problem_from(self, p):
         self.set_problem(p.K5, p.cam_RT, p.pts, p.obs_xy, p.obs_cam, p.obs_pt)
+
+    def append(self, cam_RT, pts, obs_xy, obs_cam, obs_pt):
+        """``b200ba_append``: extend the uploaded problem (needs ``keep_problem=1``); indices in the extended numbering."""
+        cam = np.ascontiguousarray(cam_RT, dtype=np.float64).reshape(-1, 12)
+        pt = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
+        oc = np.ascontiguousarray(obs_cam, dtype=np.int32); op = np.ascontiguousarray(obs_pt, dtype=np.int32)
+        self._check(self.lib.b200ba_append(self.h, C.c_int32(cam.shape[0]), _dp(cam), C.c_int32(pt.shape[0]), _dp(pt),
+                                           C.c_int32(oc.shape[0]), _dp(xy), _ip(oc), _ip(op)))
+        self.N += cam.shape[0]; self.M += pt.shape[0]; self.K += oc.shape[0]
+
+    def set_state(self, cam_RT=None, pts=None):
+        """``b200ba_set_state``: new parameter values, same observation layout."""
+        cam = None if cam_RT is None else np.ascontiguousarray(cam_RT, dtype=np.float64).reshape(-1, 12)
+        pt = None if pts is None else np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self._check(self.lib.b200ba_set_state(self.h, None if cam is None else _dp(cam), None if pt is None else _dp(pt)))
 
     def _report(self, with_trace=True):
         rep = Report()

@@ -71,7 +71,7 @@ NcclApi g_nccl;
 // One device arena per problem: every buffer is carved out of a single cudaMalloc (40 separate allocations cost
 // 40-100 ms per set_problem) and zeroed with a single memset.
 struct Arena {
-    char* base = nullptr; size_t cap = 0, off = 0;
+    char* base = nullptr; size_t cap = 0, off = 0, allocated = 0;   // cap: bytes of the current problem; allocated: grow-only size
     void* take(size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return base ? (void*)(base + o) : nullptr; }
 };
 template <class T> struct DBuf {
@@ -114,6 +114,7 @@ struct b200ba_handle {
     // host copies of the caller's problem
     int N = 0, M = 0, K = 0;
     std::vector<double> h_cam, h_pts;        // as given (un-normalised)
+    std::vector<double> s_xy; std::vector<int32_t> s_cam, s_pt; int s_K = -1;   // options.keep_problem: the marshalled observations (b200ba_append)
     double K5[5] = {0, 0, 0, 0, 0};
     double mean[3] = {0, 0, 0}, scale = 1.0;
     bool have_problem = false, begun = false, finished = false;
@@ -543,9 +544,9 @@ int b200ba_comm_open_peers(b200ba_handle* h, const void* all_handles)
     return 0;
 }
 
-int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
-                       const double* cam_RT, const double* K5, const double* pts,
-                       const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt)
+static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
+                            const double* cam_RT, const double* K5, const double* pts,
+                            const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt)
 {
     if (!h) return B200BA_E_INVALID;
     if (N <= 0 || M < 0 || K < 0 || !cam_RT || !K5 || (M && !pts) || (K && (!obs_xy || !obs_cam || !obs_pt)))
@@ -694,7 +695,8 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     int world = h->world;
     h->trace_cap = o.max_iterations + 2;
     const size_t Mp = (size_t)std::max(M, 1), Kpp = (size_t)std::max(Kp, 1), Rp = (size_t)std::max(n_rows, 1);
-    if (h->arena.base) { cudaFree(h->arena.base); h->arena = Arena(); }
+    char* const arena_old = h->arena.base;                        // grow-only: kept when the new problem fits (persistent handles)
+    h->arena.base = nullptr;
     int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (std::max(std::max(TAB_BLOCK, TAB2_BLOCK), TABC_BLOCK) / 32);
     const int step_grid = cdiv((long long)N * 6, STEP_BLOCK);
     for (int pass = 0; pass < 2; ++pass) {
@@ -722,7 +724,17 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             h->o_rec32.take(A, (Kpp / 32 + 1) * OREC32_BYTES); h->c_rec32.take(A, Rp * REC32_BYTES + 16);
             h->X32.take(A, Mp); h->v32.take(A, Mp); h->Vinv32.take(A, 8 * Mp); h->ptab32.take(A, (size_t)N * TAB32_STRIDE + 8); h->rt32.take(A, 12 * (size_t)N);
         } h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
-        if (pass == 0) { A.cap = A.off; CU(cudaMalloc((void**)&A.base, A.cap)); }
+        if (pass == 0) {
+            A.cap = A.off;
+            if (arena_old && A.cap <= A.allocated) A.base = arena_old;
+            else {
+                if (arena_old) cudaFree(arena_old);
+                const size_t want = arena_old ? A.cap + A.cap / 4 : A.cap;     // a handle that is reused grows with headroom
+                A.allocated = 0;
+                CU(cudaMalloc((void**)&A.base, want));
+                A.allocated = want;
+            }
+        }
     }
     lap("cudaMalloc");
     cudaStream_t s = h->stream;
@@ -860,6 +872,71 @@ int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     lap("plan");
     h->have_problem = true; h->begun = false; h->finished = false;
     h->ms_h2d = now_ms() - t0;
+    return 0;
+}
+
+int b200ba_set_problem(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
+                       const double* cam_RT, const double* K5, const double* pts,
+                       const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt)
+{
+    if (!h) return B200BA_E_INVALID;
+    h->s_K = -1;                                                  // the stored observations (if any) describe the previous problem
+    if (int rc = set_problem_impl(h, N, M, K, cam_RT, K5, pts, obs_xy, obs_cam, obs_pt)) return rc;
+    if (h->opt.keep_problem) {                                    // persistent handles: what b200ba_append extends
+        h->s_xy.assign(obs_xy, obs_xy + 2 * (size_t)K); h->s_cam.assign(obs_cam, obs_cam + K); h->s_pt.assign(obs_pt, obs_pt + K);
+        h->s_K = K;
+    }
+    return 0;
+}
+
+// Persistent state across keyframes: the tracker's map only GROWS between most BA calls - one new
+// camera, the points triangulated from it, and observations of old and new points in the new frame (src/sfm_tracker.cpp:
+// 117-195, 389-399, 858-866) - while src/sfm_ba_ssba.cpp:124-182 re-marshals everything through std::map look-ups every time.
+// b200ba_append takes only what is new; the handle keeps the marshalled problem, its device arena (grow-only) and its stream.
+int b200ba_append(b200ba_handle* h, int32_t n_cam, const double* cam_RT, int32_t n_pts, const double* pts,
+                  int32_t n_obs, const double* obs_xy, const int32_t* obs_cam, const int32_t* obs_pt)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->opt.keep_problem) return fail(h, B200BA_E_STATE, "b200ba_append needs options.keep_problem = 1");
+    if (!h->have_problem || h->s_K < 0) return fail(h, B200BA_E_STATE, "b200ba_append before b200ba_set_problem");
+    if (h->world > 1) return fail(h, B200BA_E_STATE, "b200ba_append on a multi-rank handle is not supported");
+    if (n_cam < 0 || n_pts < 0 || n_obs < 0 || (n_cam && !cam_RT) || (n_pts && !pts) || (n_obs && (!obs_xy || !obs_cam || !obs_pt)))
+        return fail(h, B200BA_E_INVALID, "b200ba_append: null or negative-sized arrays");
+    const int N0 = h->N, M0 = h->M, K0 = h->s_K, N = N0 + n_cam, M = M0 + n_pts, K = K0 + n_obs;
+    for (int k = 0; k < n_obs; ++k)
+        if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M || (k && obs_pt[k] < obs_pt[k - 1]))
+            return fail(h, B200BA_E_INVALID, "b200ba_append: observation %d out of range or obs_pt decreasing", k);
+    std::vector<double> cam(h->h_cam), pt(h->h_pts), xy(2 * (size_t)K);
+    cam.insert(cam.end(), cam_RT, cam_RT + 12 * (size_t)n_cam);
+    pt.insert(pt.end(), pts, pts + 3 * (size_t)n_pts);
+    std::vector<int32_t> oc((size_t)K), op((size_t)K);
+    // stable merge by point: within a point the stored observations come first, then the new ones in the order given - the order
+    // src/sfm_ba_ssba.cpp:161-182 produces when the new frame has the largest id (std::map<frame, keypoint> iterates by frame id)
+    {
+        int a = 0, b = 0, o = 0;
+        while (a < K0 || b < n_obs) {
+            const bool take_old = b >= n_obs || (a < K0 && h->s_pt[a] <= obs_pt[b]);
+            if (take_old) { oc[o] = h->s_cam[a]; op[o] = h->s_pt[a]; xy[2 * (size_t)o] = h->s_xy[2 * (size_t)a]; xy[2 * (size_t)o + 1] = h->s_xy[2 * (size_t)a + 1]; ++a; }
+            else { oc[o] = obs_cam[b]; op[o] = obs_pt[b]; xy[2 * (size_t)o] = obs_xy[2 * (size_t)b]; xy[2 * (size_t)o + 1] = obs_xy[2 * (size_t)b + 1]; ++b; }
+            ++o;
+        }
+    }
+    double K5[5]; memcpy(K5, h->K5, sizeof K5);
+    h->s_K = -1;
+    if (int rc = set_problem_impl(h, N, M, K, cam.data(), K5, pt.data(), xy.data(), oc.data(), op.data())) return rc;
+    h->s_xy.swap(xy); h->s_cam.swap(oc); h->s_pt.swap(op); h->s_K = K;
+    return 0;
+}
+
+// New parameter values for the uploaded problem (what the tracker writes into its containers between two BA calls without
+// changing the map's structure: the post-BA re-axis, src/sfm_tracker.cpp:894-908); the observation layout on the device stays.
+int b200ba_set_state(b200ba_handle* h, const double* cam_RT, const double* pts)
+{
+    if (!h) return B200BA_E_INVALID;
+    if (!h->have_problem) return fail(h, B200BA_E_STATE, "b200ba_set_state before b200ba_set_problem");
+    if (cam_RT) h->h_cam.assign(cam_RT, cam_RT + 12 * (size_t)h->N);
+    if (pts) h->h_pts.assign(pts, pts + 3 * (size_t)h->M);
+    h->begun = false; h->finished = false;
     return 0;
 }
 
