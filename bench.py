@@ -146,7 +146,20 @@ def run_reference(args, world: int, rank: int) -> int:
     if not refs.have_pba():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpba_ref.so not built"}))
         return 0
-    p = make_problem(args.shape, args.seed)
+    p = load_shape(args.shape, args.seed)
+    if args.shape.startswith("demo") and refs.have_ssba():
+        # the demo sequence runs through the reference's LIVE path: SSBA, single thread, its own 50-iteration LM
+        t0 = time.perf_counter(); r = refs.ssba_adjust(p, trace=False); dt = time.perf_counter() - t0
+        secs = r.seconds if r.seconds > 0 else dt
+        value = r.iterations / secs
+        line = {"impl": "reference", "metric": "lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "data/img_sfm_1s (captured BA call)", "config": {"workload": f"{p.name}: {p.N} cameras / {p.M} points / {p.K} observations",
+                "engine": "reference SSBA-3.0 (live path of the reference, exact sparse LDL^t step), oracle/_ref, unmodified"},
+                "cpu_baseline": {"value": value, "unit": "LM iterations/s", "cores": 1, "kind": "reference", "sample": f"SSBA minimize(): {r.iterations} LM iterations in {secs:.3f} s"},
+                "e2e": {"value": value, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
     cores = os.cpu_count() or 1
     # each reference "step" is one LM iteration of the reference's own LM loop; a bounded sample (PBA needs ~1 s per
     # iteration at Venice shape on 16 cores): min(--steps, 10) iterations, unless --ref-lm-iterations is given
@@ -179,6 +192,16 @@ def run_reference(args, world: int, rank: int) -> int:
     return 0
 
 
+def load_shape(shape: str, seed: int):
+    """Synthetic BAL shapes by name, or a captured demo-sequence BA call: --shape demo_kf49 (BASELINE.json configs[0];
+    tests/golden/demo_kf*.npz written by tools/make_demo_problem.py)."""
+    from sequencesfm_b200.synth import make_problem, load_problem_npz
+    if shape.startswith("demo"):
+        name = shape if shape != "demo" else "demo_kf49"
+        return load_problem_npz(os.path.join(ROOT, "tests", "golden", name + ".npz"), name)
+    return make_problem(shape, seed)
+
+
 def parity_block(eng, full, shape, seed, rank, n_iter) -> dict | None:
     """Untimed: restart, run n_iter LM iterations, compare the per-iteration cost with the committed oracle trace."""
     eng.restart()
@@ -187,6 +210,8 @@ def parity_block(eng, full, shape, seed, rank, n_iter) -> dict | None:
     if rank != 0:
         return None
     path = os.path.join(ROOT, "tests", "golden", f"trace50_{shape}_s{seed}.json")
+    if shape.startswith("demo"):
+        return demo_parity(full, shape if shape != "demo" else "demo_kf49")
     out = {"against": None, "iterations_compared": 0, "tolerance": 1e-9, "cost_per_iteration": [float(v) for v in tr[:n_iter, 1]],
            "accepted_per_iteration": [int(v) for v in tr[:n_iter, 5]]}
     if not os.path.exists(path):
@@ -206,6 +231,24 @@ def parity_block(eng, full, shape, seed, rank, n_iter) -> dict | None:
                 "lambda_schedule_equal": bool(np.allclose(tr[:n, 2], ref[:n, 2], rtol=1e-9))})
     out["pass"] = bool(out["inputs_match_fixture_sha256"] and out["max_rel_cost_diff"] < 1e-9 and out["accept_history_equal"])
     return out
+
+
+def demo_parity(p, name) -> dict:
+    """Demo-sequence problem: the engine in exact-step mode against the reference SSBA run stored with the fixture."""
+    from sequencesfm_b200 import binding
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+    ref = np.array([[np.nan if v is None else v for v in row] for row in fx["trace"]], dtype=np.float64)
+    with binding.Engine(cg_max_steps=4000, cg_rel_tol=1e-13) as e:
+        e.set_problem_from(p)
+        r = e.solve()
+    n = 0
+    while n < min(len(ref), len(r.trace)) and r.trace[n, 5] == ref[n, 5] and ref[n, 2] > 2e-9 * ref[0, 2]:
+        n += 1
+    rel = np.abs(r.trace[:n, 1] - ref[:n, 1]) / ref[:n, 1]
+    return {"against": f"tests/golden/{name}.json: reference SSBA (oracle/_ref/libssba_ref.so, unmodified sources) on the same captured inputs; "
+                       "engine in exact-step mode (cg_rel_tol 1e-13)", "iterations_compared": int(n), "tolerance": 1e-9,
+            "max_rel_cost_diff": float(rel.max()) if n else None, "mean_px_reference": fx["mean_px"], "mean_px": list(r.mean_px),
+            "pass": bool(n >= min(8, len(ref) - 1) and rel.max() < 1e-9)}
 
 
 def main() -> int:
@@ -243,7 +286,7 @@ def main() -> int:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, K_steps = max(3, args.warmup), max(1, args.steps)
-    full = make_problem(args.shape, args.seed)
+    full = load_shape(args.shape, args.seed)
     N, M, K = full.N, full.M, full.K
     if world > 1:
         j0, j1 = partition_points(full.obs_pt, M, world)[rank]
@@ -401,7 +444,13 @@ def main() -> int:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import refs
-            if refs.have_pba():
+            if args.shape.startswith("demo") and refs.have_ssba():
+                t0 = time.perf_counter(); sr = refs.ssba_adjust(full, trace=False); dt = time.perf_counter() - t0
+                secs = sr.seconds if sr.seconds > 0 else dt
+                cpu = {"value": sr.iterations / secs, "unit": "LM iterations/s", "cores": 1, "kind": "reference",
+                       "sample": f"reference SSBA-3.0 minimize() (the live path: single thread, exact sparse LDL^t step) on the same captured problem: "
+                                 f"{sr.iterations} LM iterations in {secs:.3f} s, final mean reprojection error {sr.mean_px[1]:.4f} px"}
+            elif refs.have_pba():
                 lmi = 2
                 q = refs.pba_adjust(full, double=True, args=("-schur", "-lmi", str(lmi), "-v", "0"))
                 v = q.lm_iterations / q.seconds if q.seconds > 0 else 0.0
@@ -468,7 +517,7 @@ def main() -> int:
     if rank == 0:
         line = {"metric": "lm_iterations_per_s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": K_steps,
                 "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
+                "dtype": "f64", "data": "synthetic" if not args.shape.startswith("demo") else "data/img_sfm_1s (BA call captured by tools/make_demo_problem.py, cv2 SIFT front end)",
                 "config": {"workload": f"{args.shape} shape: {N} cameras / {M} points / {K} observations, seed {args.seed}; "
                                        f"one step = full LM iteration (linearise + Schur-Jacobi preconditioner + {CG_STEPS}-step PCG + "
                                        f"back-substitution + trial cost + accept/reject)",

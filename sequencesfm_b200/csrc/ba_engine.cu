@@ -127,7 +127,8 @@ struct b200ba_handle {
     DBuf<unsigned char> sort_tmp;
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
-    DBuf<double> ptab, part_pq, part_rz, X_init, rt_init;
+    DBuf<double> ptab, qtab, part_pq, part_rz, X_init, rt_init;
+    bool use_tab_backsub = false; size_t cost_smem = 0;          // back-substitution + trial cost as table sweeps
     DBuf<unsigned long long> stamps;
     DBuf<int> tab_wr, tab_wr32;
     DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
@@ -205,7 +206,7 @@ int enqueue_linearize(b200ba_handle* h)
     LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
     k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++;
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
-    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0);
+    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, -1);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
     LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
     if (h->use_f32) {                                            // fp32 copies for the mixed-precision PCG sweeps
@@ -298,12 +299,28 @@ int enqueue_cg_step(b200ba_handle* h)
     return 0;
 }
 
+// back-substitution, trial point, trial cost -> ar_dec [d2p, denomp, new_cost]
+void enqueue_backsub(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    if (h->use_tab_backsub) {
+        LAUNCH(k_ptab_set_x, cdiv(6 * (long long)d.N, 256), 256, d);
+        LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 1);
+        k_backsub_tab<<<h->tab_grid, TABC_BLOCK, h->tab_smem, h->stream>>>(d);
+        k_cost_tab<<<h->tab_grid, TABC_BLOCK, h->cost_smem, h->stream>>>(d);
+        h->launches += 2;
+        LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, h->tab_grid * (TABC_BLOCK / 32));
+    } else {
+        LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
+        LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, -1);
+    }
+}
+
 int enqueue_step_and_decide(b200ba_handle* h)
 {
     Dev& d = h->d;
     LAUNCH(k_cg_finish, 1, ONE_CTA, d);
-    LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
-    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1);
+    enqueue_backsub(h);
     if (int rc = allreduce(h, d.ar_dec, 4, 1)) return rc;
     LAUNCH(k_lm_decide, 1, 1, d);
     return 0;
@@ -366,7 +383,7 @@ int mean_reproj(b200ba_handle* h, int which, double* out)
     Dev& d = h->d;
     if (d.K == 0 && h->world <= 1) { *out = 0; return 0; }
     LAUNCH(k_reproj_sum, d.n_pt_blocks, PT_BLOCK, d, which);
-    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 2);
+    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 2, -1);
     double k_local = (double)d.K;
     CU(cudaMemcpyAsync(d.ar_dec + 1, &k_local, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (int rc = allreduce(h, d.ar_dec, 4)) return rc;
@@ -713,9 +730,9 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->c_rec.take(A, Rp * REC_BYTES + 16); h->row_hdr.take(A, Rp);
         h->sort_keys.take(A, 2 * Kpp); h->sort_vals.take(A, 2 * Kpp); h->row_tab.take(A, 2 * ((size_t)N + 1)); h->sort_tmp.take(A, (size_t)16 << 20);
         h->cam_seg_beg.take(A, (size_t)N + 1);
-        h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)n_pt_blocks);
+        h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)std::max(n_pt_blocks, tab_warps_cap));
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
-        h->ptab.take(A, (size_t)N * TAB_STRIDE);
+        h->ptab.take(A, (size_t)N * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE);
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
         h->stamps.take(A, 512 * 40);
@@ -787,6 +804,14 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     }
     // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
     // one 32-byte header per warp: {first slice, end slice, first entry, end entry, deg(first), deg(first+1), 0, 0}
+    h->use_tab_backsub = false;
+    if (h->use_tab && h->tab_ilp == 3 && getenv("B200BA_NO_TAB_BACKSUB") == nullptr) {
+        h->cost_smem = ((((size_t)N * QTAB_STRIDE * sizeof(double)) + 127) & ~(size_t)127) + COST_RING_BYTES;
+        if (h->cost_smem + 256 <= (size_t)smem_optin &&
+            cudaFuncSetAttribute(k_backsub_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem) == cudaSuccess &&
+            cudaFuncSetAttribute(k_cost_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cost_smem) == cudaSuccess) h->use_tab_backsub = true;
+        else cudaGetLastError();
+    }
     int tab_warps = std::max(1, h->tab_grid) * (h->tab_block / 32);
     auto warp_headers = [&](int nwarps, int* dst) -> int {
         std::vector<int> wr((size_t)nwarps + 1, n_slices);
@@ -857,7 +882,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
     d.o_rec = h->o_rec.p; d.o_meas = h->o_meas.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
-    d.ptab = h->ptab.p;
+    d.ptab = h->ptab.p; d.qtab = h->qtab.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
@@ -1407,7 +1432,7 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
         case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;
         case 7: LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d); break;
-        case 8: LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d); break;
+        case 8: enqueue_backsub(h); break;
         case 9: LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond); break;
         }
         return 0;

@@ -139,6 +139,7 @@ struct Dev {
     unsigned char* o_rec;         // (padded entries / 32) x OREC_BYTES point-order row records [32 x camera index | 32 x weight]
     double2* o_meas; int *slice_base, *slice_deg;
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
+    double* qtab;       // N x 8 compact table [quat 4 | T 3 | pad] (swizzled, see qtab_unit) of the trial cameras for k_cost_tab
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
     // optional fp32 copies for the mixed-precision PCG (ba_kernels_f32.cuh); all null when options.pcg_fp32 = 0
@@ -580,13 +581,14 @@ __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_comput
 // mode 0 (linearisation): out = ar_lin tail  [cost | ginf slot(rank) | vmax slot(rank)]
 // mode 1 (decision):      out = ar_dec       [d2p, denomp, new_cost]
 // mode 2 (statistics):    like 1 but runs regardless of st->done (mean reprojection error)
-__global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mode)
+__global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mode, int count = -1)
 {
     __shared__ double sm[ONE_CTA / 32];
     const LMState* st = d.st;
     if ((mode != 2 && st->done) || (mode == 0 && !st->compute)) return;
     double a = 0, b = 0.0, c = (mode == 0) ? -1e30 : 0.0;
-    for (int i = threadIdx.x; i < d.n_pt_blocks; i += ONE_CTA) {
+    const int np = count >= 0 ? count : d.n_pt_blocks;
+    for (int i = threadIdx.x; i < np; i += ONE_CTA) {
         const double* p = d.pt_part + 4 * (size_t)i;
         a += p[0];
         if (mode == 0) { b = fmax(b, p[1]); c = fmax(c, p[2]); } else { b += p[1]; c += p[2]; }
@@ -1714,6 +1716,244 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
             if (!finish(Vi, Xn)) return;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K9a/K9b  back-substitution and trial cost on the shared-memory camera table (replaces k_cg_point_pass<2> when the table plan
+//      is active).  The generic kernel gathered [R|T] and x per observation from global memory twice (6 + 3 + 6 uncoalesced
+//      LDG.128 per observation): 186 us at Venice shape, L1TEX-bound at 89 %.  Here both halves are sweeps of the same structure
+//      as k_cg_point_pass_tabc (persistent, one warp = a contiguous slice range, rows staged by per-lane cp.async):
+//        k_backsub_tab   table [quaternion | T | x]: u_j = g_p,j - sum_k W_k^t x_i(k), delta_p = (V + lambda I)^-1 u_j, trial
+//                        point X + delta_p (updateParametersB, v3d_metricbundle.cpp:42-50), |delta_p|^2, delta_p . g_p
+//        k_cost_tab      compact trial table [quaternion | T] of rt[cur ^ 1] (64-byte records, XOR-swizzled so that the bank
+//                        group of a field is again a bijection of camera mod 8), rows = camera index + measurement:
+//                        residual at the trial point with the weights re-evaluated there (v3d_optimization.cpp:916-921)
+//      Per-warp partial sums go to pt_part[4 (block x warps + warp) + {0, 1, 2}] and are reduced in a fixed order.
+// ------------------------------------------------------------------------------------------------------
+constexpr int QTAB_STRIDE = 8;                                   // doubles per camera of the compact table: quaternion 4, T 3, pad
+// physical 16-byte unit of logical field f (0: qw qx, 1: qy qz, 2: T0 T1, 3: T2 pad) of camera c
+__host__ __device__ __forceinline__ int qtab_unit(int c, int f) { return 4 * c + (f ^ ((c >> 1) & 3)); }
+// R (row-major 3x3 at stride 4 of an [R|T] record) -> unit quaternion; the conversion of k_build_ptab
+__device__ __forceinline__ void rot_to_quat(const double* s, double q[4])
+{
+    double R0 = s[0], R1 = s[1], R2 = s[2], R3 = s[4], R4 = s[5], R5 = s[6], R6 = s[8], R7 = s[9], R8 = s[10];
+    double w, x, y, z, tr = R0 + R4 + R8;
+    if (tr > 0) { double t = sqrt(tr + 1.0) * 2.0; w = 0.25 * t; x = (R7 - R5) / t; y = (R2 - R6) / t; z = (R3 - R1) / t; }
+    else if (R0 > R4 && R0 > R8) { double t = sqrt(1.0 + R0 - R4 - R8) * 2.0; w = (R7 - R5) / t; x = 0.25 * t; y = (R1 + R3) / t; z = (R2 + R6) / t; }
+    else if (R4 > R8) { double t = sqrt(1.0 + R4 - R0 - R8) * 2.0; w = (R2 - R6) / t; x = (R1 + R3) / t; y = 0.25 * t; z = (R5 + R7) / t; }
+    else { double t = sqrt(1.0 + R8 - R0 - R4) * 2.0; w = (R3 - R1) / t; x = (R2 + R6) / t; y = (R5 + R7) / t; z = 0.25 * t; }
+    double n = 1.0 / sqrt(w * w + x * x + y * y + z * z);
+    q[0] = w * n; q[1] = x * n; q[2] = y * n; q[3] = z * n;
+}
+// compact [quaternion | T] table of camera set `which` (0 / 1 = rt[which]); one thread per camera
+__global__ void __launch_bounds__(128) k_build_qtab(Dev d, int trial)
+{
+    const LMState* st = d.st;
+    if (st->done || (trial && !st->solve_ok)) return;
+    int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= d.N) return;
+    const double* s = d.rt[trial ? (st->cur ^ 1) : st->cur] + 12 * (size_t)i;
+    double q[4]; rot_to_quat(s, q);
+    double2* o = reinterpret_cast<double2*>(d.qtab);
+    o[qtab_unit(i, 0)] = make_double2(q[0], q[1]); o[qtab_unit(i, 1)] = make_double2(q[2], q[3]);
+    o[qtab_unit(i, 2)] = make_double2(s[3], s[7]); o[qtab_unit(i, 3)] = make_double2(s[11], 0.0);
+}
+// delta_c into the p-slots of the packed table (zero for constant cameras): the back-substitution sweep reads it there
+__global__ void __launch_bounds__(256) k_ptab_set_x(Dev d)
+{
+    const LMState* st = d.st;
+    if (st->done || !st->solve_ok) return;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= 6 * d.N) return;
+    const int i = e / 6, a = e - 6 * i;
+    d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = i < d.first_free ? 0.0 : d.x[e];
+}
+
+__global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const LMState* st = d.st;
+    if (st->done || !st->solve_ok) return;
+    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
+    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cur = st->cur;
+    const double* Xb = d.X[cur];
+    double* Xt = d.X[cur ^ 1];
+    const int wid = blockIdx.x * (TABC_BLOCK / 32) + warp;
+    int g = 0, g_end = 0, n_rows = 0, rows_left = 0, deg_next = 0;
+    const unsigned char* src_rows = d.o_rec;
+    if (wid < d.tab_warps) {
+        const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
+        g = ha.x; g_end = ha.y; src_rows += (size_t)(ha.z >> 5) * OREC_BYTES; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
+    }
+    const uint32_t tab_bytes = (total + 127u) & ~127u;
+    const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (TABC_ROWS * OREC_BYTES);
+    const unsigned char* src_lane = src_rows + 4 * lane;
+    int fetched = 0;
+    auto fetch = [&]() {
+        if (fetched < n_rows) {
+            const uint32_t dst = ring + (uint32_t)(fetched % TABC_ROWS) * OREC_BYTES + 4u * lane;
+            cp_async4(dst, src_lane);
+            cp_async8(dst + 128u + 4u * lane, src_lane + 128 + 4 * lane);
+            src_lane += OREC_BYTES;
+        }
+        ++fetched;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < TABC_ROWS - 1; ++i) fetch();
+    double X[3] = {0, 0, 0};
+    if (g < g_end && 32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    double d2 = 0, dg = 0;                                        // this lane's share of |delta_p|^2 and delta_p . g_p
+    double u0 = 0, u1 = 0, u2 = 0;
+    // end of slice g: delta_p, trial point, partial sums; then the next slice's X
+    auto finish = [&]() -> bool {
+        const int j = 32 * g + lane;
+        if (j < d.M) {
+            double Vi[6], gp[3];
+            load6(d.Vinv, j, Vi); load3p(d.gp, j, gp);
+            const double a0 = gp[0] - u0, a1 = gp[1] - u1, a2 = gp[2] - u2;
+            const double v0 = Vi[0] * a0 + Vi[1] * a1 + Vi[2] * a2;
+            const double v1 = Vi[1] * a0 + Vi[3] * a1 + Vi[4] * a2;
+            const double v2 = Vi[2] * a0 + Vi[4] * a1 + Vi[5] * a2;
+            d2 += v0 * v0 + v1 * v1 + v2 * v2;
+            dg += v0 * gp[0] + v1 * gp[1] + v2 * gp[2];
+            double2* o = reinterpret_cast<double2*>(Xt + 4 * (size_t)j);
+            o[0] = make_double2(X[0] + v0, X[1] + v1); o[1] = make_double2(X[2] + v2, 0.0);
+        }
+        if (++g >= g_end) return false;
+        rows_left = deg_next; u0 = u1 = u2 = 0;
+        X[0] = X[1] = X[2] = 0.0;
+        if (32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
+        if (g + 1 < g_end) deg_next = __ldg(d.slice_deg + g + 1);
+        return true;
+    };
+    int r = 0;
+    bool more = g < g_end;
+    while (more) {
+        while (more && rows_left == 0) more = finish();
+        if (!more) break;
+        fetch();
+        cp_async_wait<TABC_ROWS - 1>();
+        const uint32_t ca = ring + (uint32_t)(r % TABC_ROWS) * OREC_BYTES + 4u * lane;
+        const int cam = lds_s32(ca);
+        const double w = lds_f64(ca + 128u + 4u * lane);
+        ++r;
+        TabRow o;
+        const bool pad = cam < 0;
+        tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
+        tab_row_bwd(o, u0, u1, u2);
+        if (--rows_left == 0) more = finish();
+    }
+    d2 = warp_sum(d2); dg = warp_sum(dg);
+    if (lane == 0) { double* o = d.pt_part + 4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp); o[0] = d2; o[1] = dg; }
+}
+
+// trial cost: rows of [camera index | measurement] against the compact trial table
+constexpr int COST_ROW_BYTES = 128 + 512;                        // staged per row and warp: 32 x int32 camera | 32 x double2 measurement
+constexpr int COST_ROWS = 4;
+constexpr int COST_RING_BYTES = (TABC_BLOCK / 32) * (COST_ROWS * COST_ROW_BYTES);
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__global__ void __launch_bounds__(TABC_BLOCK, 1) k_cost_tab(Dev d)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const LMState* st = d.st;
+    if (st->done || !st->solve_ok) return;
+    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
+    const uint32_t total = (uint32_t)d.N * QTAB_STRIDE * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.qtab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* Xt = d.X[st->cur ^ 1];
+    const int wid = blockIdx.x * (TABC_BLOCK / 32) + warp;
+    int g = 0, g_end = 0, n_rows = 0, rows_left = 0, deg_next = 0, e0 = 0;
+    if (wid < d.tab_warps) {
+        const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
+        g = ha.x; g_end = ha.y; e0 = ha.z; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
+    }
+    const uint32_t tab_bytes = (total + 127u) & ~127u;
+    const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (COST_ROWS * COST_ROW_BYTES);
+    const unsigned char* src_cam = d.o_rec + (size_t)(e0 >> 5) * OREC_BYTES + 4 * lane;
+    const double2* src_meas = d.o_meas + e0 + lane;
+    int fetched = 0;
+    auto fetch = [&]() {
+        if (fetched < n_rows) {
+            const uint32_t dst = ring + (uint32_t)(fetched % COST_ROWS) * COST_ROW_BYTES;
+            cp_async4(dst + 4u * lane, src_cam);
+            cp_async16(dst + 128u + 16u * lane, src_meas);
+            src_cam += OREC_BYTES; src_meas += 32;
+        }
+        ++fetched;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < COST_ROWS - 1; ++i) fetch();
+    double X[3] = {0, 0, 1};
+    if (g < g_end && 32 * g + lane < d.M) load3p(Xt, 32 * g + lane, X);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    double cost = 0;
+    const Intrinsics& in = d.in;
+    int r = 0;
+    auto next_slice = [&]() -> bool {
+        if (++g >= g_end) return false;
+        rows_left = deg_next;
+        X[0] = X[1] = 0.0; X[2] = 1.0;
+        if (32 * g + lane < d.M) load3p(Xt, 32 * g + lane, X);
+        if (g + 1 < g_end) deg_next = __ldg(d.slice_deg + g + 1);
+        return true;
+    };
+    bool more = g < g_end;
+    while (more) {
+        while (more && rows_left == 0) more = next_slice();
+        if (!more) break;
+        fetch();
+        cp_async_wait<COST_ROWS - 1>();
+        const uint32_t ca = ring + (uint32_t)(r % COST_ROWS) * COST_ROW_BYTES;
+        const int cam = lds_s32(ca + 4u * lane);
+        const double2 m = *reinterpret_cast<const double2*>(smem_raw + (ca - smem_u32(smem_raw)) + 128u + 16u * lane);
+        ++r;
+        const bool pad = cam < 0;
+        const int c = pad ? 0 : cam;
+        const double2 a0 = tab[qtab_unit(c, 0)], a1 = tab[qtab_unit(c, 1)], a2 = tab[qtab_unit(c, 2)], a3 = tab[qtab_unit(c, 3)];
+        const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
+        const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];
+        const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);
+        const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
+        const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
+        const double x = r0 + a2.x, y = r1 + a2.y, z = pad ? 1.0 : r2 + a3.x;
+        const double iz = fast_rcp(z);
+        const double uu = x * iz, vv = y * iz;
+        const double ex = in.k00 * uu + in.k01 * vv + in.k02 - m.x;
+        const double ey = in.k11 * vv + in.k12 - m.y;
+        const double w = huber_weight(ex, ey, in.huber);        // weights re-evaluated at the trial point (:917)
+        const double wa = w * ex, wb = w * ey;
+        if (!pad) cost += wa * wa + wb * wb;
+        if (--rows_left == 0) more = next_slice();
+    }
+    cost = warp_sum(cost);
+    if (lane == 0) d.pt_part[4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp) + 2] = cost;
 }
 
 // ------------------------------------------------------------------------------------------------------
