@@ -122,7 +122,7 @@ int adjustBundle_pba(std::vector<CloudPoint>& pointcloud, cv::Mat& camIntrinsic,
     // Built with USE_PBA the reference runs the PBA personality and always returns 0 (src/sfm_ba_pba.cpp:49-166,173).
     (void)camDistortion;                   // read but unused by the reference too (src/sfm_ba_pba.cpp:64-65,87,136)
     b200ba_options opt;
-    b200ba_pba_preset(&opt);               // camera 0 constant, no robustifier, sub-pixel measurements
+    b200ba_pba_lm_preset(&opt);            // camera 0 constant, no robustifier, sub-pixel measurements + PBA's own LM / PCG / normalisation
     cv::Mat Kp = camIntrinsic.clone();
     double f = (camIntrinsic.at<double>(0, 0) + camIntrinsic.at<double>(1, 1)) / 2.0;   // src/sfm_ba_pba.cpp:60
     Kp.at<double>(0, 0) = f; Kp.at<double>(1, 1) = f; Kp.at<double>(0, 1) = 0.0;

@@ -41,7 +41,8 @@ enum {
 enum {
     B200BA_STATUS_TIMEOUT      = 0,   /* max_iterations reached                          */
     B200BA_STATUS_SMALL_UPDATE = 1,   /* |delta| < 1e-8 (|params| + 1e-8) after >= min_iterations */
-    B200BA_STATUS_CONVERGED    = 2    /* |J^t e|_inf < gradient_threshold                */
+    B200BA_STATUS_CONVERGED    = 2,   /* |J^t e|_inf < gradient_threshold                */
+    B200BA_STATUS_MSE          = 3    /* PBA variant only: mean squared error <= 0.25 px^2 (ConfigBA.cpp:47, return code 'M') */
 };
 
 typedef struct b200ba_options {
@@ -76,7 +77,15 @@ typedef struct b200ba_options {
     /* --- persistent handles --- */
     int32_t keep_problem;       /* 0 (default).  1: the handle keeps the marshalled observations so that b200ba_append can extend  */
                                 /*    the problem by what a new keyframe adds                     */
-    int32_t reserved[4];
+    /* --- LM variant --- */
+    int32_t lm_variant;         /* 0 (default): SSBA's LM (additive damping, x10 / :10, v3d_optimization.cpp:879-978).                */
+                                /* 1: PBA's LM (NonlinearOptimizeLM, SparseBundleCPU.cpp:3772-3949): lambda0 = 1e-3, damping          */
+                                /*    lambda diag(J^t J), accept iff the error drops, gain ratio reduction / (2 d.g - |J d|^2),       */
+                                /*    lambda *= max(1/3, 1 - (2 rho - 1)^3) / *= 2, 4, 8 ..., stops on |delta| <= 1e-6 (column-scaled    */
+                                /*    coordinates) and on MSE <= 0.25 px^2; PCG: cg_rel_tol 0.1 after >= cg_min_steps 10, <= 100, guard 1 */
+                                /*    (b200ba_pba_lm_preset sets all of this); normalize = 2 = PBA's NormalizeData (depth scaling)    */
+    int32_t cg_min_steps;       /* PCG steps before cg_rel_tol may stop it (PBA: 10; default 0)                                     */
+    int32_t reserved[2];
 } b200ba_options;
 
 #define B200BA_TRACE_COLS 8     /* iter, err, lambda, new_err, rho, accepted(1/0/-1), cg_steps, cg_rel_residual */
@@ -105,6 +114,9 @@ typedef struct b200ba_handle b200ba_handle;
 int b200ba_default_options(b200ba_options* opt);
 /* PBA-path preset (src/sfm_ba_pba.cpp:60-62,94,136): camera 0 constant, no robustifier, sub-pixel measurements. */
 int b200ba_pba_preset(b200ba_options* opt);
+/* The same plus PBA's own LM variant, PCG stopping rule, U-block preconditioner and data normalisation (ConfigBA.cpp:42-118,
+ * SparseBundleCPU.cpp:3117-3321,3323-3450,3772-3949): what a -DUSE_PBA build of the reference runs. */
+int b200ba_pba_lm_preset(b200ba_options* opt);
 
 int b200ba_create(const b200ba_options* opt, b200ba_handle** out);
 void b200ba_destroy(b200ba_handle* h);

@@ -105,6 +105,45 @@ class _quiet_stdout:
         os.close(self._null); os.close(self._saved)
 
 
+class _captured_stdout:
+    """fd-level capture of what the reference prints (PBA reports its LM iterations only on std::cout)."""
+
+    def __enter__(self):
+        import sys, tempfile
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._tmp = tempfile.TemporaryFile(mode="w+b")
+        os.dup2(self._tmp.fileno(), 1)
+        self.text = ""
+        return self
+
+    def __exit__(self, *a):
+        C.CDLL(None).fflush(None)
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        self._tmp.seek(0)
+        self.text = self._tmp.read().decode(errors="replace")
+        self._tmp.close()
+
+
+def pba_trace(p, *, double: bool = True, args: tuple[str, ...] = ("-schur",), threads: int = 1):
+    """The reference PBA's own per-iteration report (verbosity 2, SparseBundleCPU.cpp:3880-3925) parsed into rows
+    {iteration, cg steps, e = mean squared error px^2 AFTER the step (6 digits), u = damping used, r = gain ratio (nan when the
+    step was rejected), accepted}; plus the PbaResult.  Inputs are rounded to float32 exactly like the harness does."""
+    import re
+    with _captured_stdout() as cap:
+        res = pba_adjust(p, double=double, args=tuple(args) + ("-v", "2"), threads=threads, quiet=False)
+    rows = []
+    for line in cap.text.splitlines():
+        m = re.match(r"#\s*(\d+)\s+(\d+)\s*(\S)?\s*e=\s*(\S+)\s+u=\s*(\S+)\s+r=\s*(\S+)", line)
+        if not m:
+            continue
+        r = m.group(6)
+        acc = not r.startswith("-")
+        rows.append([float(m.group(1)), float(m.group(2)), float(m.group(4)), float(m.group(5)), float(r) if acc else float("nan"), 1.0 if acc else 0.0])
+    return np.array(rows, dtype=np.float64).reshape(-1, 6), res, cap.text
+
+
 def pba_adjust(p, *, double: bool = True, args: tuple[str, ...] = (), threads: int = 0, quiet: bool = True) -> PbaResult:
     lib = C.CDLL(os.path.join(REF_DIR, "libpba_ref.so"))
     cam = np.ascontiguousarray(p.cam_RT, dtype=np.float64).copy()

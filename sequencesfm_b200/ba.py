@@ -65,7 +65,7 @@ def marshal(pointcloud: Sequence[CloudPoint], camIntrinsic: np.ndarray,
 
 def _run(preset: str, pointcloud, camIntrinsic, imgpts, Pmats, options: dict | None, report: dict | None) -> int:
     K5, cam_RT, pts, xy, oc, op, cam_ids = marshal(pointcloud, camIntrinsic, imgpts, Pmats)
-    print(f"\nadjustBundle_{preset}: \n  N (cams) = {len(cam_ids)}, M (points) = {len(pointcloud)}, K (measurements) = {len(oc)}")
+    print(f"\nadjustBundle_{preset.split('_')[0]}: \n  N (cams) = {len(cam_ids)}, M (points) = {len(pointcloud)}, K (measurements) = {len(oc)}")
     opt = binding.default_options(preset, **(options or {}))
     with binding.Engine(opt) as eng:
         eng.set_problem(K5, cam_RT, pts, xy, oc, op)
@@ -121,5 +121,5 @@ def adjustBundle_pba(pointcloud: List[CloudPoint], camIntrinsic: np.ndarray, cam
     Kmat = np.array(camIntrinsic, dtype=np.float64)
     f = (Kmat[0, 0] + Kmat[1, 1]) / 2.0                      # src/sfm_ba_pba.cpp:60
     Kp = np.array([[f, 0.0, Kmat[0, 2]], [0.0, f, Kmat[1, 2]], [0.0, 0.0, 1.0]])
-    _run("pba", pointcloud, Kp, imgpts, Pmats, options, report)
+    _run("pba_lm", pointcloud, Kp, imgpts, Pmats, options, report)   # PBA personality AND PBA's own LM / PCG / normalisation
     return 0                                                 # src/sfm_ba_pba.cpp:173

@@ -18,11 +18,11 @@ TRACE_COLS = 8
 COMM_ID_BYTES = 128
 PEER_HANDLE_BYTES = 64
 
-STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED"}
+STATUS_NAMES = {0: "TIMEOUT", 1: "SMALL_UPDATE", 2: "CONVERGED", 3: "MSE_THRESHOLD"}
 
 # every symbol include/b200ba.h declares (tests check that the library exports each of them)
 ABI_SYMBOLS = [
-    "b200ba_default_options", "b200ba_pba_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
+    "b200ba_default_options", "b200ba_pba_preset", "b200ba_pba_lm_preset", "b200ba_create", "b200ba_destroy", "b200ba_last_error",
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_last_restart_ms", "b200ba_finish", "b200ba_get_result",
     "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan", "b200ba_append", "b200ba_set_state",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
@@ -37,7 +37,7 @@ class Options(C.Structure):
                 ("round_pixels", C.c_int32), ("normalize", C.c_int32), ("fix_first_camera", C.c_int32),
                 ("discard_converged", C.c_int32), ("cg_max_steps", C.c_int32), ("cg_rel_tol", C.c_double),
                 ("precond", C.c_int32), ("poll_every", C.c_int32), ("lane_window", C.c_int32), ("pcg_fp32", C.c_int32),
-                ("keep_problem", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("keep_problem", C.c_int32), ("lm_variant", C.c_int32), ("cg_min_steps", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Report(C.Structure):
@@ -89,7 +89,8 @@ def load() -> C.CDLL:
 def default_options(preset: str = "ssba", **kw) -> Options:
     o = Options()
     lib = load()
-    rc = lib.b200ba_pba_preset(C.byref(o)) if preset == "pba" else lib.b200ba_default_options(C.byref(o))
+    rc = (lib.b200ba_pba_lm_preset(C.byref(o)) if preset == "pba_lm" else lib.b200ba_pba_preset(C.byref(o)) if preset == "pba"
+          else lib.b200ba_default_options(C.byref(o)))
     if rc:
         raise B200BAError(rc, "default options")
     for k, v in kw.items():

@@ -127,7 +127,8 @@ struct b200ba_handle {
     DBuf<unsigned char> sort_tmp;
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
-    DBuf<double> ptab, qtab, part_pq, part_rz, X_init, rt_init;
+    DBuf<double> ptab, qtab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
+    double pba_depth_scale = 1.0;                     // normalize = 2: PBA's depth scaling of T and X
     bool use_tab_backsub = false; size_t cost_smem = 0;          // back-substitution + trial cost as table sweeps
     DBuf<unsigned long long> stamps;
     DBuf<int> tab_wr, tab_wr32;
@@ -322,7 +323,7 @@ int enqueue_step_and_decide(b200ba_handle* h)
     LAUNCH(k_cg_finish, 1, ONE_CTA, d);
     enqueue_backsub(h);
     if (int rc = allreduce(h, d.ar_dec, 4, 1)) return rc;
-    LAUNCH(k_lm_decide, 1, 1, d);
+    if (h->opt.lm_variant == 1) LAUNCH(k_lm_decide_pba, 1, 1, d); else LAUNCH(k_lm_decide, 1, 1, d);
     return 0;
 }
 
@@ -441,6 +442,18 @@ int b200ba_pba_preset(b200ba_options* o)
     o->inlier_px = 0.0;           // PBA has no robustifier                SparseBundleCPU.cpp:1176-1180
     o->round_pixels = 0;          // float sub-pixel measurements          src/sfm_ba_pba.cpp:122-123
     o->discard_converged = 0;     // adjustBundle_pba always returns 0     src/sfm_ba_pba.cpp:173
+    return 0;
+}
+
+int b200ba_pba_lm_preset(b200ba_options* o)
+{
+    if (int rc = b200ba_pba_preset(o)) return rc;
+    o->lm_variant = 1;            // NonlinearOptimizeLM                   SparseBundleCPU.cpp:3772-3949
+    o->normalize = 2;             // NormalizeDataD (depth scaling)         SparseBundleCPU.cpp:3189-3282
+    o->precond = 0;               // block-Jacobi of the damped U blocks    SparseBundleCPU.cpp:1641-1783
+    o->cg_max_steps = 100; o->cg_min_steps = 10; o->cg_rel_tol = 0.1;      // __cg_max/min_iteration, __cg_norm_threshold (ConfigBA.cpp:58-62)
+    o->gradient_threshold = 0.0;  // __lm_check_gradient = false            ConfigBA.cpp:50
+    o->min_iterations = 0;
     return 0;
 }
 
@@ -623,6 +636,24 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             meas[k] = make_double2((x * rf) * r2, (y * rf) * r2);
         }
     });
+    h->pba_depth_scale = 1.0;
+    if (o.normalize == 2) {
+        // NormalizeDataD (SparseBundleCPU.cpp:3189-3282): the median depth of all observations becomes 1 / __data_normalize_median
+        // (= 2).  (Its degeneracy fix - shifting cameras that sit inside the point cloud - is not reproduced.)
+        if (h->world > 1) return fail(h, B200BA_E_INVALID, "normalize = 2 (PBA's data normalisation) is single-rank only");
+        std::vector<float> oz((size_t)std::max(K, 1));
+        parallel_for(T, [&](int t, int nt) {
+            const long long k0 = (long long)K * t / nt, k1 = (long long)K * (t + 1) / nt;
+            for (long long k = k0; k < k1; ++k) {
+                const double* P = cam_RT + 12 * (size_t)obs_cam[k]; const double* X = pts + 3 * (size_t)obs_pt[k];
+                oz[k] = (float)(P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11]);
+            }
+        });
+        std::nth_element(oz.begin(), oz.begin() + K / 2, oz.begin() + K);
+        const double med = oz[K / 2];
+        if (!(med > 0) || !std::isfinite(med)) return fail(h, B200BA_E_INVALID, "normalize = 2: median depth %g is not positive", med);
+        h->pba_depth_scale = (1.0 / med) / 0.5;
+    }
     lap("validate + measurements");
     // ---- by-point layout: SELL-32, points sorted by track length (descending, stable), quarter-warps grouped and slots
     //      assigned for conflict-free reads of the shared-memory camera table (layout_host.h) ----
@@ -733,6 +764,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)std::max(n_pt_blocks, tab_warps_cap));
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
         h->ptab.take(A, (size_t)N * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE);
+        if (o.lm_variant == 1) { h->cam_D0.take(A, n6); h->pt_D0.take(A, 4 * Mp); }
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
         h->stamps.take(A, 512 * 40);
@@ -882,7 +914,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
     d.o_rec = h->o_rec.p; d.o_meas = h->o_meas.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
-    d.ptab = h->ptab.p; d.qtab = h->qtab.p;
+    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
@@ -990,7 +1022,9 @@ int b200ba_begin(b200ba_handle* h)
         for (int t = 0; t < T; ++t) for (int c = 0; c < ncomp; ++c) out[c] += part[(size_t)t * ncomp + c];
     };
     double rs = 1.0;
-    if (o.normalize) {
+    if (o.normalize == 2) { rs = h->pba_depth_scale; h->scale = 1.0 / rs;
+        for (int i = 0; i < N; ++i) { double* P = cam.data() + 12 * (size_t)i; P[3] *= rs; P[7] *= rs; P[11] *= rs; } }
+    else if (o.normalize) {
         // ScopedBundleExtrinsicNormalizer ctor (v3d_metricbundle.h:327-356); point sums are global over ranks,
         // cameras are replicated and counted once.  (The cross-rank sums run BEFORE the pinned staging pool is leased:
         // the pool is a process-wide mutex, and a rank that lives as a thread of the same process must be able to reach
@@ -1056,6 +1090,15 @@ int b200ba_begin(b200ba_handle* h)
     st.iter = 0; st.status = 0; st.done = (o.max_iterations <= 0) ? 1 : 0; st.compute = 1; st.cur = 0; st.first = 1;
     st.cg_active = 0; st.solve_ok = 1; st.max_iter = o.max_iterations; st.min_iter = o.min_iterations;
     st.n_trace = 0; st.trace_cap = h->trace_cap;
+    st.variant = o.lm_variant == 1 ? 1 : 0; st.cg_min_steps = o.cg_min_steps; st.damp_adjust = 2.0;
+    st.cg_guard = st.variant ? 1.0 : 0.0;                        // __cg_norm_guard (ConfigBA.cpp:62)
+    if (st.variant) {
+        st.lambda = 1e-3; st.first = 1;                          // __lm_initial_damp (ConfigBA.cpp:45)
+        double kt[1] = {(double)h->K};
+        if (int rc = global_sum(h, kt, 1)) return rc;
+        st.mse_scale = h->K5[0] * h->K5[0] / std::max(1.0, kt[0]); st.mse_thr = 0.25;   // cost is in (pixel / f0)^2 units
+        st.delta_thr = 1e-6; st.norm_scale = 0.5;                // PBA's residuals are pixel x 0.5 / f (focal normalised to __data_normalize_median)
+    }
     h->h_st = st; h->h_st_init = st;
     CU(cudaMemcpyAsync(h->st.p, &h->h_st, sizeof st, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));

@@ -100,6 +100,13 @@ struct LMState {
     int cg_active, cg_steps, solve_ok, total_cg;
     int max_iter, min_iter, n_trace, trace_cap;
     int n_accept;                                 // accepted LM steps since b200ba_begin / b200ba_restart
+    // PBA's LM variant (options.lm_variant = 1; SparseBundleCPU.cpp:3772-3949): multiplicative damping, its own step control
+    int variant, cg_min_steps;
+    double damp_adjust;                           // growth factor of the damping after a rejected step (2, 4, 8, ...)
+    double cg_guard;                              // PCG aborts when sqrt(r.z / r0.z0) exceeds it (__cg_norm_guard)
+    double mse_scale, mse_thr;                    // cost * mse_scale = mean squared error in px^2; stop at <= mse_thr (__lm_mse_threshold)
+    double delta_thr, norm_scale;                 // stop when norm_scale * sqrt(sum delta^2 D0) <= delta_thr (__lm_delta_threshold)
+    double njx;                                   // |J delta|^2 (camera + point parts arrive through ar_dec[3])
 };
 
 // NVLink peer-memory exchange window (multi-rank), PUSH design.  Every rank owns one window
@@ -139,6 +146,7 @@ struct Dev {
     unsigned char* o_rec;         // (padded entries / 32) x OREC_BYTES point-order row records [32 x camera index | 32 x weight]
     double2* o_meas; int *slice_base, *slice_deg;
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
+    double *cam_D0, *pt_D0;   // PBA variant: diag(J^t J) at the first linearisation = the Jacobian column scaling (6 N, 4 M)
     double* qtab;       // N x 8 compact table [quat 4 | T 3 | pad] (swizzled, see qtab_unit) of the trial cameras for k_cost_tab
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
@@ -586,23 +594,23 @@ __global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mo
     __shared__ double sm[ONE_CTA / 32];
     const LMState* st = d.st;
     if ((mode != 2 && st->done) || (mode == 0 && !st->compute)) return;
-    double a = 0, b = 0.0, c = (mode == 0) ? -1e30 : 0.0;
+    double a = 0, b = 0.0, c = (mode == 0) ? -1e30 : 0.0, e4 = 0.0;
     const int np = count >= 0 ? count : d.n_pt_blocks;
     for (int i = threadIdx.x; i < np; i += ONE_CTA) {
         const double* p = d.pt_part + 4 * (size_t)i;
         a += p[0];
-        if (mode == 0) { b = fmax(b, p[1]); c = fmax(c, p[2]); } else { b += p[1]; c += p[2]; }
+        if (mode == 0) { b = fmax(b, p[1]); c = fmax(c, p[2]); } else { b += p[1]; c += p[2]; e4 += p[3]; }
     }
     a = block_sum<ONE_CTA>(a, sm);
     if (mode == 0) { b = block_max<ONE_CTA>(b, sm); c = block_max<ONE_CTA>(c, sm); }
-    else           { b = block_sum<ONE_CTA>(b, sm); c = block_sum<ONE_CTA>(c, sm); }
+    else           { b = block_sum<ONE_CTA>(b, sm); c = block_sum<ONE_CTA>(c, sm); e4 = block_sum<ONE_CTA>(e4, sm); }
     if (threadIdx.x == 0) {
         if (mode == 0) {
             double* o = d.ar_lin + (size_t)d.N * PART_STRIDE;
             o[0] = a;
             for (int r = 0; r < d.world; ++r) { o[1 + r] = (r == d.rank) ? b : 0.0; o[1 + d.world + r] = (r == d.rank) ? c : 0.0; }
         } else {
-            d.ar_dec[0] = a; d.ar_dec[1] = b; d.ar_dec[2] = c; d.ar_dec[3] = 0;
+            d.ar_dec[0] = a; d.ar_dec[1] = b; d.ar_dec[2] = c; d.ar_dec[3] = (mode == 1) ? e4 : 0.0;
         }
     }
 }
@@ -639,7 +647,14 @@ __global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
             st->err = t[0];
             double ginf = fmax(gmax, gp);
             if (ginf < st->grad_thr) { st->status = 2; st->done = 1; }
-            if (st->first) { st->lambda = st->tau * fmax(umax, vm); st->first = 0; }
+            // (PBA variant: lambda0 = __lm_initial_damp is set by the host and `first` is cleared by k_lm_decide_pba)
+            if (st->variant == 0 && st->first) { st->lambda = st->tau * fmax(umax, vm); st->first = 0; }
+        }
+        if (st->variant == 1 && st->first) {
+            // PrepareJacobianNormalization (SparseBundleCPU.cpp:2900-2918): the column scaling 1 / sqrt(diag J^t J) is fixed at
+            // the initial point.  Marquardt damping makes the LM step itself independent of it; what it does
+            // change is the norm in which PBA measures the update, so diag J^t J of the first linearisation is kept.
+            for (int e = threadIdx.x; e < 6 * d.N; e += ONE_CTA) d.cam_D0[e] = d.U[36 * (size_t)(e / 6) + 7 * (e % 6)];
         }
     }
     if (threadIdx.x == 0) { st->solve_ok = 1; }
@@ -655,7 +670,9 @@ __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
     if (j >= d.M) return;
     double V[6]; load6(d.V, j, V);
     double l = st->lambda;
-    double a = V[0] + l, b = V[1], c = V[2], e = V[3] + l, f = V[4], g = V[5] + l;
+    const bool pba = st->variant == 1;                            // diag (1 + lambda) instead of + lambda (SparseBundleCPU.cpp:1793-1794)
+    if (pba && st->first && st->compute) { double2* o = reinterpret_cast<double2*>(d.pt_D0 + 4 * (size_t)j); o[0] = make_double2(V[0], V[3]); o[1] = make_double2(V[5], 0.0); }
+    double a = pba ? V[0] * (1.0 + l) : V[0] + l, b = V[1], c = V[2], e = pba ? V[3] * (1.0 + l) : V[3] + l, f = V[4], g = pba ? V[5] * (1.0 + l) : V[5] + l;
     double c00 = e * g - f * f, c01 = c * f - b * g, c02 = b * f - c * e;
     double det = a * c00 + b * c01 + c * c02;
     bool ok = (det > 0) && (a > 0) && (a * e - b * b > 0);
@@ -757,8 +774,13 @@ __global__ void __launch_bounds__(128) k_precond_invert(Dev d, int precond)
     double lam = st->lambda;
 #pragma unroll
     for (int a = 0; a < 36; ++a) L[a] = U[a];
+    const bool pba = st->variant == 1;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) L[7 * a] += lam;
+    for (int a = 0; a < 6; ++a) L[7 * a] = pba ? L[7 * a] * (1.0 + lam) : L[7 * a] + lam;
+    if (pba && i < d.first_free) {                                // constant camera: all-zero rows (SparseBundleCPU.cpp:1384-1390), skipped by PBA's inverse
+        for (int a = 0; a < 36; ++a) L[a] = 0.0;
+        for (int a = 0; a < 6; ++a) L[7 * a] = 1.0;
+    }
     if (precond == 1) {
         const double* s = d.ar_sd + 21 * (size_t)i;
         int q = 0;
@@ -788,7 +810,7 @@ __global__ void __launch_bounds__(128) k_precond_invert(Dev d, int precond)
 }
 
 // one observation of the by-point CG sweep against the packed camera table [quaternion 4 | T 3 | p 6 | pad]
-struct TabRow { double h0, h1, h2, qw, qx, qy, qz; };
+struct TabRow { double h0, h1, h2, qw, qx, qy, qz, t0, t1; };   // t = A~ p is only read by the back-substitution (|J delta|^2)
 // first half of a row body: forward rotation, projection Jacobian, t = A~ p, h = P~^t t  (table fields die here)
 // GLOBAL = false: the table lives in shared memory (k_cg_point_pass_tab); true: read-only global loads (problems whose
 // camera table does not fit one SM's shared memory: 7 x LDG.128 instead of the 9 of [R|T] + p)
@@ -817,7 +839,7 @@ __device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int
     const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
     const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
     o.h0 = pa * t0; o.h1 = pc * t1; o.h2 = pb * t0 + pd * t1;
-    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz;
+    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz; o.t0 = t0; o.t1 = t1;
 }
 // second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion
 __device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
@@ -844,9 +866,10 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
     if (MODE == 0 && !st->cg_active) return;
     if (MODE != 0 && !st->solve_ok) return;
     int j = blockIdx.x * PT_BLOCK + threadIdx.x;
-    double d2 = 0, dg = 0, cost = 0;
+    double d2 = 0, dg = 0, cost = 0, njx = 0;
     if (j < d.M) {
         int cur = st->cur;
+        double tt = 0;
         double u[3] = {0, 0, 0}, X[3], g[3];
         if (MODE != 1) load3p(d.X[cur], j, X);
         if (MODE != 0) load3p(d.gp, j, g);
@@ -871,6 +894,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
                 double p[6]; load6(vec, i, p);
                 double t0, t1; apply_A(o, p, t0, t1);
                 if (i < d.first_free) { t0 = 0; t1 = 0; }
+                tt += t0 * t0 + t1 * t1;
                 double h[3]; apply_Pt(o, t0, t1, h);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) u[c] += cm.R[c] * h[0] + cm.R[3 + c] * h[1] + cm.R[6 + c] * h[2];
@@ -888,6 +912,14 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
         } else {
             d2 = v0 * v0 + v1 * v1 + v2 * v2;
             dg = v0 * g[0] + v1 * g[1] + v2 * g[2];
+            if (st->variant == 1) {                                     // PBA: see k_backsub_tab
+                double Vu[6]; load6(d.V, j, Vu);
+                const double ub0 = g[0] - u[0], ub1 = g[1] - u[1], ub2 = g[2] - u[2];      // sum B~^t A~ dc (u holds g - that sum here)
+                njx = tt + 2.0 * (v0 * ub0 + v1 * ub1 + v2 * ub2)
+                    + v0 * (Vu[0] * v0 + Vu[1] * v1 + Vu[2] * v2) + v1 * (Vu[1] * v0 + Vu[3] * v1 + Vu[4] * v2) + v2 * (Vu[2] * v0 + Vu[4] * v1 + Vu[5] * v2);
+                const double* D0 = d.pt_D0 + 4 * (size_t)j;
+                d2 = v0 * v0 * D0[0] + v1 * v1 * D0[1] + v2 * v2 * D0[2];
+            }
             double Xn[3] = {X[0] + v0, X[1] + v1, X[2] + v2};           // updateParametersB, v3d_metricbundle.cpp:42-50
             double2* o = reinterpret_cast<double2*>(d.X[cur ^ 1] + 4 * (size_t)j);
             o[0] = make_double2(Xn[0], Xn[1]); o[1] = make_double2(Xn[2], 0.0);
@@ -908,9 +940,10 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
         d2 = block_sum<PT_BLOCK>(d2, sm);
         dg = block_sum<PT_BLOCK>(dg, sm);
         cost = block_sum<PT_BLOCK>(cost, sm);
+        njx = block_sum<PT_BLOCK>(njx, sm);
         if (threadIdx.x == 0) {
             double* o = d.pt_part + 4 * (size_t)blockIdx.x;
-            o[0] = d2; o[1] = dg; o[2] = cost; o[3] = 0;
+            o[0] = d2; o[1] = dg; o[2] = cost; o[3] = njx;
         }
     }
 }
@@ -1174,7 +1207,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
     double pq = 0;
     for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
         int i = e / 6, a = e - 6 * i;
-        double q = lam * d.p[e] + matvec6_row(d.U + 36 * (size_t)i, d.p + 6 * (size_t)i, a) - d.ar_q[e];
+        double q = lam * (st->variant == 1 ? d.U[36 * (size_t)i + 7 * a] : 1.0) * d.p[e] + matvec6_row(d.U + 36 * (size_t)i, d.p + 6 * (size_t)i, a) - d.ar_q[e];
         d.q[e] = q; pq += d.p[e] * q;
     }
     pq = block_sum<ONE_CTA>(pq, sm);
@@ -1193,7 +1226,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
     }
     rzn = block_sum<ONE_CTA>(rzn, sm);
     double rel = sqrt(fabs(rzn) / rz0);
-    bool stop = (tol > 0 && rel < tol) || !(rzn > 0);
+    bool stop = (tol > 0 && rel < tol && st->cg_steps + 1 >= st->cg_min_steps) || !(rzn > 0) || (st->cg_guard > 0 && rel > st->cg_guard);
     if (!stop) {
         double beta = rzn / rz;
         for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
@@ -1817,8 +1850,9 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
     if (g < g_end && 32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
     __syncthreads();
     mbar_wait(&bar, 0);
-    double d2 = 0, dg = 0;                                        // this lane's share of |delta_p|^2 and delta_p . g_p
-    double u0 = 0, u1 = 0, u2 = 0;
+    double d2 = 0, dg = 0, njx = 0;                               // this lane's share of |delta_p|^2, delta_p . g_p, |J delta|^2
+    double u0 = 0, u1 = 0, u2 = 0, tt = 0;                        // tt: sum over the point's observations of |A~ delta_c|^2
+    const bool pba = st->variant == 1;
     // end of slice g: delta_p, trial point, partial sums; then the next slice's X
     auto finish = [&]() -> bool {
         const int j = 32 * g + lane;
@@ -1829,13 +1863,22 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
             const double v0 = Vi[0] * a0 + Vi[1] * a1 + Vi[2] * a2;
             const double v1 = Vi[1] * a0 + Vi[3] * a1 + Vi[4] * a2;
             const double v2 = Vi[2] * a0 + Vi[4] * a1 + Vi[5] * a2;
-            d2 += v0 * v0 + v1 * v1 + v2 * v2;
             dg += v0 * gp[0] + v1 * gp[1] + v2 * gp[2];
+            if (pba) {
+                // |J delta|^2 of this point's observations = sum |A~ dc|^2 + 2 dp . (sum B~^t A~ dc) + dp^t V dp (V undamped), for
+                // PBA's gain ratio (SaveUpdatedSystem, SparseBundleCPU.cpp:3681-3739); |dp|^2 in column-scaled coordinates
+                double Vu[6]; load6(d.V, j, Vu);
+                const double2* D0 = reinterpret_cast<const double2*>(d.pt_D0 + 4 * (size_t)j);
+                const double2 da = D0[0], db = D0[1];
+                njx += tt + 2.0 * (v0 * u0 + v1 * u1 + v2 * u2)
+                     + v0 * (Vu[0] * v0 + Vu[1] * v1 + Vu[2] * v2) + v1 * (Vu[1] * v0 + Vu[3] * v1 + Vu[4] * v2) + v2 * (Vu[2] * v0 + Vu[4] * v1 + Vu[5] * v2);
+                d2 += v0 * v0 * da.x + v1 * v1 * da.y + v2 * v2 * db.x;
+            } else d2 += v0 * v0 + v1 * v1 + v2 * v2;
             double2* o = reinterpret_cast<double2*>(Xt + 4 * (size_t)j);
             o[0] = make_double2(X[0] + v0, X[1] + v1); o[1] = make_double2(X[2] + v2, 0.0);
         }
         if (++g >= g_end) return false;
-        rows_left = deg_next; u0 = u1 = u2 = 0;
+        rows_left = deg_next; u0 = u1 = u2 = 0; tt = 0;
         X[0] = X[1] = X[2] = 0.0;
         if (32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
         if (g + 1 < g_end) deg_next = __ldg(d.slice_deg + g + 1);
@@ -1856,10 +1899,11 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
         const bool pad = cam < 0;
         tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
         tab_row_bwd(o, u0, u1, u2);
+        if (pba) tt += o.t0 * o.t0 + o.t1 * o.t1;
         if (--rows_left == 0) more = finish();
     }
-    d2 = warp_sum(d2); dg = warp_sum(dg);
-    if (lane == 0) { double* o = d.pt_part + 4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp); o[0] = d2; o[1] = dg; }
+    d2 = warp_sum(d2); dg = warp_sum(dg); njx = warp_sum(njx);
+    if (lane == 0) { double* o = d.pt_part + 4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp); o[0] = d2; o[1] = dg; o[3] = njx; }
 }
 
 // trial cost: rows of [camera index | measurement] against the compact trial table
@@ -1979,7 +2023,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;    // lc: first thread of this camera inside the block
     // Every load whose address does not depend on this step's scalars is issued up front (U row, M^-1 row, x, r, segment
     // range): the kernel is a chain of dependent L2 round trips with almost no parallelism, so overlapping them is what counts.
-    double pe = 0.0, xe0 = 0.0, re0 = 0.0, urow[6] = {0, 0, 0, 0, 0, 0}, mrow[6] = {0, 0, 0, 0, 0, 0};
+    double pe = 0.0, xe0 = 0.0, re0 = 0.0, urow[6] = {0, 0, 0, 0, 0, 0}, mrow[6] = {0, 0, 0, 0, 0, 0}, dmul = 1.0;
     int sg0 = 0, sg1 = 0;
     if (on) {
         pe = d.p[e]; xe0 = d.x[e]; re0 = d.r[e];
@@ -1987,6 +2031,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
         const double* ur = d.U + 36 * (size_t)i + 6 * a; const double* mr = d.Minv + 36 * (size_t)i + 6 * a;
 #pragma unroll
         for (int c = 0; c < 6; ++c) { urow[c] = ur[c]; mrow[c] = mr[c]; }
+        if (st->variant == 1) dmul = ur[a];                      // PBA: lambda diag(U) p instead of lambda p
     }
     sv[threadIdx.x] = pe;
     __syncthreads();
@@ -2006,7 +2051,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
         p2p_wait_all(d.p2p, coll, 1 + (int)blockIdx.x);           // block b of every rank pushes exactly the elements block b reads
         if (on) s = p2p_sum(d.p2p, coll, (size_t)e);
     }
-    if (on) q = lam * pe + (urow[0] * sv[lc] + urow[1] * sv[lc + 1] + urow[2] * sv[lc + 2] + urow[3] * sv[lc + 3] + urow[4] * sv[lc + 4] + urow[5] * sv[lc + 5]) - s;
+    if (on) q = lam * dmul * pe + (urow[0] * sv[lc] + urow[1] * sv[lc + 1] + urow[2] * sv[lc + 2] + urow[3] * sv[lc + 3] + urow[4] * sv[lc + 4] + urow[5] * sv[lc + 5]) - s;
     double bp = block_sum<STEP_BLOCK>(pe * q, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_pq[blockIdx.x] = bp;
     grid.sync();
@@ -2027,7 +2072,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     grid.sync();
     const double rzn = grid_total(part_rz, step_blocks);
     const double rel = sqrt(fabs(rzn) / rz0);
-    const bool stop = (tol > 0 && rel < tol) || !(rzn > 0);
+    const bool stop = (tol > 0 && rel < tol && steps + 1 >= st->cg_min_steps) || !(rzn > 0) || (st->cg_guard > 0 && rel > st->cg_guard);
     if (!stop && on) {
         double pn = z + (rzn / rz) * pe;
         d.p[e] = pn; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = pn;
@@ -2063,7 +2108,11 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_finish(Dev d)
     int bad = 0;
     if (ok) for (int i = threadIdx.x; i < d.N; i += ONE_CTA) {
         double x[6];
-        for (int a = 0; a < 6; ++a) { x[a] = d.x[6 * (size_t)i + a]; d2 += x[a] * x[a]; dg += x[a] * d.gc[6 * (size_t)i + a]; if (!isfinite(x[a])) bad = 1; }
+        for (int a = 0; a < 6; ++a) {
+            x[a] = d.x[6 * (size_t)i + a]; if (i < d.first_free) x[a] = 0.0;
+            d2 += x[a] * x[a] * (st->variant == 1 ? d.cam_D0[6 * (size_t)i + a] : 1.0);      // PBA measures the update in column-scaled coordinates
+            dg += x[a] * d.gc[6 * (size_t)i + a]; if (!isfinite(x[a])) bad = 1;
+        }
         const double* s = d.rt[cur] + 12 * (size_t)i; double* o = d.rt[cur ^ 1] + 12 * (size_t)i;
         double R[9] = {s[0], s[1], s[2], s[4], s[5], s[6], s[8], s[9], s[10]};
         double T[3] = {s[3] + x[0], s[7] + x[1], s[11] + x[2]};
@@ -2112,6 +2161,52 @@ __global__ void k_lm_decide(Dev d)
     }
     if (accept) { st->lambda = fmax(1e-10, st->lambda * 0.1); st->compute = 1; st->cur ^= 1; st->n_accept += 1; }
     else        { st->lambda *= 10.0; st->compute = 0; }
+    st->iter = it + 1;
+    if (it + 1 >= st->max_iter) st->done = 1;
+}
+
+// K13' lm_decide_pba (one thread): PBA's step control (NonlinearOptimizeLM, SparseBundleCPU.cpp:3772-3949; options.lm_variant = 1).
+//      quit when the update is small (|delta| in the column-scaled coordinates of PrepareJacobianNormalization, <= 1e-6: 'S');
+//      accept iff the squared error decreases; gain ratio rho = reduction / (2 delta.g - |J delta|^2) (SaveUpdatedSystem :3681-3739,
+//      __accurate_gain_ratio; a non-positive denominator is replaced by 0.001 x reduction); quit when the mean squared error
+//      is <= 0.25 px^2 ('M'); damping *= max(1/3, 1 - (2 rho - 1)^3) after an accepted step and *= 2, 4, 8, ... after rejected
+//      ones, clamped to [1e-10, 1e5].  PBA keeps these scalars in fp32; here they are fp64 (tolerance in the parity tests).
+__global__ void k_lm_decide_pba(Dev d)
+{
+    LMState* st = d.st;
+    if (st->done) return;
+    const int it = st->iter;
+    double* tr = (d.trace && st->n_trace < st->trace_cap) ? d.trace + TRACE_COLS * (size_t)st->n_trace : nullptr;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (tr) { tr[0] = it; tr[1] = st->err; tr[2] = st->lambda; tr[3] = nan; tr[4] = nan; tr[5] = 0; tr[6] = st->cg_steps; tr[7] = st->cg_rel; st->n_trace += 1; }
+    st->first = 0;
+    bool accept = false;
+    if (st->solve_ok) {
+        const double d2 = st->d2c + d.ar_dec[0], dxtg = st->denomc + d.ar_dec[1], new_err = d.ar_dec[2], njx = d.ar_dec[3];
+        if (st->norm_scale * sqrt(d2) <= st->delta_thr) {          // "quit on too small change"
+            st->status = 1; st->done = 1;
+            if (tr) tr[5] = -1;
+            return;
+        }
+        // PBA keeps the squared error in fp32 (float _projection_sse, new_residual: SparseBundleCPU.cpp:3855-3859), so an improvement
+        // below fp32 resolution counts as "no better solution"; mirrored here, otherwise the run would keep accepting at the noise floor
+        const double reduction = (double)((float)st->err - (float)new_err);
+        st->new_err = new_err;
+        if (tr) tr[3] = new_err;
+        if (isfinite(new_err) && reduction > 0) {
+            double expected = 2.0 * dxtg - njx;
+            if (expected <= 0) expected = 0.001 * reduction;
+            const double rho = reduction / expected;
+            st->rho = rho; accept = true;
+            if (tr) { tr[4] = rho; tr[5] = 1; }
+            st->compute = 1; st->cur ^= 1; st->n_accept += 1;
+            if (new_err * st->mse_scale <= st->mse_thr) { st->status = 3; st->done = 1; st->iter = it + 1; st->err = new_err; return; }   // "satisfies MSE threshold"
+            const double t = 2.0 * rho - 1.0;
+            st->lambda = fmin(1e5, fmax(1e-10, st->lambda * fmax(1.0 / 3.0, 1.0 - t * t * t)));
+            st->damp_adjust = 2.0;
+        }
+    }
+    if (!accept) { st->lambda *= st->damp_adjust; st->damp_adjust *= 2.0; st->compute = 0; }
     st->iter = it + 1;
     if (it + 1 >= st->max_iter) st->done = 1;
 }

@@ -89,6 +89,16 @@ def load_problem_npz(path: str, name: str = "") -> Problem:
                    name or "fixture", 0)
 
 
+def pba_inputs(p: Problem) -> Problem:
+    """The numbers the reference's PBA path hands to ParallelBA (src/sfm_ba_pba.cpp:56-130): cameras, points and measurements as
+    float32 (CameraT / Point3D / Point2D are float), f = (fx + fy) / 2, principal point subtracted in float."""
+    f32 = lambda a: np.asarray(a, dtype=np.float64).astype(np.float32)
+    f = np.float32((p.K5[0] + p.K5[3]) / 2.0)
+    xy = np.stack([f32(p.obs_xy[:, 0]) - np.float32(p.K5[2]), f32(p.obs_xy[:, 1]) - np.float32(p.K5[4])], axis=1).astype(np.float64)
+    K5 = np.array([float(f), 0.0, 0.0, float(f), 0.0])
+    return Problem(K5, f32(p.cam_RT).astype(np.float64), f32(p.pts).astype(np.float64), np.ascontiguousarray(xy), p.obs_cam.copy(), p.obs_pt.copy(), p.name, p.seed)
+
+
 def rodrigues(w: np.ndarray) -> np.ndarray:
     """Batch Rodrigues: (n,3) rotation vectors -> (n,3,3) rotation matrices."""
     w = np.asarray(w, dtype=np.float64).reshape(-1, 3)
