@@ -129,7 +129,8 @@ struct b200ba_handle {
     DBuf<unsigned char> c_rec, o_rec;
     DBuf<double> ptab, qtab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
     double pba_depth_scale = 1.0;                     // normalize = 2: PBA's depth scaling of T and X
-    bool use_tab_backsub = false; size_t cost_smem = 0;          // back-substitution + trial cost as table sweeps
+    bool use_tab_backsub = false; size_t cost_smem = 0;          // linearisation / back-substitution / trial cost as table sweeps
+    bool quat_ok = true;                             // the caller's rotations are orthonormal (checked by b200ba_begin): quaternion tables may stand in for R
     DBuf<unsigned long long> stamps;
     DBuf<int> tab_wr, tab_wr32;
     DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
@@ -204,10 +205,13 @@ int enqueue_linearize(b200ba_handle* h)
 {
     Dev& d = h->d;
     LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
-    LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
+    if (h->use_tab_backsub && h->quat_ok) {                      // table plan: by-point linearisation as a shared-memory-table sweep
+        LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 0);
+        k_lin_tab<<<h->tab_grid, TABC_BLOCK, h->cost_smem, h->stream>>>(d); h->launches++;
+    } else LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
     k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++;
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
-    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, -1);
+    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, (h->use_tab_backsub && h->quat_ok) ? h->tab_grid * (TABC_BLOCK / 32) : -1);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
     LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
     if (h->use_f32) {                                            // fp32 copies for the mixed-precision PCG sweeps
@@ -304,7 +308,7 @@ int enqueue_cg_step(b200ba_handle* h)
 void enqueue_backsub(b200ba_handle* h)
 {
     Dev& d = h->d;
-    if (h->use_tab_backsub) {
+    if (h->use_tab_backsub && h->quat_ok) {
         LAUNCH(k_ptab_set_x, cdiv(6 * (long long)d.N, 256), 256, d);
         LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 1);
         k_backsub_tab<<<h->tab_grid, TABC_BLOCK, h->tab_smem, h->stream>>>(d);
@@ -841,7 +845,8 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->cost_smem = ((((size_t)N * QTAB_STRIDE * sizeof(double)) + 127) & ~(size_t)127) + COST_RING_BYTES;
         if (h->cost_smem + 256 <= (size_t)smem_optin &&
             cudaFuncSetAttribute(k_backsub_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tab_smem) == cudaSuccess &&
-            cudaFuncSetAttribute(k_cost_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cost_smem) == cudaSuccess) h->use_tab_backsub = true;
+            cudaFuncSetAttribute(k_cost_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cost_smem) == cudaSuccess &&
+            cudaFuncSetAttribute(k_lin_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cost_smem) == cudaSuccess) h->use_tab_backsub = true;
         else cudaGetLastError();
     }
     int tab_warps = std::max(1, h->tab_grid) * (h->tab_block / 32);
@@ -1005,6 +1010,21 @@ int b200ba_begin(b200ba_handle* h)
     const int N = h->N, M = h->M;
     const b200ba_options& o = h->opt;
     std::vector<double> cam(h->h_cam);
+    {
+        // The residual, the Jacobians and the trial cost use R exactly as given (the reference never re-orthonormalises,
+        // v3d_metricbundle.cpp:17-39); their shared-memory-table versions carry R as a unit quaternion, which is the same thing only
+        // for orthonormal input.  Rotations that are not (e.g. the float32 cameras of the PBA path, 1e-7 off) keep the generic sweeps.
+        double defect = 0;
+        for (int i = 0; i < N; ++i) {
+            const double* P = cam.data() + 12 * (size_t)i;
+            for (int a = 0; a < 3; ++a) for (int b = a; b < 3; ++b) {
+                const double v = P[4 * a] * P[4 * b] + P[4 * a + 1] * P[4 * b + 1] + P[4 * a + 2] * P[4 * b + 2] - (a == b ? 1.0 : 0.0);
+                defect = std::max(defect, std::fabs(v));
+            }
+        }
+        const bool ok = defect < 1e-11;
+        if (ok != h->quat_ok) { h->quat_ok = ok; if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } }
+    }
     const double* P0 = h->h_pts.data();
     h->mean[0] = h->mean[1] = h->mean[2] = 0; h->scale = 1.0;
     std::vector<double> C(3 * (size_t)N);
@@ -1457,7 +1477,9 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
     CU(cudaMemcpy(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice));
     auto one = [&]() {
         switch (which) {
-        case 0: LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d); break;
+        case 0: if (h->use_tab_backsub && h->quat_ok) { LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 0); k_lin_tab<<<h->tab_grid, TABC_BLOCK, h->cost_smem, h->stream>>>(d); h->launches++; }
+                else LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
+                break;
         case 1: k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++; break;
         case 2: if (h->use_tab) launch_point_tab(h);
                 else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);

@@ -2000,6 +2000,119 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cost_tab(Dev d)
     if (lane == 0) d.pt_part[4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp) + 2] = cost;
 }
 
+// K1t linearize_points on the compact shared-memory table (replaces k_linearize_points when the table plan is active): the same
+//     sweep structure as k_cost_tab - persistent, rows of [camera index | measurement] staged by per-lane cp.async, [quaternion | T]
+//     of the CURRENT cameras in shared memory - instead of 6 uncoalesced LDG.128 of [R|T] per observation (111 us at Venice shape,
+//     L1TEX-bound at 65 %).  Residual + Huber weight (written into the point-order row record), cost, V_j = sum B~^t B~,
+//     g_p,j = sum B~^t (-w e)  (v3d_optimization.cpp:512-524, 543-558, 616-630).  R is rebuilt from the unit quaternion per
+//     observation (9 products); per-warp partials (cost, max |g_p|, max diag V) are reduced in a fixed order.
+__global__ void __launch_bounds__(TABC_BLOCK, 1) k_lin_tab(Dev d)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const LMState* st = d.st;
+    if (st->done || !st->compute) return;
+    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
+    const uint32_t total = (uint32_t)d.N * QTAB_STRIDE * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.qtab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* Xb = d.X[st->cur];
+    const int wid = blockIdx.x * (TABC_BLOCK / 32) + warp;
+    int g = 0, g_end = 0, n_rows = 0, rows_left = 0, deg_next = 0, e0 = 0;
+    if (wid < d.tab_warps) {
+        const int4 ha = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid), hb = __ldg(reinterpret_cast<const int4*>(d.tab_wr) + 2 * wid + 1);
+        g = ha.x; g_end = ha.y; e0 = ha.z; n_rows = (ha.w - ha.z) >> 5; rows_left = hb.x; deg_next = hb.y;
+    }
+    const uint32_t tab_bytes = (total + 127u) & ~127u;
+    const uint32_t ring = smem_u32(smem_raw) + tab_bytes + (uint32_t)warp * (COST_ROWS * COST_ROW_BYTES);
+    const unsigned char* src_cam = d.o_rec + (size_t)(e0 >> 5) * OREC_BYTES + 4 * lane;
+    const double2* src_meas = d.o_meas + e0 + lane;
+    double* w_out = reinterpret_cast<double*>(d.o_rec + (size_t)(e0 >> 5) * OREC_BYTES + 128) + lane;    // weight slot of this lane in row 0 of the range
+    int fetched = 0;
+    auto fetch = [&]() {
+        if (fetched < n_rows) {
+            const uint32_t dst = ring + (uint32_t)(fetched % COST_ROWS) * COST_ROW_BYTES;
+            cp_async4(dst + 4u * lane, src_cam);
+            cp_async16(dst + 128u + 16u * lane, src_meas);
+            src_cam += OREC_BYTES; src_meas += 32;
+        }
+        ++fetched;
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < COST_ROWS - 1; ++i) fetch();
+    double X[3] = {0, 0, 1};
+    if (g < g_end && 32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    double cost = 0, gmax = 0, vmax = -1e30;
+    double V[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
+    const Intrinsics& in = d.in;
+    int r = 0;
+    auto next_slice = [&]() -> bool {
+        const int j = 32 * g + lane;
+        if (j < d.M) {
+            double2* Vo = reinterpret_cast<double2*>(d.V + 6 * (size_t)j);
+            Vo[0] = make_double2(V[0], V[1]); Vo[1] = make_double2(V[2], V[3]); Vo[2] = make_double2(V[4], V[5]);
+            double2* go = reinterpret_cast<double2*>(d.gp + 4 * (size_t)j);
+            go[0] = make_double2(gp[0], gp[1]); go[1] = make_double2(gp[2], 0.0);
+            gmax = fmax(gmax, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+            vmax = fmax(vmax, fmax(V[0], fmax(V[3], V[5])));
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) V[q] = 0.0;
+        gp[0] = gp[1] = gp[2] = 0.0;
+        if (++g >= g_end) return false;
+        rows_left = deg_next;
+        X[0] = X[1] = 0.0; X[2] = 1.0;
+        if (32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
+        if (g + 1 < g_end) deg_next = __ldg(d.slice_deg + g + 1);
+        return true;
+    };
+    bool more = g < g_end;
+    while (more) {
+        while (more && rows_left == 0) more = next_slice();
+        if (!more) break;
+        fetch();
+        cp_async_wait<COST_ROWS - 1>();
+        const uint32_t ca = ring + (uint32_t)(r % COST_ROWS) * COST_ROW_BYTES;
+        const int cam = lds_s32(ca + 4u * lane);
+        const double2 m = *reinterpret_cast<const double2*>(smem_raw + (ca - smem_u32(smem_raw)) + 128u + 16u * lane);
+        double* wp = w_out + (size_t)r * (OREC_BYTES / 8);
+        ++r;
+        if (cam >= 0) {                                           // padding entries only occur where track lengths differ inside a slice
+            const double2 a0 = tab[qtab_unit(cam, 0)], a1 = tab[qtab_unit(cam, 1)], a2 = tab[qtab_unit(cam, 2)], a3 = tab[qtab_unit(cam, 3)];
+            const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
+            Cam cm;                                               // R from the unit quaternion
+            const double xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
+            cm.R[0] = 1.0 - 2.0 * (yy + zz); cm.R[1] = 2.0 * (xy - wz); cm.R[2] = 2.0 * (xz + wy);
+            cm.R[3] = 2.0 * (xy + wz); cm.R[4] = 1.0 - 2.0 * (xx + zz); cm.R[5] = 2.0 * (yz - wx);
+            cm.R[6] = 2.0 * (xz - wy); cm.R[7] = 2.0 * (yz + wx); cm.R[8] = 1.0 - 2.0 * (xx + yy);
+            cm.T[0] = a2.x; cm.T[1] = a2.y; cm.T[2] = a3.x;
+            Obs o; obs_full(cm, X, m, in, o);
+            *wp = o.w;
+            const double we0 = o.w * o.e0, we1 = o.w * o.e1;
+            cost += we0 * we0 + we1 * we1;
+            double B0[3], B1[3]; jac_rows_B(o, cm, B0, B1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gp[c] += B0[c] * (-we0) + B1[c] * (-we1);
+            V[0] += B0[0] * B0[0] + B1[0] * B1[0]; V[1] += B0[0] * B0[1] + B1[0] * B1[1]; V[2] += B0[0] * B0[2] + B1[0] * B1[2];
+            V[3] += B0[1] * B0[1] + B1[1] * B1[1]; V[4] += B0[1] * B0[2] + B1[1] * B1[2]; V[5] += B0[2] * B0[2] + B1[2] * B1[2];
+        }
+        if (--rows_left == 0) more = next_slice();
+    }
+    cost = warp_sum(cost); gmax = warp_max(gmax); vmax = warp_max(vmax);
+    if (lane == 0) { double* o = d.pt_part + 4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp); o[0] = cost; o[1] = gmax; o[2] = vmax; o[3] = 0.0; }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K11' cg_camera_step: the whole camera side of one PCG step in ONE cooperative kernel (grid-wide syncs instead of
 //      three kernel boundaries): second-level segment sums, q = (U + lambda I) p - sum W v, alpha, x, r, z = M r, beta, p.
