@@ -61,14 +61,16 @@ def kernel_models(N: int, M: int, K: int, s: int = 8) -> dict:
 
 def ncu_traffic() -> tuple[dict, str | None]:
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full digest (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "ncu_r1_final_summary.json")
-    try:
-        out = {}
-        for d in json.load(open(path)):
-            out[d["Kernel Name"].split("(")[0].replace("void ", "")] = d["dram_traffic_bytes_per_launch"]
-        return out, "profiles/ncu_r1_final_summary.json"
-    except Exception:
-        return {}, None
+    for name in ("ncu_r2_final_summary.json", "ncu_r1_final_summary.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            out = {}
+            for d in json.load(open(path)):
+                out[d["Kernel Name"].split("(")[0].replace("void ", "")] = d["dram_traffic_bytes_per_launch"]
+            return out, "profiles/" + name
+        except Exception:
+            continue
+    return {}, None
 
 
 def measured_peak() -> tuple[float, str]:
@@ -361,19 +363,20 @@ def main() -> int:
         achieved = abl["cg_step"] / (cg_ms * 1e-3) / 1e9
         traf, traf_src = ncu_traffic()
         step_traffic = None
-        if world == 1 and all(k in traf for k in ("k_cg_point_pass_tab", "k_cg_camera_pass", "k_cg_camera_step")):
-            step_traffic = traf["k_cg_point_pass_tab"] + traf["k_cg_camera_pass"] + traf["k_cg_camera_step"]
+        pp_name = "k_cg_point_pass_tabc" if "k_cg_point_pass_tabc" in traf else "k_cg_point_pass_tab"
+        if world == 1 and all(k in traf for k in (pp_name, "k_cg_camera_pass", "k_cg_camera_step")):
+            step_traffic = traf[pp_name] + traf["k_cg_camera_pass"] + traf["k_cg_camera_step"]
         km = kernel_models(N, Ml, Kl)
         lin_ms = kt["linearize_points"] + kt["linearize_cameras"]
         per_kernel = {
-            "k_cg_point_pass_tab": {"ms": kt["cg_point_pass"], "algorithmic_bytes": km["cg_point_pass"]},
+            "k_cg_point_pass_tabc": {"ms": kt["cg_point_pass"], "algorithmic_bytes": km["cg_point_pass"]},
             "k_cg_camera_pass": {"ms": kt["cg_camera_pass"], "algorithmic_bytes": km["cg_camera_pass"]},
-            "k_linearize_points+k_linearize_cameras": {"ms": lin_ms, "algorithmic_bytes": km["linearize"]},
-            "k_cg_point_pass<2> (back-substitution + trial cost)": {"ms": kt["backsub_cost_points"], "algorithmic_bytes": km["backsub_cost_points"]}}
+            "k_lin_tab+k_linearize_cameras": {"ms": lin_ms, "algorithmic_bytes": km["linearize"]},
+            "k_backsub_tab+k_cost_tab (back-substitution + trial cost)": {"ms": kt["backsub_cost_points"], "algorithmic_bytes": km["backsub_cost_points"]}}
         for v in per_kernel.values():
             v["achieved_gbs"] = v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9
             v["frac"] = v["achieved_gbs"] / peak
-        roof = {"bound": "hbm", "kernel": "one PCG step = k_cg_point_pass_tab + k_cg_camera_pass + k_cg_camera_step (timed back to back, CUDA events on the engine stream)",
+        roof = {"bound": "hbm", "kernel": "one PCG step = k_cg_point_pass_tabc + k_cg_camera_pass + k_cg_camera_step (timed back to back, CUDA events on the engine stream)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": step_traffic,
                 "traffic_source": (traf_src + ": dram__bytes_read.sum + dram__bytes_write.sum of the three kernels, per launch") if step_traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": abl["cg_step"], "ms_per_launch": cg_ms,

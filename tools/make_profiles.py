@@ -42,7 +42,7 @@ if len(ends) >= 3:
     for i in range(a, b):
         x = it.setdefault(names[i], [0, 0.0]); x[0] += 1; x[1] += float(rows[i][-1])
     it_tot = sum(x[1] for x in it.values())
-    cg = sum(x[1] for k, x in it.items() if k in ("k_cg_point_pass_tab", "k_cg_camera_pass", "k_cg_camera_step")) / it_tot
+    cg = sum(x[1] for k, x in it.items() if k in ("k_cg_point_pass_tab", "k_cg_point_pass_tabc", "k_cg_point_pass_tab2", "k_cg_camera_pass", "k_cg_camera_step")) / it_tot
     summ["one_lm_iteration"] = {"launches": b - a, "total_us": it_tot / 1e3, "pcg_step_share": cg,
                                 "kernels": {k: {"launches": x[0], "mean_us": x[1] / x[0] / 1e3, "share": x[1] / it_tot} for k, x in sorted(it.items(), key=lambda kv: -kv[1][1])}}
 json.dump(summ, open(os.path.join(P, f"launches_{name}_summary.json"), "w"), indent=1)
