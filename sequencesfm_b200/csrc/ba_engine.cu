@@ -127,7 +127,7 @@ struct b200ba_handle {
     DBuf<unsigned char> sort_tmp;
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
-    DBuf<double> ptab, qtab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
+    DBuf<double> fin_part, ptab, qtab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
     double pba_depth_scale = 1.0;                     // normalize = 2: PBA's depth scaling of T and X
     bool use_tab_backsub = false; size_t cost_smem = 0;          // linearisation / back-substitution / trial cost as table sweeps
     bool quat_ok = true;                             // the caller's rotations are orthonormal (checked by b200ba_begin): quaternion tables may stand in for R
@@ -213,6 +213,7 @@ int enqueue_linearize(b200ba_handle* h)
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, (h->use_tab_backsub && h->quat_ok) ? h->tab_grid * (TABC_BLOCK / 32) : -1);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
+    LAUNCH(k_lm_unpack, cdiv(36 * (long long)d.N, 256), 256, d);
     LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
     if (h->use_f32) {                                            // fp32 copies for the mixed-precision PCG sweeps
         LAUNCH(k_f32_points, cdiv(d.M, 256), 256, d, 0);
@@ -246,7 +247,8 @@ int enqueue_cg_init(b200ba_handle* h)
     LAUNCH(k_cg_point_pass<1>, d.n_pt_blocks, PT_BLOCK, d);
     if (int rc = enqueue_camera_half(h, 1)) return rc;
     if (int rc = enqueue_camera_sums(h)) return rc;
-    LAUNCH(k_cg_init, 1, ONE_CTA, d);
+    LAUNCH(k_cg_init, h->step_grid, STEP_BLOCK, d, h->part_rz.p);
+    LAUNCH(k_cg_init_finish, 1, 32, d, h->part_rz.p, h->step_grid);
     return 0;
 }
 
@@ -324,7 +326,7 @@ void enqueue_backsub(b200ba_handle* h)
 int enqueue_step_and_decide(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_cg_finish, 1, ONE_CTA, d);
+    LAUNCH(k_cg_finish, cdiv(d.N, FIN_BLOCK), FIN_BLOCK, d, h->fin_part.p);
     enqueue_backsub(h);
     if (int rc = allreduce(h, d.ar_dec, 4, 1)) return rc;
     if (h->opt.lm_variant == 1) LAUNCH(k_lm_decide_pba, 1, 1, d); else LAUNCH(k_lm_decide, 1, 1, d);
@@ -767,7 +769,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->cam_seg_beg.take(A, (size_t)N + 1);
         h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)std::max(n_pt_blocks, tab_warps_cap));
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
-        h->ptab.take(A, (size_t)N * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE);
+        h->ptab.take(A, (size_t)N * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE); h->fin_part.take(A, 4 * (size_t)cdiv(N, FIN_BLOCK) + 4);
         if (o.lm_variant == 1) { h->cam_D0.take(A, n6); h->pt_D0.take(A, 4 * Mp); }
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
@@ -919,7 +921,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
     d.o_rec = h->o_rec.p; d.o_meas = h->o_meas.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
-    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
+    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.fin_part = h->fin_part.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;

@@ -147,6 +147,7 @@ struct Dev {
     double2* o_meas; int *slice_base, *slice_deg;
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
     double *cam_D0, *pt_D0;   // PBA variant: diag(J^t J) at the first linearisation = the Jacobian column scaling (6 N, 4 M)
+    double* fin_part;   // 4 x blocks of k_cg_finish: camera part of |delta|^2, delta . g, non-finite flag
     double* qtab;       // N x 8 compact table [quat 4 | T 3 | pad] (swizzled, see qtab_unit) of the trial cameras for k_cost_tab
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
@@ -619,6 +620,24 @@ __global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mo
 // K4  lm_prepare (single CTA): unpack U / g_c, |J^t e|_inf stop (v3d_optimization.cpp:587), lambda0 on the
 //     first linearisation (v3d_optimization.cpp:711-782).
 // ------------------------------------------------------------------------------------------------------
+// (a) one thread per (camera, element of the 6x6 block): unpack the reduced [21 unique | 6] record into U and g_c.  This used to be a
+//     loop inside the single-CTA kernel below (one thread per camera, ~70 strided memory operations each): 68 us of an LM iteration.
+__global__ void __launch_bounds__(256) k_lm_unpack(Dev d)
+{
+    const LMState* st = d.st;
+    if (st->done || !st->compute) return;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= 36 * d.N) return;
+    const int i = t / 36, e = t - 36 * i, a = e / 6, b = e - 6 * a;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    const int q = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);        // index of (lo, hi) in the row-wise upper triangle
+    const double* s = d.ar_lin + (size_t)i * PART_STRIDE;
+    const double v = s[q];
+    d.U[36 * (size_t)i + e] = v;
+    if (e < 6) d.gc[6 * (size_t)i + e] = s[21 + e];
+    if (st->variant == 1 && st->first && a == b) d.cam_D0[6 * (size_t)i + a] = v;   // PrepareJacobianNormalization (SparseBundleCPU.cpp:2900-2918)
+}
+// (b) single CTA: |J^t e|_inf, max diag U, lambda0
 __global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
 {
     __shared__ double sm[ONE_CTA / 32];
@@ -626,17 +645,9 @@ __global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
     if (st->done) return;
     if (st->compute) {
         double gmax = 0, umax = -1e30;
-        for (int i = threadIdx.x; i < d.N; i += ONE_CTA) {
-            const double* s = d.ar_lin + (size_t)i * PART_STRIDE;
-            double* U = d.U + 36 * (size_t)i;
-            int q = 0;
-            for (int a = 0; a < 6; ++a)
-                for (int b = a; b < 6; ++b) { double v = s[q++]; U[6 * a + b] = v; U[6 * b + a] = v; }
-            for (int a = 0; a < 6; ++a) {
-                double g = s[21 + a];
-                d.gc[6 * (size_t)i + a] = g;
-                if (i >= d.first_free) { gmax = fmax(gmax, fabs(g)); umax = fmax(umax, U[7 * a]); }
-            }
+        for (int e = threadIdx.x; e < 6 * d.N; e += ONE_CTA) {
+            const int i = e / 6, a = e - 6 * i;
+            if (i >= d.first_free) { gmax = fmax(gmax, fabs(d.gc[e])); umax = fmax(umax, d.U[36 * (size_t)i + 7 * a]); }
         }
         gmax = block_max<ONE_CTA>(gmax, sm);
         umax = block_max<ONE_CTA>(umax, sm);
@@ -649,12 +660,6 @@ __global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
             if (ginf < st->grad_thr) { st->status = 2; st->done = 1; }
             // (PBA variant: lambda0 = __lm_initial_damp is set by the host and `first` is cleared by k_lm_decide_pba)
             if (st->variant == 0 && st->first) { st->lambda = st->tau * fmax(umax, vm); st->first = 0; }
-        }
-        if (st->variant == 1 && st->first) {
-            // PrepareJacobianNormalization (SparseBundleCPU.cpp:2900-2918): the column scaling 1 / sqrt(diag J^t J) is fixed at
-            // the initial point.  Marquardt damping makes the LM step itself independent of it; what it does
-            // change is the norm in which PBA measures the update, so diag J^t J of the first linearisation is kept.
-            for (int e = threadIdx.x; e < 6 * d.N; e += ONE_CTA) d.cam_D0[e] = d.U[36 * (size_t)(e / 6) + 7 * (e % 6)];
         }
     }
     if (threadIdx.x == 0) { st->solve_ok = 1; }
@@ -1171,27 +1176,46 @@ __device__ __forceinline__ double matvec6_row(const double* __restrict__ Mblk, c
     return r[0] * v6[0] + r[1] * v6[1] + r[2] * v6[2] + r[3] * v6[3] + r[4] * v6[4] + r[5] * v6[5];
 }
 
-// K10 cg_init: rhs = g_c - W Vinv g_p ; x = 0 ; r = rhs ; z = M r ; p = z
-__global__ void __launch_bounds__(ONE_CTA) k_cg_init(Dev d)
+__device__ __forceinline__ double grid_total_warp(const double* part, int n)
 {
-    __shared__ double sm[ONE_CTA / 32];
-    LMState* st = d.st;
+    double s = 0;
+    for (int b = (threadIdx.x & 31); b < n; b += 32) s += part[b];
+    return warp_sum(s);
+}
+// K10 cg_init: rhs = g_c - W Vinv g_p ; x = 0 ; r = rhs ; z = M r ; p = z   (one thread per (camera, component), block partials of r.z)
+__global__ void __launch_bounds__(STEP_BLOCK) k_cg_init(Dev d, double* __restrict__ part)
+{
+    __shared__ double sv[STEP_BLOCK];
+    __shared__ double sm[STEP_BLOCK / 32];
+    const LMState* st = d.st;
     if (st->done) return;
-    int n6 = 6 * d.N;
-    bool ok = st->solve_ok != 0;
-    if (ok) for (int e = threadIdx.x; e < n6; e += ONE_CTA) { d.x[e] = 0.0; d.r[e] = d.gc[e] - d.ar_q[e]; }
+    const bool ok = st->solve_ok != 0;
+    const int e = blockIdx.x * STEP_BLOCK + threadIdx.x, n6 = 6 * d.N;       // a block owns 32 whole cameras
+    const bool on = ok && e < n6;
+    const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;
+    double re = 0;
+    if (on) { re = d.gc[e] - d.ar_q[e]; d.x[e] = 0.0; d.r[e] = re; }
+    sv[threadIdx.x] = re;
     __syncthreads();
-    double rz = 0;
-    if (ok) for (int e = threadIdx.x; e < n6; e += ONE_CTA) {
-        int i = e / 6, a = e - 6 * i;
-        double z = matvec6_row(d.Minv + 36 * (size_t)i, d.r + 6 * (size_t)i, a);
-        d.z[e] = z; d.p[e] = z; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = z; rz += d.r[e] * z;
+    double z = 0;
+    if (on) {
+        const double* mr = d.Minv + 36 * (size_t)i + 6 * a;
+        z = mr[0] * sv[lc] + mr[1] * sv[lc + 1] + mr[2] * sv[lc + 2] + mr[3] * sv[lc + 3] + mr[4] * sv[lc + 4] + mr[5] * sv[lc + 5];
+        d.z[e] = z; d.p[e] = z; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = z;
         if (d.ptab32) d.ptab32[(size_t)i * 20 + 8 + a] = (float)z;
     }
-    rz = block_sum<ONE_CTA>(rz, sm);
+    const double rz = block_sum<STEP_BLOCK>(re * z, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = rz;
+}
+// fixed-order sum of the block partials of k_cg_init -> PCG control words
+__global__ void __launch_bounds__(32) k_cg_init_finish(Dev d, const double* __restrict__ part, int nblocks)
+{
+    LMState* st = d.st;
+    if (st->done) return;
+    const double rz = grid_total_warp(part, nblocks);
     if (threadIdx.x == 0) {
         st->rz = rz; st->rz0 = rz; st->cg_rel = 0; st->cg_steps = 0;
-        st->cg_active = (ok && rz > 0) ? 1 : 0;
+        st->cg_active = (st->solve_ok && rz > 0) ? 1 : 0;
     }
 }
 
@@ -2210,16 +2234,18 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
 
 // K12 cg_finish: delta_c = x; trial cameras T += dt, R <- Rodrigues(dw) R (v3d_metricbundle.cpp:17-39,
 //     v3d_mathutilities.h:173-194); camera part of |delta|^2 and delta . J^t e.
-__global__ void __launch_bounds__(ONE_CTA) k_cg_finish(Dev d)
+constexpr int FIN_BLOCK = 128;
+__global__ void __launch_bounds__(FIN_BLOCK) k_cg_finish(Dev d, double* __restrict__ part)
 {
-    __shared__ double sm[ONE_CTA / 32];
-    LMState* st = d.st;
+    __shared__ double sm[FIN_BLOCK / 32];
+    const LMState* st = d.st;
     if (st->done) return;
-    bool ok = st->solve_ok != 0;
-    int cur = st->cur;
+    const bool ok = st->solve_ok != 0;
+    const int cur = st->cur;
     double d2 = 0, dg = 0;
     int bad = 0;
-    if (ok) for (int i = threadIdx.x; i < d.N; i += ONE_CTA) {
+    const int i = blockIdx.x * FIN_BLOCK + threadIdx.x;
+    if (ok && i < d.N) {
         double x[6];
         for (int a = 0; a < 6; ++a) {
             x[a] = d.x[6 * (size_t)i + a]; if (i < d.first_free) x[a] = 0.0;
@@ -2243,10 +2269,18 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_finish(Dev d)
             o[4 * r + 3] = T[r];
         }
     }
-    d2 = block_sum<ONE_CTA>(d2, sm);
-    dg = block_sum<ONE_CTA>(dg, sm);
+    d2 = block_sum<FIN_BLOCK>(d2, sm);
+    dg = block_sum<FIN_BLOCK>(dg, sm);
     bad = __syncthreads_or(bad);
-    if (threadIdx.x == 0) { st->d2c = d2; st->denomc = dg; if (bad) st->solve_ok = 0; }
+    if (threadIdx.x == 0) { double* o = part + 4 * (size_t)blockIdx.x; o[0] = d2; o[1] = dg; o[2] = bad ? 1.0 : 0.0; o[3] = 0.0; }
+}
+// camera part of |delta|^2 and delta . J^t e: fixed-order sum of k_cg_finish's block partials (called by the decide kernels)
+__device__ __forceinline__ void camera_update_sums(const Dev& d, LMState* st)
+{
+    double d2 = 0, dg = 0; bool bad = false;
+    const int nb = (d.N + FIN_BLOCK - 1) / FIN_BLOCK;
+    for (int b = 0; b < nb; ++b) { d2 += d.fin_part[4 * b]; dg += d.fin_part[4 * b + 1]; bad = bad || d.fin_part[4 * b + 2] != 0.0; }
+    st->d2c = d2; st->denomc = dg; if (bad) st->solve_ok = 0;
 }
 
 // K13 lm_decide (one thread): update stop test, gain ratio, accept/reject, damping update
@@ -2255,6 +2289,7 @@ __global__ void k_lm_decide(Dev d)
 {
     LMState* st = d.st;
     if (st->done) return;
+    if (st->solve_ok) camera_update_sums(d, st);
     int it = st->iter;
     double* tr = (d.trace && st->n_trace < st->trace_cap) ? d.trace + TRACE_COLS * (size_t)st->n_trace : nullptr;
     double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -2288,6 +2323,7 @@ __global__ void k_lm_decide_pba(Dev d)
 {
     LMState* st = d.st;
     if (st->done) return;
+    if (st->solve_ok) camera_update_sums(d, st);
     const int it = st->iter;
     double* tr = (d.trace && st->n_trace < st->trace_cap) ? d.trace + TRACE_COLS * (size_t)st->n_trace : nullptr;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
