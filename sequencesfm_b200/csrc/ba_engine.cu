@@ -35,6 +35,9 @@ namespace b200ba { PinnedPool g_pinned; }
 #ifndef B200BA_TAB_ILP_DEFAULT
 #define B200BA_TAB_ILP_DEFAULT 3
 #endif
+#ifndef B200BA_PDL_DEFAULT
+#define B200BA_PDL_DEFAULT 0
+#endif
 #ifndef B200BA_SLICE_W_NUM
 #define B200BA_SLICE_W_NUM 2
 #endif
@@ -130,6 +133,7 @@ struct b200ba_handle {
     DBuf<double> fin_part, ptab, qtab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
     double pba_depth_scale = 1.0;                     // normalize = 2: PBA's depth scaling of T and X
     bool use_tab_backsub = false; size_t cost_smem = 0;          // linearisation / back-substitution / trial cost as table sweeps
+    bool use_pdl = false;                            // programmatic dependent launch of the two PCG sweeps (B200BA_PDL=1)
     bool quat_ok = true;                             // the caller's rotations are orthonormal (checked by b200ba_begin): quaternion tables may stand in for R
     DBuf<unsigned long long> stamps;
     DBuf<int> tab_wr, tab_wr32;
@@ -195,7 +199,14 @@ int allreduce(b200ba_handle* h, double* buf, size_t count, int need = 0)
 // by-point PCG sweep against the shared-memory camera table (one or two rows in flight per trip)
 void launch_point_tab(b200ba_handle* h)
 {
-    if (h->tab_ilp == 3) k_cg_point_pass_tabc<<<h->tab_grid, TABC_BLOCK, h->tab_smem, h->stream>>>(h->d);
+    if (h->tab_ilp == 3 && h->use_pdl) {
+        cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(h->tab_grid); cfg.blockDim = dim3(TABC_BLOCK); cfg.dynamicSmemBytes = h->tab_smem; cfg.stream = h->stream;
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_cg_point_pass_tabc, h->d);
+    }
+    else if (h->tab_ilp == 3) k_cg_point_pass_tabc<<<h->tab_grid, TABC_BLOCK, h->tab_smem, h->stream>>>(h->d);
     else if (h->tab_ilp == 2) k_cg_point_pass_tab2<<<h->tab_grid, TAB2_BLOCK, h->tab_smem, h->stream>>>(h->d);
     else k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(h->d);
     h->launches++;
@@ -256,7 +267,13 @@ int enqueue_cg_init(b200ba_handle* h)
 int enqueue_camera_half(b200ba_handle* h, int rhs_pass)
 {
     Dev& d = h->d;
-    k_cg_camera_pass<<<h->cam_grid, CW * 32, CAMPASS_SMEM, h->stream>>>(d, rhs_pass);
+    if (h->use_pdl && !rhs_pass) {
+        cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(h->cam_grid); cfg.blockDim = dim3(CW * 32); cfg.dynamicSmemBytes = CAMPASS_SMEM; cfg.stream = h->stream;
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_cg_camera_pass, d, rhs_pass);
+    } else k_cg_camera_pass<<<h->cam_grid, CW * 32, CAMPASS_SMEM, h->stream>>>(d, rhs_pass);
     h->launches++;
     return 0;
 }
@@ -842,6 +859,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     }
     // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
     // one 32-byte header per warp: {first slice, end slice, first entry, end entry, deg(first), deg(first+1), 0, 0}
+    { const char* e = getenv("B200BA_PDL"); h->use_pdl = e ? atoi(e) != 0 : B200BA_PDL_DEFAULT; }
     h->use_tab_backsub = false;
     if (h->use_tab && h->tab_ilp == 3 && getenv("B200BA_NO_TAB_BACKSUB") == nullptr) {
         h->cost_smem = ((((size_t)N * QTAB_STRIDE * sizeof(double)) + 127) & ~(size_t)127) + COST_RING_BYTES;

@@ -262,6 +262,8 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 // ---- mbarrier / TMA bulk-copy helpers (sm_90+ PTX; the only async-copy engine used here is cp.async.bulk) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
@@ -303,6 +305,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 constexpr int STAMP_STRIDE = 40;   // per CTA: [0] entry (globaltimer) [1] table ready [2] entry clock64 [3] ready clock64 [8 + w] end clock64 of warp w
 #endif
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still running; everything it does before pdl_wait() must not depend on the predecessor's output.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // SELL-32 addressing: first entry and (warp-uniform) trip count of point j
 __device__ __forceinline__ void slice_of(const Dev& d, int j, int& k0, int& deg)
 {
@@ -985,6 +991,7 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LMState* st = d.st;
+    pdl_wait();                                                   // (programmatic dependent launch: v and the control words come from the by-point sweep)
     if (st->done) return;
     if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1062,7 +1069,8 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
                 if (t * CG + g < n) {
                     if (h[g].y != seg) {
                         if (seg >= 0) seg_flush<6>(d, seg, acc, lane);
-                        seg = h[g].y; cam = h[g].x; load_cam(rt, cam, cm);
+                        seg = h[g].y; cam = h[g].x;
+                        load_cam(rt, cam, cm);
                     }
                     if (cam >= first_free) {
                         const unsigned char* rec = sb + g * REC_BYTES;
@@ -1349,8 +1357,6 @@ constexpr int PR = 4;                                            // rows of the 
 #endif
 constexpr int TAB_PF = B200BA_TAB_PF;
 constexpr int TAB_RING_BYTES = (TAB_BLOCK / 32) * (PR * OREC_BYTES + 2 * 8);   // rings + their two mbarriers per warp
-__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 #ifdef B200BA_TAB_MAXNREG
 __global__ void __maxnreg__(B200BA_TAB_MAXNREG) k_cg_point_pass_tab(Dev d)
 #else
@@ -1674,22 +1680,13 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
-    if (st->done || !st->cg_active) return;
     const double2* tab = reinterpret_cast<const double2*>(smem_raw);
     const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
 #ifdef B200BA_STAMPS
     unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
     if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
 #endif
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, total);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
-        for (uint32_t off = 0; off < total; off += 32768u) {
-            uint32_t n = total - off < 32768u ? total - off : 32768u;
-            bulk_g2s(smem_raw + off, src + off, n, &bar);
-        }
-    }
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* Xb = d.X[st->cur];
     const int wid = blockIdx.x * (TABC_BLOCK / 32) + warp;
@@ -1720,6 +1717,19 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     for (int i = 0; i < TABC_ROWS - 1; ++i) fetch();
     double X[3] = {0, 0, 0};
     if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
+    // Everything above reads what no PCG kernel writes (slice headers, row records, X): with programmatic dependent launch it runs
+    // while the camera-side step of the previous PCG step is still in flight.  The control words and the camera table are its output.
+    pdl_wait();
+    if (st->done || !st->cg_active) { cp_async_wait<0>(); return; }         // uniform over the grid
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(smem_raw + off, src + off, n, &bar);
+        }
+        pdl_trigger();                                            // the by-camera sweep may take this SM as soon as this CTA leaves it
+    }
     __syncthreads();
     mbar_wait(&bar, 0);
 #ifdef B200BA_STAMPS
@@ -1878,11 +1888,15 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
     double u0 = 0, u1 = 0, u2 = 0, tt = 0;                        // tt: sum over the point's observations of |A~ delta_c|^2
     const bool pba = st->variant == 1;
     // end of slice g: delta_p, trial point, partial sums; then the next slice's X
-    auto finish = [&]() -> bool {
+    // what the END of slice g needs (requested in the middle of its last row body, like k_cg_point_pass_tabc)
+    auto request = [&](double Vi[6], double gp[3], double Xn[3]) {
+        const int j = 32 * g + lane;
+        if (j < d.M) { load6(d.Vinv, j, Vi); load3p(d.gp, j, gp); }
+        if (g + 1 < g_end && j + 32 < d.M) load3p(Xb, j + 32, Xn);
+    };
+    auto finish = [&](const double Vi[6], const double gp[3], const double Xn[3]) -> bool {
         const int j = 32 * g + lane;
         if (j < d.M) {
-            double Vi[6], gp[3];
-            load6(d.Vinv, j, Vi); load3p(d.gp, j, gp);
             const double a0 = gp[0] - u0, a1 = gp[1] - u1, a2 = gp[2] - u2;
             const double v0 = Vi[0] * a0 + Vi[1] * a1 + Vi[2] * a2;
             const double v1 = Vi[1] * a0 + Vi[3] * a1 + Vi[4] * a2;
@@ -1903,15 +1917,14 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
         }
         if (++g >= g_end) return false;
         rows_left = deg_next; u0 = u1 = u2 = 0; tt = 0;
-        X[0] = X[1] = X[2] = 0.0;
-        if (32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
+        X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2];
         if (g + 1 < g_end) deg_next = __ldg(d.slice_deg + g + 1);
         return true;
     };
     int r = 0;
     bool more = g < g_end;
     while (more) {
-        while (more && rows_left == 0) more = finish();
+        while (more && rows_left == 0) { double Vi[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0}, Xn[3] = {0, 0, 0}; request(Vi, gp, Xn); more = finish(Vi, gp, Xn); }
         if (!more) break;
         fetch();
         cp_async_wait<TABC_ROWS - 1>();
@@ -1922,9 +1935,14 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
         TabRow o;
         const bool pad = cam < 0;
         tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
-        tab_row_bwd(o, u0, u1, u2);
         if (pba) tt += o.t0 * o.t0 + o.t1 * o.t1;
-        if (--rows_left == 0) more = finish();
+        if (--rows_left != 0) tab_row_bwd(o, u0, u1, u2);
+        else {
+            double Vi[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0}, Xn[3] = {0, 0, 0};
+            request(Vi, gp, Xn);
+            tab_row_bwd(o, u0, u1, u2);
+            more = finish(Vi, gp, Xn);
+        }
     }
     d2 = warp_sum(d2); dg = warp_sum(dg); njx = warp_sum(njx);
     if (lane == 0) { double* o = d.pt_part + 4 * (size_t)(blockIdx.x * (TABC_BLOCK / 32) + warp); o[0] = d2; o[1] = dg; o[3] = njx; }
@@ -2228,6 +2246,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
     __shared__ double sv[STEP_BLOCK];
     __shared__ double sm[STEP_BLOCK / 32];
     const LMState* st = d.st;
+    if (threadIdx.x == 0) pdl_trigger();                          // the by-point sweep of the next PCG step may start its prologue
     if (st->done || !st->cg_active) return;                      // uniform over the grid
     camera_step_phases(d, grid, sums_ready, part_pq, part_rz, gridDim.x, sv, sm, st->lambda, st->rz, st->rz0, st->cg_tol, st->cg_steps);
 }
