@@ -196,3 +196,21 @@ def test_bench_byte_model_is_the_surveys():
     km = bench.kernel_models(N, M, K)
     assert km["cg_point_pass"] + km["cg_camera_pass"] == ab["cg_step"]
     assert km["linearize"] == ab["lin"]
+
+
+def test_layout_conflict_factor():
+    """Host side of b200ba_set_problem, no device needed (b200ba_debug_layout_stats): grouping points into quarter-warps and
+    colouring their observations over the slots brings the shared-memory camera-table reads of the by-point sweeps from ~2.5
+    wavefronts per quarter-warp phase (random cameras) to nearly conflict-free; the slot assignment is a permutation of every
+    point's observations (checked inside the call) and the SELL padding stays negligible."""
+    p = make_problem("trafalgar", 1)
+    st = binding.layout_stats(p, 64)
+    assert st["conflict_factor_plain"] > 2.2 and st["conflict_factor"] < 1.2, st
+    assert st["padding"] < 1.01
+    off = binding.layout_stats(p, 0)                                     # lane_window = 0: input order kept
+    assert abs(off["conflict_factor"] - off["conflict_factor_plain"]) < 1e-12
+    # tiny and degenerate graphs go through the same code: every point seen by the same two cameras, long tracks
+    q = make_problem((3, 40, 120), 2)
+    assert binding.layout_stats(q, 64)["conflict_factor"] <= binding.layout_stats(q, 0)["conflict_factor"] + 1e-12
+    r = make_problem((400, 64, 64 * 50), 3)                              # track length ~50 > COLOUR_DMAX: input order kept, still valid
+    assert binding.layout_stats(r, 64)["padding"] < 1.5
