@@ -13,6 +13,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/stat.h>
+#include <cmath>
+#include <stdexcept>
 
 namespace {
 
@@ -24,9 +27,13 @@ struct Tokens {
     std::vector<char> buf; char* p = nullptr; char* end = nullptr;
     bool open(const char* path)
     {
+        struct stat sb;
+        if (stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) { errno = errno ? errno : EINVAL; return false; }   // no FIFOs, directories, devices
         FILE* f = fopen(path, "rb");
         if (!f) return false;
-        fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+        if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return false; }
+        const long n = ftell(f);
+        if (n < 0 || fseek(f, 0, SEEK_SET) != 0) { fclose(f); return false; }
         buf.resize((size_t)n + 1);
         const size_t got = fread(buf.data(), 1, (size_t)n, f);
         fclose(f);
@@ -40,10 +47,10 @@ struct Tokens {
         skip_ws();
         if (p >= end) return false;
         char* q = nullptr; v = strtod(p, &q);
-        if (q == p) return false;
+        if (q == p || !std::isfinite(v)) return false;                       // "nan" / "inf" tokens are not numbers of these formats
         p = q; return true;
     }
-    bool integer(long long& v) { double d; if (!number(d)) return false; v = (long long)d; return true; }
+    bool integer(long long& v) { double d; if (!number(d) || std::fabs(d) > 9.0e15) return false; v = (long long)d; return true; }
     bool word(std::string& s)
     {
         skip_ws();
@@ -98,8 +105,11 @@ bool parse_all_numbers(const char* p, const char* end, std::vector<double>& out)
             while (c < cut[t + 1] && is_ws(*c)) ++c;
             if (c >= cut[t + 1]) break;
             char* q = nullptr;
-            out[k++] = strtod(c, &q);                          // the buffer is NUL-terminated
-            if (q == c || (q < end && !is_ws(*q))) { bad[t] = 1; return; }
+            // decimal tokens only: strtod would also take "nan", "inf" and hex floats, none of which these formats hold
+            if (!((*c >= '0' && *c <= '9') || *c == '-' || *c == '+' || *c == '.') || (c[0] == '0' && (c[1] == 'x' || c[1] == 'X'))) { bad[t] = 1; return; }
+            const double d = strtod(c, &q);                    // the buffer is NUL-terminated
+            out[k++] = d;
+            if (q == c || (q < end && !is_ws(*q)) || !std::isfinite(d)) { bad[t] = 1; return; }
             c = q;
         }
     });
@@ -199,7 +209,7 @@ int load_bal(Tokens& in, b200io_model** out)
 {
     std::vector<double> v;
     if (!parse_all_numbers(in.p, in.end, v)) return io_fail(B200BA_E_INVALID, "BAL: not a number where one was expected");
-    if (v.size() < 3 || v[0] < 0 || v[1] < 0 || v[2] < 0 || v[0] > 2e9 || v[1] > 2e9 || v[2] > 2e9)
+    if (v.size() < 3 || !(v[0] >= 0 && v[1] >= 0 && v[2] >= 0 && v[0] <= 2e9 && v[1] <= 2e9 && v[2] <= 2e9))
         return io_fail(B200BA_E_INVALID, "BAL: bad header (expected: cameras points projections)");
     const long long ncam = (long long)v[0], npt = (long long)v[1], nproj = (long long)v[2];
     const size_t o_obs = 3, o_cam = o_obs + 4 * (size_t)nproj, o_pt = o_cam + 9 * (size_t)ncam, need = o_pt + 3 * (size_t)npt;
@@ -211,7 +221,9 @@ int load_bal(Tokens& in, b200io_model** out)
     io_parallel(io_threads((size_t)nproj * 32), [&](int t, int nt) {
         for (long long i = nproj * t / nt, e = nproj * (t + 1) / nt; i < e; ++i) {
             const double* o = &v[o_obs + 4 * (size_t)i];
-            m->obs_cam[i] = (int32_t)o[0]; m->obs_pt[i] = (int32_t)o[1];
+            // an index outside int32 must not wrap into range: -1 fails check_indices
+            m->obs_cam[i] = (o[0] >= 0 && o[0] < 2147483647.0) ? (int32_t)o[0] : -1;
+            m->obs_pt[i] = (o[1] >= 0 && o[1] < 2147483647.0) ? (int32_t)o[1] : -1;
             m->obs_xy[2 * i] = o[2]; m->obs_xy[2 * i + 1] = -o[3];       // measurements[i].SetPoint2D(x, -y)
         }
     });
@@ -257,11 +269,12 @@ int load_point_lists(Tokens& in, long long npoint, double y_sign, std::vector<do
         bool ok = in.number(pts[3 * i]) && in.number(pts[3 * i + 1]) && in.number(pts[3 * i + 2]) &&
                   in.integer(cc[0]) && in.integer(cc[1]) && in.integer(cc[2]) && in.integer(npj);
         if (!ok || npj < 0) return io_fail(B200BA_E_INVALID, std::string(fmt) + ": truncated point record");
-        for (int c = 0; c < 3; ++c) rgb[3 * i + c] = (int32_t)cc[c];
+        for (int c = 0; c < 3; ++c) rgb[3 * i + c] = (int32_t)std::max(-2147483647LL, std::min(2147483647LL, cc[c]));
         for (long long j = 0; j < npj; ++j) {
             long long cidx, fidx; double x, y;
             if (!in.integer(cidx) || !in.integer(fidx) || !in.number(x) || !in.number(y)) return io_fail(B200BA_E_INVALID, std::string(fmt) + ": truncated observation");
-            oc.push_back((int32_t)cidx); op.push_back((int32_t)i); xy.push_back(x); xy.push_back(y_sign * y);
+            oc.push_back((cidx >= 0 && cidx < 2147483647LL) ? (int32_t)cidx : -1);    // never wraps into range: -1 fails check_indices
+            op.push_back((int32_t)i); xy.push_back(x); xy.push_back(y_sign * y);
         }
     }
     return 0;
@@ -429,59 +442,76 @@ void b200io_free(b200io_model* m)
 
 int b200io_load(const char* path, b200io_model** out)
 {
-    if (!path || !out) return io_fail(B200BA_E_INVALID, "b200io_load: null argument");
-    *out = nullptr;
-    Tokens in;
-    if (!in.open(path)) return io_fail(B200BA_E_INVALID, std::string("b200io_load: cannot open ") + path + ": " + strerror(errno));
-    int rc = ends_with(path, ".nvm") ? load_nvm(in, out) : ends_with(path, ".out") ? load_out(in, out) : load_bal(in, out);
-    if (rc) return rc;
-    std::string why;
-    if (!check_indices(*out, why)) { b200io_free(*out); *out = nullptr; return io_fail(B200BA_E_INVALID, std::string("b200io_load: ") + why); }
-    return 0;
+    try {
+        if (!path || !out) return io_fail(B200BA_E_INVALID, "b200io_load: null argument");
+        *out = nullptr;
+        Tokens in;
+        if (!in.open(path)) return io_fail(B200BA_E_INVALID, std::string("b200io_load: cannot open ") + path + ": " + strerror(errno));
+        int rc = ends_with(path, ".nvm") ? load_nvm(in, out) : ends_with(path, ".out") ? load_out(in, out) : load_bal(in, out);
+        if (rc) return rc;
+        std::string why;
+        if (!check_indices(*out, why)) { b200io_free(*out); *out = nullptr; return io_fail(B200BA_E_INVALID, std::string("b200io_load: ") + why); }
+        return 0;
+    
+    } catch (const std::exception& ex) { return io_fail(B200BA_E_INVALID, std::string("b200io_load: ") + ex.what()); }
+      catch (...) { return io_fail(B200BA_E_INVALID, "b200io_load: unexpected exception"); }
 }
 
 int b200io_save(const char* path, const b200io_model* m)
 {
-    if (!path || !m) return io_fail(B200BA_E_INVALID, "b200io_save: null argument");
-    std::string why;
-    if (!check_indices(m, why)) return io_fail(B200BA_E_INVALID, std::string("b200io_save: ") + why);
-    FILE* f = fopen(path, "w");
-    if (!f) return io_fail(B200BA_E_INVALID, std::string("b200io_save: cannot open ") + path + ": " + strerror(errno));
-    const int rc = ends_with(path, ".nvm") ? save_nvm(f, m) : ends_with(path, ".out") ? save_out(f, m) : save_bal(f, m);
-    if (fclose(f) != 0 && rc == 0) return io_fail(B200BA_E_INVALID, std::string("b200io_save: write failed: ") + strerror(errno));
-    return rc;
+    try {
+        if (!path || !m) return io_fail(B200BA_E_INVALID, "b200io_save: null argument");
+        std::string why;
+        if (!check_indices(m, why)) return io_fail(B200BA_E_INVALID, std::string("b200io_save: ") + why);
+        FILE* f = fopen(path, "w");
+        if (!f) return io_fail(B200BA_E_INVALID, std::string("b200io_save: cannot open ") + path + ": " + strerror(errno));
+        const int rc = ends_with(path, ".nvm") ? save_nvm(f, m) : ends_with(path, ".out") ? save_out(f, m) : save_bal(f, m);
+        if (fclose(f) != 0 && rc == 0) return io_fail(B200BA_E_INVALID, std::string("b200io_save: write failed: ") + strerror(errno));
+        return rc;
+    
+    } catch (const std::exception& ex) { return io_fail(B200BA_E_INVALID, std::string("b200io_save: ") + ex.what()); }
+      catch (...) { return io_fail(B200BA_E_INVALID, "b200io_save: unexpected exception"); }
 }
 
 int b200io_sort_by_point(b200io_model* m)
 {
-    if (!m) return io_fail(B200BA_E_INVALID, "b200io_sort_by_point: null model");
-    std::vector<int32_t> idx((size_t)m->K);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
-        return m->obs_pt[a] != m->obs_pt[b] ? m->obs_pt[a] < m->obs_pt[b] : m->obs_cam[a] < m->obs_cam[b];
-    });
-    std::vector<double> xy(2 * (size_t)m->K); std::vector<int32_t> oc((size_t)m->K), op((size_t)m->K);
-    for (int k = 0; k < m->K; ++k) { xy[2 * k] = m->obs_xy[2 * idx[k]]; xy[2 * k + 1] = m->obs_xy[2 * idx[k] + 1]; oc[k] = m->obs_cam[idx[k]]; op[k] = m->obs_pt[idx[k]]; }
-    std::memcpy(m->obs_xy, xy.data(), xy.size() * sizeof(double));
-    std::memcpy(m->obs_cam, oc.data(), oc.size() * sizeof(int32_t));
-    std::memcpy(m->obs_pt, op.data(), op.size() * sizeof(int32_t));
-    return 0;
+    try {
+        if (!m) return io_fail(B200BA_E_INVALID, "b200io_sort_by_point: null model");
+        std::vector<int32_t> idx((size_t)m->K);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) {
+            return m->obs_pt[a] != m->obs_pt[b] ? m->obs_pt[a] < m->obs_pt[b] : m->obs_cam[a] < m->obs_cam[b];
+        });
+        std::vector<double> xy(2 * (size_t)m->K); std::vector<int32_t> oc((size_t)m->K), op((size_t)m->K);
+        for (int k = 0; k < m->K; ++k) { xy[2 * k] = m->obs_xy[2 * idx[k]]; xy[2 * k + 1] = m->obs_xy[2 * idx[k] + 1]; oc[k] = m->obs_cam[idx[k]]; op[k] = m->obs_pt[idx[k]]; }
+        std::memcpy(m->obs_xy, xy.data(), xy.size() * sizeof(double));
+        std::memcpy(m->obs_cam, oc.data(), oc.size() * sizeof(int32_t));
+        std::memcpy(m->obs_pt, op.data(), op.size() * sizeof(int32_t));
+        return 0;
+    
+    } catch (const std::exception& ex) { return io_fail(B200BA_E_INVALID, std::string("b200io_sort_by_point: ") + ex.what()); }
+      catch (...) { return io_fail(B200BA_E_INVALID, "b200io_sort_by_point: unexpected exception"); }
 }
 
 int b200io_shared_focal(b200io_model* m, double* K5)
 {
-    if (!m || !K5 || m->N < 1) return io_fail(B200BA_E_INVALID, "b200io_shared_focal: null / empty model");
-    std::vector<double> f(m->focal, m->focal + m->N);
-    std::nth_element(f.begin(), f.begin() + m->N / 2, f.end());
-    const double f0 = f[m->N / 2];
-    if (!(f0 > 0)) return io_fail(B200BA_E_INVALID, "b200io_shared_focal: non-positive focal length");
-    for (int k = 0; k < m->K; ++k) {
-        const double s = f0 / m->focal[m->obs_cam[k]];
-        m->obs_xy[2 * k] *= s; m->obs_xy[2 * k + 1] *= s;
-    }
-    for (int i = 0; i < m->N; ++i) m->focal[i] = f0;
-    K5[0] = f0; K5[1] = 0; K5[2] = 0; K5[3] = f0; K5[4] = 0;
-    return 0;
+    try {
+        if (!m || !K5 || m->N < 1) return io_fail(B200BA_E_INVALID, "b200io_shared_focal: null / empty model");
+        std::vector<double> f(m->focal, m->focal + m->N);
+        std::nth_element(f.begin(), f.begin() + m->N / 2, f.end());
+        const double f0 = f[m->N / 2];
+        for (int i = 0; i < m->N; ++i)
+            if (!(m->focal[i] > 0) || !std::isfinite(m->focal[i])) return io_fail(B200BA_E_INVALID, "b200io_shared_focal: non-positive focal length");
+        for (int k = 0; k < m->K; ++k) {
+            const double s = f0 / m->focal[m->obs_cam[k]];
+            m->obs_xy[2 * k] *= s; m->obs_xy[2 * k + 1] *= s;
+        }
+        for (int i = 0; i < m->N; ++i) m->focal[i] = f0;
+        K5[0] = f0; K5[1] = 0; K5[2] = 0; K5[3] = f0; K5[4] = 0;
+        return 0;
+    
+    } catch (const std::exception& ex) { return io_fail(B200BA_E_INVALID, std::string("b200io_shared_focal: ") + ex.what()); }
+      catch (...) { return io_fail(B200BA_E_INVALID, "b200io_shared_focal: unexpected exception"); }
 }
 
 }  // extern "C"

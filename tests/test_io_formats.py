@@ -147,6 +147,29 @@ def test_error_behaviour(tmp_path):
         bio.save(tmp_path / "x.nvm", m)
 
 
+def test_hostile_inputs_are_errors_not_crashes(tmp_path):
+    """The C entry points never throw and never cast a non-finite / out-of-range token to an index."""
+    with pytest.raises(B200BAError, match="cannot open"):
+        bio.load(tmp_path)                                       # a directory
+    fifo = tmp_path / "pipe.txt"
+    os.mkfifo(fifo)
+    with pytest.raises(B200BAError, match="cannot open"):
+        bio.load(fifo)                                           # unseekable: refused before any read blocks
+    for i, head in enumerate(["nan 3 1", "2 inf 1", "2 3 1e30", "0x2 3 1"]):
+        f = tmp_path / f"h{i}.txt"
+        f.write_text(head + "\n0 0 1.0 2.0\n" + "0 0 0 0 0 0 1 0 0\n" * 2 + "0 0 1\n" * 3)
+        with pytest.raises(B200BAError):
+            bio.load(f)
+    f = tmp_path / "idx.txt"
+    f.write_text("2 3 1\n0 4294967296 1.0 2.0\n" + "0 0 0 0 0 0 1 0 0\n" * 2 + "0 0 1\n" * 3)   # would wrap to 0 as int32
+    with pytest.raises(B200BAError):
+        bio.load(f)
+    m = _model(5)
+    m.focal = m.focal.copy(); m.focal[1] = 0.0
+    with pytest.raises(B200BAError, match="focal"):
+        m.to_problem()
+
+
 def test_io_header_symbols_exported():
     import re
     from sequencesfm_b200 import binding

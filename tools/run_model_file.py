@@ -21,11 +21,25 @@ def main():
     ap.add_argument("--iterations", type=int, default=50)
     ap.add_argument("--ground", action="store_true", help="post-BA ground-plane fit, outlier drop and re-axis")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--force", action="store_true", help="adjust files with radial distortion / per-camera focals anyway (distortion ignored)")
+    ap.add_argument("--round-pixels", action="store_true", help="round measurements to whole pixels like the tracker's SSBA call (off for files)")
     a = ap.parse_args()
     m = bio.load(a.input)
+    src_xy, src_focal, src_radial = m.obs_xy.copy(), m.focal.copy(), m.radial.copy()
+    if np.any(src_radial != 0) or np.ptp(src_focal) > 1e-9 * abs(np.median(src_focal)):
+        if not a.force:
+            sys.exit(f"{a.input}: cameras carry radial distortion ({int(np.count_nonzero(src_radial))} non-zero) or different focal lengths "
+                     f"({src_focal.min():.3f} .. {src_focal.max():.3f}); the BA boundary (src/sfm_ba.h) has ONE pinhole calibration, so the "
+                     f"refinement would ignore the distortion and rescale every measurement to the median focal. Re-run with --force to do "
+                     f"that anyway (the output keeps the source measurements, focals and distortion; only poses and points change).")
+        print("WARNING: radial distortion ignored and measurements rescaled to the median focal for the adjustment (--force)", file=sys.stderr)
     p = m.to_problem(os.path.basename(a.input))
+    order = np.lexsort((m.obs_cam, m.obs_pt))          # the stable (point, camera) order b200io_sort_by_point produces
+    assert np.array_equal(m.obs_cam[order], p.obs_cam) and np.array_equal(m.obs_pt[order], p.obs_pt)
+    src_xy = src_xy[order]
     print(f"{a.input}: {p.N} cameras, {p.M} points, {p.K} observations, shared focal {p.K5[0]:.3f}")
-    opt = binding.default_options("pba" if a.pba else "ssba", device=a.device, max_iterations=a.iterations, discard_converged=0)
+    opt = binding.default_options("pba" if a.pba else "ssba", device=a.device, max_iterations=a.iterations, discard_converged=0,
+                                 **({} if (a.pba or a.round_pixels) else {"round_pixels": 0}))
     with binding.Engine(opt) as eng:
         eng.set_problem_from(p)
         r = eng.solve()
@@ -37,12 +51,13 @@ def main():
                 fit, pts, cams, axes = st.ground_stage_ba(eng, post.draw_triples(p.M, 100))
             keep = fit.keep != 0
             print(f"ground plane {fit.plane}, kept {fit.n_kept} of {p.M} points, {fit.ms_device:.2f} ms on the device")
-    out = bio.Model(cams, np.full(p.N, p.K5[0]), np.zeros(p.N), np.zeros(p.N, np.int32), pts, m.pt_rgb if keep is None else m.pt_rgb[keep],
-                    p.obs_xy, p.obs_cam, p.obs_pt, m.names)
+    # the source file's own measurements, focals and distortion go back out; only cameras and points changed
+    out = bio.Model(cams, src_focal, src_radial, np.zeros(p.N, np.int32), pts, m.pt_rgb if keep is None else m.pt_rgb[keep],
+                    src_xy, p.obs_cam, p.obs_pt, m.names)
     if keep is not None:                       # drop the observations of dropped points, renumber the rest
         new_id = np.cumsum(keep) - 1
         ok = keep[p.obs_pt]
-        out.obs_xy, out.obs_cam, out.obs_pt = p.obs_xy[ok], p.obs_cam[ok], new_id[p.obs_pt[ok]].astype(np.int32)
+        out.obs_xy, out.obs_cam, out.obs_pt = src_xy[ok], p.obs_cam[ok], new_id[p.obs_pt[ok]].astype(np.int32)
     bio.save(a.output, out)
     print(f"wrote {a.output}: {out.N} cameras, {out.M} points, {out.K} observations")
 
