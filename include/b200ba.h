@@ -85,7 +85,13 @@ typedef struct b200ba_options {
                                 /*    coordinates) and on MSE <= 0.25 px^2; PCG: cg_rel_tol 0.1 after >= cg_min_steps 10, <= 100, guard 1 */
                                 /*    (b200ba_pba_lm_preset sets all of this); normalize = 2 = PBA's NormalizeData (depth scaling)    */
     int32_t cg_min_steps;       /* PCG steps before cg_rel_tol may stop it (PBA: 10; default 0)                                     */
-    int32_t reserved[2];
+    /* --- reduced camera system --- */
+    int32_t reduced_system;     /* 0 (default): automatic - tracker-sized problems (up to ~300 cameras, single rank, fp64) assemble   */
+                                /*    S = (U + damping) - W (V + damping)^-1 W^t explicitly once per LM iteration and run the whole  */
+                                /*    PCG loop in ONE kernel with S resident in the shared memory of a thread-block cluster (or of   */
+                                /*    the whole grid); larger problems apply S matrix-free in two sweeps per step.                    */
+                                /* 1: always matrix-free.  2: explicit whenever it fits (same as 0 today)                             */
+    int32_t reserved[1];
 } b200ba_options;
 
 #define B200BA_TRACE_COLS 8     /* iter, err, lambda, new_err, rho, accepted(1/0/-1), cg_steps, cg_rel_residual */
@@ -193,7 +199,10 @@ typedef struct b200ba_plan {
     int32_t n_rows, n_segments;       /* camera-order rows of 32 / partial-sum segments                               */
     int32_t fp32_pcg;
     int64_t device_bytes;             /* size of the problem's device arena                                           */
-    int32_t reserved[8];
+    int32_t explicit_schur;           /* 0: matrix-free PCG; else CTAs that hold the explicit reduced system in shared  */
+                                      /* memory (8 / 16 = one thread-block cluster, more = the whole cooperative grid)    */
+    int32_t explicit_pairs;           /* observation pairs summed into the reduced system per LM iteration               */
+    int32_t reserved[6];
 } b200ba_plan;
 int b200ba_get_plan(const b200ba_handle* h, b200ba_plan* plan);
 

@@ -37,7 +37,8 @@ class Options(C.Structure):
                 ("round_pixels", C.c_int32), ("normalize", C.c_int32), ("fix_first_camera", C.c_int32),
                 ("discard_converged", C.c_int32), ("cg_max_steps", C.c_int32), ("cg_rel_tol", C.c_double),
                 ("precond", C.c_int32), ("poll_every", C.c_int32), ("lane_window", C.c_int32), ("pcg_fp32", C.c_int32),
-                ("keep_problem", C.c_int32), ("lm_variant", C.c_int32), ("cg_min_steps", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("keep_problem", C.c_int32), ("lm_variant", C.c_int32), ("cg_min_steps", C.c_int32), ("reduced_system", C.c_int32),
+                ("reserved", C.c_int32 * 1)]
 
 
 class Report(C.Structure):
@@ -53,7 +54,8 @@ class Plan(C.Structure):
                 ("cooperative_step", C.c_int32), ("cuda_graph", C.c_int32), ("peer_windows", C.c_int32),
                 ("world", C.c_int32), ("rank", C.c_int32), ("launches_per_iteration", C.c_int32),
                 ("n_slices", C.c_int32), ("padded_entries", C.c_int32), ("n_rows", C.c_int32), ("n_segments", C.c_int32),
-                ("fp32_pcg", C.c_int32), ("device_bytes", C.c_int64), ("reserved", C.c_int32 * 8)]
+                ("fp32_pcg", C.c_int32), ("device_bytes", C.c_int64), ("explicit_schur", C.c_int32), ("explicit_pairs", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
 
 
 TABLE_NAMES = {0: "global", 1: "shared", 2: "cluster"}

@@ -8,6 +8,8 @@
 #include "../../include/b200ba.h"
 #include "ba_kernels.cuh"
 #include "ba_kernels_f32.cuh"
+#include "ba_dense.cuh"
+#include "dense_host.h"
 #include "pinned_pool.h"
 #include "layout_host.h"
 
@@ -139,6 +141,10 @@ struct b200ba_handle {
     DBuf<int> tab_wr, tab_wr32;
     DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
     bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
+    // explicit reduced camera system (small problems): pair lists on the device, S, the per-observation blocks
+    bool use_dense = false; int dense_ctas = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
+    DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik;
+    DBuf<double> dn_Wobs, dn_Yobs, dn_Tobs, dn_chunk_part, dn_chunk_rhs, dn_S, dn_zg, dn_pq, dn_rz;
     std::vector<int> orig_of_new;                    // SELL permutation (new point index -> caller's)
     std::unique_ptr<int[]> entry_of_obs;             // obs -> padded SELL entry
     int Kp = 0;                                      // padded SELL entries
@@ -356,7 +362,9 @@ int enqueue_lm_iteration_raw(b200ba_handle* h);
 // fixed-step mode it is captured once into a CUDA graph and replayed.
 int enqueue_lm_iteration(b200ba_handle* h)
 {
-    if (!h->use_graph || h->opt.cg_rel_tol > 0) return enqueue_lm_iteration_raw(h);
+    // (the convergence-controlled PCG of the matrix-free plan polls a device flag between batches of steps: not capturable;
+    //  the explicit plan runs its whole PCG loop, stop rule included, inside one kernel)
+    if (!h->use_graph || (h->opt.cg_rel_tol > 0 && !h->use_dense)) return enqueue_lm_iteration_raw(h);
     if (!h->graph_exec) {
         cudaGraph_t g = nullptr;
         long long before = h->launches;
@@ -378,9 +386,38 @@ int enqueue_lm_iteration(b200ba_handle* h)
     return 0;
 }
 
+// Explicit plan (small problems): S assembled from the pair lists, preconditioner from its diagonal blocks, the whole PCG
+// loop in one cluster / cooperative kernel (ba_dense.cuh).
+int enqueue_dense_solve(b200ba_handle* h)
+{
+    Dev& d = h->d;
+    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
+    LAUNCH(k_dense_wobs, d.n_pt_blocks, PT_BLOCK, d);
+    if (d.dn.n_chunks) LAUNCH(k_dense_pairs, cdiv(d.dn.n_chunks, DPAIR_BLOCK / 36), DPAIR_BLOCK, d);
+    LAUNCH(k_dense_finalize, cdiv(36ll * d.dn.n_blocks, 256), 256, d);
+    LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond);
+    int max_steps = h->opt.cg_max_steps;
+    if (h->dense_grid) {
+        void* args[] = {(void*)&d, (void*)&max_steps};
+        CU(cudaLaunchCooperativeKernel((const void*)k_dense_pcg<true>, dim3(h->dense_ctas), dim3(DPCG_THREADS), args, h->dense_smem, h->stream));
+    } else {
+        cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(h->dense_ctas); cfg.blockDim = dim3(DPCG_THREADS); cfg.dynamicSmemBytes = h->dense_smem; cfg.stream = h->stream;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->dense_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k_dense_pcg<false>, d, max_steps));
+    }
+    h->launches++;
+    return 0;
+}
+
 int enqueue_lm_iteration_raw(b200ba_handle* h)
 {
     if (int rc = enqueue_linearize(h)) return rc;
+    if (h->use_dense) {
+        if (int rc = enqueue_dense_solve(h)) return rc;
+        return enqueue_step_and_decide(h);
+    }
     if (int rc = enqueue_precond(h)) return rc;
     if (int rc = enqueue_cg_init(h)) return rc;
     const int steps = h->opt.cg_max_steps;
@@ -761,6 +798,43 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
 
     lap("SELL placement + camera counts");
 
+    // ---- explicit reduced camera system for small problems (dense_host.h): S in the shared memory of one thread-block
+    //      cluster (8 or 16 CTAs) or, for a few hundred cameras, of the whole cooperative grid ----
+    h->use_dense = false; h->dense_ctas = 0; h->dense_grid = false; h->dense_smem = 0; h->dense_pairs = 0;
+    DenseLists dl; DenseShape dsh;
+    {
+        int mode = o.reduced_system;
+        if (const char* e = getenv("B200BA_DENSE")) mode = atoi(e) ? 2 : 1;
+        int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+        if (mode != 1 && h->world <= 1 && !o.pcg_fp32 && K > 0) {
+            const int cands[3] = {8, 16, coop ? n_sm : 0};
+            for (int c = 0; c < 3 && !dsh.ctas; ++c) {
+                if (cands[c] <= 0) continue;
+                const DenseShape t = dense_shape(N, cands[c]);
+                if (t.rows > DPCG_MAX_ROWS || t.smem + 1024 > (size_t)smem_optin) continue;
+                if (c < 2) {                                            // can one such cluster be resident?
+                    cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
+                    cfg.gridDim = dim3(cands[c]); cfg.blockDim = dim3(DPCG_THREADS); cfg.dynamicSmemBytes = t.smem;
+                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cands[c]; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    int nclusters = 0;
+                    if (cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess ||
+                        (cands[c] > 8 && cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+                        cudaOccupancyMaxActiveClusters(&nclusters, k_dense_pcg<false>, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+                } else {
+                    int per_sm = 0;
+                    if (cudaFuncSetAttribute(k_dense_pcg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess ||
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_pcg<true>, DPCG_THREADS, t.smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); continue; }
+                }
+                dsh = t; h->dense_grid = c == 2;
+            }
+            if (dsh.ctas && build_dense_lists(N, M, K, obs_cam, obs_pt, h->entry_of_obs.get(), dl)) {
+                h->use_dense = true; h->dense_ctas = dsh.ctas; h->dense_smem = dsh.smem; h->dense_pairs = (long long)dl.pairs.size();
+            }
+        }
+        lap("explicit reduced system: pair lists");
+    }
+
     // ---- device allocation ----
     size_t n6 = 6 * (size_t)N;
     int world = h->world;
@@ -796,6 +870,13 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             h->o_rec32.take(A, (Kpp / 32 + 1) * OREC32_BYTES); h->c_rec32.take(A, Rp * REC32_BYTES + 16);
             h->X32.take(A, Mp); h->v32.take(A, Mp); h->Vinv32.take(A, 8 * Mp); h->ptab32.take(A, (size_t)N * TAB32_STRIDE + 8); h->rt32.take(A, 12 * (size_t)N);
         } h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
+        if (h->use_dense) {
+            h->dn_pairs.take(A, dl.pairs.size() + 1); h->dn_chunks.take(A, dl.chunks.size() + 1);
+            h->dn_blk_chunk_beg.take(A, dl.blk_chunk_beg.size()); h->dn_blk_ik.take(A, dl.blk_ik.size());
+            h->dn_Wobs.take(A, 18 * Kpp); h->dn_Yobs.take(A, 18 * Kpp); h->dn_Tobs.take(A, 6 * Kpp);
+            h->dn_chunk_part.take(A, 36 * (dl.chunks.size() + 1)); h->dn_chunk_rhs.take(A, 6 * (dl.chunks.size() + 1));
+            h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 256); h->dn_rz.take(A, 256);
+        }
         if (pass == 0) {
             A.cap = A.off;
             if (arena_old && A.cap <= A.allocated) A.base = arena_old;
@@ -817,6 +898,13 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     CU(cudaMemcpyAsync(h->slice_base.p, slice_base.data(), sizeof(int) * ((size_t)n_slices + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->slice_deg.p, slice_deg.data(), sizeof(int) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->cam_seg_beg.p, cam_seg_beg.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+    if (h->use_dense) {
+        static_assert(sizeof(DensePair) == sizeof(int2) && sizeof(DenseChunk) == sizeof(int4), "device views of the pair lists");
+        if (!dl.pairs.empty()) CU(cudaMemcpyAsync(h->dn_pairs.p, dl.pairs.data(), sizeof(int2) * dl.pairs.size(), cudaMemcpyHostToDevice, s));
+        if (!dl.chunks.empty()) CU(cudaMemcpyAsync(h->dn_chunks.p, dl.chunks.data(), sizeof(int4) * dl.chunks.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->dn_blk_chunk_beg.p, dl.blk_chunk_beg.data(), sizeof(int) * dl.blk_chunk_beg.size(), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->dn_blk_ik.p, dl.blk_ik.data(), sizeof(int) * dl.blk_ik.size(), cudaMemcpyHostToDevice, s));
+    }
     if (Kp) {
         Dev dr{}; dr.o_rec = h->o_rec.p;
         k_fill_orows<<<cdiv(Kp / 32, 8), 256, 0, s>>>(dr, h->o_cam.p, Kp / 32);
@@ -944,6 +1032,19 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
     d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p; d.stamps = h->stamps.p;
+    if (h->use_dense) {
+        DenseDev& dn = d.dn;
+        dn.on = 1; dn.rows = dsh.rows; dn.ld = dsh.ld; dn.n_chunks = (int)dl.chunks.size(); dn.n_blocks = dl.n_blocks;
+        dn.pairs = h->dn_pairs.p; dn.chunks = h->dn_chunks.p; dn.blk_chunk_beg = h->dn_blk_chunk_beg.p; dn.blk_ik = h->dn_blk_ik.p;
+        dn.Wobs = h->dn_Wobs.p; dn.Yobs = h->dn_Yobs.p; dn.Tobs = h->dn_Tobs.p; dn.chunk_part = h->dn_chunk_part.p; dn.chunk_rhs = h->dn_chunk_rhs.p;
+        dn.S = h->dn_S.p; dn.zg = h->dn_zg.p; dn.pq_slots = h->dn_pq.p; dn.rz_slots = h->dn_rz.p;
+        // (the function attributes were set when the shape was chosen; the largest shape tried last is the one in force)
+        if (h->dense_grid) CU(cudaFuncSetAttribute(k_dense_pcg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
+        else {
+            CU(cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
+            if (h->dense_ctas > 8) CU(cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+    }
     if (h->use_f32) {
         d.o_rec32 = h->o_rec32.p; d.c_rec32 = h->c_rec32.p; d.X32 = h->X32.p; d.v32 = h->v32.p; d.Vinv32 = h->Vinv32.p;
         d.ptab32 = h->ptab32.p; d.rt32 = h->rt32.p; d.tab_wr32 = h->tab_wr32.p; d.tab_warps32 = tab_warps32;
@@ -1316,7 +1417,7 @@ int b200ba_get_plan(const b200ba_handle* h, b200ba_plan* plan)
     plan->camera_table = h->use_tab ? B200BA_TABLE_SHARED : B200BA_TABLE_GLOBAL;
     plan->cluster_size = 1;
     plan->cooperative_step = h->use_coop ? 1 : 0;
-    plan->cuda_graph = (h->use_graph && !(h->opt.cg_rel_tol > 0)) ? 1 : 0;
+    plan->cuda_graph = (h->use_graph && (h->use_dense || !(h->opt.cg_rel_tol > 0))) ? 1 : 0;
     plan->peer_windows = h->p2p_ready ? 1 : 0;
     plan->world = h->world; plan->rank = h->rank;
     plan->launches_per_iteration = (int32_t)h->launches_per_graph;
@@ -1324,6 +1425,8 @@ int b200ba_get_plan(const b200ba_handle* h, b200ba_plan* plan)
     plan->n_rows = h->d.n_rows; plan->n_segments = h->d.n_segs;
     plan->fp32_pcg = h->use_f32 ? 1 : 0;
     plan->device_bytes = (int64_t)h->arena.cap;
+    plan->explicit_schur = h->use_dense ? h->dense_ctas : 0;
+    plan->explicit_pairs = h->use_dense ? (int32_t)h->dense_pairs : 0;
     return 0;
 }
 

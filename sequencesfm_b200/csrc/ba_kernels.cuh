@@ -130,8 +130,18 @@ struct P2P {
     unsigned int* done_blocks;               // last-block-done counter of k_p2p_reduce
     int* err;                                // set when a peer's flag did not arrive (spin limit)
 };
+// explicit reduced camera system of small problems (ba_dense.cuh, dense_host.h); all null / 0 when the plan is matrix-free
+struct DenseDev {
+    int on, rows, ld, n_chunks, n_blocks, pad;
+    const int2* pairs; const int4* chunks; const int* blk_chunk_beg; const int* blk_ik;
+    double *Wobs, *Yobs, *Tobs;           // per SELL entry: W (6x3), W (V + damping)^-1 (6x3), W (V + damping)^-1 g_p (6)
+    double *chunk_part, *chunk_rhs;       // per chunk of pairs: 36 + 6 partial sums
+    double* S;                            // 6N x 6N, both triangles
+    double *zg, *pq_slots, *rz_slots;     // exchange buffers of the grid-wide variant of k_dense_pcg
+};
 struct Dev {
     P2P p2p;
+    DenseDev dn;
     int N, M, K, n_rows, n_vwarps, n_segs, first_free, n_pt_blocks, world, rank, n_slices, tab_ok;
     Intrinsics in;
     LMState* st;
