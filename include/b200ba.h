@@ -238,6 +238,14 @@ const char* b200ba_kernel_name(int32_t which);   /* NULL past the last kernel */
  * milliseconds of the layout build, padded SELL entries / K}.  B200BA_E_STATE if the slot assignment is not a permutation. */
 int b200ba_debug_layout_stats(int32_t N, int32_t M, int32_t K, const int32_t* obs_cam, const int32_t* obs_pt,
                               int32_t lane_window, double* out);
+/* Host-only, needs no device: the pair lists of the explicit reduced camera system (options.reduced_system) for these
+ * observations, with observation k standing for its own layout entry.  n[4] = {pairs, chunks, blocks, 0}; when the arrays
+ * are non-NULL and cap >= pairs: pair_a / pair_b = the two observations of every pair in summation order, pair_block = index of
+ * the destination block in the row-major upper block triangle.  B200BA_E_INVALID when the problem has more pairs than the
+ * explicit plan accepts.  shape[6] (may be NULL) = {kind, CTAs, rows per CTA, padded row length, threads, shared-memory bytes}
+ * of the PCG kernel that would hold a problem of N cameras on a device with n_sm multiprocessors (kind -1: matrix-free). */
+int b200ba_debug_dense_lists(int32_t N, int32_t M, int32_t K, const int32_t* obs_cam, const int32_t* obs_pt, int64_t* n,
+                             int32_t* pair_a, int32_t* pair_b, int32_t* pair_block, int64_t cap, int32_t n_sm, int64_t* shape);
 int b200ba_version(void);
 
 #ifdef __cplusplus

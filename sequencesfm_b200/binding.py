@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "b200ba_set_problem", "b200ba_solve", "b200ba_begin", "b200ba_iterate", "b200ba_restart", "b200ba_last_iterate_ms", "b200ba_last_restart_ms", "b200ba_finish", "b200ba_get_result",
     "b200ba_get_result_device", "b200ba_problem_size", "b200ba_get_plan", "b200ba_append", "b200ba_set_state",
     "b200ba_comm_unique_id", "b200ba_comm_init", "b200ba_comm_peer_handle", "b200ba_comm_open_peers", "b200ba_debug_linearize", "b200ba_debug_schur_matvec",
-    "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version", "b200ba_debug_layout_stats",
+    "b200ba_debug_time_kernel", "b200ba_kernel_name", "b200ba_version", "b200ba_debug_layout_stats", "b200ba_debug_dense_lists",
 ]
 
 
@@ -108,6 +108,26 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def dense_lists(p, n_sm: int = 148) -> dict:
+    """``b200ba_debug_dense_lists`` (host only, no device needed): the pair lists and the PCG-kernel shape of the explicit
+    reduced camera system for a problem's observation graph."""
+    oc = np.ascontiguousarray(p.obs_cam, dtype=np.int32); op = np.ascontiguousarray(p.obs_pt, dtype=np.int32)
+    n = np.zeros(4, dtype=np.int64); shape = np.zeros(6, dtype=np.int64)
+    lib = load()
+    lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    rc = lib.b200ba_debug_dense_lists(C.c_int32(p.N), C.c_int32(p.M), C.c_int32(p.K), _ip(oc), _ip(op), lp(n), None, None, None,
+                                      C.c_int64(0), C.c_int32(n_sm), lp(shape))
+    if rc:
+        raise B200BAError(rc, "b200ba_debug_dense_lists")
+    a = np.zeros(int(n[0]), dtype=np.int32); b = np.zeros_like(a); blk = np.zeros_like(a)
+    rc = lib.b200ba_debug_dense_lists(C.c_int32(p.N), C.c_int32(p.M), C.c_int32(p.K), _ip(oc), _ip(op), lp(n), _ip(a), _ip(b), _ip(blk),
+                                      C.c_int64(len(a)), C.c_int32(n_sm), None)
+    if rc:
+        raise B200BAError(rc, "b200ba_debug_dense_lists")
+    return {"pairs": int(n[0]), "chunks": int(n[1]), "blocks": int(n[2]), "a": a, "b": b, "block": blk,
+            "shape": dict(zip(("kind", "ctas", "rows", "ld", "threads", "smem"), (int(v) for v in shape)))}
 
 
 @dataclass

@@ -15,75 +15,109 @@
 //                     Same recurrences, stop rule and breakdown handling as k_cg_camera_step; all sums in fixed order.
 #pragma once
 #include "ba_kernels.cuh"
+#include "dense_host.h"
 #include <cooperative_groups.h>
 
 namespace b200ba {
 
-constexpr int DPCG_THREADS = 512;
-constexpr int DPCG_LPR = 8;                 // lanes per row of the S p product
-constexpr int DPCG_MAX_ROWS = 64;           // rows per CTA (the per-row vector state lives in the first 64 threads)
 constexpr int DPAIR_BLOCK = 288;            // 8 chunks x 36 entries
 
-__global__ void __launch_bounds__(PT_BLOCK) k_dense_wobs(Dev d)
+// one thread per SELL entry (a thread per point would walk a 49-observation track serially: 31 us at the demo sequence's size)
+__global__ void __launch_bounds__(256) k_dense_wobs(Dev d, int n_entries)
 {
     const LMState* st = d.st;
     if (st->done) return;
-    const int j = blockIdx.x * PT_BLOCK + threadIdx.x;
-    if (j >= d.M) return;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n_entries) return;
+    const int i = __ldg(o_cam_ptr(d, k));
+    if (i < 0) return;                                            // SELL padding
+    const int code = __ldg(d.dn.entry_pt + k);                     // point of the entry; one's complement marks the point's first slot
+    const bool first = code < 0;
+    const int j = first ? ~code : code;
     const int cur = st->cur;
-    double X[3], g[3], Vi[6];
-    load3p(d.X[cur], j, X); load3p(d.gp, j, g); load6(d.Vinv, j, Vi);
+    double X[3], g[3], V[6], Vi[6];
+    load3p(d.X[cur], j, X); load3p(d.gp, j, g); load6(d.V, j, V);
+    // (V + damping)^-1 here instead of a k_point_vinv launch: every entry of the point evaluates it, the first slot stores it
+    const bool pba = st->variant == 1;
+    const bool vok = point_vinv_eval(V, st->lambda, pba, Vi);
+    if (first) {
+        if (pba && st->first && st->compute) { double2* o = reinterpret_cast<double2*>(d.pt_D0 + 4 * (size_t)j); o[0] = make_double2(V[0], V[3]); o[1] = make_double2(V[5], 0.0); }
+        double2* o = reinterpret_cast<double2*>(d.Vinv + 6 * (size_t)j);
+        o[0] = make_double2(Vi[0], Vi[1]); o[1] = make_double2(Vi[2], Vi[3]); o[2] = make_double2(Vi[4], Vi[5]);
+        if (!vok) d.st->solve_ok = 0;
+    }
     const double vg0 = Vi[0] * g[0] + Vi[1] * g[1] + Vi[2] * g[2];
     const double vg1 = Vi[1] * g[0] + Vi[3] * g[1] + Vi[4] * g[2];
     const double vg2 = Vi[2] * g[0] + Vi[4] * g[1] + Vi[5] * g[2];
-    int k0, deg; slice_of(d, j, k0, deg);
-    const double* rt = d.rt[cur];
-    for (int s = 0, k = k0; s < deg; ++s, k += 32) {
-        const int i = __ldg(o_cam_ptr(d, k));
-        if (i < 0) continue;
-        Cam cm; load_cam(rt, i, cm);
-        Obs o; obs_jac(cm, X, __ldg(o_w_ptr(d, k)), d.in, o);
-        double A0[6], A1[6], B0[3], B1[3];
-        jac_rows_A(o, A0, A1); jac_rows_B(o, cm, B0, B1);
-        const double live = i < d.first_free ? 0.0 : 1.0;       // constant camera: its W block is zero
-        double2* Wo = reinterpret_cast<double2*>(d.dn.Wobs + 18 * (size_t)k);
-        double2* Yo = reinterpret_cast<double2*>(d.dn.Yobs + 18 * (size_t)k);
-        double* To = d.dn.Tobs + 6 * (size_t)k;
-        double w[18], y[18];
+    Cam cm; load_cam(d.rt[cur], i, cm);
+    Obs o; obs_jac(cm, X, __ldg(o_w_ptr(d, k)), d.in, o);
+    double A0[6], A1[6], B0[3], B1[3];
+    jac_rows_A(o, A0, A1); jac_rows_B(o, cm, B0, B1);
+    const double live = i < d.first_free ? 0.0 : 1.0;           // constant camera: its W block is zero
+    double2* Wo = reinterpret_cast<double2*>(d.dn.Wobs + 18 * (size_t)k);
+    double2* Yo = reinterpret_cast<double2*>(d.dn.Yobs + 18 * (size_t)k);
+    double2* To = reinterpret_cast<double2*>(d.dn.Tobs + 6 * (size_t)k);
+    double w[18], y[18], t[6];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const double w0 = live * (A0[a] * B0[0] + A1[a] * B1[0]), w1 = live * (A0[a] * B0[1] + A1[a] * B1[1]), w2 = live * (A0[a] * B0[2] + A1[a] * B1[2]);
-            w[3 * a] = w0; w[3 * a + 1] = w1; w[3 * a + 2] = w2;
-            y[3 * a]     = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
-            y[3 * a + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
-            y[3 * a + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
-            To[a] = w0 * vg0 + w1 * vg1 + w2 * vg2;
-        }
-#pragma unroll
-        for (int q = 0; q < 9; ++q) { Wo[q] = make_double2(w[2 * q], w[2 * q + 1]); Yo[q] = make_double2(y[2 * q], y[2 * q + 1]); }
+    for (int a = 0; a < 6; ++a) {
+        const double w0 = live * (A0[a] * B0[0] + A1[a] * B1[0]), w1 = live * (A0[a] * B0[1] + A1[a] * B1[1]), w2 = live * (A0[a] * B0[2] + A1[a] * B1[2]);
+        w[3 * a] = w0; w[3 * a + 1] = w1; w[3 * a + 2] = w2;
+        y[3 * a]     = w0 * Vi[0] + w1 * Vi[1] + w2 * Vi[2];
+        y[3 * a + 1] = w0 * Vi[1] + w1 * Vi[3] + w2 * Vi[4];
+        y[3 * a + 2] = w0 * Vi[2] + w1 * Vi[4] + w2 * Vi[5];
+        t[a] = w0 * vg0 + w1 * vg1 + w2 * vg2;
     }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { Wo[q] = make_double2(w[2 * q], w[2 * q + 1]); Yo[q] = make_double2(y[2 * q], y[2 * q + 1]); }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) To[q] = make_double2(t[2 * q], t[2 * q + 1]);
 }
 
+// 36 threads per chunk, 8 chunks per block.  The chunk's pairs are staged in shared memory by one coalesced load; the operand
+// loads of 8 pairs are issued together (L2 / L1 hits: independent loads hide the latency) and summed by a fixed tree, the groups
+// of 8 in pair order.  (Measured alternatives at Trafalgar size, 552 K pairs: 16 pairs in flight 110 us, operand blocks staged
+// through shared memory by coalesced loads 120 us, this form 81 us.)
 __global__ void __launch_bounds__(DPAIR_BLOCK) k_dense_pairs(Dev d)
 {
+    constexpr int CPB = DPAIR_BLOCK / 36;
+    __shared__ int2 spair[CPB][DENSE_CHUNK];
+    __shared__ int4 schunk[CPB];
     if (d.st->done) return;
-    const int c = blockIdx.x * (DPAIR_BLOCK / 36) + threadIdx.x / 36, e = threadIdx.x % 36;
+    if (threadIdx.x < CPB) { const int c = blockIdx.x * CPB + threadIdx.x; schunk[threadIdx.x] = c < d.dn.n_chunks ? __ldg(d.dn.chunks + c) : make_int4(0, 0, 0, 0); }
+    __syncthreads();
+    if (threadIdx.x < CPB * DENSE_CHUNK) {
+        const int cq = threadIdx.x / DENSE_CHUNK, l = threadIdx.x % DENSE_CHUNK;
+        const int4 ch = schunk[cq];
+        if (ch.y + l < ch.z) spair[cq][l] = __ldg(d.dn.pairs + ch.y + l);
+    }
+    __syncthreads();
+    const int cl = threadIdx.x / 36, e = threadIdx.x % 36, c = blockIdx.x * CPB + cl;
     if (c >= d.dn.n_chunks) return;
-    const int4 ch = __ldg(d.dn.chunks + c);                       // block, first pair, end pair, diagonal flag
-    const int a = e / 6, b = e - 6 * a;
+    const int4 ch = schunk[cl];                                   // block, first pair, end pair, diagonal flag
+    const int a = e / 6, b = e - 6 * a, cnt = ch.z - ch.y;
     const bool diag = ch.w != 0;
     if (diag && b < a) return;                                    // diagonal blocks: upper triangle, mirrored by the finalising kernel
     const double* Y = d.dn.Yobs + 3 * a; const double* W = d.dn.Wobs + 3 * b;
+    const bool want_rhs = diag && a == 0;
     double acc = 0, rhs = 0;
-#pragma unroll 4
-    for (int q = ch.y; q < ch.z; ++q) {
-        const int2 pr = __ldg(d.dn.pairs + q);
-        const double* y = Y + 18 * (size_t)pr.x; const double* w = W + 18 * (size_t)pr.y;
-        acc += y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
-        if (diag && a == 0 && pr.x == pr.y) rhs += d.dn.Tobs[6 * (size_t)pr.x + b];
+    for (int q0 = 0; q0 < cnt; q0 += 8) {
+        double pr_[8], tt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool on = q0 + u < cnt;
+            const int2 pr = on ? spair[cl][q0 + u] : make_int2(0, 0);
+            const double* yp = Y + 18 * (size_t)pr.x; const double* wp = W + 18 * (size_t)pr.y;
+            pr_[u] = on ? (yp[0] * wp[0] + yp[1] * wp[1]) + yp[2] * wp[2] : 0.0;
+            tt[u] = (want_rhs && on && pr.x == pr.y) ? d.dn.Tobs[6 * (size_t)pr.x + b] : 0.0;
+        }
+#pragma unroll
+        for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+            for (int u = 0; u < 8; u += 2 * w) { pr_[u] += pr_[u + w]; tt[u] += tt[u + w]; }
+        acc += pr_[0]; rhs += tt[0];
     }
     d.dn.chunk_part[36 * (size_t)c + e] = acc;
-    if (diag && a == 0) d.dn.chunk_rhs[6 * (size_t)c + b] = rhs;
+    if (want_rhs) d.dn.chunk_rhs[6 * (size_t)c + b] = rhs;
 }
 
 __global__ void __launch_bounds__(256) k_dense_finalize(Dev d)
@@ -91,6 +125,7 @@ __global__ void __launch_bounds__(256) k_dense_finalize(Dev d)
     const LMState* st = d.st;
     if (st->done) return;
     const int idx = blockIdx.x * 256 + threadIdx.x, blk = idx / 36, e = idx - 36 * blk;
+    if (idx == 0) *d.dn.bar_counter = 0u;                         // counting barrier of the grid-wide PCG kernel that follows
     if (blk >= d.dn.n_blocks) return;
     const int i = __ldg(d.dn.blk_ik + 2 * blk), k = __ldg(d.dn.blk_ik + 2 * blk + 1);
     const int a = e / 6, b = e - 6 * a;
@@ -121,25 +156,67 @@ __global__ void __launch_bounds__(256) k_dense_finalize(Dev d)
 }
 
 // ---- the PCG loop ---------------------------------------------------------------------------------------
-// shared-memory carve-up (doubles): Ssm[rows x ld] | p[ld] | z[ld] | qrow[rows] | rrow[rows] | pq_slot[256] | rz_slot[256] | red[64]
+// shared-memory carve-up (doubles): [Ssm[rows4 x ld] (kind 1)] | p[ld] | z[ld] | q[4 rows4] | r[rows4] | pq_slot | rz_slot | red[64] incl. 2 mbarriers
 struct DensePcgSmem {
-    double *S, *p, *z, *q, *r, *pq, *rz, *red;
-    __device__ DensePcgSmem(double* base, int rows, int ld)
+    double *S, *p, *z, *q, *r, *pq, *rz, *red; uint64_t* bar;
+    __device__ DensePcgSmem(double* base, int rows, int ld, bool s_in_smem, int slots)
     {
-        S = base; p = S + (size_t)rows * ld; z = p + ld; q = z + ld; r = q + rows; pq = r + rows; rz = pq + 256; red = rz + 256;
+        const int rows4 = (rows + 3) & ~3;
+        S = base; p = S + (s_in_smem ? (size_t)rows4 * ld : 0); z = p + ld; q = z + ld; r = q + 4 * rows4; pq = r + rows4; rz = pq + slots; red = rz + slots;
+        bar = reinterpret_cast<uint64_t*>(red + 60);
     }
 };
 
-// sum of the first `count` values of a (shared or global) array in a FIXED order, identical in every thread of every CTA:
-// warp 0 adds strided partials and reduces them by the fixed butterfly, the result goes through shared memory
+// ---- exchange inside a thread-block cluster: st.async into a peer's shared memory, completing bytes on the PEER's mbarrier ----
+// A value and the signal that it has arrived travel in one DSMEM transaction; the receiver waits on its OWN mbarrier for the
+// byte count of the phase.  No cluster-wide barrier, no fence: measured 330 cycles from the sends to the completed wait.
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, int cta)
+{
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr), "d"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n .reg .pred P1;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n selp.u32 %0, 1, 0, P1;\n }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// ---- exchange across the whole (cooperative, co-resident) grid: global memory + a counting barrier ----
+// One atomic per CTA and phase on a counter that only grows (zeroed by k_dense_finalize); the waiters poll it with acquire
+// loads.  cooperative_groups' grid.sync() cost ~5 us per call here (12.8 us per PCG step with two of them).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target)
+{
+    __syncthreads();                                               // the CTA's global stores of this phase are issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+}
+
+// sum of `count` values in a FIXED order (pairwise tree over strided partials: fp64 adds have ~30 cycles of latency, a serial
+// chain over 8 slots cost 280 cycles); identical in every thread of every CTA
+__device__ __forceinline__ double fixed_sum_smem(const double* v, int count)
+{
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int c = 0;
+    for (; c + 4 <= count; c += 4) { s0 += v[c]; s1 += v[c + 1]; s2 += v[c + 2]; s3 += v[c + 3]; }
+    if (c < count) s0 += v[c];
+    if (c + 1 < count) s1 += v[c + 1];
+    if (c + 2 < count) s2 += v[c + 2];
+    return (s0 + s1) + (s2 + s3);
+}
 template <bool GRID>
 __device__ __forceinline__ double dense_slot_sum(const double* slots, int count, double* red)
 {
-    if (!GRID) {                                                   // <= 16 slots in shared memory: every thread adds them itself
-        double s = 0;
-        for (int c = 0; c < count; ++c) s += slots[c];
-        return s;
-    }
+    if (!GRID) return fixed_sum_smem(slots, count);                 // <= 16 slots in shared memory: every thread adds them itself
     if (threadIdx.x < 32) {
         double s = 0;
         for (int c = threadIdx.x; c < count; c += 32) s += __ldcg(slots + c);
@@ -147,35 +224,70 @@ __device__ __forceinline__ double dense_slot_sum(const double* slots, int count,
         if (threadIdx.x == 0) red[32] = s;
     }
     __syncthreads();
-    const double s = red[32];
-    __syncthreads();
-    return s;
+    return red[32];
 }
 
-template <bool GRID>
-__global__ void __launch_bounds__(DPCG_THREADS, 1) k_dense_pcg(Dev d, int max_steps)
+// Work split of q = S p inside a CTA: warp (rb, cq) owns the 4 rows 4 rb .. 4 rb + 3 and every CQ-th group of 32 column pairs;
+// lane l of it owns the column pairs l + 32 (cq + CQ t), t < NP.  Every p value a lane reads is used for 4 rows (the first
+// version gave a row to 8 lanes: 40 p values per lane, and the sweep sat on shared-memory bandwidth: 123 KB of reads per step).
+template <int KIND> struct DenseCfg {
+    static constexpr bool GRID = KIND == 2;
+    static constexpr int NT = DENSE_THREADS[KIND], CQ = DENSE_CQ[KIND], NP = DENSE_NP[KIND];
+    static constexpr bool SREG = NP > 0;                           // S in registers (4 rows x 2 NP values per lane)
+    static constexpr int NP_ = NP > 0 ? NP : 1;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int max_steps)
 {
     namespace cg = cooperative_groups;
+    using Cfg = DenseCfg<KIND>;
+    constexpr bool GRID = Cfg::GRID;
+    constexpr int NT = Cfg::NT, CQ = Cfg::CQ, NP = Cfg::NP, NWARP = NT / 32;
+    constexpr bool SREG = Cfg::SREG;
     extern __shared__ __align__(16) double dsm[];
     LMState* st = d.st;
     if (st->done) return;                                          // uniform over the grid
     cg::cluster_group cl = cg::this_cluster();
-    cg::grid_group grid = cg::this_grid();
     const int G = GRID ? (int)gridDim.x : (int)cl.num_blocks();
     const int rank = GRID ? (int)blockIdx.x : (int)cl.block_rank();
     const int tid = threadIdx.x, n = 6 * d.N, rows = d.dn.rows, ld = d.dn.ld;
-    DensePcgSmem sm(dsm, rows, ld);
+    DensePcgSmem sm(dsm, rows, ld, !SREG, GRID ? 256 : 32);
     const int row0 = rank * rows, nrows = max(0, min(rows, n - row0));
-    auto group_sync = [&]() { if (GRID) grid.sync(); else cl.sync(); };
     if (!st->solve_ok) {                                           // (V + damping) was not positive definite: the step is rejected
         if (rank == 0 && tid == 0) { st->cg_active = 0; st->cg_steps = 0; st->cg_rel = 0; }
         return;
     }
-    // ---- prologue: owned rows of S -> shared memory; r = rhs, x = 0, z = M^-1 r ----
-    for (int r = tid >> 5; r < nrows; r += DPCG_THREADS / 32) {
-        const double* src = d.dn.S + (size_t)(row0 + r) * n; double* dst = sm.S + (size_t)r * ld;
-        for (int c = tid & 31; c < n; c += 32) dst[c] = __ldcg(src + c);
+    uint32_t par_a = 0, par_b = 0; unsigned int gbar = 0;          // mbarrier phase parities / grid-barrier phase count
+    if (!GRID) {
+        if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); }
+        cl.sync();                                                 // every CTA's mbarriers exist before the first st.async
     }
+    // ---- prologue: the CTA's rows of S -> registers (kinds 0, 2) or shared memory (kind 1); r = rhs, x = 0, z = M^-1 r ----
+    const int warp = tid >> 5, lane = tid & 31, rb = warp / CQ, cq = warp - rb * CQ;
+    const int qrow = 4 * rb + (lane >> 3);                         // the row whose sum this lane holds after the butterfly
+    double sreg[4][2 * Cfg::NP_];
+    if (SREG) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = 4 * rb + rr;
+            const bool on = r < nrows;
+            const double* src = d.dn.S + (size_t)(row0 + (on ? r : 0)) * n;
+#pragma unroll
+            for (int t = 0; t < NP; ++t) {
+                const int c = 2 * (lane + 32 * (cq + CQ * t));
+                sreg[rr][2 * t]     = (on && c < n) ? __ldcg(src + c) : 0.0;
+                sreg[rr][2 * t + 1] = (on && c + 1 < n) ? __ldcg(src + c + 1) : 0.0;
+            }
+        }
+    } else {
+        for (int r = warp; r < ((rows + 3) & ~3); r += NWARP) {
+            const double* src = d.dn.S + (size_t)(row0 + r) * n; double* dst = sm.S + (size_t)r * ld;
+            for (int c = lane; c < ld; c += 32) dst[c] = (r < nrows && c < n) ? __ldcg(src + c) : 0.0;
+        }
+    }
+    for (int i = n + tid; i < ld; i += NT) { sm.p[i] = 0.0; sm.z[i] = 0.0; }   // zero padding of the vectors
+    if (tid < 40) sm.red[tid] = 0.0;                               // (warps that own no row never write their p.q partial)
     const bool own = tid < nrows;
     const int e = row0 + tid, cam = e / 6, a = e - 6 * cam, lc = tid - a;
     double mrow[6] = {0, 0, 0, 0, 0, 0}, xe = 0, re = 0, ze = 0;
@@ -187,8 +299,15 @@ __global__ void __launch_bounds__(DPCG_THREADS, 1) k_dense_pcg(Dev d, int max_st
         sm.r[tid] = re;
     }
     __syncthreads();
-    // z on the owned rows, r.z partial, both to every CTA of the group
-    auto publish_z = [&](double zval, double partial) {
+    const uint32_t z_addr = smem_u32(sm.z), rz_addr = smem_u32(sm.rz), pq_addr = smem_u32(sm.pq), bar_a = smem_u32(&sm.bar[0]), bar_b = smem_u32(&sm.bar[1]);
+#ifdef B200BA_STAMPS
+    long long ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define DSTAMP(i) do { const long long tn_ = clock64(); ph[i] += tn_ - tprev; tprev = tn_; } while (0)
+#else
+#define DSTAMP(i) do {} while (0)
+#endif
+    // z on the owned rows and the CTA's r.z partial go to every CTA of the group (phase B)
+    auto exchange_z = [&](double zval, double partial) -> double {
         // partial = this thread's r * z (0 outside the owned rows); fixed-order sum over the (<= 64) owned rows
         if (tid < 64) { const double s = warp_sum(partial); if ((tid & 31) == 0) sm.red[tid >> 5] = s; }
         __syncthreads();
@@ -196,51 +315,101 @@ __global__ void __launch_bounds__(DPCG_THREADS, 1) k_dense_pcg(Dev d, int max_st
         if (GRID) {
             if (own) d.dn.zg[e] = zval;
             if (tid == 0) d.dn.rz_slots[rank] = tot;
+            gbar += (unsigned int)G; grid_barrier(d.dn.bar_counter, gbar);
         } else {
-            if (own) for (int c = 0; c < G; ++c) cl.map_shared_rank(sm.z, c)[e] = zval;
-            if (tid < G) cl.map_shared_rank(sm.rz, tid)[rank] = tot;
+            if (tid == 0) mbar_expect_tx(&sm.bar[1], (uint32_t)(8 * (n + G)));
+            if (own) for (int c = 0; c < G; ++c) st_async_f64(cluster_map(z_addr + 8u * (uint32_t)e, c), zval, cluster_map(bar_b, c));
+            if (tid < G) st_async_f64(cluster_map(rz_addr + 8u * (uint32_t)rank, tid), tot, cluster_map(bar_b, tid));
+            mbar_wait_cluster(&sm.bar[1], par_b); par_b ^= 1u;
         }
+        return dense_slot_sum<GRID>(GRID ? d.dn.rz_slots : sm.rz, G, sm.red);
     };
-    auto publish_pq = [&](double partial) {
-        if (tid < 64) { const double s = warp_sum(partial); if ((tid & 31) == 0) sm.red[2 + (tid >> 5)] = s; }
-        __syncthreads();
-        const double tot = sm.red[2] + sm.red[3];
-        if (GRID) { if (tid == 0) d.dn.pq_slots[rank] = tot; }
-        else if (tid < G) cl.map_shared_rank(sm.pq, tid)[rank] = tot;
+    // the CTA's p.q (its warps' partials are in red[8 ..]) goes to every CTA of the group (phase A)
+    auto exchange_pq = [&]() -> double {
+        const double tot = fixed_sum_smem(sm.red + 8, NWARP);
+        DSTAMP(5);
+        if (GRID) {
+            if (tid == 0) d.dn.pq_slots[rank] = tot;
+            gbar += (unsigned int)G; grid_barrier(d.dn.bar_counter, gbar);
+        } else {
+            if (tid == 0) mbar_expect_tx(&sm.bar[0], (uint32_t)(8 * G));
+            if (tid < G) st_async_f64(cluster_map(pq_addr + 8u * (uint32_t)rank, tid), tot, cluster_map(bar_a, tid));
+            mbar_wait_cluster(&sm.bar[0], par_a); par_a ^= 1u;
+        }
+        DSTAMP(6);
+        return dense_slot_sum<GRID>(GRID ? d.dn.pq_slots : sm.pq, G, sm.red);
     };
-    if (own) ze = mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1] + mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3] + mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5];
-    publish_z(ze, own ? re * ze : 0.0);
-    group_sync();
-    double rz = dense_slot_sum<GRID>(GRID ? d.dn.rz_slots : sm.rz, G, sm.red);
+    if (own) ze = (mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1]) + (mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3]) + (mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5]);
+    double rz = exchange_z(ze, own ? re * ze : 0.0);
     const double rz0 = rz;
-    for (int i = tid; i < n; i += DPCG_THREADS) sm.p[i] = GRID ? __ldcg(d.dn.zg + i) : sm.z[i];
+    for (int i = tid; i < n; i += NT) sm.p[i] = GRID ? __ldcg(d.dn.zg + i) : sm.z[i];
     __syncthreads();
     int steps = 0;
     double rel = 0;
     const double tol = st->cg_tol, guard = st->cg_guard;
     const int min_steps = st->cg_min_steps;
+    const bool watch = tol > 0 || guard > 0;                       // fixed-step mode: the relative residual is only reported, not tested
     bool active = rz > 0;
     // ---- the loop ----
-    const int grp = tid / DPCG_LPR, gl = tid % DPCG_LPR;            // 64 row groups of 8 lanes
     while (active && steps < max_steps) {
-        // q = S p on the owned rows: 8 lanes per row, two accumulators per lane, fixed butterfly over the 8 lanes
+        DSTAMP(9);
+        // q = S p on the CTA's rows: 4 rows per lane share every p value, two accumulators per row (fp64 latency); the four
+        // row sums are reduced over the 32 lanes by a butterfly that halves the number of values per lane in its first two
+        // levels (6 value-shuffles instead of 20), all in a fixed order
         {
-            const bool on = grp < nrows;
-            const double* srow = sm.S + (size_t)(on ? grp : 0) * ld;
-            double a0 = 0, a1 = 0;
-            int c = gl;
-            for (; c + DPCG_LPR < n; c += 2 * DPCG_LPR) { a0 = fma(srow[c], sm.p[c], a0); a1 = fma(srow[c + DPCG_LPR], sm.p[c + DPCG_LPR], a1); }
-            if (c < n) a0 = fma(srow[c], sm.p[c], a0);
-            double acc = a0 + a1;
+            double a[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            if (SREG) {
 #pragma unroll
-            for (int o = DPCG_LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (on && gl == 0) sm.q[grp] = acc;
+                for (int t = 0; t < NP; ++t) {
+                    const double2 pv = *reinterpret_cast<const double2*>(sm.p + 2 * (lane + 32 * (cq + CQ * t)));
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) { a[rr][0] = fma(sreg[rr][2 * t], pv.x, a[rr][0]); a[rr][1] = fma(sreg[rr][2 * t + 1], pv.y, a[rr][1]); }
+                }
+            } else {
+                const int rows4 = (rows + 3) & ~3;
+                const double* s0 = sm.S + (size_t)min(4 * rb, rows4 - 4) * ld;   // (warps beyond the CTA's rows read valid memory and write nothing)
+                const int np = (n + 63) >> 6;
+                for (int t = 0; t < np; ++t) {
+                    const int c = 2 * (lane + 32 * t);
+                    const double2 pv = *reinterpret_cast<const double2*>(sm.p + c);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const double2 sv = *reinterpret_cast<const double2*>(s0 + (size_t)rr * ld + c);
+                        a[rr][0] = fma(sv.x, pv.x, a[rr][0]); a[rr][1] = fma(sv.y, pv.y, a[rr][1]);
+                    }
+                }
+            }
+            const double v0 = a[0][0] + a[0][1], v1 = a[1][0] + a[1][1], v2 = a[2][0] + a[2][1], v3 = a[3][0] + a[3][1];
+            const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+            double k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;
+            k0 += __shfl_xor_sync(0xffffffffu, hi16 ? v0 : v2, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, hi16 ? v1 : v3, 16);
+            double acc = hi8 ? k1 : k0;
+            acc += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);           // every lane of an 8-lane group: the sum of row `qrow` over this warp's columns
+            const bool writer = (lane & 7) == 0 && qrow < nrows;
+            if (CQ == 1) {
+                if (writer) sm.q[qrow] = acc;
+                double pqp = writer ? sm.p[row0 + qrow] * acc : 0.0;
+                pqp += __shfl_xor_sync(0xffffffffu, pqp, 8);
+                pqp += __shfl_xor_sync(0xffffffffu, pqp, 16);
+                if (lane == 0) sm.red[8 + warp] = pqp;
+            } else if (writer) sm.q[qrow * CQ + cq] = acc;          // partial of one column split; summed by the row's owner below
         }
         __syncthreads();
-        const double pe = own ? sm.p[e] : 0.0, qe = own ? sm.q[tid] : 0.0;
-        publish_pq(pe * qe);
-        group_sync();
-        const double pq = dense_slot_sum<GRID>(GRID ? d.dn.pq_slots : sm.pq, G, sm.red);
+        DSTAMP(0);
+        const double pe = own ? sm.p[e] : 0.0;
+        double qe = 0.0;
+        if (CQ == 1) { if (own) qe = sm.q[tid]; }
+        else {
+            if (own) { for (int c = 0; c < CQ; ++c) qe += sm.q[tid * CQ + c]; }
+            if (tid < 64) { const double sp = warp_sum(pe * qe); if (lane == 0) sm.red[8 + warp] = sp; }
+            __syncthreads();
+        }
+        const double pq = exchange_pq();
+        DSTAMP(1);
         if (!(pq > 0) || !isfinite(pq)) {                          // breakdown (uniform): keep x; first-step breakdown = failed solve
             if (rank == 0 && tid == 0 && steps == 0) st->solve_ok = 0;
             break;
@@ -248,24 +417,29 @@ __global__ void __launch_bounds__(DPCG_THREADS, 1) k_dense_pcg(Dev d, int max_st
         const double alpha = rz / pq;
         if (own) { xe += alpha * pe; re -= alpha * qe; sm.r[tid] = re; }
         __syncthreads();
-        if (own) ze = mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1] + mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3] + mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5];
-        publish_z(ze, own ? re * ze : 0.0);
-        group_sync();
-        const double rzn = dense_slot_sum<GRID>(GRID ? d.dn.rz_slots : sm.rz, G, sm.red);
-        rel = sqrt(fabs(rzn) / rz0);
+        if (own) ze = (mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1]) + (mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3]) + (mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5]);
+        DSTAMP(2);
+        const double rzn = exchange_z(ze, own ? re * ze : 0.0);
+        DSTAMP(3);
+        if (watch) rel = sqrt(fabs(rzn) / rz0);
         const bool stop = (tol > 0 && rel < tol && steps + 1 >= min_steps) || !(rzn > 0) || (guard > 0 && rel > guard);
         if (!stop) {
             const double beta = rzn / rz;
-            for (int i = tid; i < n; i += DPCG_THREADS) sm.p[i] = (GRID ? __ldcg(d.dn.zg + i) : sm.z[i]) + beta * sm.p[i];
+            for (int i = tid; i < n; i += NT) sm.p[i] = (GRID ? __ldcg(d.dn.zg + i) : sm.z[i]) + beta * sm.p[i];
         }
         rz = rzn; ++steps;
         __syncthreads();
+        DSTAMP(4);
         if (stop) active = false;
     }
+#ifdef B200BA_STAMPS
+    if (rank == 0 && tid == 0) { for (int i = 0; i < 10; ++i) d.stamps[i] = (unsigned long long)ph[i]; d.stamps[10] = (unsigned long long)steps; }
+#endif
+    if (!watch && steps > 0) rel = sqrt(fabs(rz) / rz0);
     if (own) d.x[e] = xe;
     if (rank == 0 && tid == 0) { st->cg_steps = steps; st->total_cg += steps; st->cg_rel = rel; st->rz = rz; st->rz0 = rz0; st->cg_active = 0; }
-    // a CTA must not exit while a peer may still store into its shared memory: every remote store precedes a barrier that
-    // all CTAs pass, except after a breakdown (between the two barriers of a step) - one more barrier covers that
+    // a CTA must not exit while a peer may still store into its shared memory; every st.async of a phase has landed when the
+    // receiver passes the phase's wait, so nothing is in flight here - the barrier only keeps the exit order tidy
     if (!GRID) cl.sync();
 }
 

@@ -137,13 +137,13 @@ struct b200ba_handle {
     bool use_tab_backsub = false; size_t cost_smem = 0;          // linearisation / back-substitution / trial cost as table sweeps
     bool use_pdl = false;                            // programmatic dependent launch of the two PCG sweeps (B200BA_PDL=1)
     bool quat_ok = true;                             // the caller's rotations are orthonormal (checked by b200ba_begin): quaternion tables may stand in for R
-    DBuf<unsigned long long> stamps;
+    DBuf<unsigned long long> stamps, step_bar;
     DBuf<int> tab_wr, tab_wr32;
     DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
     bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
     // explicit reduced camera system (small problems): pair lists on the device, S, the per-observation blocks
-    bool use_dense = false; int dense_ctas = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
-    DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik;
+    bool use_dense = false; int dense_ctas = 0, dense_kind = -1, dense_threads = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
+    DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik, dn_entry_pt;
     DBuf<double> dn_Wobs, dn_Yobs, dn_Tobs, dn_chunk_part, dn_chunk_rhs, dn_S, dn_zg, dn_pq, dn_rz;
     std::vector<int> orig_of_new;                    // SELL permutation (new point index -> caller's)
     std::unique_ptr<int[]> entry_of_obs;             // obs -> padded SELL entry
@@ -227,7 +227,7 @@ int enqueue_linearize(b200ba_handle* h)
         k_lin_tab<<<h->tab_grid, TABC_BLOCK, h->cost_smem, h->stream>>>(d); h->launches++;
     } else LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
     k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++;
-    LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27, 256), 256, d, d.ar_lin, 1);
+    LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27 * 4, 256), 256, d, d.ar_lin, 1);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, (h->use_tab_backsub && h->quat_ok) ? h->tab_grid * (TABC_BLOCK / 32) : -1);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
     LAUNCH(k_lm_unpack, cdiv(36 * (long long)d.N, 256), 256, d);
@@ -248,15 +248,16 @@ int enqueue_precond(b200ba_handle* h)
     if (h->use_f32) LAUNCH(k_f32_points, cdiv(d.M, 256), 256, d, 1);
     if (h->opt.precond == 1) {
         LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
-        LAUNCH((k_camera_reduce<21, 21>), cdiv((long long)d.N * 21, 256), 256, d, d.ar_sd, 0);
+        LAUNCH((k_camera_reduce<21, 21>), cdiv((long long)d.N * 21 * 4, 256), 256, d, d.ar_sd, 0);
         if (int rc = allreduce(h, d.ar_sd, (size_t)d.N * 21, 1)) return rc;
     }
-    LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond);
+    LAUNCH(k_precond_invert, cdiv(6ll * d.N, 192), 192, d, h->opt.precond);
     return 0;
 }
 
 int enqueue_camera_half(b200ba_handle* h, int rhs_pass);
 int enqueue_camera_sums(b200ba_handle* h);
+const void* dense_pcg_kernel(int kind);
 
 int enqueue_cg_init(b200ba_handle* h)
 {
@@ -287,7 +288,7 @@ int enqueue_camera_half(b200ba_handle* h, int rhs_pass)
 int enqueue_camera_sums(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0);
+    LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6 * 4, 256), 256, d, d.ar_q, 0);
     return allreduce(h, d.ar_q, (size_t)d.N * 6, 1);
 }
 
@@ -386,26 +387,31 @@ int enqueue_lm_iteration(b200ba_handle* h)
     return 0;
 }
 
+const void* dense_pcg_kernel(int kind)
+{
+    return kind == 0 ? (const void*)k_dense_pcg<0> : kind == 1 ? (const void*)k_dense_pcg<1> : (const void*)k_dense_pcg<2>;
+}
+
 // Explicit plan (small problems): S assembled from the pair lists, preconditioner from its diagonal blocks, the whole PCG
 // loop in one cluster / cooperative kernel (ba_dense.cuh).
 int enqueue_dense_solve(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
-    LAUNCH(k_dense_wobs, d.n_pt_blocks, PT_BLOCK, d);
+    LAUNCH(k_dense_wobs, cdiv(h->Kp, 256), 256, d, h->Kp);      // (V + damping)^-1 included
     if (d.dn.n_chunks) LAUNCH(k_dense_pairs, cdiv(d.dn.n_chunks, DPAIR_BLOCK / 36), DPAIR_BLOCK, d);
     LAUNCH(k_dense_finalize, cdiv(36ll * d.dn.n_blocks, 256), 256, d);
-    LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond);
+    LAUNCH(k_precond_invert, cdiv(6ll * d.N, 192), 192, d, h->opt.precond);
     int max_steps = h->opt.cg_max_steps;
+    const void* fn = dense_pcg_kernel(h->dense_kind);
+    void* args[] = {(void*)&d, (void*)&max_steps};
     if (h->dense_grid) {
-        void* args[] = {(void*)&d, (void*)&max_steps};
-        CU(cudaLaunchCooperativeKernel((const void*)k_dense_pcg<true>, dim3(h->dense_ctas), dim3(DPCG_THREADS), args, h->dense_smem, h->stream));
+        CU(cudaLaunchCooperativeKernel(fn, dim3(h->dense_ctas), dim3(h->dense_threads), args, h->dense_smem, h->stream));
     } else {
         cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
-        cfg.gridDim = dim3(h->dense_ctas); cfg.blockDim = dim3(DPCG_THREADS); cfg.dynamicSmemBytes = h->dense_smem; cfg.stream = h->stream;
+        cfg.gridDim = dim3(h->dense_ctas); cfg.blockDim = dim3(h->dense_threads); cfg.dynamicSmemBytes = h->dense_smem; cfg.stream = h->stream;
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->dense_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, k_dense_pcg<false>, d, max_steps));
+        CU(cudaLaunchKernelExC(&cfg, fn, args));
     }
     h->launches++;
     return 0;
@@ -801,35 +807,39 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     // ---- explicit reduced camera system for small problems (dense_host.h): S in the shared memory of one thread-block
     //      cluster (8 or 16 CTAs) or, for a few hundred cameras, of the whole cooperative grid ----
     h->use_dense = false; h->dense_ctas = 0; h->dense_grid = false; h->dense_smem = 0; h->dense_pairs = 0;
-    DenseLists dl; DenseShape dsh;
+    DenseLists dl; DenseShape dsh; std::vector<int> dense_entry_pt;
     {
         int mode = o.reduced_system;
         if (const char* e = getenv("B200BA_DENSE")) mode = atoi(e) ? 2 : 1;
         int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
         if (mode != 1 && h->world <= 1 && !o.pcg_fp32 && K > 0) {
-            const int cands[3] = {8, 16, coop ? n_sm : 0};
-            for (int c = 0; c < 3 && !dsh.ctas; ++c) {
-                if (cands[c] <= 0) continue;
-                const DenseShape t = dense_shape(N, cands[c]);
-                if (t.rows > DPCG_MAX_ROWS || t.smem + 1024 > (size_t)smem_optin) continue;
-                if (c < 2) {                                            // can one such cluster be resident?
+            const int cand_kind[4] = {0, 1, 1, 2}, cand_ctas[4] = {8, 8, 16, coop ? n_sm : 0};
+            for (int c = 0; c < 4 && !dsh.ctas; ++c) {
+                if (cand_ctas[c] <= 0) continue;
+                const DenseShape t = dense_shape(N, cand_kind[c], cand_ctas[c]);
+                if (t.kind < 0 || t.smem + 1024 > (size_t)smem_optin) continue;
+                const void* fn = dense_pcg_kernel(t.kind);
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess) { cudaGetLastError(); continue; }
+                if (t.kind != 2) {                                      // can one such cluster be resident?
                     cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
-                    cfg.gridDim = dim3(cands[c]); cfg.blockDim = dim3(DPCG_THREADS); cfg.dynamicSmemBytes = t.smem;
-                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cands[c]; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.gridDim = dim3(t.ctas); cfg.blockDim = dim3(t.threads); cfg.dynamicSmemBytes = t.smem;
+                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = t.ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                     cfg.attrs = at; cfg.numAttrs = 1;
                     int nclusters = 0;
-                    if (cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess ||
-                        (cands[c] > 8 && cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
-                        cudaOccupancyMaxActiveClusters(&nclusters, k_dense_pcg<false>, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+                    if ((t.ctas > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+                        cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
                 } else {
                     int per_sm = 0;
-                    if (cudaFuncSetAttribute(k_dense_pcg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess ||
-                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_pcg<true>, DPCG_THREADS, t.smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); continue; }
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, t.threads, t.smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); continue; }
                 }
-                dsh = t; h->dense_grid = c == 2;
+                dsh = t; h->dense_grid = t.kind == 2;
             }
             if (dsh.ctas && build_dense_lists(N, M, K, obs_cam, obs_pt, h->entry_of_obs.get(), dl)) {
                 h->use_dense = true; h->dense_ctas = dsh.ctas; h->dense_smem = dsh.smem; h->dense_pairs = (long long)dl.pairs.size();
+                h->dense_kind = dsh.kind; h->dense_threads = dsh.threads;
+                dense_entry_pt.assign((size_t)std::max(Kp, 1), 0);
+                for (int jn = 0; jn < M; ++jn)
+                    for (int sl = 0, e = slice_base[jn >> 5] + (jn & 31); sl < deg_new[jn]; ++sl, e += 32) dense_entry_pt[e] = sl == 0 ? ~jn : jn;
             }
         }
         lap("explicit reduced system: pair lists");
@@ -864,7 +874,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (o.lm_variant == 1) { h->cam_D0.take(A, n6); h->pt_D0.take(A, 4 * Mp); }
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
-        h->stamps.take(A, 512 * 40);
+        h->stamps.take(A, 512 * 40); h->step_bar.take(A, 4);
         if (o.pcg_fp32) {
             h->tab_wr32.take(A, (size_t)(n_sm > 0 ? n_sm : 148) * (TAB32_BLOCK / 32) * 8 + 8);
             h->o_rec32.take(A, (Kpp / 32 + 1) * OREC32_BYTES); h->c_rec32.take(A, Rp * REC32_BYTES + 16);
@@ -872,7 +882,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         } h->part_pq.take(A, (size_t)step_grid); h->part_rz.take(A, (size_t)step_grid);
         if (h->use_dense) {
             h->dn_pairs.take(A, dl.pairs.size() + 1); h->dn_chunks.take(A, dl.chunks.size() + 1);
-            h->dn_blk_chunk_beg.take(A, dl.blk_chunk_beg.size()); h->dn_blk_ik.take(A, dl.blk_ik.size());
+            h->dn_blk_chunk_beg.take(A, dl.blk_chunk_beg.size()); h->dn_blk_ik.take(A, dl.blk_ik.size()); h->dn_entry_pt.take(A, Kpp);
             h->dn_Wobs.take(A, 18 * Kpp); h->dn_Yobs.take(A, 18 * Kpp); h->dn_Tobs.take(A, 6 * Kpp);
             h->dn_chunk_part.take(A, 36 * (dl.chunks.size() + 1)); h->dn_chunk_rhs.take(A, 6 * (dl.chunks.size() + 1));
             h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 256); h->dn_rz.take(A, 256);
@@ -904,6 +914,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (!dl.chunks.empty()) CU(cudaMemcpyAsync(h->dn_chunks.p, dl.chunks.data(), sizeof(int4) * dl.chunks.size(), cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->dn_blk_chunk_beg.p, dl.blk_chunk_beg.data(), sizeof(int) * dl.blk_chunk_beg.size(), cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(h->dn_blk_ik.p, dl.blk_ik.data(), sizeof(int) * dl.blk_ik.size(), cudaMemcpyHostToDevice, s));
+        if (Kp) CU(cudaMemcpyAsync(h->dn_entry_pt.p, dense_entry_pt.data(), sizeof(int) * (size_t)Kp, cudaMemcpyHostToDevice, s));
     }
     if (Kp) {
         Dev dr{}; dr.o_rec = h->o_rec.p;
@@ -1031,19 +1042,17 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
-    d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p; d.stamps = h->stamps.p;
+    d.seg_part = h->seg_part.p; d.pt_part = h->pt_part.p; d.trace = h->trace.p; d.stamps = h->stamps.p; d.step_bar = h->step_bar.p;
     if (h->use_dense) {
         DenseDev& dn = d.dn;
         dn.on = 1; dn.rows = dsh.rows; dn.ld = dsh.ld; dn.n_chunks = (int)dl.chunks.size(); dn.n_blocks = dl.n_blocks;
-        dn.pairs = h->dn_pairs.p; dn.chunks = h->dn_chunks.p; dn.blk_chunk_beg = h->dn_blk_chunk_beg.p; dn.blk_ik = h->dn_blk_ik.p;
+        dn.pairs = h->dn_pairs.p; dn.chunks = h->dn_chunks.p; dn.blk_chunk_beg = h->dn_blk_chunk_beg.p; dn.blk_ik = h->dn_blk_ik.p; dn.entry_pt = h->dn_entry_pt.p;
         dn.Wobs = h->dn_Wobs.p; dn.Yobs = h->dn_Yobs.p; dn.Tobs = h->dn_Tobs.p; dn.chunk_part = h->dn_chunk_part.p; dn.chunk_rhs = h->dn_chunk_rhs.p;
         dn.S = h->dn_S.p; dn.zg = h->dn_zg.p; dn.pq_slots = h->dn_pq.p; dn.rz_slots = h->dn_rz.p;
-        // (the function attributes were set when the shape was chosen; the largest shape tried last is the one in force)
-        if (h->dense_grid) CU(cudaFuncSetAttribute(k_dense_pcg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
-        else {
-            CU(cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
-            if (h->dense_ctas > 8) CU(cudaFuncSetAttribute(k_dense_pcg<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        }
+        dn.bar_counter = reinterpret_cast<unsigned int*>(h->dn_rz.p + 200);          // (the slot arrays hold at most 148 entries)
+        // (function attributes are per kernel, not per handle: set again for THIS problem's shape)
+        CU(cudaFuncSetAttribute(dense_pcg_kernel(h->dense_kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
+        if (!h->dense_grid && h->dense_ctas > 8) CU(cudaFuncSetAttribute(dense_pcg_kernel(h->dense_kind), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
     if (h->use_f32) {
         d.o_rec32 = h->o_rec32.p; d.c_rec32 = h->c_rec32.p; d.X32 = h->X32.p; d.v32 = h->v32.p; d.Vinv32 = h->Vinv32.p;
@@ -1569,6 +1578,41 @@ int b200ba_debug_layout_stats(int32_t N, int32_t M, int32_t K, const int32_t* ob
     return 0;
 }
 
+int b200ba_debug_dense_lists(int32_t N, int32_t M, int32_t K, const int32_t* obs_cam, const int32_t* obs_pt, int64_t* n,
+                             int32_t* pair_a, int32_t* pair_b, int32_t* pair_block, int64_t cap, int32_t n_sm, int64_t* shape)
+{
+    if (N <= 0 || M <= 0 || K <= 0 || !obs_cam || !obs_pt || !n) return B200BA_E_INVALID;
+    for (int k = 0; k < K; ++k) if (obs_cam[k] < 0 || obs_cam[k] >= N || obs_pt[k] < 0 || obs_pt[k] >= M || (k && obs_pt[k] < obs_pt[k - 1])) return B200BA_E_INVALID;
+    if (shape) {
+        const int cand_kind[4] = {0, 1, 1, 2}, cand_ctas[4] = {8, 8, 16, n_sm};
+        DenseShape pick;
+        for (int c = 0; c < 4 && pick.kind < 0; ++c) {
+            if (cand_ctas[c] <= 0) continue;
+            const DenseShape t = dense_shape(N, cand_kind[c], cand_ctas[c]);
+            if (t.kind >= 0 && t.smem + 1024 <= (size_t)MAX_SMEM) pick = t;
+        }
+        shape[0] = pick.kind; shape[1] = pick.ctas; shape[2] = pick.rows; shape[3] = pick.ld; shape[4] = pick.threads; shape[5] = (int64_t)pick.smem;
+    }
+    std::vector<int> ident((size_t)K);
+    for (int k = 0; k < K; ++k) ident[k] = k;
+    DenseLists dl;
+    if (!build_dense_lists(N, M, K, obs_cam, obs_pt, ident.data(), dl)) return B200BA_E_INVALID;
+    n[0] = (int64_t)dl.pairs.size(); n[1] = (int64_t)dl.chunks.size(); n[2] = dl.n_blocks; n[3] = 0;
+    if (pair_a && pair_b && pair_block && cap >= (int64_t)dl.pairs.size()) {
+        for (const DenseChunk& ch : dl.chunks) {
+            if (ch.end - ch.beg > DENSE_CHUNK || ch.end <= ch.beg) return B200BA_E_STATE;
+            for (int q = ch.beg; q < ch.end; ++q) { pair_a[q] = dl.pairs[q].a; pair_b[q] = dl.pairs[q].b; pair_block[q] = ch.block; }
+        }
+        for (int b = 0; b < dl.n_blocks; ++b)                     // chunks of a block are contiguous and in pair order
+            for (int c = dl.blk_chunk_beg[b]; c < dl.blk_chunk_beg[b + 1]; ++c) {
+                if (dl.chunks[c].block != b) return B200BA_E_STATE;
+                if (c > dl.blk_chunk_beg[b] && dl.chunks[c].beg != dl.chunks[c - 1].end) return B200BA_E_STATE;
+                if ((dl.chunks[c].diag != 0) != (dl.blk_ik[2 * b] == dl.blk_ik[2 * b + 1])) return B200BA_E_STATE;
+            }
+    }
+    return 0;
+}
+
 #ifdef B200BA_STAMPS
 // profiling builds only (not part of include/b200ba.h): the clock stamps written by the last launches of the two PCG sweeps
 int b200ba_debug_stamps(b200ba_handle* h, unsigned long long* out, int32_t cap)
@@ -1616,12 +1660,12 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
         case 13: if (int rc = enqueue_camera_half(h, 0)) return rc; break;
         case 14: if (h->use_f32) { k_cg_point_pass_tab32<<<h->tab32_grid, TAB32_BLOCK, h->tab32_smem, h->stream>>>(d); h->launches++; } break;
         case 15: if (h->use_f32) { k_cg_camera_pass32<<<h->cam_grid, CW * 32, CAMPASS32_SMEM, h->stream>>>(d); h->launches++; } break;
-        case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6, 256), 256, d, d.ar_q, 0); break;
+        case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6 * 4, 256), 256, d, d.ar_q, 0); break;
         case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;
         case 7: LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d); break;
         case 8: enqueue_backsub(h); break;
-        case 9: LAUNCH(k_precond_invert, cdiv(d.N, 128), 128, d, h->opt.precond); break;
+        case 9: LAUNCH(k_precond_invert, cdiv(6ll * d.N, 192), 192, d, h->opt.precond); break;
         }
         return 0;
     };

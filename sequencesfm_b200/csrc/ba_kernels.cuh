@@ -134,10 +134,12 @@ struct P2P {
 struct DenseDev {
     int on, rows, ld, n_chunks, n_blocks, pad;
     const int2* pairs; const int4* chunks; const int* blk_chunk_beg; const int* blk_ik;
+    const int* entry_pt;                  // SELL entry -> point (new order)
     double *Wobs, *Yobs, *Tobs;           // per SELL entry: W (6x3), W (V + damping)^-1 (6x3), W (V + damping)^-1 g_p (6)
     double *chunk_part, *chunk_rhs;       // per chunk of pairs: 36 + 6 partial sums
     double* S;                            // 6N x 6N, both triangles
     double *zg, *pq_slots, *rz_slots;     // exchange buffers of the grid-wide variant of k_dense_pcg
+    unsigned int* bar_counter;            // its counting barrier (zeroed by k_dense_finalize)
 };
 struct Dev {
     P2P p2p;
@@ -170,6 +172,7 @@ struct Dev {
     double* seg_part;     // n_segs x PART_STRIDE
     double* pt_part;      // n_pt_blocks x 4
     double* trace;
+    unsigned long long* step_bar;  // counting barrier of k_cg_camera_step: [arrivals, launches completed]
     unsigned long long* stamps;   // profiling builds only (-DB200BA_STAMPS): per-CTA / per-warp clock stamps of the two PCG sweeps
 };
 
@@ -188,30 +191,27 @@ __device__ __forceinline__ double warp_max(double v)
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// deterministic block reductions (fixed butterfly + fixed-order cross-warp sum); result valid in all threads
+// deterministic block reductions (fixed butterfly inside a warp, then the same butterfly over the warps' partials: a serial
+// sum over 32 partials is 32 dependent fp64 adds, ~1500 cycles on this chip); result valid in all threads
 template <int NT> __device__ __forceinline__ double block_sum(double v, double* sm)
 {
+    static_assert(NT % 32 == 0 && NT <= 1024, "block size");
     v = warp_sum(v);
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     __syncthreads();
     if (l == 0) sm[w] = v;
     __syncthreads();
-    double t = 0;
-#pragma unroll
-    for (int i = 0; i < NT / 32; ++i) t += sm[i];
-    return t;
+    return warp_sum(l < NT / 32 ? sm[l] : 0.0);
 }
 template <int NT> __device__ __forceinline__ double block_max(double v, double* sm)
 {
+    static_assert(NT % 32 == 0 && NT <= 1024, "block size");
     v = warp_max(v);
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     __syncthreads();
     if (l == 0) sm[w] = v;
     __syncthreads();
-    double t = sm[0];
-#pragma unroll
-    for (int i = 1; i < NT / 32; ++i) t = fmax(t, sm[i]);
-    return t;
+    return warp_max(sm[l < NT / 32 ? l : 0]);
 }
 
 // 1/z to within an ulp without the IEEE-division slow path (~20 instructions with a branch): MUFU.RCP64H seed
@@ -588,18 +588,27 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
     if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
 }
 
-// second level of every by-camera reduction: fixed-order sum of a camera's segment partials
+// second level of every by-camera reduction: fixed-order sum of a camera's segment partials.  Four lanes per (camera, value)
+// take every fourth segment and are combined by a fixed butterfly (a small problem still has ~2400 virtual warps, i.e. one
+// segment per row: 13-48 serial L2 round trips per camera in the one-thread version, 13 us at the demo sequence's size).
 template <int NV, int OSTRIDE>
 __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_compute)
 {
     const LMState* st = d.st;
     if (st->done || (need_compute && !st->compute)) return;
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = t / NV, c = t - i * NV;
-    if (i >= d.N) return;
-    double s = 0;
-    for (int sg = d.cam_seg_beg[i]; sg < d.cam_seg_beg[i + 1]; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + c];
-    out[(size_t)i * OSTRIDE + c] = s;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, u = t >> 2, q = t & 3;
+    const int i = u / NV, c = u - i * NV;
+    double s0 = 0, s1 = 0;
+    if (i < d.N) {
+        const int b = d.cam_seg_beg[i], e = d.cam_seg_beg[i + 1];
+        int sg = b + q;
+        for (; sg + 4 < e; sg += 8) { s0 += d.seg_part[PART_STRIDE * (size_t)sg + c]; s1 += d.seg_part[PART_STRIDE * (size_t)(sg + 4) + c]; }
+        if (sg < e) s0 += d.seg_part[PART_STRIDE * (size_t)sg + c];
+    }
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (i < d.N && q == 0) out[(size_t)i * OSTRIDE + c] = s;
 }
 
 // reduce the per-block partials of a thread-per-point kernel in a fixed order (single CTA).
@@ -683,6 +692,17 @@ __global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
 
 // K5  point_vinv: (V_j + lambda I)^-1 in registers (adjugate / determinant); not positive definite => the
 //     step is rejected like an LDL failure (v3d_optimization.cpp:869-874).
+// (V + damping)^-1 of one point by adjugate / determinant: Vi = (xx xy xz yy yz zz); returns false when the block is not positive definite
+__device__ __forceinline__ bool point_vinv_eval(const double V[6], double l, bool pba, double Vi[6])
+{
+    double a = pba ? V[0] * (1.0 + l) : V[0] + l, b = V[1], c = V[2], e = pba ? V[3] * (1.0 + l) : V[3] + l, f = V[4], g = pba ? V[5] * (1.0 + l) : V[5] + l;
+    double c00 = e * g - f * f, c01 = c * f - b * g, c02 = b * f - c * e;
+    double det = a * c00 + b * c01 + c * c02;
+    bool ok = (det > 0) && (a > 0) && (a * e - b * b > 0);
+    double id = 1.0 / det;
+    Vi[0] = c00 * id; Vi[1] = c01 * id; Vi[2] = c02 * id; Vi[3] = (a * g - c * c) * id; Vi[4] = (b * c - a * f) * id; Vi[5] = (a * e - b * b) * id;
+    return ok;
+}
 __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
 {
     LMState* st = d.st;
@@ -690,18 +710,14 @@ __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
     int j = blockIdx.x * 256 + threadIdx.x;
     if (j >= d.M) return;
     double V[6]; load6(d.V, j, V);
-    double l = st->lambda;
     const bool pba = st->variant == 1;                            // diag (1 + lambda) instead of + lambda (SparseBundleCPU.cpp:1793-1794)
     if (pba && st->first && st->compute) { double2* o = reinterpret_cast<double2*>(d.pt_D0 + 4 * (size_t)j); o[0] = make_double2(V[0], V[3]); o[1] = make_double2(V[5], 0.0); }
-    double a = pba ? V[0] * (1.0 + l) : V[0] + l, b = V[1], c = V[2], e = pba ? V[3] * (1.0 + l) : V[3] + l, f = V[4], g = pba ? V[5] * (1.0 + l) : V[5] + l;
-    double c00 = e * g - f * f, c01 = c * f - b * g, c02 = b * f - c * e;
-    double det = a * c00 + b * c01 + c * c02;
-    bool ok = (det > 0) && (a > 0) && (a * e - b * b > 0);
-    double id = 1.0 / det;
+    double Vi[6];
+    const bool ok = point_vinv_eval(V, st->lambda, pba, Vi);
     double2* o = reinterpret_cast<double2*>(d.Vinv + 6 * (size_t)j);
-    o[0] = make_double2(c00 * id, c01 * id);
-    o[1] = make_double2(c02 * id, (a * g - c * c) * id);
-    o[2] = make_double2((b * c - a * f) * id, (a * e - b * b) * id);
+    o[0] = make_double2(Vi[0], Vi[1]);
+    o[1] = make_double2(Vi[2], Vi[3]);
+    o[2] = make_double2(Vi[4], Vi[5]);
     if (!ok) st->solve_ok = 0;
 }
 
@@ -783,51 +799,75 @@ __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
     }
 }
 
-// K7  precond_invert: one thread per camera, M_i = (U_i + lambda I - [precond] sum W Vinv W^t)^-1 by Cholesky.
-__global__ void __launch_bounds__(128) k_precond_invert(Dev d, int precond)
+// K7  precond_invert: M_i = (U_i + damping - [precond] sum W Vinv W^t)^-1 by Cholesky.  Six threads per camera: each factors the
+//     6x6 block itself (reciprocal pivots: 6 square roots and 6 divisions instead of 21 + 72 divisions in one serial thread,
+//     14 us of a 213 us LM iteration at the demo sequence's size) and solves for ONE column of the inverse.
+__global__ void __launch_bounds__(192) k_precond_invert(Dev d, int precond)
 {
     LMState* st = d.st;
     if (st->done) return;
-    int i = blockIdx.x * 128 + threadIdx.x;
+    const int t = blockIdx.x * 192 + threadIdx.x, i = t / 6, c = t - 6 * i;
     if (i >= d.N) return;
     double L[36];
     const double* U = d.U + 36 * (size_t)i;
-    double lam = st->lambda;
+    const double lam = st->lambda;
 #pragma unroll
     for (int a = 0; a < 36; ++a) L[a] = U[a];
     const bool pba = st->variant == 1;
 #pragma unroll
     for (int a = 0; a < 6; ++a) L[7 * a] = pba ? L[7 * a] * (1.0 + lam) : L[7 * a] + lam;
     if (pba && i < d.first_free) {                                // constant camera: all-zero rows (SparseBundleCPU.cpp:1384-1390), skipped by PBA's inverse
+#pragma unroll
         for (int a = 0; a < 36; ++a) L[a] = 0.0;
+#pragma unroll
         for (int a = 0; a < 6; ++a) L[7 * a] = 1.0;
     }
     if (precond == 1) {
         const double* s = d.ar_sd + 21 * (size_t)i;
         int q = 0;
+#pragma unroll
         for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b) { double v = s[q++]; L[6 * a + b] -= v; if (a != b) L[6 * b + a] -= v; }
+#pragma unroll
+            for (int b = a; b < 6; ++b) { const double v = s[q++]; L[6 * a + b] -= v; if (a != b) L[6 * b + a] -= v; }
     }
     bool ok = true;
+    double rd[6];                                                 // reciprocal pivots
+    // (all loops run over the full 0..5 range with guards: constant trip counts keep L, rd and x in registers)
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double dd = L[7 * j];
-        for (int k = 0; k < j; ++k) dd -= L[6 * j + k] * L[6 * j + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < j) dd -= L[6 * j + k] * L[6 * j + k];
         if (!(dd > 0)) { ok = false; dd = 1.0; }
-        dd = sqrt(dd); L[7 * j] = dd;
-        for (int r = j + 1; r < 6; ++r) {
+        dd = sqrt(dd); L[7 * j] = dd; rd[j] = 1.0 / dd;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) if (r > j) {
             double v = L[6 * r + j];
-            for (int k = 0; k < j; ++k) v -= L[6 * r + k] * L[6 * j + k];
-            L[6 * r + j] = v / dd;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) if (k < j) v -= L[6 * r + k] * L[6 * j + k];
+            L[6 * r + j] = v * rd[j];
         }
     }
-    double* Mi = d.Minv + 36 * (size_t)i;
-    for (int c = 0; c < 6; ++c) {
-        double x[6];
-        for (int r = 0; r < 6; ++r) { double v = (r == c) ? 1.0 : 0.0; for (int k = 0; k < r; ++k) v -= L[6 * r + k] * x[k]; x[r] = v / L[7 * r]; }
-        for (int r = 5; r >= 0; --r) { double v = x[r]; for (int k = r + 1; k < 6; ++k) v -= L[6 * k + r] * x[k]; x[r] = v / L[7 * r]; }
-        for (int r = 0; r < 6; ++r) Mi[6 * r + c] = x[r];
+    double x[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < r) v -= L[6 * r + k] * x[k];
+        x[r] = v * rd[r];
     }
-    if (!ok) st->solve_ok = 0;
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+        const int r = 5 - rr;
+        double v = x[r];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k > r) v -= L[6 * k + r] * x[k];
+        x[r] = v * rd[r];
+    }
+    double* Mi = d.Minv + 36 * (size_t)i;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Mi[6 * r + c] = x[r];
+    if (!ok && c == 0) st->solve_ok = 0;
 }
 
 // one observation of the by-point CG sweep against the packed camera table [quaternion 4 | T 3 | p 6 | pad]
@@ -2174,15 +2214,34 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_lin_tab(Dev d)
 __device__ __forceinline__ double grid_total(const double* part, int n)
 {
     double s = 0;
-    for (int b = (threadIdx.x & 31); b < n; b += 32) s += part[b];
+    for (int b = (threadIdx.x & 31); b < n; b += 32) s += __ldcg(part + b);
     return warp_sum(s);
 }
+// Grid-wide barrier of the (cooperative, co-resident) camera-side step: one atomic per block on a counter that only grows, the
+// waiters poll it with acquire loads.  cooperative_groups' grid.sync() measured ~3.9 us per call on 148 blocks against ~1.3 us
+// for this form (tools/dense_stamps.py); the step kernel has two of them in each of the 50 PCG steps of an LM iteration.
+// bar[0] = arrivals so far (every launch that reaches the barriers adds exactly 2 x gridDim.x), bar[1] = launches completed.
+__device__ __forceinline__ void step_barrier_arrive(unsigned long long* ctr)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(ctr, 1ull); }
+}
+__device__ __forceinline__ void step_barrier(unsigned long long* ctr, unsigned long long target)
+{
+    step_barrier_arrive(ctr);
+    if (threadIdx.x == 0) {
+        unsigned long long v;
+        do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+}
 // phases of the camera-side step (after the by-camera partial sums exist); every thread of the grid must call it
-__device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_groups::grid_group& grid, int sums_ready,
+__device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
                                                    double* part_pq, double* part_rz, int step_blocks, double* sv, double* sm,
                                                    double lam, double rz, double rz0, double tol, int steps)
 {
     LMState* st = d.st;
+    const unsigned long long gen = __ldcg(d.step_bar + 1), bar_base = 2ull * gen * gridDim.x;   // read by every block before it arrives at the first barrier
     const int e = blockIdx.x * STEP_BLOCK + threadIdx.x, n6 = 6 * d.N;
     const bool on = e < n6;
     const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;    // lc: first thread of this camera inside the block
@@ -2219,10 +2278,11 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     if (on) q = lam * dmul * pe + (urow[0] * sv[lc] + urow[1] * sv[lc + 1] + urow[2] * sv[lc + 2] + urow[3] * sv[lc + 3] + urow[4] * sv[lc + 4] + urow[5] * sv[lc + 5]) - s;
     double bp = block_sum<STEP_BLOCK>(pe * q, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_pq[blockIdx.x] = bp;
-    grid.sync();
+    step_barrier(d.step_bar, bar_base + gridDim.x);
     const double pq = grid_total(part_pq, step_blocks);
     if (!(pq > 0) || !isfinite(pq)) {                            // breakdown (uniform): keep x; first-step breakdown = failed solve
-        if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; if (sums_ready == 2) *d.p2p.seq = coll + 1ull; }
+        step_barrier_arrive(d.step_bar);                         // (keeps the arrival count at 2 per block and launch)
+        if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; if (sums_ready == 2) *d.p2p.seq = coll + 1ull; *(d.step_bar + 1) = gen + 1ull; }
         return;
     }
     const double alpha = rz / pq;
@@ -2234,7 +2294,7 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
     double z = on ? (mrow[0] * sv[lc] + mrow[1] * sv[lc + 1] + mrow[2] * sv[lc + 2] + mrow[3] * sv[lc + 3] + mrow[4] * sv[lc + 4] + mrow[5] * sv[lc + 5]) : 0.0;
     double br = block_sum<STEP_BLOCK>(re * z, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_rz[blockIdx.x] = br;
-    grid.sync();
+    step_barrier(d.step_bar, bar_base + 2ull * gridDim.x);
     const double rzn = grid_total(part_rz, step_blocks);
     const double rel = sqrt(fabs(rzn) / rz0);
     const bool stop = (tol > 0 && rel < tol && steps + 1 >= st->cg_min_steps) || !(rzn > 0) || (st->cg_guard > 0 && rel > st->cg_guard);
@@ -2247,18 +2307,17 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, cooperative_gro
         st->cg_steps = steps + 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
         if (stop) st->cg_active = 0;
         if (sums_ready == 2) *d.p2p.seq = coll + 1ull;           // every thread read the counter before the first grid sync
+        *(d.step_bar + 1) = gen + 1ull;                          // every block read the launch count before the first barrier
     }
 }
 __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_ready, double* part_pq, double* part_rz)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
     __shared__ double sv[STEP_BLOCK];
     __shared__ double sm[STEP_BLOCK / 32];
     const LMState* st = d.st;
     if (threadIdx.x == 0) pdl_trigger();                          // the by-point sweep of the next PCG step may start its prologue
     if (st->done || !st->cg_active) return;                      // uniform over the grid
-    camera_step_phases(d, grid, sums_ready, part_pq, part_rz, gridDim.x, sv, sm, st->lambda, st->rz, st->rz0, st->cg_tol, st->cg_steps);
+    camera_step_phases(d, sums_ready, part_pq, part_rz, gridDim.x, sv, sm, st->lambda, st->rz, st->rz0, st->cg_tol, st->cg_steps);
 }
 
 // K12 cg_finish: delta_c = x; trial cameras T += dt, R <- Rodrigues(dw) R (v3d_metricbundle.cpp:17-39,

@@ -93,18 +93,31 @@ inline bool build_dense_lists(int N, int M, int K, const int32_t* obs_cam, const
     return true;
 }
 
-// Shape of the cluster / grid that holds S in shared memory.  rows = rows of S per CTA (whole cameras, so that the block-Jacobi
-// preconditioner is CTA-local), ld = padded row stride in doubles (ld = 8 mod 16: the 8-lanes-per-row product reads two rows
-// per shared-memory wavefront without bank conflicts).
-struct DenseShape { int ctas = 0, rows = 0, ld = 0; size_t smem = 0; };
-inline DenseShape dense_shape(int N, int ctas)
+// Shapes of the PCG kernel (ba_dense.cuh).  A CTA owns `rows` rows of S (whole cameras, so that the block-Jacobi preconditioner
+// is CTA-local); a warp owns 4 of them (and, when cq > 1, every cq-th group of 32 column pairs).
+//   kind 0  one 8-CTA thread-block cluster, S in REGISTERS (4 rows x 10 columns per lane): up to 53 cameras
+//   kind 1  one 8- or 16-CTA cluster, S in shared memory: up to ~105 cameras
+//   kind 2  the whole cooperative grid (one CTA per SM), S in registers (4 rows x 14 columns per lane, 4 column splits): up to 2 cameras per SM
+struct DenseShape { int kind = -1, ctas = 0, rows = 0, ld = 0, threads = 0; size_t smem = 0; };
+constexpr int DENSE_KINDS = 3;
+constexpr int DENSE_THREADS[DENSE_KINDS] = {384, 512, 384};
+constexpr int DENSE_CQ[DENSE_KINDS]      = {1, 1, 4};      // column splits (warps sharing a block of 4 rows)
+constexpr int DENSE_NP[DENSE_KINDS]      = {5, 0, 7};      // column pairs per lane kept in registers (0: S in shared memory)
+inline DenseShape dense_shape(int N, int kind, int ctas)
 {
-    DenseShape s; s.ctas = ctas;
-    const int n = 6 * N;
+    DenseShape s; s.kind = kind; s.ctas = ctas; s.threads = DENSE_THREADS[kind];
+    const int n = 6 * N, cq = DENSE_CQ[kind], np = DENSE_NP[kind];
     s.rows = 6 * ((N + ctas - 1) / ctas);
-    s.ld = n + ((8 - n % 16) + 16) % 16;
-    // S rows | p | z | q rows | r rows | slots (2 x 256) | reduction scratch
-    s.smem = sizeof(double) * ((size_t)s.rows * s.ld + 2 * (size_t)s.ld + 2 * (size_t)s.rows + 2 * 256 + 64);
+    const int rows4 = (s.rows + 3) & ~3;
+    // padded vector length: every column pair a lane touches exists (zeros beyond n), so the product runs without bounds checks
+    const int plen = np ? 64 * cq * np : ((n + 63) / 64) * 64;
+    s.ld = plen + 8;
+    const bool fits_threads = rows4 / 4 * cq <= s.threads / 32 && s.rows <= 64;
+    const bool fits_regs = !np || n <= plen;
+    if (!fits_threads || !fits_regs) { s.kind = -1; return s; }
+    // [S rows (kind 1)] | p | z | q (4 x rows4) | r (rows4) | pq slots | rz slots | scratch + mbarriers
+    const int slots = kind == 2 ? 256 : 32;
+    s.smem = sizeof(double) * ((kind == 1 ? (size_t)rows4 * s.ld : 0) + 2 * (size_t)s.ld + 5 * (size_t)rows4 + 2 * (size_t)slots + 64);
     return s;
 }
 

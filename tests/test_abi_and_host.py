@@ -214,3 +214,40 @@ def test_layout_conflict_factor():
     assert binding.layout_stats(q, 64)["conflict_factor"] <= binding.layout_stats(q, 0)["conflict_factor"] + 1e-12
     r = make_problem((400, 64, 64 * 50), 3)                              # track length ~50 > COLOUR_DMAX: input order kept, still valid
     assert binding.layout_stats(r, 64)["padding"] < 1.5
+
+
+def test_explicit_reduced_system_pair_lists():
+    """Host side of the explicit reduced camera system (csrc/dense_host.h, no device needed): every ordered pair of observations
+    of one point with camera(a) <= camera(b) appears exactly once, filed under its destination block, pairs of a block in point
+    order; the kernel shape follows the camera count (cluster with S in registers, cluster with S in shared memory, whole grid,
+    matrix-free)."""
+    rng = np.random.default_rng(5)
+    p = make_problem((9, 60, 260), 3)
+    oc, op = p.obs_cam.copy(), p.obs_pt.copy()
+    # a point seen twice by the same camera: both orders of the two observations go to the diagonal block
+    k0 = int(np.flatnonzero(op == op[10])[0]); oc[k0 + 1] = oc[k0]
+    q = type(p)(p.K5, p.cam_RT, p.pts, p.obs_xy, oc, op, "dup", 0)
+    dl = binding.dense_lists(q)
+    want = []
+    for j in range(q.M):
+        ks = np.flatnonzero(op == j)
+        for a in ks:
+            for b in ks:
+                if oc[a] <= oc[b]:
+                    i, k = int(oc[a]), int(oc[b])
+                    want.append((i * q.N - i * (i - 1) // 2 + (k - i), int(a), int(b)))
+    want.sort(key=lambda t: t[0])                                        # stable: point order inside a block
+    got = list(zip(dl["block"].tolist(), dl["a"].tolist(), dl["b"].tolist()))
+    assert got == want
+    assert dl["pairs"] == len(want) and dl["blocks"] == q.N * (q.N + 1) // 2
+    assert dl["chunks"] >= dl["pairs"] // 32
+    dup = [(a, b) for _, a, b in want if oc[a] == oc[b] and a != b]
+    assert (k0, k0 + 1) in dup and (k0 + 1, k0) in dup
+    # shapes by camera count
+    kinds = {n: binding.dense_lists(make_problem((n, 40, 120), 1))["shape"] for n in (5, 49, 53, 54, 90, 120, 257, 296, 400)}
+    assert [kinds[n]["kind"] for n in (5, 49, 53)] == [0, 0, 0] and kinds[49]["ctas"] == 8 and kinds[49]["rows"] == 42
+    assert kinds[54]["kind"] == 1 and kinds[54]["ctas"] == 8 and kinds[90]["kind"] == 1 and kinds[90]["ctas"] == 16
+    assert kinds[120]["kind"] == 2 and kinds[257]["kind"] == 2 and kinds[257]["ctas"] == 148 and kinds[257]["rows"] == 12
+    assert kinds[296]["kind"] == 2 and kinds[400]["kind"] == -1         # more than two cameras per multiprocessor: matrix-free
+    for s in kinds.values():
+        assert s["smem"] <= 227 * 1024 and (s["kind"] < 0 or s["rows"] % 6 == 0)

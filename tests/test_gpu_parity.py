@@ -167,11 +167,13 @@ def test_fp32_pcg_mode(shape, seed, env, monkeypatch):
     """Optional mixed-precision mode (options.pcg_fp32): the two PCG sweeps in fp32, everything else fp64.  North star:
     per-iteration cost within 1e-5 relative of the fp64 path."""
     p = make_problem(shape, seed, outlier_frac=0.01)
-    a = _solve(p, max_iterations=12)
+    a = _solve(p, max_iterations=12, reduced_system=1)                  # the fp64 matrix-free plan: the mixed mode replaces ITS two sweeps
     if env:
         monkeypatch.setenv(env, "1")                                    # the fp32 sweeps with the single-CTA step / without graph replay
     b = _solve(p, max_iterations=12, pcg_fp32=1)
-    k = parity_window(b.trace, a.trace)
+    # (first 10 iterations: a fixed 50-step PCG is not converged once the damping has fallen, and from there on ANY change of
+    #  rounding - fp32 sweeps, but also two fp64 summation orders - is amplified from 1e-9 to 1e-4 within three iterations)
+    k = min(parity_window(b.trace, a.trace), 10)
     assert k >= 8
     d = rel_cost_diff(b.trace, a.trace, k)
     assert d.max() < 1e-5, d
@@ -582,3 +584,79 @@ def test_venice_shape_properties():
     assert np.all(r.trace[acc, 3] < r.trace[acc, 1])                    # accepted steps decrease the cost
     assert r.mean_px[1] < 0.7 and r.mean_px[0] > 2.0
     assert r.gpu_launches > 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# explicit reduced camera system (options.reduced_system; csrc/ba_dense.cuh): small problems
+# ---------------------------------------------------------------------------------------------------------
+def _demo_problem():
+    return load_demo("demo_kf49")[1]
+
+
+@pytest.mark.parametrize("shape,seed,want_ctas", [("small", 3, 8), ("ladybug", 2, 8), ("demo", 0, 8), ((60, 900, 5000), 4, 8),
+                                                  ((90, 1500, 9000), 5, 16), ((130, 2500, 12000), 6, None), ("trafalgar", 1, None)])
+def test_explicit_reduced_system_matches_matrix_free_and_oracle(shape, seed, want_ctas):
+    """The explicit plan (S assembled from the pair lists, whole PCG loop in one cluster / cooperative kernel) against the
+    matrix-free plan and the CPU restatement: exact-step mode, per-iteration cost within 1e-9 over the parity window; the
+    kernel shapes (S in registers / shared memory, cluster of 8 / 16, whole grid) are all exercised."""
+    p = _demo_problem() if shape == "demo" else make_problem(shape, seed, outlier_frac=0.02)
+    kw = dict(max_iterations=10, cg_rel_tol=1e-13, cg_max_steps=3000)
+    with binding.Engine(reduced_system=0, **kw) as eng:
+        eng.set_problem_from(p)
+        plan = eng.plan()
+        a = eng.solve()
+    n_sm = 148
+    assert plan["explicit_schur"] == (want_ctas if want_ctas else plan["explicit_schur"]) and plan["explicit_schur"] > 0
+    if want_ctas is None:
+        assert plan["explicit_schur"] > 16 and plan["explicit_schur"] <= 2 * n_sm       # one CTA per multiprocessor
+    assert plan["explicit_pairs"] == binding.dense_lists(p)["pairs"]
+    assert plan["cuda_graph"] == 1                                       # no host polling inside the PCG loop: captured even in exact-step mode
+    b = _solve(p, reduced_system=1, **kw)
+    k = parity_window(a.trace, b.trace)
+    assert k >= 6 and rel_cost_diff(a.trace, b.trace, k).max() < COST_RTOL
+    c = oracle.solve(p, max_iterations=10, solver=1)
+    kk = parity_window(a.trace, c.trace)
+    assert kk >= 6 and rel_cost_diff(a.trace, c.trace, kk).max() < COST_RTOL
+    # bit-reproducible: fixed-order sums everywhere (no atomics on any accumulator)
+    a2 = _solve(p, reduced_system=0, **kw)
+    assert np.array_equal(a.trace, a2.trace) and np.array_equal(a.cam_RT, a2.cam_RT) and np.array_equal(a.pts, a2.pts)
+
+
+@pytest.mark.parametrize("preset", ["pba", "pba_lm"])
+def test_explicit_reduced_system_with_the_pba_personalities(preset):
+    """Constant first camera (its W blocks are zero), multiplicative damping, PBA's PCG stop rule (tolerance 0.1 after >= 10 steps,
+    guard): the explicit plan takes the same number of PCG steps and the same decisions as the matrix-free plan."""
+    p = make_problem("ladybug", 3, outlier_frac=0.0)
+    p32 = type(p)(p.K5, p.cam_RT.astype(np.float32).astype(np.float64), p.pts.astype(np.float32).astype(np.float64), p.obs_xy, p.obs_cam, p.obs_pt, p.name, 0)
+    res = []
+    for mode in (0, 1):
+        opt = binding.default_options(preset, reduced_system=mode, max_iterations=8)
+        with binding.Engine(opt) as eng:
+            eng.set_problem_from(p32)
+            res.append((eng.plan()["explicit_schur"], eng.solve()))
+    (pa, a), (pb, b) = res
+    assert pa == 8 and pb == 0
+    k = min(len(a.trace), len(b.trace), 6)
+    assert k >= 4
+    assert np.array_equal(a.trace[:k, 5], b.trace[:k, 5])                # accept decisions
+    assert np.array_equal(a.trace[:k, 6], b.trace[:k, 6])                # PCG steps per LM iteration
+    # (pba_lm stops its PCG at a relative residual of 0.1: the step is a truncated Krylov iterate, so the two plans' rounding
+    #  shows in the next cost at 1e-8; with the fixed 50 steps of the pba preset it stays below 1e-9)
+    assert rel_cost_diff(a.trace, b.trace, k).max() < (1e-7 if preset == "pba_lm" else 1e-9)
+    assert np.abs(a.trace[:k, 2] / b.trace[:k, 2] - 1).max() < 1e-6      # damping schedule
+
+
+def test_explicit_reduced_system_edge_cases():
+    """A point seen twice by one camera, cameras that see nothing, unobserved points, fewer cameras than CTAs in the cluster."""
+    p = make_problem((5, 300, 1100), 9, outlier_frac=0.02)
+    oc, op, xy = p.obs_cam.copy(), p.obs_pt.copy(), p.obs_xy.copy()
+    k0 = int(np.flatnonzero(op == op[40])[0]); oc[k0 + 1] = oc[k0]       # duplicate camera inside one track
+    keep = (op % 17 != 3) & (oc != 4)                                    # points 3, 20, 37 ... unobserved; camera 4 sees nothing
+    q = type(p)(p.K5, p.cam_RT, p.pts, xy[keep], oc[keep], op[keep], "edge", 0)
+    kw = dict(max_iterations=8, cg_rel_tol=1e-13, cg_max_steps=2000)
+    a = _solve(q, reduced_system=0, **kw); b = _solve(q, reduced_system=1, **kw)
+    k = parity_window(a.trace, b.trace)
+    assert k >= 5 and rel_cost_diff(a.trace, b.trace, k).max() < COST_RTOL
+    c = oracle.solve(q, max_iterations=8, solver=1)
+    kk = parity_window(a.trace, c.trace)
+    assert kk >= 5 and rel_cost_diff(a.trace, c.trace, kk).max() < COST_RTOL
