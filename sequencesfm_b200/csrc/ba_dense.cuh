@@ -25,6 +25,7 @@ constexpr int DPAIR_BLOCK = 288;            // 8 chunks x 36 entries
 // one thread per SELL entry (a thread per point would walk a 49-observation track serially: 31 us at the demo sequence's size)
 __global__ void __launch_bounds__(256) k_dense_wobs(Dev d, int n_entries)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done) return;
     const int k = blockIdx.x * 256 + threadIdx.x;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k_dense_wobs(Dev d, int n_entries)
 // through shared memory by coalesced loads 120 us, this form 81 us.)
 __global__ void __launch_bounds__(DPAIR_BLOCK) k_dense_pairs(Dev d)
 {
+    pdl_chain_enter();
     constexpr int CPB = DPAIR_BLOCK / 36;
     __shared__ int2 spair[CPB][DENSE_CHUNK];
     __shared__ int4 schunk[CPB];
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(DPAIR_BLOCK) k_dense_pairs(Dev d)
 
 __global__ void __launch_bounds__(256) k_dense_finalize(Dev d)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done) return;
     const int idx = blockIdx.x * 256 + threadIdx.x, blk = idx / 36, e = idx - 36 * blk;
@@ -187,8 +190,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // ---- exchange across the whole (cooperative, co-resident) grid: global memory + a counting barrier ----
-// One atomic per CTA and phase on a counter that only grows (zeroed by k_dense_finalize); the waiters poll it with acquire
-// loads.  cooperative_groups' grid.sync() cost ~5 us per call here (12.8 us per PCG step with two of them).
+// One atomic per CTA and phase on a counter that only grows (zeroed by k_dense_finalize); the waiters poll that ONE word with
+// acquire loads, then warp 0 sums the slots.  Measured alternatives at 257 cameras / 148 CTAs: cooperative_groups' grid.sync()
+// 12.8 us per PCG step; this form 6.7 us; slots tagged with a "not written yet" sentinel and polled directly (barrier and data in
+// one round trip on paper) 9.8 us - 148 CTAs polling 148 words keep the L2 lines bouncing while the writers try to update them.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target)
 {
     __syncthreads();                                               // the CTA's global stores of this phase are issued
@@ -199,6 +204,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
     }
     __syncthreads();
+}
+__device__ __forceinline__ double grid_slot_sum(const double* slots, int count, double* red)
+{
+    if (threadIdx.x < 32) {
+        double s = 0;
+        for (int c = threadIdx.x; c < count; c += 32) s += __ldcg(slots + c);
+        s = warp_sum(s);
+        if (threadIdx.x == 0) red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
 }
 
 // sum of `count` values in a FIXED order (pairwise tree over strided partials: fp64 adds have ~30 cycles of latency, a serial
@@ -213,20 +229,6 @@ __device__ __forceinline__ double fixed_sum_smem(const double* v, int count)
     if (c + 2 < count) s2 += v[c + 2];
     return (s0 + s1) + (s2 + s3);
 }
-template <bool GRID>
-__device__ __forceinline__ double dense_slot_sum(const double* slots, int count, double* red)
-{
-    if (!GRID) return fixed_sum_smem(slots, count);                 // <= 16 slots in shared memory: every thread adds them itself
-    if (threadIdx.x < 32) {
-        double s = 0;
-        for (int c = threadIdx.x; c < count; c += 32) s += __ldcg(slots + c);
-        s = warp_sum(s);
-        if (threadIdx.x == 0) red[32] = s;
-    }
-    __syncthreads();
-    return red[32];
-}
-
 // Work split of q = S p inside a CTA: warp (rb, cq) owns the 4 rows 4 rb .. 4 rb + 3 and every CQ-th group of 32 column pairs;
 // lane l of it owns the column pairs l + 32 (cq + CQ t), t < NP.  Every p value a lane reads is used for 4 rows (the first
 // version gave a row to 8 lanes: 40 p values per lane, and the sweep sat on shared-memory bandwidth: 123 KB of reads per step).
@@ -240,6 +242,7 @@ template <int KIND> struct DenseCfg {
 template <int KIND>
 __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int max_steps)
 {
+    pdl_chain_enter();
     namespace cg = cooperative_groups;
     using Cfg = DenseCfg<KIND>;
     constexpr bool GRID = Cfg::GRID;
@@ -316,13 +319,14 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
             if (own) d.dn.zg[e] = zval;
             if (tid == 0) d.dn.rz_slots[rank] = tot;
             gbar += (unsigned int)G; grid_barrier(d.dn.bar_counter, gbar);
+            return grid_slot_sum(d.dn.rz_slots, G, sm.red);
         } else {
             if (tid == 0) mbar_expect_tx(&sm.bar[1], (uint32_t)(8 * (n + G)));
             if (own) for (int c = 0; c < G; ++c) st_async_f64(cluster_map(z_addr + 8u * (uint32_t)e, c), zval, cluster_map(bar_b, c));
             if (tid < G) st_async_f64(cluster_map(rz_addr + 8u * (uint32_t)rank, tid), tot, cluster_map(bar_b, tid));
             mbar_wait_cluster(&sm.bar[1], par_b); par_b ^= 1u;
         }
-        return dense_slot_sum<GRID>(GRID ? d.dn.rz_slots : sm.rz, G, sm.red);
+        return fixed_sum_smem(sm.rz, G);
     };
     // the CTA's p.q (its warps' partials are in red[8 ..]) goes to every CTA of the group (phase A)
     auto exchange_pq = [&]() -> double {
@@ -331,13 +335,15 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
         if (GRID) {
             if (tid == 0) d.dn.pq_slots[rank] = tot;
             gbar += (unsigned int)G; grid_barrier(d.dn.bar_counter, gbar);
+            DSTAMP(6);
+            return grid_slot_sum(d.dn.pq_slots, G, sm.red);
         } else {
             if (tid == 0) mbar_expect_tx(&sm.bar[0], (uint32_t)(8 * G));
             if (tid < G) st_async_f64(cluster_map(pq_addr + 8u * (uint32_t)rank, tid), tot, cluster_map(bar_a, tid));
             mbar_wait_cluster(&sm.bar[0], par_a); par_a ^= 1u;
         }
         DSTAMP(6);
-        return dense_slot_sum<GRID>(GRID ? d.dn.pq_slots : sm.pq, G, sm.red);
+        return fixed_sum_smem(sm.pq, G);
     };
     if (own) ze = (mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1]) + (mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3]) + (mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5]);
     double rz = exchange_z(ze, own ? re * ze : 0.0);

@@ -142,6 +142,7 @@ struct b200ba_handle {
     DBuf<unsigned char> o_rec32, c_rec32; DBuf<float4> X32, v32; DBuf<float> Vinv32, ptab32, rt32;
     bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
     // explicit reduced camera system (small problems): pair lists on the device, S, the per-observation blocks
+    bool pdl_chain = false;                          // programmatic dependent launch of every kernel of the iteration (explicit plan)
     bool use_dense = false; int dense_ctas = 0, dense_kind = -1, dense_threads = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
     DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik, dn_entry_pt;
     DBuf<double> dn_Wobs, dn_Yobs, dn_Tobs, dn_chunk_part, dn_chunk_rhs, dn_S, dn_zg, dn_pq, dn_rz;
@@ -200,7 +201,21 @@ int allreduce(b200ba_handle* h, double* buf, size_t count, int need = 0)
 }
 
 // ---- kernel launch sequences ---------------------------------------------------------------------------
-#define LAUNCH(kern, grid, block, ...) do { kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+// Every kernel of an LM iteration goes through here.  h->pdl_chain (explicit small-problem plan): programmatic dependent launch,
+// see pdl_chain_enter() in ba_kernels.cuh.
+template <class... KA, class... A>
+void launch_chain(b200ba_handle* h, void (*kern)(KA...), int grid, int block, size_t smem, A&&... a)
+{
+    if (h->pdl_chain) {
+        cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(a)...);
+    } else kern<<<grid, block, smem, h->stream>>>(static_cast<KA>(a)...);
+    h->launches++;
+}
+#define LAUNCH(kern, grid, block, ...) launch_chain(h, kern, (grid), (block), 0, __VA_ARGS__)
 
 // by-point PCG sweep against the shared-memory camera table (one or two rows in flight per trip)
 void launch_point_tab(b200ba_handle* h)
@@ -224,9 +239,9 @@ int enqueue_linearize(b200ba_handle* h)
     LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
     if (h->use_tab_backsub && h->quat_ok) {                      // table plan: by-point linearisation as a shared-memory-table sweep
         LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 0);
-        k_lin_tab<<<h->tab_grid, TABC_BLOCK, h->cost_smem, h->stream>>>(d); h->launches++;
+        launch_chain(h, k_lin_tab, h->tab_grid, TABC_BLOCK, h->cost_smem, d);
     } else LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
-    k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++;
+    launch_chain(h, k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, d);
     LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27 * 4, 256), 256, d, d.ar_lin, 1);
     LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, (h->use_tab_backsub && h->quat_ok) ? h->tab_grid * (TABC_BLOCK / 32) : -1);
     if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
@@ -337,9 +352,8 @@ void enqueue_backsub(b200ba_handle* h)
     if (h->use_tab_backsub && h->quat_ok) {
         LAUNCH(k_ptab_set_x, cdiv(6 * (long long)d.N, 256), 256, d);
         LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 1);
-        k_backsub_tab<<<h->tab_grid, TABC_BLOCK, h->tab_smem, h->stream>>>(d);
-        k_cost_tab<<<h->tab_grid, TABC_BLOCK, h->cost_smem, h->stream>>>(d);
-        h->launches += 2;
+        launch_chain(h, k_backsub_tab, h->tab_grid, TABC_BLOCK, h->tab_smem, d);
+        launch_chain(h, k_cost_tab, h->tab_grid, TABC_BLOCK, h->cost_smem, d);
         LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, h->tab_grid * (TABC_BLOCK / 32));
     } else {
         LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
@@ -404,15 +418,13 @@ int enqueue_dense_solve(b200ba_handle* h)
     int max_steps = h->opt.cg_max_steps;
     const void* fn = dense_pcg_kernel(h->dense_kind);
     void* args[] = {(void*)&d, (void*)&max_steps};
-    if (h->dense_grid) {
-        CU(cudaLaunchCooperativeKernel(fn, dim3(h->dense_ctas), dim3(h->dense_threads), args, h->dense_smem, h->stream));
-    } else {
-        cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
-        cfg.gridDim = dim3(h->dense_ctas); cfg.blockDim = dim3(h->dense_threads); cfg.dynamicSmemBytes = h->dense_smem; cfg.stream = h->stream;
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->dense_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        CU(cudaLaunchKernelExC(&cfg, fn, args));
-    }
+    cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[2];
+    cfg.gridDim = dim3(h->dense_ctas); cfg.blockDim = dim3(h->dense_threads); cfg.dynamicSmemBytes = h->dense_smem; cfg.stream = h->stream;
+    if (h->dense_grid) { at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1; }
+    else { at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->dense_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1; }
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (h->pdl_chain) { at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1; cfg.numAttrs = 2; }
+    CU(cudaLaunchKernelExC(&cfg, fn, args));
     h->launches++;
     return 0;
 }
@@ -806,6 +818,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
 
     // ---- explicit reduced camera system for small problems (dense_host.h): S in the shared memory of one thread-block
     //      cluster (8 or 16 CTAs) or, for a few hundred cameras, of the whole cooperative grid ----
+    h->pdl_chain = false;
     h->use_dense = false; h->dense_ctas = 0; h->dense_grid = false; h->dense_smem = 0; h->dense_pairs = 0;
     DenseLists dl; DenseShape dsh; std::vector<int> dense_entry_pt;
     {
@@ -837,6 +850,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             if (dsh.ctas && build_dense_lists(N, M, K, obs_cam, obs_pt, h->entry_of_obs.get(), dl)) {
                 h->use_dense = true; h->dense_ctas = dsh.ctas; h->dense_smem = dsh.smem; h->dense_pairs = (long long)dl.pairs.size();
                 h->dense_kind = dsh.kind; h->dense_threads = dsh.threads;
+                { const char* e = getenv("B200BA_PDL_CHAIN"); h->pdl_chain = e ? atoi(e) != 0 : true; }
                 dense_entry_pt.assign((size_t)std::max(Kp, 1), 0);
                 for (int jn = 0; jn < M; ++jn)
                     for (int sl = 0, e = slice_base[jn >> 5] + (jn & 31); sl < deg_new[jn]; ++sl, e += 32) dense_entry_pt[e] = sl == 0 ? ~jn : jn;
@@ -885,7 +899,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             h->dn_blk_chunk_beg.take(A, dl.blk_chunk_beg.size()); h->dn_blk_ik.take(A, dl.blk_ik.size()); h->dn_entry_pt.take(A, Kpp);
             h->dn_Wobs.take(A, 18 * Kpp); h->dn_Yobs.take(A, 18 * Kpp); h->dn_Tobs.take(A, 6 * Kpp);
             h->dn_chunk_part.take(A, 36 * (dl.chunks.size() + 1)); h->dn_chunk_rhs.take(A, 6 * (dl.chunks.size() + 1));
-            h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 256); h->dn_rz.take(A, 256);
+            h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 512); h->dn_rz.take(A, 512);
         }
         if (pass == 0) {
             A.cap = A.off;
@@ -1049,7 +1063,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         dn.pairs = h->dn_pairs.p; dn.chunks = h->dn_chunks.p; dn.blk_chunk_beg = h->dn_blk_chunk_beg.p; dn.blk_ik = h->dn_blk_ik.p; dn.entry_pt = h->dn_entry_pt.p;
         dn.Wobs = h->dn_Wobs.p; dn.Yobs = h->dn_Yobs.p; dn.Tobs = h->dn_Tobs.p; dn.chunk_part = h->dn_chunk_part.p; dn.chunk_rhs = h->dn_chunk_rhs.p;
         dn.S = h->dn_S.p; dn.zg = h->dn_zg.p; dn.pq_slots = h->dn_pq.p; dn.rz_slots = h->dn_rz.p;
-        dn.bar_counter = reinterpret_cast<unsigned int*>(h->dn_rz.p + 200);          // (the slot arrays hold at most 148 entries)
+        dn.bar_counter = reinterpret_cast<unsigned int*>(h->dn_rz.p + 400);          // (the slot arrays hold at most 148 entries)
         // (function attributes are per kernel, not per handle: set again for THIS problem's shape)
         CU(cudaFuncSetAttribute(dense_pcg_kernel(h->dense_kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
         if (!h->dense_grid && h->dense_ctas > 8) CU(cudaFuncSetAttribute(dense_pcg_kernel(h->dense_kind), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -319,6 +319,12 @@ constexpr int STAMP_STRIDE = 40;   // per CTA: [0] entry (globaltimer) [1] table
 // while its predecessor is still running; everything it does before pdl_wait() must not depend on the predecessor's output.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// First statement of every kernel of the small-problem LM iteration (options.reduced_system explicit plan): ~20 tiny kernels
+// that depend on each other, i.e. ~20 launch gaps per iteration.  Launched with the programmatic-stream-serialization
+// attribute, a kernel lets its successor be scheduled at once (the successor's blocks become resident and wait here) and then
+// waits until its predecessor has COMPLETED and flushed - the same ordering as plain stream order, minus the launch latency.
+// Without the attribute both instructions are no-ops.  Nothing may be read before this call (LMState included).
+__device__ __forceinline__ void pdl_chain_enter() { pdl_trigger(); pdl_wait(); }
 // SELL-32 addressing: first entry and (warp-uniform) trip count of point j
 __device__ __forceinline__ void slice_of(const Dev& d, int j, int& k0, int& deg)
 {
@@ -422,6 +428,7 @@ __device__ __forceinline__ void apply_Pt(const Obs& o, double y0, double y1, dou
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
 {
+    pdl_chain_enter();
     __shared__ double sm[PT_BLOCK / 32];
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
@@ -494,6 +501,7 @@ constexpr int LC_STAGE_BYTES = CG * (REC_BYTES + 512);           // CG row recor
 constexpr int LINCAM_SMEM = (CH_BLOCK / 32) * LC_NS * (LC_STAGE_BYTES + 8);
 __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 {
+    pdl_chain_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
@@ -594,6 +602,7 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 template <int NV, int OSTRIDE>
 __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_compute)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || (need_compute && !st->compute)) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x, u = t >> 2, q = t & 3;
@@ -617,6 +626,7 @@ __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_comput
 // mode 2 (statistics):    like 1 but runs regardless of st->done (mean reprojection error)
 __global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mode, int count = -1)
 {
+    pdl_chain_enter();
     __shared__ double sm[ONE_CTA / 32];
     const LMState* st = d.st;
     if ((mode != 2 && st->done) || (mode == 0 && !st->compute)) return;
@@ -649,6 +659,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_point_partials_reduce(Dev d, int mo
 //     loop inside the single-CTA kernel below (one thread per camera, ~70 strided memory operations each): 68 us of an LM iteration.
 __global__ void __launch_bounds__(256) k_lm_unpack(Dev d)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
     const int t = blockIdx.x * 256 + threadIdx.x;
@@ -665,6 +676,7 @@ __global__ void __launch_bounds__(256) k_lm_unpack(Dev d)
 // (b) single CTA: |J^t e|_inf, max diag U, lambda0
 __global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
 {
+    pdl_chain_enter();
     __shared__ double sm[ONE_CTA / 32];
     LMState* st = d.st;
     if (st->done) return;
@@ -705,6 +717,7 @@ __device__ __forceinline__ bool point_vinv_eval(const double V[6], double l, boo
 }
 __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
 {
+    pdl_chain_enter();
     LMState* st = d.st;
     if (st->done) return;
     int j = blockIdx.x * 256 + threadIdx.x;
@@ -804,6 +817,7 @@ __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
 //     14 us of a 213 us LM iteration at the demo sequence's size) and solves for ONE column of the inverse.
 __global__ void __launch_bounds__(192) k_precond_invert(Dev d, int precond)
 {
+    pdl_chain_enter();
     LMState* st = d.st;
     if (st->done) return;
     const int t = blockIdx.x * 192 + threadIdx.x, i = t / 6, c = t - 6 * i;
@@ -921,6 +935,7 @@ __device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double&
 template <int MODE>
 __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
 {
+    pdl_chain_enter();
     __shared__ double sm[PT_BLOCK / 32];
     const LMState* st = d.st;
     if (st->done) return;
@@ -1336,6 +1351,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_build_ptab(Dev d)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
     int i = blockIdx.x * 128 + threadIdx.x;
@@ -1865,6 +1881,7 @@ __device__ __forceinline__ void rot_to_quat(const double* s, double q[4])
 // compact [quaternion | T] table of camera set `which` (0 / 1 = rt[which]); one thread per camera
 __global__ void __launch_bounds__(128) k_build_qtab(Dev d, int trial)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || (trial && !st->solve_ok)) return;
     int i = blockIdx.x * 128 + threadIdx.x;
@@ -1878,6 +1895,7 @@ __global__ void __launch_bounds__(128) k_build_qtab(Dev d, int trial)
 // delta_c into the p-slots of the packed table (zero for constant cameras): the back-substitution sweep reads it there
 __global__ void __launch_bounds__(256) k_ptab_set_x(Dev d)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || !st->solve_ok) return;
     const int e = blockIdx.x * 256 + threadIdx.x;
@@ -1888,6 +1906,7 @@ __global__ void __launch_bounds__(256) k_ptab_set_x(Dev d)
 
 __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
 {
+    pdl_chain_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
@@ -2005,6 +2024,7 @@ constexpr int COST_RING_BYTES = (TABC_BLOCK / 32) * (COST_ROWS * COST_ROW_BYTES)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
 __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cost_tab(Dev d)
 {
+    pdl_chain_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
@@ -2100,6 +2120,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cost_tab(Dev d)
 //     observation (9 products); per-warp partials (cost, max |g_p|, max diag V) are reduced in a fixed order.
 __global__ void __launch_bounds__(TABC_BLOCK, 1) k_lin_tab(Dev d)
 {
+    pdl_chain_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
@@ -2325,6 +2346,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
 constexpr int FIN_BLOCK = 128;
 __global__ void __launch_bounds__(FIN_BLOCK) k_cg_finish(Dev d, double* __restrict__ part)
 {
+    pdl_chain_enter();
     __shared__ double sm[FIN_BLOCK / 32];
     const LMState* st = d.st;
     if (st->done) return;
@@ -2375,6 +2397,7 @@ __device__ __forceinline__ void camera_update_sums(const Dev& d, LMState* st)
 //     (v3d_optimization.cpp:879-978, v3d_optimization.h:49-50,60-64).
 __global__ void k_lm_decide(Dev d)
 {
+    pdl_chain_enter();
     LMState* st = d.st;
     if (st->done) return;
     if (st->solve_ok) camera_update_sums(d, st);
@@ -2409,6 +2432,7 @@ __global__ void k_lm_decide(Dev d)
 //      ones, clamped to [1e-10, 1e5].  PBA keeps these scalars in fp32; here they are fp64 (tolerance in the parity tests).
 __global__ void k_lm_decide_pba(Dev d)
 {
+    pdl_chain_enter();
     LMState* st = d.st;
     if (st->done) return;
     if (st->solve_ok) camera_update_sums(d, st);
