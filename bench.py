@@ -303,6 +303,7 @@ def main() -> int:
     if world > 1:
         eng.comm_setup_torch(rank, world, N)
     eng.set_problem_from(prob)
+    plan = eng.plan()
 
     def barrier():
         if world > 1:
@@ -440,7 +441,7 @@ def main() -> int:
            "ms_set_problem": r2.ms_h2d, "ms_solve_device": r2.ms_solve, "ms_solve_and_get_result_wall": e2e_solve_s * 1e3,
            "note": "caller-owned pageable host arrays (the reference's calling convention) -> b200ba_set_problem (marshal, layout, upload; "
                    "camera-order records built on the device) -> b200ba_solve -> b200ba_get_result; bytes amortised over the solve's LM "
-                   "iterations; best of two complete calls"}
+                   "iterations; three complete calls on fresh handles, the MEDIAN is reported, every wall time listed"}
 
     # ---------------- CPU baseline (rank 0, N = 1 only, bounded sample) ----------------
     cpu = None
@@ -524,7 +525,14 @@ def main() -> int:
                 "config": {"workload": f"{args.shape} shape: {N} cameras / {M} points / {K} observations, seed {args.seed}; "
                                        f"one step = full LM iteration (linearise + Schur-Jacobi preconditioner + {CG_STEPS}-step PCG + "
                                        f"back-substitution + trial cost + accept/reject)",
-                           "partition": f"by point over {world} rank(s)", "l2": "inputs larger than L2 (per-step working set >= 260 MB vs 126 MB L2)",
+                           "partition": f"by point over {world} rank(s)",
+                           "l2": ("inputs larger than L2 (per-step working set >= 260 MB vs 126 MB L2)" if K * 52 > 126e6 else
+                                  "inputs FIT L2 (tracker-sized problem, no flush between steps: this line is latency-bound, not an HBM measurement)"),
+                           "plan": {"reduced_system": ("explicit: S assembled per LM iteration, whole PCG loop in one kernel on "
+                                                       f"{plan['explicit_schur']} CTAs ({'one thread-block cluster' if plan['explicit_schur'] <= 16 else 'cooperative grid'}), "
+                                                       f"{plan['explicit_pairs']} observation pairs") if plan.get("explicit_schur") else "matrix-free (two sweeps + camera-side step per PCG step)",
+                                    "camera_table": plan["camera_table"], "cuda_graph": plan["cuda_graph"],
+                                    "launches_per_iteration": int(round(launches_per_iter))},
                            "lm_iterations_run": int(iters_total), "accepted_steps": int(accepted_total),
                            "note_accepts": "warm-up + every timed block; equal counts = every timed step was a full accepted LM iteration", "restart_every": BLOCK,
                            "timed": "b200ba_restart (device-to-device copies) + b200ba_iterate, CUDA events on the engine stream"},

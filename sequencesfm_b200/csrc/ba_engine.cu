@@ -236,17 +236,25 @@ void launch_point_tab(b200ba_handle* h)
 int enqueue_linearize(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d);
-    if (h->use_tab_backsub && h->quat_ok) {                      // table plan: by-point linearisation as a shared-memory-table sweep
-        LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 0);
+    const bool tabs = h->use_tab_backsub && h->quat_ok;
+    const bool fuse = h->use_dense;                               // explicit plan (single rank): fused small kernels, 20 -> 15 launches per iteration
+    const int lin_parts = tabs ? h->tab_grid * (TABC_BLOCK / 32) : d.n_pt_blocks;
+    LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d, (fuse && tabs) ? 1 : 0);
+    if (tabs) {                                                  // table plan: by-point linearisation as a shared-memory-table sweep
+        if (!fuse) LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 0);
         launch_chain(h, k_lin_tab, h->tab_grid, TABC_BLOCK, h->cost_smem, d);
     } else LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
     launch_chain(h, k_linearize_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, d);
-    LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27 * 4, 256), 256, d, d.ar_lin, 1);
-    LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, (h->use_tab_backsub && h->quat_ok) ? h->tab_grid * (TABC_BLOCK / 32) : -1);
-    if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
-    LAUNCH(k_lm_unpack, cdiv(36 * (long long)d.N, 256), 256, d);
-    LAUNCH(k_lm_prepare, 1, ONE_CTA, d);
+    if (fuse) {
+        LAUNCH(k_camera_reduce_unpack, cdiv((long long)d.N * 27 * 4, 256), 256, d);
+        LAUNCH(k_lm_prepare, 1, ONE_CTA, d, lin_parts);
+    } else {
+        LAUNCH((k_camera_reduce<27, PART_STRIDE>), cdiv((long long)d.N * 27 * 4, 256), 256, d, d.ar_lin, 1);
+        LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 0, tabs ? lin_parts : -1);
+        if (int rc = allreduce(h, d.ar_lin, (size_t)d.N * PART_STRIDE + 1 + 2 * h->world, 2)) return rc;
+        LAUNCH(k_lm_unpack, cdiv(36 * (long long)d.N, 256), 256, d);
+        LAUNCH(k_lm_prepare, 1, ONE_CTA, d, -1);
+    }
     if (h->use_f32) {                                            // fp32 copies for the mixed-precision PCG sweeps
         LAUNCH(k_f32_points, cdiv(d.M, 256), 256, d, 0);
         LAUNCH(k_f32_cameras, cdiv(d.N, 128), 128, d);
@@ -350,24 +358,29 @@ void enqueue_backsub(b200ba_handle* h)
 {
     Dev& d = h->d;
     if (h->use_tab_backsub && h->quat_ok) {
-        LAUNCH(k_ptab_set_x, cdiv(6 * (long long)d.N, 256), 256, d);
-        LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 1);
+        if (!h->use_dense) {                                     // (explicit plan: both written by k_cg_finish)
+            LAUNCH(k_ptab_set_x, cdiv(6 * (long long)d.N, 256), 256, d);
+            LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 1);
+        }
         launch_chain(h, k_backsub_tab, h->tab_grid, TABC_BLOCK, h->tab_smem, d);
         launch_chain(h, k_cost_tab, h->tab_grid, TABC_BLOCK, h->cost_smem, d);
-        LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, h->tab_grid * (TABC_BLOCK / 32));
+        if (!h->use_dense) LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, h->tab_grid * (TABC_BLOCK / 32));
     } else {
         LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
-        LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, -1);
+        if (!h->use_dense) LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, -1);
     }
 }
 
 int enqueue_step_and_decide(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_cg_finish, cdiv(d.N, FIN_BLOCK), FIN_BLOCK, d, h->fin_part.p);
+    const bool tabs = h->use_tab_backsub && h->quat_ok;
+    LAUNCH(k_cg_finish, cdiv(d.N, FIN_BLOCK), FIN_BLOCK, d, h->fin_part.p, (h->use_dense && tabs) ? 1 : 0);
     enqueue_backsub(h);
     if (int rc = allreduce(h, d.ar_dec, 4, 1)) return rc;
-    if (h->opt.lm_variant == 1) LAUNCH(k_lm_decide_pba, 1, 1, d); else LAUNCH(k_lm_decide, 1, 1, d);
+    const int dec_parts = h->use_dense ? (tabs ? h->tab_grid * (TABC_BLOCK / 32) : d.n_pt_blocks) : -1;
+    const int dec_threads = h->use_dense ? ONE_CTA : 1;
+    if (h->opt.lm_variant == 1) LAUNCH(k_lm_decide_pba, 1, dec_threads, d, dec_parts); else LAUNCH(k_lm_decide, 1, dec_threads, d, dec_parts);
     return 0;
 }
 
@@ -733,10 +746,47 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->pba_depth_scale = (1.0 / med) / 0.5;
     }
     lap("validate + measurements");
+    h->pdl_chain = false;
+    h->use_dense = false; h->dense_ctas = 0; h->dense_grid = false; h->dense_smem = 0; h->dense_pairs = 0;
+    DenseLists dl; DenseShape dsh; std::vector<int> dense_entry_pt;
+    int smem_optin = 0, n_sm = 0;
+    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    h->num_sms = n_sm;
+    {
+        int mode = o.reduced_system;
+        if (const char* e = getenv("B200BA_DENSE")) mode = atoi(e) ? 2 : 1;
+        int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+        if (mode != 1 && h->world <= 1 && !o.pcg_fp32 && K > 0) {
+            const int cand_kind[4] = {0, 1, 1, 2}, cand_ctas[4] = {8, 8, 16, coop ? n_sm : 0};
+            for (int c = 0; c < 4 && !dsh.ctas; ++c) {
+                if (cand_ctas[c] <= 0) continue;
+                const DenseShape t = dense_shape(N, cand_kind[c], cand_ctas[c]);
+                if (t.kind < 0 || t.smem + 1024 > (size_t)smem_optin) continue;
+                const void* fn = dense_pcg_kernel(t.kind);
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess) { cudaGetLastError(); continue; }
+                if (t.kind != 2) {                                      // can one such cluster be resident?
+                    cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
+                    cfg.gridDim = dim3(t.ctas); cfg.blockDim = dim3(t.threads); cfg.dynamicSmemBytes = t.smem;
+                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = t.ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    int nclusters = 0;
+                    if ((t.ctas > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+                        cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+                } else {
+                    int per_sm = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, t.threads, t.smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); continue; }
+                }
+                dsh = t; h->dense_grid = t.kind == 2;
+            }
+        }
+    }
     // ---- by-point layout: SELL-32, points sorted by track length (descending, stable), quarter-warps grouped and slots
     //      assigned for conflict-free reads of the shared-memory camera table (layout_host.h) ----
     PointLayout lay;
-    build_point_layout(M, K, obs_cam, obs_pt, getenv("B200BA_NO_LANE_OPT") ? 0 : o.lane_window, T, lay);
+    // (the conflict-free grouping serves the shared-memory-table PCG sweep of the matrix-free plan; a problem that will run the
+    //  explicit plan skips it: 0.9 of the 1.8 ms of b200ba_set_problem at the demo sequence's size)
+    build_point_layout(M, K, obs_cam, obs_pt, (getenv("B200BA_NO_LANE_OPT") || dsh.ctas) ? 0 : o.lane_window, T, lay);
     h->orig_of_new.swap(lay.orig_of_new);
     const std::vector<int>& pstart = lay.pstart;
     const std::vector<int>& deg_new = lay.deg_new;
@@ -761,10 +811,6 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     double2* o_meas_p = reinterpret_cast<double2*>(stage.p);
     int* o_cam_p = reinterpret_cast<int*>(stage.p + stage_meas);
     h->entry_of_obs.reset(new int[(size_t)std::max(K, 1)]);
-    int smem_optin = 0, n_sm = 0;
-    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
-    h->num_sms = n_sm;
     // camera order.  The host only COUNTS (per-camera histogram -> rows, first sorted position, segments); the row records
     // themselves are built on the device from the uploaded point-order arrays (radix sort by (camera, point), see k_rows_*):
     // every camera's run is padded to whole ROWS of 32 observations (point index -1 = padding); see REC_* in ba_kernels.cuh.
@@ -818,46 +864,16 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
 
     // ---- explicit reduced camera system for small problems (dense_host.h): S in the shared memory of one thread-block
     //      cluster (8 or 16 CTAs) or, for a few hundred cameras, of the whole cooperative grid ----
-    h->pdl_chain = false;
-    h->use_dense = false; h->dense_ctas = 0; h->dense_grid = false; h->dense_smem = 0; h->dense_pairs = 0;
-    DenseLists dl; DenseShape dsh; std::vector<int> dense_entry_pt;
-    {
-        int mode = o.reduced_system;
-        if (const char* e = getenv("B200BA_DENSE")) mode = atoi(e) ? 2 : 1;
-        int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-        if (mode != 1 && h->world <= 1 && !o.pcg_fp32 && K > 0) {
-            const int cand_kind[4] = {0, 1, 1, 2}, cand_ctas[4] = {8, 8, 16, coop ? n_sm : 0};
-            for (int c = 0; c < 4 && !dsh.ctas; ++c) {
-                if (cand_ctas[c] <= 0) continue;
-                const DenseShape t = dense_shape(N, cand_kind[c], cand_ctas[c]);
-                if (t.kind < 0 || t.smem + 1024 > (size_t)smem_optin) continue;
-                const void* fn = dense_pcg_kernel(t.kind);
-                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess) { cudaGetLastError(); continue; }
-                if (t.kind != 2) {                                      // can one such cluster be resident?
-                    cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
-                    cfg.gridDim = dim3(t.ctas); cfg.blockDim = dim3(t.threads); cfg.dynamicSmemBytes = t.smem;
-                    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = t.ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                    cfg.attrs = at; cfg.numAttrs = 1;
-                    int nclusters = 0;
-                    if ((t.ctas > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
-                        cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
-                } else {
-                    int per_sm = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, t.threads, t.smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); continue; }
-                }
-                dsh = t; h->dense_grid = t.kind == 2;
-            }
-            if (dsh.ctas && build_dense_lists(N, M, K, obs_cam, obs_pt, h->entry_of_obs.get(), dl)) {
-                h->use_dense = true; h->dense_ctas = dsh.ctas; h->dense_smem = dsh.smem; h->dense_pairs = (long long)dl.pairs.size();
-                h->dense_kind = dsh.kind; h->dense_threads = dsh.threads;
-                { const char* e = getenv("B200BA_PDL_CHAIN"); h->pdl_chain = e ? atoi(e) != 0 : true; }
-                dense_entry_pt.assign((size_t)std::max(Kp, 1), 0);
-                for (int jn = 0; jn < M; ++jn)
-                    for (int sl = 0, e = slice_base[jn >> 5] + (jn & 31); sl < deg_new[jn]; ++sl, e += 32) dense_entry_pt[e] = sl == 0 ? ~jn : jn;
-            }
-        }
-        lap("explicit reduced system: pair lists");
+    //      (the kernel shape was chosen above, before the layout; here the pair lists, which need the SELL entry of every observation)
+    if (dsh.ctas && build_dense_lists(N, M, K, obs_cam, obs_pt, h->entry_of_obs.get(), dl)) {
+        h->use_dense = true; h->dense_ctas = dsh.ctas; h->dense_smem = dsh.smem; h->dense_pairs = (long long)dl.pairs.size();
+        h->dense_kind = dsh.kind; h->dense_threads = dsh.threads;
+        { const char* e = getenv("B200BA_PDL_CHAIN"); h->pdl_chain = e ? atoi(e) != 0 : true; }
+        dense_entry_pt.assign((size_t)std::max(Kp, 1), 0);
+        for (int jn = 0; jn < M; ++jn)
+            for (int sl = 0, e = slice_base[jn >> 5] + (jn & 31); sl < deg_new[jn]; ++sl, e += 32) dense_entry_pt[e] = sl == 0 ? ~jn : jn;
     }
+    lap("explicit reduced system: pair lists");
 
     // ---- device allocation ----
     size_t n6 = 6 * (size_t)N;

@@ -620,6 +620,36 @@ __global__ void k_camera_reduce(Dev d, double* __restrict__ out, int need_comput
     if (i < d.N && q == 0) out[(size_t)i * OSTRIDE + c] = s;
 }
 
+// single-rank form of k_camera_reduce<27, PART_STRIDE> + k_lm_unpack: the reduced [21 unique | 6] record goes straight into U and g_c
+__global__ void k_camera_reduce_unpack(Dev d)
+{
+    pdl_chain_enter();
+    const LMState* st = d.st;
+    if (st->done || !st->compute) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, u = t >> 2, q = t & 3;
+    const int i = u / 27, c = u - i * 27;
+    double s0 = 0, s1 = 0;
+    if (i < d.N) {
+        const int b = d.cam_seg_beg[i], e = d.cam_seg_beg[i + 1];
+        int sg = b + q;
+        for (; sg + 4 < e; sg += 8) { s0 += d.seg_part[PART_STRIDE * (size_t)sg + c]; s1 += d.seg_part[PART_STRIDE * (size_t)(sg + 4) + c]; }
+        if (sg < e) s0 += d.seg_part[PART_STRIDE * (size_t)sg + c];
+    }
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (i < d.N && q == 0) {
+        if (c >= 21) d.gc[6 * (size_t)i + (c - 21)] = s;
+        else {
+            int a = 0, rem = c;                                    // (a, b) of index c in the row-wise upper triangle
+            while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+            const int bb = a + rem;
+            d.U[36 * (size_t)i + 6 * a + bb] = s; d.U[36 * (size_t)i + 6 * bb + a] = s;
+            if (st->variant == 1 && st->first && a == bb) d.cam_D0[6 * (size_t)i + a] = s;
+        }
+    }
+}
+
 // reduce the per-block partials of a thread-per-point kernel in a fixed order (single CTA).
 // mode 0 (linearisation): out = ar_lin tail  [cost | ginf slot(rank) | vmax slot(rank)]
 // mode 1 (decision):      out = ar_dec       [d2p, denomp, new_cost]
@@ -674,12 +704,21 @@ __global__ void __launch_bounds__(256) k_lm_unpack(Dev d)
     if (st->variant == 1 && st->first && a == b) d.cam_D0[6 * (size_t)i + a] = v;   // PrepareJacobianNormalization (SparseBundleCPU.cpp:2900-2918)
 }
 // (b) single CTA: |J^t e|_inf, max diag U, lambda0
-__global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d)
+// fuse_count >= 0 (single rank): the block partials of the by-point linearisation (cost, max |g_p|, max diag V) are reduced
+// here instead of by a k_point_partials_reduce launch
+__global__ void __launch_bounds__(ONE_CTA) k_lm_prepare(Dev d, int fuse_count)
 {
     pdl_chain_enter();
     __shared__ double sm[ONE_CTA / 32];
     LMState* st = d.st;
     if (st->done) return;
+    if (st->compute && fuse_count >= 0) {
+        double a = 0, b = 0.0, c = -1e30;
+        for (int i = threadIdx.x; i < fuse_count; i += ONE_CTA) { const double* p = d.pt_part + 4 * (size_t)i; a += p[0]; b = fmax(b, p[1]); c = fmax(c, p[2]); }
+        a = block_sum<ONE_CTA>(a, sm); b = block_max<ONE_CTA>(b, sm); c = block_max<ONE_CTA>(c, sm);
+        if (threadIdx.x == 0) { double* o = d.ar_lin + (size_t)d.N * PART_STRIDE; o[0] = a; o[1] = b; o[2] = c; }   // world = 1: [cost | ginf | vmax]
+        __syncthreads();
+    }
     if (st->compute) {
         double gmax = 0, umax = -1e30;
         for (int e = threadIdx.x; e < 6 * d.N; e += ONE_CTA) {
@@ -1349,7 +1388,10 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
 // copies (cp.async.bulk, one mbarrier), read with 7 LDS.128 per observation.  k_build_ptab converts R -> quaternion
 // once per linearisation; the CG kernels keep the p-part current.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_build_ptab(Dev d)
+__host__ __device__ __forceinline__ int qtab_unit(int c, int f);
+// also_qtab: the compact [quaternion | T] table of the same cameras in the same launch (k_build_qtab(d, 0); its only reader,
+// k_lin_tab, runs under the same `compute` flag)
+__global__ void __launch_bounds__(128) k_build_ptab(Dev d, int also_qtab)
 {
     pdl_chain_enter();
     const LMState* st = d.st;
@@ -1366,6 +1408,11 @@ __global__ void __launch_bounds__(128) k_build_ptab(Dev d)
     double n = 1.0 / sqrt(w * w + x * x + y * y + z * z);
     double* o = d.ptab + (size_t)i * TAB_STRIDE;
     o[0] = w * n; o[1] = x * n; o[2] = y * n; o[3] = z * n; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
+    if (also_qtab) {
+        double2* t = reinterpret_cast<double2*>(d.qtab);
+        t[qtab_unit(i, 0)] = make_double2(w * n, x * n); t[qtab_unit(i, 1)] = make_double2(y * n, z * n);
+        t[qtab_unit(i, 2)] = make_double2(s[3], s[7]); t[qtab_unit(i, 3)] = make_double2(s[11], 0.0);
+    }
 }
 
 // one warp per point-order row: camera indices into the row record (the weights are written by the linearisation)
@@ -1865,7 +1912,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
 // ------------------------------------------------------------------------------------------------------
 constexpr int QTAB_STRIDE = 8;                                   // doubles per camera of the compact table: quaternion 4, T 3, pad
 // physical 16-byte unit of logical field f (0: qw qx, 1: qy qz, 2: T0 T1, 3: T2 pad) of camera c
-__host__ __device__ __forceinline__ int qtab_unit(int c, int f) { return 4 * c + (f ^ ((c >> 1) & 3)); }
+__host__ __device__ __forceinline__ int qtab_unit(int c, int f) { return 4 * c + (f ^ ((c >> 1) & 3)); }   // (declared above k_build_ptab)
 // R (row-major 3x3 at stride 4 of an [R|T] record) -> unit quaternion; the conversion of k_build_ptab
 __device__ __forceinline__ void rot_to_quat(const double* s, double q[4])
 {
@@ -2344,7 +2391,10 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
 // K12 cg_finish: delta_c = x; trial cameras T += dt, R <- Rodrigues(dw) R (v3d_metricbundle.cpp:17-39,
 //     v3d_mathutilities.h:173-194); camera part of |delta|^2 and delta . J^t e.
 constexpr int FIN_BLOCK = 128;
-__global__ void __launch_bounds__(FIN_BLOCK) k_cg_finish(Dev d, double* __restrict__ part)
+// fuse_tabs: also delta_c into the p-slots of the packed table (k_ptab_set_x) and the compact table of the TRIAL cameras
+// (k_build_qtab(d, 1)) - three launches in one for the explicit plan
+__device__ __forceinline__ void rot_to_quat(const double* s, double q[4]);
+__global__ void __launch_bounds__(FIN_BLOCK) k_cg_finish(Dev d, double* __restrict__ part, int fuse_tabs)
 {
     pdl_chain_enter();
     __shared__ double sm[FIN_BLOCK / 32];
@@ -2374,9 +2424,18 @@ __global__ void __launch_bounds__(FIN_BLOCK) k_cg_finish(Dev d, double* __restri
             double c1 = sin(th) / th, c2 = (1.0 - cos(th)) / (th * th);
             for (int a = 0; a < 9; ++a) dR[a] += c1 * J[a] + c2 * J2[a];
         }
+        double Rt[12];
         for (int r = 0; r < 3; ++r) {
-            for (int c = 0; c < 3; ++c) o[4 * r + c] = dR[3 * r] * R[c] + dR[3 * r + 1] * R[3 + c] + dR[3 * r + 2] * R[6 + c];
-            o[4 * r + 3] = T[r];
+            for (int c = 0; c < 3; ++c) Rt[4 * r + c] = dR[3 * r] * R[c] + dR[3 * r + 1] * R[3 + c] + dR[3 * r + 2] * R[6 + c];
+            Rt[4 * r + 3] = T[r];
+        }
+        for (int a = 0; a < 12; ++a) o[a] = Rt[a];
+        if (fuse_tabs) {
+            for (int a = 0; a < 6; ++a) d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = x[a];          // (already zero for constant cameras)
+            double q[4]; rot_to_quat(Rt, q);
+            double2* t = reinterpret_cast<double2*>(d.qtab);
+            t[qtab_unit(i, 0)] = make_double2(q[0], q[1]); t[qtab_unit(i, 1)] = make_double2(q[2], q[3]);
+            t[qtab_unit(i, 2)] = make_double2(Rt[3], Rt[7]); t[qtab_unit(i, 3)] = make_double2(Rt[11], 0.0);
         }
     }
     d2 = block_sum<FIN_BLOCK>(d2, sm);
@@ -2395,11 +2454,22 @@ __device__ __forceinline__ void camera_update_sums(const Dev& d, LMState* st)
 
 // K13 lm_decide (one thread): update stop test, gain ratio, accept/reject, damping update
 //     (v3d_optimization.cpp:879-978, v3d_optimization.h:49-50,60-64).
-__global__ void k_lm_decide(Dev d)
+// fuse_count >= 0 (single rank, launched with ONE_CTA threads): the per-warp partials of the back-substitution / trial-cost
+// sweeps (|delta_p|^2, delta_p . g_p, trial cost, |J delta|^2) are reduced here instead of by a k_point_partials_reduce launch
+__device__ __forceinline__ void decide_reduce(const Dev& d, int fuse_count, double* sm)
+{
+    double a = 0, b = 0, c = 0, e4 = 0;
+    for (int i = threadIdx.x; i < fuse_count; i += ONE_CTA) { const double* p = d.pt_part + 4 * (size_t)i; a += p[0]; b += p[1]; c += p[2]; e4 += p[3]; }
+    a = block_sum<ONE_CTA>(a, sm); b = block_sum<ONE_CTA>(b, sm); c = block_sum<ONE_CTA>(c, sm); e4 = block_sum<ONE_CTA>(e4, sm);
+    if (threadIdx.x == 0) { d.ar_dec[0] = a; d.ar_dec[1] = b; d.ar_dec[2] = c; d.ar_dec[3] = e4; }
+}
+__global__ void k_lm_decide(Dev d, int fuse_count)
 {
     pdl_chain_enter();
+    __shared__ double sm[ONE_CTA / 32];
     LMState* st = d.st;
     if (st->done) return;
+    if (fuse_count >= 0) { decide_reduce(d, fuse_count, sm); if (threadIdx.x != 0) return; }
     if (st->solve_ok) camera_update_sums(d, st);
     int it = st->iter;
     double* tr = (d.trace && st->n_trace < st->trace_cap) ? d.trace + TRACE_COLS * (size_t)st->n_trace : nullptr;
@@ -2430,11 +2500,13 @@ __global__ void k_lm_decide(Dev d)
 //      __accurate_gain_ratio; a non-positive denominator is replaced by 0.001 x reduction); quit when the mean squared error
 //      is <= 0.25 px^2 ('M'); damping *= max(1/3, 1 - (2 rho - 1)^3) after an accepted step and *= 2, 4, 8, ... after rejected
 //      ones, clamped to [1e-10, 1e5].  PBA keeps these scalars in fp32; here they are fp64 (tolerance in the parity tests).
-__global__ void k_lm_decide_pba(Dev d)
+__global__ void k_lm_decide_pba(Dev d, int fuse_count)
 {
     pdl_chain_enter();
+    __shared__ double sm[ONE_CTA / 32];
     LMState* st = d.st;
     if (st->done) return;
+    if (fuse_count >= 0) { decide_reduce(d, fuse_count, sm); if (threadIdx.x != 0) return; }
     if (st->solve_ok) camera_update_sums(d, st);
     const int it = st->iter;
     double* tr = (d.trace && st->n_trace < st->trace_cap) ? d.trace + TRACE_COLS * (size_t)st->n_trace : nullptr;
