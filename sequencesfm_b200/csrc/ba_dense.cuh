@@ -21,6 +21,7 @@
 namespace b200ba {
 
 constexpr int DPAIR_BLOCK = 288;            // 8 chunks x 36 entries
+constexpr int DENSE_OBS_STRIDE = 24;        // doubles per observation block: 6 rows x [3 values | pad]
 
 // one thread per SELL entry (a thread per point would walk a 49-observation track serially: 31 us at the demo sequence's size)
 __global__ void __launch_bounds__(256) k_dense_wobs(Dev d, int n_entries)
@@ -55,8 +56,8 @@ __global__ void __launch_bounds__(256) k_dense_wobs(Dev d, int n_entries)
     double A0[6], A1[6], B0[3], B1[3];
     jac_rows_A(o, A0, A1); jac_rows_B(o, cm, B0, B1);
     const double live = i < d.first_free ? 0.0 : 1.0;           // constant camera: its W block is zero
-    double2* Wo = reinterpret_cast<double2*>(d.dn.Wobs + 18 * (size_t)k);
-    double2* Yo = reinterpret_cast<double2*>(d.dn.Yobs + 18 * (size_t)k);
+    double* Wo = d.dn.Wobs + DENSE_OBS_STRIDE * (size_t)k;         // 6 rows of [3 values | pad]: one 32-byte sector per row
+    double* Yo = d.dn.Yobs + DENSE_OBS_STRIDE * (size_t)k;
     double2* To = reinterpret_cast<double2*>(d.dn.Tobs + 6 * (size_t)k);
     double w[18], y[18], t[6];
 #pragma unroll
@@ -69,7 +70,10 @@ __global__ void __launch_bounds__(256) k_dense_wobs(Dev d, int n_entries)
         t[a] = w0 * vg0 + w1 * vg1 + w2 * vg2;
     }
 #pragma unroll
-    for (int q = 0; q < 9; ++q) { Wo[q] = make_double2(w[2 * q], w[2 * q + 1]); Yo[q] = make_double2(y[2 * q], y[2 * q + 1]); }
+    for (int a = 0; a < 6; ++a) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(Wo + 4 * a), "d"(w[3 * a]), "d"(w[3 * a + 1]), "d"(w[3 * a + 2]), "d"(0.0) : "memory");
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(Yo + 4 * a), "d"(y[3 * a]), "d"(y[3 * a + 1]), "d"(y[3 * a + 2]), "d"(0.0) : "memory");
+    }
 #pragma unroll
     for (int q = 0; q < 3; ++q) To[q] = make_double2(t[2 * q], t[2 * q + 1]);
 }
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(DPAIR_BLOCK) k_dense_pairs(Dev d)
     const int a = e / 6, b = e - 6 * a, cnt = ch.z - ch.y;
     const bool diag = ch.w != 0;
     if (diag && b < a) return;                                    // diagonal blocks: upper triangle, mirrored by the finalising kernel
-    const double* Y = d.dn.Yobs + 3 * a; const double* W = d.dn.Wobs + 3 * b;
+    const double* Y = d.dn.Yobs + 4 * a; const double* W = d.dn.Wobs + 4 * b;
     const bool want_rhs = diag && a == 0;
     double acc = 0, rhs = 0;
     for (int q0 = 0; q0 < cnt; q0 += 8) {
@@ -108,8 +112,9 @@ __global__ void __launch_bounds__(DPAIR_BLOCK) k_dense_pairs(Dev d)
         for (int u = 0; u < 8; ++u) {
             const bool on = q0 + u < cnt;
             const int2 pr = on ? spair[cl][q0 + u] : make_int2(0, 0);
-            const double* yp = Y + 18 * (size_t)pr.x; const double* wp = W + 18 * (size_t)pr.y;
-            pr_[u] = on ? (yp[0] * wp[0] + yp[1] * wp[1]) + yp[2] * wp[2] : 0.0;
+            double yv[3], wv[3];                                  // one 256-bit load per operand row (rows are 32-byte records)
+            load3p_256(Y + DENSE_OBS_STRIDE * (size_t)pr.x, 0, yv); load3p_256(W + DENSE_OBS_STRIDE * (size_t)pr.y, 0, wv);
+            pr_[u] = on ? (yv[0] * wv[0] + yv[1] * wv[1]) + yv[2] * wv[2] : 0.0;
             tt[u] = (want_rhs && on && pr.x == pr.y) ? d.dn.Tobs[6 * (size_t)pr.x + b] : 0.0;
         }
 #pragma unroll

@@ -913,7 +913,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (h->use_dense) {
             h->dn_pairs.take(A, dl.pairs.size() + 1); h->dn_chunks.take(A, dl.chunks.size() + 1);
             h->dn_blk_chunk_beg.take(A, dl.blk_chunk_beg.size()); h->dn_blk_ik.take(A, dl.blk_ik.size()); h->dn_entry_pt.take(A, Kpp);
-            h->dn_Wobs.take(A, 18 * Kpp); h->dn_Yobs.take(A, 18 * Kpp); h->dn_Tobs.take(A, 6 * Kpp);
+            h->dn_Wobs.take(A, DENSE_OBS_STRIDE * Kpp); h->dn_Yobs.take(A, DENSE_OBS_STRIDE * Kpp); h->dn_Tobs.take(A, 6 * Kpp);
             h->dn_chunk_part.take(A, 36 * (dl.chunks.size() + 1)); h->dn_chunk_rhs.take(A, 6 * (dl.chunks.size() + 1));
             h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 512); h->dn_rz.take(A, 512);
         }

@@ -135,7 +135,7 @@ struct DenseDev {
     int on, rows, ld, n_chunks, n_blocks, pad;
     const int2* pairs; const int4* chunks; const int* blk_chunk_beg; const int* blk_ik;
     const int* entry_pt;                  // SELL entry -> point (new order)
-    double *Wobs, *Yobs, *Tobs;           // per SELL entry: W (6x3), W (V + damping)^-1 (6x3), W (V + damping)^-1 g_p (6)
+    double *Wobs, *Yobs, *Tobs;           // per SELL entry: W, W (V + damping)^-1 (6 rows of [3 | pad] = 24 doubles each), W (V + damping)^-1 g_p (6)
     double *chunk_part, *chunk_rhs;       // per chunk of pairs: 36 + 6 partial sums
     double* S;                            // 6N x 6N, both triangles
     double *zg, *pq_slots, *rz_slots;     // exchange buffers of the grid-wide variant of k_dense_pcg
