@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """SASS opcode histogram of the kernels of sequencesfm_b200/libb200ba.so -> profiles/sass_<name>_summary.json.
 Shows which async-copy / barrier / wide-load instructions each hot kernel really contains (UBLKCP = TMA bulk copy, LDGSTS =
-cp.async, SYNCS = mbarrier, LDG.E.*.256, UBLKPF = bulk L2 prefetch) and its FP64 instruction count.  Usage: tools/sass_summary.py <name>"""
+cp.async, SYNCS = mbarrier, LDG.E.*.256, UBLKPF = bulk L2 prefetch, STAS = st.async into a cluster peer's shared memory,
+UCGABAR = barrier.cluster, PREEXIT / ACQBULK = griddepcontrol.launch_dependents / .wait) and its FP64 instruction count.  Usage: tools/sass_summary.py <name>"""
 import collections, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 name = sys.argv[1] if len(sys.argv) > 1 else "r2"
@@ -25,7 +26,9 @@ for fn, c in res.items():
     summ[fn] = {"instructions": sum(c.values()), "fp64": sum(n for op, n in grp.items() if op in ("DFMA", "DMUL", "DADD", "DSETP", "MUFU")),
                 "tma_bulk_copy_UBLKCP": grp.get("UBLKCP", 0), "bulk_prefetch_UBLKPF": grp.get("UBLKPF", 0), "cp_async_LDGSTS": grp.get("LDGSTS", 0),
                 "mbarrier_SYNCS": grp.get("SYNCS", 0), "LDG_256": sum(n for op, n in c.items() if op.startswith("LDG") and ".256" in op),
-                "STG_256": sum(n for op, n in c.items() if op.startswith("STG") and ".256" in op), "LDS": grp.get("LDS", 0), "atomics_ATOM_RED": grp.get("ATOM", 0) + grp.get("ATOMG", 0) + grp.get("RED", 0) + grp.get("ATOMS", 0),
+                "STG_256": sum(n for op, n in c.items() if op.startswith("STG") and ".256" in op), "LDS": grp.get("LDS", 0),
+                "st_async_STAS": grp.get("STAS", 0), "cluster_barrier_UCGABAR": grp.get("UCGABAR_ARV", 0) + grp.get("UCGABAR_WAIT", 0),
+                "griddepcontrol_PREEXIT_ACQBULK": grp.get("PREEXIT", 0) + grp.get("ACQBULK", 0), "atomics_ATOM_RED": grp.get("ATOM", 0) + grp.get("ATOMG", 0) + grp.get("RED", 0) + grp.get("ATOMS", 0),
                 "top_opcodes": dict(grp.most_common(10))}
 json.dump(summ, open(os.path.join(ROOT, "profiles", f"sass_{name}_summary.json"), "w"), indent=1)
 for fn in ("k_cg_point_pass_tabc", "k_cg_camera_pass", "k_cg_camera_step", "k_lin_tab", "k_backsub_tab", "k_cost_tab", "k_linearize_cameras"):
