@@ -151,7 +151,7 @@ struct b200ba_handle {
     int Kp = 0;                                      // padded SELL entries
     int num_sms = 148, tab_grid = 0, step_grid = 0, cam_grid = 0;
     size_t tab_smem = 0;
-    bool use_tab = false, use_coop = false, use_graph = false;
+    bool use_tab = false, use_coop = false, use_graph = false, fuse_step = false;
     int tab_ilp = 1, tab_block = TAB_BLOCK;          // rows of a slice in flight per trip of the shared-memory-table sweep (1 or 2)
     cudaGraphExec_t graph_exec = nullptr;
     long long launches_per_graph = 0;
@@ -344,6 +344,13 @@ int enqueue_cg_step(b200ba_handle* h)
     }
     if (h->use_tab) launch_point_tab(h);
     else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    if (h->fuse_step) {                                          // single rank: by-camera sweep + camera-side step in one cooperative launch
+        double* ppq = h->part_pq.p; double* prz = h->part_rz.p; int sb = h->step_grid;
+        void* args[] = {(void*)&d, (void*)&ppq, (void*)&prz, (void*)&sb};
+        CU(cudaLaunchCooperativeKernel((const void*)k_cg_camera_pass_step, dim3(h->cam_grid), dim3(CW * 32), args, CAMPASS_SMEM, h->stream));
+        h->launches++;
+        return 0;
+    }
     if (int rc = enqueue_camera_half(h, 0)) return rc;
     if (h->use_coop && h->world <= 1) return launch_camera_step(h, 0);
     if (h->use_coop && h->p2p_ready && h->step_grid <= P2P_MAX_BLOCKS) return launch_camera_step(h, 2);   // all-reduce fused into the step kernel (NVLink peer memory)
@@ -1047,6 +1054,19 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_camera_step, STEP_BLOCK, 0);
         h->use_coop = coop && (long long)per_sm * h->num_sms >= h->step_grid && getenv("B200BA_NO_COOP") == nullptr;
+    }
+    {   // by-camera sweep + camera-side step in one cooperative launch: B200BA_FUSE_STEP=1.  Measured at Venice shape with the
+        // counting barrier (1.3 us) in place of grid.sync(): 5.57 vs 5.48 ms per LM iteration - 148 CTAs x 512 threads go through
+        // three barriers for a step that 56 blocks of 192 threads do in two, and the cooperative launch costs more than the
+        // kernel boundary it removes.  Off by default.
+        const char* e = getenv("B200BA_FUSE_STEP");
+        int per_sm = 0;
+        h->fuse_step = false;
+        if (h->use_coop && h->world <= 1 && !h->use_f32 && h->step_grid <= h->cam_grid && (e ? atoi(e) != 0 : false) &&
+            cudaFuncSetAttribute(k_cg_camera_pass_step, cudaFuncAttributeMaxDynamicSharedMemorySize, CAMPASS_SMEM) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_camera_pass_step, CW * 32, CAMPASS_SMEM) == cudaSuccess &&
+            (long long)per_sm * h->num_sms >= h->cam_grid) h->fuse_step = true;
+        else cudaGetLastError();
     }
     // NCCL collectives are enqueued eagerly (outside any capture); with the peer windows mapped the multi-rank iteration
     // contains no host-side collective and is captured like the single-rank one

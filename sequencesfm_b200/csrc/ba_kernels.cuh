@@ -1091,13 +1091,9 @@ __device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in
     acc[4] += r2 * h0 - r0 * h2;
     acc[5] += r0 * h1 - r1 * h0;
 }
-__global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pass)
+// the sweep of one warp over its row range (returns early for warps without rows: no CTA-wide barrier inside)
+__device__ __forceinline__ void camera_pass_sweep(const Dev& d, const LMState* st, unsigned char* smem_raw)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const LMState* st = d.st;
-    pdl_wait();                                                   // (programmatic dependent launch: v and the control words come from the by-point sweep)
-    if (st->done) return;
-    if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef B200BA_STAMPS
     unsigned long long* stp = d.stamps + (size_t)(256 + blockIdx.x) * STAMP_STRIDE;
@@ -1198,6 +1194,15 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
         }
     }
     if (seg >= 0) seg_flush<6>(d, seg, acc, lane);
+}
+__global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pass)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const LMState* st = d.st;
+    pdl_wait();                                                   // (programmatic dependent launch: v and the control words come from the by-point sweep)
+    if (st->done) return;
+    if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
+    camera_pass_sweep(d, st, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -2304,14 +2309,20 @@ __device__ __forceinline__ void step_barrier(unsigned long long* ctr, unsigned l
     __syncthreads();
 }
 // phases of the camera-side step (after the by-camera partial sums exist); every thread of the grid must call it
+// NT = threads per block; FUSED: called at the end of the by-camera sweep (k_cg_camera_pass_step, NT = 512, only the first
+// STEP_BLOCK threads of the first step_blocks blocks own elements): one more barrier up front ("every segment partial of the
+// sweep is visible") replaces the kernel boundary, and the loads that do not depend on the sweep are in flight while it waits.
+template <int NT, bool FUSED>
 __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
                                                    double* part_pq, double* part_rz, int step_blocks, double* sv, double* sm,
                                                    double lam, double rz, double rz0, double tol, int steps)
 {
     LMState* st = d.st;
-    const unsigned long long gen = __ldcg(d.step_bar + 1), bar_base = 2ull * gen * gridDim.x;   // read by every block before it arrives at the first barrier
+    unsigned long long* const bar = d.step_bar + (FUSED ? 2 : 0);                                // [arrivals, launches completed] of this kernel
+    constexpr unsigned long long NBAR = FUSED ? 3ull : 2ull;
+    const unsigned long long gen = __ldcg(bar + 1), bar_base = NBAR * gen * gridDim.x;           // read by every block before it arrives at the first barrier
     const int e = blockIdx.x * STEP_BLOCK + threadIdx.x, n6 = 6 * d.N;
-    const bool on = e < n6;
+    const bool on = threadIdx.x < STEP_BLOCK && (int)blockIdx.x < step_blocks && e < n6;
     const int i = e / 6, a = e - 6 * i, lc = threadIdx.x - a;    // lc: first thread of this camera inside the block
     // Every load whose address does not depend on this step's scalars is issued up front (U row, M^-1 row, x, r, segment
     // range): the kernel is a chain of dependent L2 round trips with almost no parallelism, so overlapping them is what counts.
@@ -2325,12 +2336,13 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
         for (int c = 0; c < 6; ++c) { urow[c] = ur[c]; mrow[c] = mr[c]; }
         if (st->variant == 1) dmul = ur[a];                      // PBA: lambda diag(U) p instead of lambda p
     }
-    sv[threadIdx.x] = pe;
+    if (threadIdx.x < STEP_BLOCK) sv[threadIdx.x] = pe;
     __syncthreads();
+    if (FUSED) step_barrier(bar, bar_base + gridDim.x);          // the sweep's segment partials of every block are visible
     double q = 0, s = 0;
     if (on) {
         if (sums_ready == 1) s = d.ar_q[e];
-        else for (int sg = sg0; sg < sg1; ++sg) s += d.seg_part[PART_STRIDE * (size_t)sg + a];
+        else for (int sg = sg0; sg < sg1; ++sg) s += FUSED ? __ldcg(d.seg_part + PART_STRIDE * (size_t)sg + a) : d.seg_part[PART_STRIDE * (size_t)sg + a];
     }
     unsigned long long coll = 0;
     if (sums_ready == 2) {
@@ -2344,25 +2356,25 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
         if (on) s = p2p_sum(d.p2p, coll, (size_t)e);
     }
     if (on) q = lam * dmul * pe + (urow[0] * sv[lc] + urow[1] * sv[lc + 1] + urow[2] * sv[lc + 2] + urow[3] * sv[lc + 3] + urow[4] * sv[lc + 4] + urow[5] * sv[lc + 5]) - s;
-    double bp = block_sum<STEP_BLOCK>(pe * q, sm);
+    double bp = block_sum<NT>(pe * q, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_pq[blockIdx.x] = bp;
-    step_barrier(d.step_bar, bar_base + gridDim.x);
+    step_barrier(bar, bar_base + (NBAR - 1ull) * gridDim.x);
     const double pq = grid_total(part_pq, step_blocks);
     if (!(pq > 0) || !isfinite(pq)) {                            // breakdown (uniform): keep x; first-step breakdown = failed solve
-        step_barrier_arrive(d.step_bar);                         // (keeps the arrival count at 2 per block and launch)
-        if (e == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; if (sums_ready == 2) *d.p2p.seq = coll + 1ull; *(d.step_bar + 1) = gen + 1ull; }
+        step_barrier_arrive(bar);                                // (keeps the arrival count at NBAR per block and launch)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->cg_active = 0; if (steps == 0) st->solve_ok = 0; if (sums_ready == 2) *d.p2p.seq = coll + 1ull; *(bar + 1) = gen + 1ull; }
         return;
     }
     const double alpha = rz / pq;
     double re = 0, xe = 0;
     if (on) { xe = xe0 + alpha * pe; re = re0 - alpha * q; d.x[e] = xe; d.r[e] = re; }
     __syncthreads();
-    sv[threadIdx.x] = re;
+    if (threadIdx.x < STEP_BLOCK) sv[threadIdx.x] = re;
     __syncthreads();
     double z = on ? (mrow[0] * sv[lc] + mrow[1] * sv[lc + 1] + mrow[2] * sv[lc + 2] + mrow[3] * sv[lc + 3] + mrow[4] * sv[lc + 4] + mrow[5] * sv[lc + 5]) : 0.0;
-    double br = block_sum<STEP_BLOCK>(re * z, sm);
+    double br = block_sum<NT>(re * z, sm);
     if (threadIdx.x == 0 && (int)blockIdx.x < step_blocks) part_rz[blockIdx.x] = br;
-    step_barrier(d.step_bar, bar_base + 2ull * gridDim.x);
+    step_barrier(bar, bar_base + NBAR * gridDim.x);
     const double rzn = grid_total(part_rz, step_blocks);
     const double rel = sqrt(fabs(rzn) / rz0);
     const bool stop = (tol > 0 && rel < tol && steps + 1 >= st->cg_min_steps) || !(rzn > 0) || (st->cg_guard > 0 && rel > st->cg_guard);
@@ -2371,11 +2383,11 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
         d.p[e] = pn; d.ptab[(size_t)i * TAB_STRIDE + 7 + a] = pn;
         if (d.ptab32) d.ptab32[(size_t)i * 20 + 8 + a] = (float)pn;
     }
-    if (e == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->cg_steps = steps + 1; st->total_cg += 1; st->cg_rel = rel; st->rz = rzn;
         if (stop) st->cg_active = 0;
         if (sums_ready == 2) *d.p2p.seq = coll + 1ull;           // every thread read the counter before the first grid sync
-        *(d.step_bar + 1) = gen + 1ull;                          // every block read the launch count before the first barrier
+        *(bar + 1) = gen + 1ull;                                 // every block read the launch count before the first barrier
     }
 }
 __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_ready, double* part_pq, double* part_rz)
@@ -2385,7 +2397,21 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_camera_step(Dev d, int sums_r
     const LMState* st = d.st;
     if (threadIdx.x == 0) pdl_trigger();                          // the by-point sweep of the next PCG step may start its prologue
     if (st->done || !st->cg_active) return;                      // uniform over the grid
-    camera_step_phases(d, sums_ready, part_pq, part_rz, gridDim.x, sv, sm, st->lambda, st->rz, st->rz0, st->cg_tol, st->cg_steps);
+    camera_step_phases<STEP_BLOCK, false>(d, sums_ready, part_pq, part_rz, gridDim.x, sv, sm, st->lambda, st->rz, st->rz0, st->cg_tol, st->cg_steps);
+}
+// K9 + K11' in one launch (single rank, cooperative: one CTA per SM): the by-camera sweep, then - after a grid-wide counting
+// barrier instead of a kernel boundary - the camera-side step in the first step_blocks blocks.  Two launches per PCG step
+// instead of three.  (Round 1 tried this with cooperative_groups' grid.sync(), ~3.9 us per call on 148 CTAs: no gain.)
+__global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass_step(Dev d, double* part_pq, double* part_rz, int step_blocks)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double sv[STEP_BLOCK];
+    __shared__ double sm[CW];
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;                      // uniform over the grid
+    const double lam = st->lambda, rz = st->rz, rz0 = st->rz0, tol = st->cg_tol; const int steps = st->cg_steps;
+    camera_pass_sweep(d, st, smem_raw);
+    camera_step_phases<CW * 32, true>(d, 0, part_pq, part_rz, step_blocks, sv, sm, lam, rz, rz0, tol, steps);
 }
 
 // K12 cg_finish: delta_c = x; trial cameras T += dt, R <- Rodrigues(dw) R (v3d_metricbundle.cpp:17-39,

@@ -18,6 +18,9 @@
 //            virtual classes, so only the unavoidable excess collides.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -155,6 +158,7 @@ inline void build_point_layout(int M, int K, const int32_t* obs_cam, const int32
     });
     host_parallel_for(T, [&](int t, int nt) {
         const long long a = (long long)(M / 32) * t / nt * 32, b = (t + 1 == nt) ? M : (long long)(M / 32) * (t + 1) / nt * 32;
+        struct Tm { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); int t; long long a, b; ~Tm() { if (getenv("B200BA_LAYOUT_TIMES")) fprintf(stderr, "[layout] thread %d points %lld..%lld: %.2f ms\n", t, a, b, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } } tm_; tm_.t = t; tm_.a = a; tm_.b = b;
         std::vector<int> run, out, pool, cams, slot_edge, head, nxt;
         std::vector<uint64_t> key, hkey;
         std::vector<unsigned char> taken;

@@ -31,6 +31,8 @@ BIG_CASES = {
     "venice": ("venice", 1, 6),
     "final": ("final", 1, 3),
     "camheavy": ((13682, 250000, 1250000), 1, 4),
+    "ladybug": ("ladybug", 1, 8),        # BASELINE configs 2 and 3: the shapes the explicit reduced-system plan runs
+    "trafalgar": ("trafalgar", 1, 8),
 }
 
 

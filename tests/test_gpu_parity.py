@@ -518,6 +518,21 @@ def test_venice_shape_matches_oracle():
     assert r.gpu_launches > 0
 
 
+@pytest.mark.parametrize("name,want", [("ladybug", "cluster"), ("trafalgar", "grid")])
+def test_small_shapes_fifty_step_traces_on_the_explicit_plan(name, want):
+    """BASELINE configs 2 and 3 in the throughput mode (fixed 50-step PCG) on the plan they actually run - the explicit reduced
+    camera system (one 8-CTA cluster / the cooperative grid) - against the oracle live and against the committed oracle trace that
+    bench.py --shape <name> prints its `parity` block from."""
+    from sequencesfm_b200.synth import BIG_CASES, input_checksum
+    shape, seed, iters = BIG_CASES[name]
+    fx = load_golden(f"trace50_{name}_s{seed}")
+    p = make_problem(shape, seed)
+    assert input_checksum(p) == fx["input_sha256"]
+    r, plan = _stage_and_trace_vs_oracle(p, iters, fx)
+    assert (plan["explicit_schur"] == 8) if want == "cluster" else (plan["explicit_schur"] > 16)
+    assert plan["launches_per_iteration"] <= 20
+
+
 def test_final_camera_count_matches_oracle():
     """13 682 cameras (Final's camera count; points cut to 250 000 so that the oracle runs in seconds): the camera table does
     not fit one SM's shared memory, so this exercises the large-camera-count plan at scale."""
