@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_dense_finalize(Dev d)
     const LMState* st = d.st;
     if (st->done) return;
     const int idx = blockIdx.x * 256 + threadIdx.x, blk = idx / 36, e = idx - 36 * blk;
-    if (idx == 0) *d.dn.bar_counter = 0u;                         // counting barrier of the grid-wide PCG kernel that follows
+    if (idx < 32) d.dn.bar_counter[32 * idx] = 0u;                // counting barrier (top + group counters) of the grid-wide PCG kernel that follows
     if (blk >= d.dn.n_blocks) return;
     const int i = __ldg(d.dn.blk_ik + 2 * blk), k = __ldg(d.dn.blk_ik + 2 * blk + 1);
     const int a = e / 6, b = e - 6 * a;
@@ -199,12 +199,27 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // acquire loads, then warp 0 sums the slots.  Measured alternatives at 257 cameras / 148 CTAs: cooperative_groups' grid.sync()
 // 12.8 us per PCG step; this form 6.7 us; slots tagged with a "not written yet" sentinel and polled directly (barrier and data in
 // one round trip on paper) 9.8 us - 148 CTAs polling 148 words keep the L2 lines bouncing while the writers try to update them.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target)
+#ifndef B200BA_GRID_BAR_GROUP
+#define B200BA_GRID_BAR_GROUP 0
+#endif
+constexpr int GRID_BAR_GROUP = B200BA_GRID_BAR_GROUP;            // > 0: two-level arrival (groups of that many CTAs), see below
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int phase, int G, int rank)
 {
     __syncthreads();                                               // the CTA's global stores of this phase are issued
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(counter, 1u);
+        unsigned int target;
+        if (GRID_BAR_GROUP > 0) {
+            // two levels: the last arriver of a group of CTAs (its own counter, 128 bytes apart) arrives at the top counter
+            const int g = rank / GRID_BAR_GROUP, ng = (G + GRID_BAR_GROUP - 1) / GRID_BAR_GROUP;
+            const unsigned int size_g = (unsigned int)min(GRID_BAR_GROUP, G - g * GRID_BAR_GROUP);
+            const unsigned int old = atomicAdd(counter + 32 * (1 + g), 1u);
+            if (old + 1u == phase * size_g) { __threadfence(); atomicAdd(counter, 1u); }
+            target = phase * (unsigned int)ng;
+        } else {
+            atomicAdd(counter, 1u);
+            target = phase * (unsigned int)G;
+        }
         unsigned int v;
         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
     }
@@ -323,7 +338,7 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
         if (GRID) {
             if (own) d.dn.zg[e] = zval;
             if (tid == 0) d.dn.rz_slots[rank] = tot;
-            gbar += (unsigned int)G; grid_barrier(d.dn.bar_counter, gbar);
+            grid_barrier(d.dn.bar_counter, ++gbar, G, rank);
             return grid_slot_sum(d.dn.rz_slots, G, sm.red);
         } else {
             if (tid == 0) mbar_expect_tx(&sm.bar[1], (uint32_t)(8 * (n + G)));
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
         DSTAMP(5);
         if (GRID) {
             if (tid == 0) d.dn.pq_slots[rank] = tot;
-            gbar += (unsigned int)G; grid_barrier(d.dn.bar_counter, gbar);
+            grid_barrier(d.dn.bar_counter, ++gbar, G, rank);
             DSTAMP(6);
             return grid_slot_sum(d.dn.pq_slots, G, sm.red);
         } else {

@@ -145,7 +145,7 @@ struct b200ba_handle {
     bool pdl_chain = false;                          // programmatic dependent launch of every kernel of the iteration (explicit plan)
     bool use_dense = false; int dense_ctas = 0, dense_kind = -1, dense_threads = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
     DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik, dn_entry_pt;
-    DBuf<double> dn_Wobs, dn_Yobs, dn_Tobs, dn_chunk_part, dn_chunk_rhs, dn_S, dn_zg, dn_pq, dn_rz;
+    DBuf<double> dn_Wobs, dn_Yobs, dn_Tobs, dn_chunk_part, dn_chunk_rhs, dn_S, dn_zg, dn_pq, dn_rz; DBuf<unsigned int> dn_bar;
     std::vector<int> orig_of_new;                    // SELL permutation (new point index -> caller's)
     std::unique_ptr<int[]> entry_of_obs;             // obs -> padded SELL entry
     int Kp = 0;                                      // padded SELL entries
@@ -764,14 +764,19 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         int mode = o.reduced_system;
         if (const char* e = getenv("B200BA_DENSE")) mode = atoi(e) ? 2 : 1;
         int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-        if (mode != 1 && h->world <= 1 && !o.pcg_fp32 && K > 0) {
+        // (pair count bounded here, before the layout is built for one plan or the other: sum over points of d^2)
+        long long pair_cap = DENSE_MAX_PAIRS;
+        if (const char* e = getenv("B200BA_DENSE_MAX_PAIRS")) pair_cap = std::min<long long>(DENSE_MAX_PAIRS, std::max(0ll, atoll(e)));   // (tests: force the fallback)
+        if (mode != 1 && h->world <= 1 && !o.pcg_fp32 && K > 0 && dense_pair_bound(K, obs_pt) <= pair_cap) {
             const int cand_kind[4] = {0, 1, 1, 2}, cand_ctas[4] = {8, 8, 16, coop ? n_sm : 0};
             for (int c = 0; c < 4 && !dsh.ctas; ++c) {
                 if (cand_ctas[c] <= 0) continue;
                 const DenseShape t = dense_shape(N, cand_kind[c], cand_ctas[c]);
                 if (t.kind < 0 || t.smem + 1024 > (size_t)smem_optin) continue;
                 const void* fn = dense_pcg_kernel(t.kind);
-                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem) != cudaSuccess) { cudaGetLastError(); continue; }
+                // (function attributes are per kernel and process, not per handle: always the device's limit, so that handles with
+                //  different camera counts on different threads cannot lower each other's)
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin) != cudaSuccess) { cudaGetLastError(); continue; }
                 if (t.kind != 2) {                                      // can one such cluster be resident?
                     cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
                     cfg.gridDim = dim3(t.ctas); cfg.blockDim = dim3(t.threads); cfg.dynamicSmemBytes = t.smem;
@@ -922,7 +927,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             h->dn_blk_chunk_beg.take(A, dl.blk_chunk_beg.size()); h->dn_blk_ik.take(A, dl.blk_ik.size()); h->dn_entry_pt.take(A, Kpp);
             h->dn_Wobs.take(A, DENSE_OBS_STRIDE * Kpp); h->dn_Yobs.take(A, DENSE_OBS_STRIDE * Kpp); h->dn_Tobs.take(A, 6 * Kpp);
             h->dn_chunk_part.take(A, 36 * (dl.chunks.size() + 1)); h->dn_chunk_rhs.take(A, 6 * (dl.chunks.size() + 1));
-            h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 512); h->dn_rz.take(A, 512);
+            h->dn_S.take(A, n6 * n6); h->dn_zg.take(A, n6); h->dn_pq.take(A, 512); h->dn_rz.take(A, 512); h->dn_bar.take(A, 32 * 32);
         }
         if (pass == 0) {
             A.cap = A.off;
@@ -1099,10 +1104,8 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         dn.pairs = h->dn_pairs.p; dn.chunks = h->dn_chunks.p; dn.blk_chunk_beg = h->dn_blk_chunk_beg.p; dn.blk_ik = h->dn_blk_ik.p; dn.entry_pt = h->dn_entry_pt.p;
         dn.Wobs = h->dn_Wobs.p; dn.Yobs = h->dn_Yobs.p; dn.Tobs = h->dn_Tobs.p; dn.chunk_part = h->dn_chunk_part.p; dn.chunk_rhs = h->dn_chunk_rhs.p;
         dn.S = h->dn_S.p; dn.zg = h->dn_zg.p; dn.pq_slots = h->dn_pq.p; dn.rz_slots = h->dn_rz.p;
-        dn.bar_counter = reinterpret_cast<unsigned int*>(h->dn_rz.p + 400);          // (the slot arrays hold at most 148 entries)
-        // (function attributes are per kernel, not per handle: set again for THIS problem's shape)
-        CU(cudaFuncSetAttribute(dense_pcg_kernel(h->dense_kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dense_smem));
-        if (!h->dense_grid && h->dense_ctas > 8) CU(cudaFuncSetAttribute(dense_pcg_kernel(h->dense_kind), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        dn.bar_counter = h->dn_bar.p;
+        // (the kernel's function attributes were set when the shape was chosen: shared memory = the device limit, non-portable cluster size)
     }
     if (h->use_f32) {
         d.o_rec32 = h->o_rec32.p; d.c_rec32 = h->c_rec32.p; d.X32 = h->X32.p; d.v32 = h->v32.p; d.Vinv32 = h->Vinv32.p;

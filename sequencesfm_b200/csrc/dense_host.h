@@ -39,20 +39,25 @@ struct DenseLists {
 // upper-triangle block index of (i, k), i <= k, row-major
 inline long long dense_block_index(int N, int i, int k) { return (long long)i * N - (long long)i * (i - 1) / 2 + (k - i); }
 
+// Upper bound of the pair count (exact when no point is seen twice by one camera would be sum d (d + 1) / 2): sum over points of d^2.
+inline long long dense_pair_bound(int K, const int32_t* obs_pt)
+{
+    long long bound = 0;
+    for (int k0 = 0; k0 < K;) {
+        int k1 = k0 + 1; while (k1 < K && obs_pt[k1] == obs_pt[k0]) ++k1;
+        const long long dd = k1 - k0; bound += dd * dd;
+        k0 = k1;
+    }
+    return bound;
+}
+
 // Returns false (lists untouched) when the pair count exceeds DENSE_MAX_PAIRS.
 // obs_pt must be non-decreasing (the precondition of b200ba_set_problem); entry_of_obs maps an observation to its SELL entry.
 inline bool build_dense_lists(int N, int M, int K, const int32_t* obs_cam, const int32_t* obs_pt, const int* entry_of_obs, DenseLists& out)
 {
     (void)M;
     const long long nb = (long long)N * (N + 1) / 2;
-    // cheap upper bound first: sum over points of d^2
-    long long bound = 0;
-    for (int k0 = 0; k0 < K;) {
-        int k1 = k0 + 1; while (k1 < K && obs_pt[k1] == obs_pt[k0]) ++k1;
-        const long long dd = k1 - k0; bound += dd * (dd + 1) / 2 + dd;      // (+ d: room for duplicate cameras)
-        k0 = k1;
-        if (bound > 4 * DENSE_MAX_PAIRS) return false;
-    }
+    if (dense_pair_bound(K, obs_pt) > 2 * DENSE_MAX_PAIRS) return false;
     std::vector<int32_t> count((size_t)nb + 1, 0);
     long long total = 0;
     for (int k0 = 0; k0 < K;) {
@@ -108,6 +113,10 @@ inline DenseShape dense_shape(int N, int kind, int ctas)
     DenseShape s; s.kind = kind; s.ctas = ctas; s.threads = DENSE_THREADS[kind];
     const int n = 6 * N, cq = DENSE_CQ[kind], np = DENSE_NP[kind];
     s.rows = 6 * ((N + ctas - 1) / ctas);
+    if (kind == 2) {                                              // two cameras per CTA (12 rows = 3 row blocks x 4 column splits = its 12 warps) and
+        if (N > 2 * ctas) { s.kind = -1; return s; }              // no CTA without rows: every CTA of the grid is a participant of the two barriers per step
+        s.rows = 12; s.ctas = (N + 1) / 2;
+    }
     const int rows4 = (s.rows + 3) & ~3;
     // padded vector length: every column pair a lane touches exists (zeros beyond n), so the product runs without bounds checks
     const int plen = np ? 64 * cq * np : ((n + 63) / 64) * 64;

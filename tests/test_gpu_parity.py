@@ -623,7 +623,7 @@ def test_explicit_reduced_system_matches_matrix_free_and_oracle(shape, seed, wan
     n_sm = 148
     assert plan["explicit_schur"] == (want_ctas if want_ctas else plan["explicit_schur"]) and plan["explicit_schur"] > 0
     if want_ctas is None:
-        assert plan["explicit_schur"] > 16 and plan["explicit_schur"] <= 2 * n_sm       # one CTA per multiprocessor
+        assert plan["explicit_schur"] == (p.N + 1) // 2 and plan["explicit_schur"] <= n_sm   # cooperative grid, two cameras per CTA
     assert plan["explicit_pairs"] == binding.dense_lists(p)["pairs"]
     assert plan["cuda_graph"] == 1                                       # no host polling inside the PCG loop: captured even in exact-step mode
     b = _solve(p, reduced_system=1, **kw)
@@ -659,6 +659,21 @@ def test_explicit_reduced_system_with_the_pba_personalities(preset):
     #  shows in the next cost at 1e-8; with the fixed 50 steps of the pba preset it stays below 1e-9)
     assert rel_cost_diff(a.trace, b.trace, k).max() < (1e-7 if preset == "pba_lm" else 1e-9)
     assert np.abs(a.trace[:k, 2] / b.trace[:k, 2] - 1).max() < 1e-6      # damping schedule
+
+
+def test_explicit_reduced_system_falls_back_when_the_pair_lists_would_be_too_long(monkeypatch):
+    """More observation pairs than the explicit plan accepts (bounded by sum d^2 before the layout is built): the matrix-free
+    plan runs, with its conflict-free layout, and gives the same trajectory."""
+    p = make_problem("ladybug", 4, outlier_frac=0.01)
+    kw = dict(max_iterations=6, cg_rel_tol=1e-13, cg_max_steps=2000)
+    with binding.Engine(**kw) as eng:
+        eng.set_problem_from(p); pa = eng.plan(); a = eng.solve()
+    monkeypatch.setenv("B200BA_DENSE_MAX_PAIRS", "1000")
+    with binding.Engine(**kw) as eng:
+        eng.set_problem_from(p); pb = eng.plan(); b = eng.solve()
+    assert pa["explicit_schur"] == 8 and pb["explicit_schur"] == 0 and pb["explicit_pairs"] == 0
+    k = parity_window(a.trace, b.trace)
+    assert k >= 5 and rel_cost_diff(a.trace, b.trace, k).max() < COST_RTOL
 
 
 def test_explicit_reduced_system_edge_cases():
