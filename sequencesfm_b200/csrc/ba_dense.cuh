@@ -252,6 +252,26 @@ __device__ __forceinline__ double fixed_sum_smem(const double* v, int count)
 // Work split of q = S p inside a CTA: warp (rb, cq) owns the 4 rows 4 rb .. 4 rb + 3 and every CQ-th group of 32 column pairs;
 // lane l of it owns the column pairs l + 32 (cq + CQ t), t < NP.  Every p value a lane reads is used for 4 rows (the first
 // version gave a row to 8 lanes: 40 p values per lane, and the sweep sat on shared-memory bandwidth: 123 KB of reads per step).
+// the same for a compile-time count: all loads first, then a pairwise tree (depth log2 N instead of N / 4 + 2 chained adds)
+template <int N>
+__device__ __forceinline__ double fixed_sum_tree(const double* v)
+{
+    constexpr int P2 = N <= 8 ? 8 : 16;
+    static_assert(N <= 16, "slot count");
+    double a[P2];
+#pragma unroll
+    for (int u = 0; u < P2; ++u) a[u] = u < N ? v[u] : 0.0;
+#pragma unroll
+    for (int w = 1; w < P2; w <<= 1)
+#pragma unroll
+        for (int u = 0; u < P2; u += 2 * w) a[u] += a[u + w];
+    return a[0];
+}
+__device__ __forceinline__ double fixed_sum_slots(const double* v, int count)      // cluster of 8 or 16 CTAs
+{
+    return count == 8 ? fixed_sum_tree<8>(v) : count == 16 ? fixed_sum_tree<16>(v) : fixed_sum_smem(v, count);
+}
+
 template <int KIND> struct DenseCfg {
     static constexpr bool GRID = KIND == 2;
     static constexpr int NT = DENSE_THREADS[KIND], CQ = DENSE_CQ[KIND], NP = DENSE_NP[KIND];
@@ -331,6 +351,10 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
 #endif
     // z on the owned rows and the CTA's r.z partial go to every CTA of the group (phase B)
     auto exchange_z = [&](double zval, double partial) -> double {
+        if (!GRID) {                                               // the z values travel while the r.z partial is being reduced
+            if (tid == 0) mbar_expect_tx(&sm.bar[1], (uint32_t)(8 * (n + G)));
+            if (own) for (int c = 0; c < G; ++c) st_async_f64(cluster_map(z_addr + 8u * (uint32_t)e, c), zval, cluster_map(bar_b, c));
+        }
         // partial = this thread's r * z (0 outside the owned rows); fixed-order sum over the (<= 64) owned rows
         if (tid < 64) { const double s = warp_sum(partial); if ((tid & 31) == 0) sm.red[tid >> 5] = s; }
         __syncthreads();
@@ -341,16 +365,14 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
             grid_barrier(d.dn.bar_counter, ++gbar, G, rank);
             return grid_slot_sum(d.dn.rz_slots, G, sm.red);
         } else {
-            if (tid == 0) mbar_expect_tx(&sm.bar[1], (uint32_t)(8 * (n + G)));
-            if (own) for (int c = 0; c < G; ++c) st_async_f64(cluster_map(z_addr + 8u * (uint32_t)e, c), zval, cluster_map(bar_b, c));
             if (tid < G) st_async_f64(cluster_map(rz_addr + 8u * (uint32_t)rank, tid), tot, cluster_map(bar_b, tid));
             mbar_wait_cluster(&sm.bar[1], par_b); par_b ^= 1u;
         }
-        return fixed_sum_smem(sm.rz, G);
+        return fixed_sum_slots(sm.rz, G);
     };
     // the CTA's p.q (its warps' partials are in red[8 ..]) goes to every CTA of the group (phase A)
     auto exchange_pq = [&]() -> double {
-        const double tot = fixed_sum_smem(sm.red + 8, NWARP);
+        const double tot = fixed_sum_tree<NWARP>(sm.red + 8);
         DSTAMP(5);
         if (GRID) {
             if (tid == 0) d.dn.pq_slots[rank] = tot;
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
             mbar_wait_cluster(&sm.bar[0], par_a); par_a ^= 1u;
         }
         DSTAMP(6);
-        return fixed_sum_smem(sm.pq, G);
+        return fixed_sum_slots(sm.pq, G);
     };
     if (own) ze = (mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1]) + (mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3]) + (mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5]);
     double rz = exchange_z(ze, own ? re * ze : 0.0);
@@ -379,6 +401,7 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
     // ---- the loop ----
     while (active && steps < max_steps) {
         DSTAMP(9);
+        const double inv_rz = 1.0 / rz;                            // for beta: issued here, its latency hides behind the product
         // q = S p on the CTA's rows: 4 rows per lane share every p value, two accumulators per row (fp64 latency); the four
         // row sums are reduced over the 32 lanes by a butterfly that halves the number of values per lane in its first two
         // levels (6 value-shuffles instead of 20), all in a fixed order
@@ -440,7 +463,7 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
             if (rank == 0 && tid == 0 && steps == 0) st->solve_ok = 0;
             break;
         }
-        const double alpha = rz / pq;
+        const double alpha = rz * fast_rcp(pq);                    // (within an ulp of rz / pq, without the IEEE division's slow path)
         if (own) { xe += alpha * pe; re -= alpha * qe; sm.r[tid] = re; }
         __syncthreads();
         if (own) ze = (mrow[0] * sm.r[lc] + mrow[1] * sm.r[lc + 1]) + (mrow[2] * sm.r[lc + 2] + mrow[3] * sm.r[lc + 3]) + (mrow[4] * sm.r[lc + 4] + mrow[5] * sm.r[lc + 5]);
@@ -450,7 +473,7 @@ __global__ void __launch_bounds__(DenseCfg<KIND>::NT, 1) k_dense_pcg(Dev d, int 
         if (watch) rel = sqrt(fabs(rzn) / rz0);
         const bool stop = (tol > 0 && rel < tol && steps + 1 >= min_steps) || !(rzn > 0) || (guard > 0 && rel > guard);
         if (!stop) {
-            const double beta = rzn / rz;
+            const double beta = rzn * inv_rz;
             for (int i = tid; i < n; i += NT) sm.p[i] = (GRID ? __ldcg(d.dn.zg + i) : sm.z[i]) + beta * sm.p[i];
         }
         rz = rzn; ++steps;

@@ -202,7 +202,8 @@ int allreduce(b200ba_handle* h, double* buf, size_t count, int need = 0)
 
 // ---- kernel launch sequences ---------------------------------------------------------------------------
 // Every kernel of an LM iteration goes through here.  h->pdl_chain (explicit small-problem plan): programmatic dependent launch,
-// see pdl_chain_enter() in ba_kernels.cuh.
+// see pdl_chain_enter() in ba_kernels.cuh.  EVERY kernel that can be launched through this helper starts with pdl_chain_enter()
+// (or pdl_wait()): one that did not could start before its predecessor has finished.
 template <class... KA, class... A>
 void launch_chain(b200ba_handle* h, void (*kern)(KA...), int grid, int block, size_t smem, A&&... a)
 {

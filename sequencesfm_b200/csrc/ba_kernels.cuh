@@ -780,6 +780,7 @@ __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done) return;
     const int lane = threadIdx.x & 31, wpb = CH_BLOCK / 32, nw = gridDim.x * wpb;
@@ -1302,6 +1303,7 @@ __device__ __forceinline__ double grid_total_warp(const double* part, int n)
 // K10 cg_init: rhs = g_c - W Vinv g_p ; x = 0 ; r = rhs ; z = M r ; p = z   (one thread per (camera, component), block partials of r.z)
 __global__ void __launch_bounds__(STEP_BLOCK) k_cg_init(Dev d, double* __restrict__ part)
 {
+    pdl_chain_enter();
     __shared__ double sv[STEP_BLOCK];
     __shared__ double sm[STEP_BLOCK / 32];
     const LMState* st = d.st;
@@ -1327,6 +1329,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_cg_init(Dev d, double* __restric
 // fixed-order sum of the block partials of k_cg_init -> PCG control words
 __global__ void __launch_bounds__(32) k_cg_init_finish(Dev d, const double* __restrict__ part, int nblocks)
 {
+    pdl_chain_enter();
     LMState* st = d.st;
     if (st->done) return;
     const double rz = grid_total_warp(part, nblocks);
@@ -1340,6 +1343,7 @@ __global__ void __launch_bounds__(32) k_cg_init_finish(Dev d, const double* __re
 //     beta = r.z' / r.z ; p = z + beta p
 __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
 {
+    pdl_chain_enter();
     __shared__ double sm[ONE_CTA / 32];
     LMState* st = d.st;
     if (st->done || !st->cg_active) return;
@@ -2574,6 +2578,7 @@ __global__ void k_lm_decide_pba(Dev d, int fuse_count)
 // block partial sums of f0 * |e_k| (unweighted), thread per point.
 __global__ void __launch_bounds__(PT_BLOCK) k_reproj_sum(Dev d, int which)
 {
+    pdl_chain_enter();
     __shared__ double sm[PT_BLOCK / 32];
     int j = blockIdx.x * PT_BLOCK + threadIdx.x;
     double s = 0;

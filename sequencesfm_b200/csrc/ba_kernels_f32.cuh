@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128) k_f32_cameras(Dev d)               // rt3
 // weights of the point-order rows: one thread per padded entry
 __global__ void __launch_bounds__(256) k_f32_orows(Dev d, int n_entries)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
     const int k = blockIdx.x * 256 + threadIdx.x;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) k_f32_orows(Dev d, int n_entries)
 // weights and cached R X of the camera-order rows: one warp per row
 __global__ void __launch_bounds__(256) k_f32_crows(Dev d)
 {
+    pdl_chain_enter();
     const LMState* st = d.st;
     if (st->done || !st->compute) return;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
