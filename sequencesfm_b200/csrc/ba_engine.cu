@@ -152,6 +152,8 @@ struct b200ba_handle {
     int num_sms = 148, tab_grid = 0, step_grid = 0, cam_grid = 0;
     size_t tab_smem = 0;
     bool use_tab = false, use_coop = false, use_graph = false, fuse_step = false;
+    bool use_wb = false;                             // large-camera-count plan: B~ records + world-axes direction table (k_cg_point_pass_wB)
+    DBuf<double> obs_B, wtab;
     int tab_ilp = 1, tab_block = TAB_BLOCK;          // rows of a slice in flight per trip of the shared-memory-table sweep (1 or 2)
     cudaGraphExec_t graph_exec = nullptr;
     long long launches_per_graph = 0;
@@ -232,6 +234,20 @@ void launch_point_tab(b200ba_handle* h)
     else if (h->tab_ilp == 2) k_cg_point_pass_tab2<<<h->tab_grid, TAB2_BLOCK, h->tab_smem, h->stream>>>(h->d);
     else k_cg_point_pass_tab<<<h->tab_grid, TAB_BLOCK, h->tab_smem, h->stream>>>(h->d);
     h->launches++;
+}
+
+// by-point PCG sweep: shared-memory camera table (<= 2075 cameras), else B~ records + world-axes direction table
+// (k_cg_point_pass_wB; needs orthonormal input rotations like every table plan), else the generic packed-table gathers
+void launch_point_sweep(b200ba_handle* h, bool allow_tab = true)
+{
+    Dev& d = h->d;
+    if (h->use_tab && allow_tab) { launch_point_tab(h); return; }
+    if (h->use_wb && h->quat_ok) {
+        LAUNCH(k_build_wtab, cdiv(d.N, 128), 128, d);
+        LAUNCH(k_cg_point_pass_wB, d.n_pt_blocks, PT_BLOCK, d);
+        return;
+    }
+    LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
 }
 
 int enqueue_linearize(b200ba_handle* h)
@@ -343,8 +359,7 @@ int enqueue_cg_step(b200ba_handle* h)
         if (int rc = enqueue_camera_sums(h)) return rc;
         return launch_camera_step(h, 1);
     }
-    if (h->use_tab) launch_point_tab(h);
-    else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    launch_point_sweep(h);
     if (h->fuse_step) {                                          // single rank: by-camera sweep + camera-side step in one cooperative launch
         double* ppq = h->part_pq.p; double* prz = h->part_rz.p; int sb = h->step_grid;
         void* args[] = {(void*)&d, (void*)&ppq, (void*)&prz, (void*)&sb};
@@ -897,9 +912,13 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     h->arena.base = nullptr;
     int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (std::max(std::max(TAB_BLOCK, TAB2_BLOCK), TABC_BLOCK) / 32);
     const int step_grid = cdiv((long long)N * 6, STEP_BLOCK);
+    // large-camera-count plan: the packed camera table will not fit one SM's shared memory (same test as `use_tab` below)
+    const bool want_wb = (((size_t)N * TAB_STRIDE * sizeof(double) + 127) & ~(size_t)127) + TABC_RING_BYTES + 256 > (size_t)smem_optin || getenv("B200BA_NO_TAB") != nullptr;
+    h->use_wb = want_wb && !h->use_dense && getenv("B200BA_NO_WB") == nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         Arena& A = h->arena;
         A.off = 0;
+        if (h->use_wb) { h->obs_B.take(A, (Kpp / 32 + 1) * 192); h->wtab.take(A, 8 * (size_t)N); } else { h->obs_B.p = nullptr; h->wtab.p = nullptr; }
         h->rt0.take(A, 12 * (size_t)N); h->rt1.take(A, 12 * (size_t)N);
         h->U.take(A, 36 * (size_t)N); h->Minv.take(A, 36 * (size_t)N);
         h->gc.take(A, n6); h->x.take(A, n6); h->r.take(A, n6); h->z.take(A, n6); h->p.take(A, n6); h->q.take(A, n6);
@@ -1094,7 +1113,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
     d.o_rec = h->o_rec.p; d.o_meas = h->o_meas.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
-    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.fin_part = h->fin_part.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
+    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.obs_B = h->use_wb ? h->obs_B.p : nullptr; d.wtab = h->use_wb ? h->wtab.p : nullptr; d.fin_part = h->fin_part.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;
@@ -1591,8 +1610,7 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
         for (int i = 0; i < N; ++i) for (int a = 0; a < 6; ++a) tab[(size_t)i * TAB_STRIDE + 7 + a] = x[6 * (size_t)i + a];
         CU(cudaMemcpy(d.ptab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
-    if (h->use_tab && getenv("B200BA_DEBUG_GENERIC") == nullptr) launch_point_tab(h);
-    else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
+    launch_point_sweep(h, getenv("B200BA_DEBUG_GENERIC") == nullptr);
     if (int rc = enqueue_camera_half(h, 0)) return rc;
     if (int rc = enqueue_camera_sums(h)) return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -1702,9 +1720,7 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
                 else LAUNCH(k_linearize_points, d.n_pt_blocks, PT_BLOCK, d);
                 break;
         case 1: k_linearize_cameras<<<cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, LINCAM_SMEM, h->stream>>>(d); h->launches++; break;
-        case 2: if (h->use_tab) launch_point_tab(h);
-                else LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d);
-                break;
+        case 2: launch_point_sweep(h); break;
         case 10: LAUNCH(k_cg_point_pass<0>, d.n_pt_blocks, PT_BLOCK, d); break;
         case 11: if (h->use_coop) { if (int rc = launch_camera_step(h, 0)) return rc; } else LAUNCH(k_cg_update, 1, ONE_CTA, d);
                  CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;

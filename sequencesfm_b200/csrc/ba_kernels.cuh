@@ -160,6 +160,8 @@ struct Dev {
     double* ptab;       // N x 14 packed camera table [quat 4 | T 3 | p 6 | pad] staged into shared memory by the CG point sweep
     double *cam_D0, *pt_D0;   // PBA variant: diag(J^t J) at the first linearisation = the Jacobian column scaling (6 N, 4 M)
     double* fin_part;   // 4 x blocks of k_cg_finish: camera part of |delta|^2, delta . g, non-finite flag
+    double* obs_B;      // large-camera-count plan: per SELL row of 32 entries, the weighted point Jacobian B~ = w dp/dXX R (2 x 3) as 6 x 32 doubles
+    double* wtab;       // N x 8: the PCG direction in WORLD axes [R^t p_t | R^t p_w | pad] for k_cg_point_pass_wB
     double* qtab;       // N x 8 compact table [quat 4 | T 3 | pad] (swizzled, see qtab_unit) of the trial cameras for k_cost_tab
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
@@ -448,6 +450,11 @@ __global__ void __launch_bounds__(PT_BLOCK) k_linearize_points(Dev d)
             double we0 = o.w * o.e0, we1 = o.w * o.e1;
             cost += we0 * we0 + we1 * we1;
             double B0[3], B1[3]; jac_rows_B(o, cm, B0, B1);
+            if (d.obs_B) {                                        // kept for the PCG by-point sweep of the large-camera-count plan (k_cg_point_pass_wB)
+                double* ob = d.obs_B + (size_t)(k >> 5) * 192 + (k & 31);
+                const double live = ci < d.first_free ? 0.0 : 1.0;    // constant camera: no contribution to S
+                ob[0] = live * B0[0]; ob[32] = live * B0[1]; ob[64] = live * B0[2]; ob[96] = live * B1[0]; ob[128] = live * B1[1]; ob[160] = live * B1[2];
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) g[c] += B0[c] * (-we0) + B1[c] * (-we1);
             V[0] += B0[0] * B0[0] + B1[0] * B1[0]; V[1] += B0[0] * B0[1] + B1[0] * B1[1]; V[2] += B0[0] * B0[2] + B1[0] * B1[2];
@@ -1062,6 +1069,67 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
             o[0] = d2; o[1] = dg; o[2] = cost; o[3] = njx;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K8w  by-point PCG sweep of the LARGE-CAMERA-COUNT plan (camera table larger than one SM's shared memory: > 2075 cameras).
+//      The generic sweep gathers the packed record [quaternion | T | p] - 7 x LDG.128 = 112 bytes per observation out of L2,
+//      3.2 GB per sweep at Final shape (498 us: L2-gather bound) - and rebuilds R, the projection Jacobian and two rotations
+//      from it (71 fp64 instructions per observation).  Here
+//          W^t p = B~^t B~ (R^t p_t + (R^t p_w) x X),      B~ = w dp/dXX R  (2 x 3),
+//      i.e. with the direction rotated into WORLD axes once per step and camera (k_build_wtab: 64-byte records, 2 x LDG.256
+//      per observation) the rotation disappears from the sweep, and B~ - fixed for a linearisation - is STREAMED (48 bytes per
+//      observation, coalesced, written by k_linearize_points) instead of recomputed: 21 fp64 instructions per observation.
+//      More HBM bytes per observation (52 instead of 12), less than half the L2 gather traffic.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_build_wtab(Dev d)
+{
+    pdl_chain_enter();
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= d.N) return;
+    const double* s = d.rt[st->cur] + 12 * (size_t)i;
+    const double* p = d.ptab + (size_t)i * TAB_STRIDE + 7;
+    const double p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4], p5 = p[5];
+    double2* o = reinterpret_cast<double2*>(d.wtab + 8 * (size_t)i);
+    // R^t v: column a of R (row-major at stride 4) dotted with v
+    o[0] = make_double2(s[0] * p0 + s[4] * p1 + s[8] * p2, s[1] * p0 + s[5] * p1 + s[9] * p2);
+    o[1] = make_double2(s[2] * p0 + s[6] * p1 + s[10] * p2, s[0] * p3 + s[4] * p4 + s[8] * p5);
+    o[2] = make_double2(s[1] * p3 + s[5] * p4 + s[9] * p5, s[2] * p3 + s[6] * p4 + s[10] * p5);
+    o[3] = make_double2(0.0, 0.0);
+}
+__global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass_wB(Dev d)
+{
+    pdl_chain_enter();
+    const LMState* st = d.st;
+    if (st->done || !st->cg_active) return;
+    const int j = blockIdx.x * PT_BLOCK + threadIdx.x;
+    if (j >= d.M) return;
+    double X[3]; load3p(d.X[st->cur], j, X);
+    int k0, deg; slice_of(d, j, k0, deg);
+    double u0 = 0, u1 = 0, u2 = 0;
+    const double* wt = d.wtab;
+#pragma unroll 2
+    for (int s = 0, k = k0; s < deg; ++s, k += 32) {
+        const int i = __ldg(o_cam_ptr(d, k));
+        if (i < 0) continue;
+        const double* ob = d.obs_B + (size_t)(k >> 5) * 192 + (k & 31);
+        const double b00 = __ldg(ob), b01 = __ldg(ob + 32), b02 = __ldg(ob + 64), b10 = __ldg(ob + 96), b11 = __ldg(ob + 128), b12 = __ldg(ob + 160);
+        double t[3], w[3];                                        // [R^t p_t | first of R^t p_w], [rest of R^t p_w | pad]
+        double w0;
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(t[0]), "=d"(t[1]), "=d"(t[2]), "=d"(w0) : "l"(wt + 8 * (size_t)i));
+        load3p_256(wt + 4, 2 * i, w);                             // record i's second half: (w1, w2, pad)
+        const double a0 = t[0] + (w[0] * X[2] - w[1] * X[1]);     // a = t~ + w~ x X,  w~ = (w0, w[0], w[1])
+        const double a1 = t[1] + (w[1] * X[0] - w0 * X[2]);
+        const double a2 = t[2] + (w0 * X[1] - w[0] * X[0]);
+        const double y0 = b00 * a0 + b01 * a1 + b02 * a2, y1 = b10 * a0 + b11 * a1 + b12 * a2;
+        u0 += b00 * y0 + b10 * y1; u1 += b01 * y0 + b11 * y1; u2 += b02 * y0 + b12 * y1;
+    }
+    double Vi[6]; load6(d.Vinv, j, Vi);
+    double2* o = reinterpret_cast<double2*>(d.v + 4 * (size_t)j);
+    o[0] = make_double2(Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2);
+    o[1] = make_double2(Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0);
 }
 
 // K9  cg_camera_pass: sum_k W_k v_j(k) = sum_k A~^t P~ R v_j   (second half of S p), persistent row sweep.

@@ -67,11 +67,13 @@ def test_schur_operator_is_symmetric_and_linear():
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["ssba_tiny_s1", "ssba_tiny_s2", "ssba_tiny_s3", "ssba_small_s1", "ssba_small_s2",
                                   "ssba_small_s3", "ssba_ladybug_s1", "ssba_ladybug_s2", "ssba_ladybug_s3"])
-def test_cost_trajectory_matches_reference_golden(name):
-    """Tightly converged PCG (parity mode) reproduces the reference SSBA run: per-iteration cost <= 1e-9 relative."""
+@pytest.mark.parametrize("plan", ["explicit", "matrix_free"])
+def test_cost_trajectory_matches_reference_golden(name, plan):
+    """Tightly converged PCG (parity mode) reproduces the reference SSBA run: per-iteration cost <= 1e-9 relative - on the plan
+    a problem of this size runs by default (explicit reduced camera system) and on the matrix-free plan of the large shapes."""
     fx = load_golden(name)
     p = golden_problem(fx)
-    r = _solve(p, cg_max_steps=4000, cg_rel_tol=1e-13)
+    r = _solve(p, cg_max_steps=4000, cg_rel_tol=1e-13, reduced_system=0 if plan == "explicit" else 1)
     ref = fx["trace"]
     k = parity_window(r.trace, ref)
     assert k >= min(8, len(ref) - 1), (k, len(ref))
@@ -125,10 +127,11 @@ def test_poses_and_rms_match_reference_pba(name):
     ("ladybug", 5, {}, {"fix_first_camera": 1, "inlier_px": 0.0, "round_pixels": 0}),
     ((30, 400, 800), 8, {}, {}),                                         # every point seen exactly twice
 ])
-def test_fifty_step_mode_matches_oracle(shape, seed, kw, opts):
-    """Same algorithm on both sides (fixed 50-step PCG): the GPU follows the CPU restatement."""
+@pytest.mark.parametrize("plan", ["explicit", "matrix_free"])
+def test_fifty_step_mode_matches_oracle(shape, seed, kw, opts, plan):
+    """Same algorithm on both sides (fixed 50-step PCG): the GPU follows the CPU restatement (both execution plans)."""
     p = make_problem(shape, seed, **kw)
-    r = _solve(p, **opts)
+    r = _solve(p, reduced_system=0 if plan == "explicit" else 1, **opts)
     c = oracle.solve(p, **opts)
     k = parity_window(r.trace, c.trace)
     assert k >= min(8, len(c.trace) - 1)
@@ -137,21 +140,26 @@ def test_fifty_step_mode_matches_oracle(shape, seed, kw, opts):
     assert np.array_equal(r.trace[:k, 6], c.trace[:k, 6])               # same PCG step counts
 
 
-@pytest.mark.parametrize("env", ["B200BA_NO_TAB", "B200BA_NO_COOP", "B200BA_NO_GRAPH", "B200BA_NO_LANE_OPT"])
+@pytest.mark.parametrize("env", ["B200BA_NO_TAB", "B200BA_NO_TAB,B200BA_NO_WB", "B200BA_NO_COOP", "B200BA_NO_GRAPH", "B200BA_NO_LANE_OPT", "B200BA_FUSE_STEP",
+                                 "B200BA_PDL_CHAIN=0"])
 def test_alternative_execution_plans_agree(env, monkeypatch):
     """The engine picks its execution plan at set_problem (shared-memory camera table vs generic by-point sweep through the
     packed table in global memory - the plan for problems with more than ~1800 cameras -, cooperative camera-side step vs
     single-CTA kernels, CUDA-graph replay vs stream launches, bank-conflict-aware point grouping).  Every plan must reproduce
     the default one and the oracle."""
     p = make_problem("ladybug", 3, outlier_frac=0.02)
-    base = _solve(p, max_iterations=10)
+    # (a problem of this size runs the explicit reduced-system plan by default; the plans under test belong to the matrix-free
+    #  path - reduced_system = 1 - except the launch mode of the explicit plan's own kernels)
+    mode = 0 if env.startswith("B200BA_PDL_CHAIN") else 1
+    base = _solve(p, max_iterations=10, reduced_system=mode)
     x = np.random.default_rng(5).normal(size=(p.N, 6))
-    with binding.Engine() as eng:
+    with binding.Engine(reduced_system=mode) as eng:
         eng.set_problem_from(p); eng.begin(); g = eng.debug_linearize()
         S0 = eng.debug_schur_matvec(g["lambda0"], x)
-    monkeypatch.setenv(env, "1")
-    alt = _solve(p, max_iterations=10)
-    with binding.Engine() as eng:
+    for e in env.split(","):
+        monkeypatch.setenv(*(e.split("=") if "=" in e else (e, "1")))
+    alt = _solve(p, max_iterations=10, reduced_system=mode)
+    with binding.Engine(reduced_system=mode) as eng:
         eng.set_problem_from(p); eng.begin(); g1 = eng.debug_linearize()
         S1 = eng.debug_schur_matvec(g1["lambda0"], x)
     assert rel(S1, S0) < 1e-12
@@ -204,16 +212,19 @@ def test_ragged_random_problems_match_oracle(seed):
     q = p.copy(); q.obs_xy, q.obs_cam, q.obs_pt = p.obs_xy[keep], p.obs_cam[keep], p.obs_pt[keep]
     o = oracle.linearize(q)
     x = rng.normal(size=(q.N, 6))
-    for generic in (False, True):
-        if generic:
-            os.environ["B200BA_NO_TAB"] = "1"
+    # plans: shared-memory camera table; B~ records + world-axes direction table (the > 2075-camera plan, forced); generic
+    # packed-table gathers; explicit reduced camera system (what a problem of this size runs by default)
+    for generic, (env, mode) in enumerate([((), 1), (("B200BA_NO_TAB",), 1), (("B200BA_NO_TAB", "B200BA_NO_WB"), 1), ((), 0)]):
+        for e in env:
+            os.environ[e] = "1"
         try:
-            with binding.Engine(max_iterations=4) as eng:
+            with binding.Engine(max_iterations=4, reduced_system=mode) as eng:
                 eng.set_problem_from(q); eng.begin(); g = eng.debug_linearize()
                 Sx = eng.debug_schur_matvec(o["lambda0"], x)
                 r = eng.solve()
         finally:
-            os.environ.pop("B200BA_NO_TAB", None)
+            for e in env:
+                os.environ.pop(e, None)
         assert abs(g["cost"] - o["cost"]) < 1e-12 * o["cost"]
         for k in ("gc", "gp", "U", "V"):
             assert rel(g[k], o[k]) < 1e-11, (k, generic)
