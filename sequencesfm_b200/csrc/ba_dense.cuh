@@ -1,17 +1,18 @@
-// ba_dense.cuh -- explicit reduced camera system for small problems (see dense_host.h for why and for the pair lists).
+// ba_dense.cuh -- explicit reduced camera system for tracker-sized problems (see dense_host.h for why and for the pair lists;
+// DESIGN.md section 4b for the measurements behind every choice).
 //
-//   k_dense_wobs      per observation (thread per point over its SELL slots):  W = A~^t B~ (6x3),  Y = W (V + damping)^-1,
-//                     t = Y g_p  (the observation's share of the reduced right-hand side)
+//   k_dense_wobs      thread per observation (SELL entry):  W = A~^t B~ (6x3),  Y = W (V + damping)^-1,  t = Y g_p (the
+//                     observation's share of the reduced right-hand side); also evaluates and stores (V + damping)^-1
 //   k_dense_pairs     36 threads per chunk of <= 32 pairs of one block:  partial  sum  Y_a W_b^t   (+ partial sum of t on the diagonal)
 //   k_dense_finalize  thread per (block, entry): fixed-order sum of the chunk partials ->  S = [U + damping] - sum  (both
 //                     triangles, exactly symmetric), the diagonal blocks' sums for the preconditioner (ar_sd), sum W Vinv g_p (ar_q)
-//   k_dense_pcg       the WHOLE block-Jacobi PCG loop in one launch.  CTA c of the group owns `rows` rows of S in shared memory
-//                     (whole cameras); per step: q = S p on the owned rows, p.q -> every CTA, alpha, x, r, z = M^-1 r on the
-//                     owned rows, z and r.z -> every CTA, beta, p = z + beta p (every CTA, all rows).  Two barriers per step.
-//                       CLUSTER variant: the group is one thread-block cluster (8 or 16 CTAs); the exchange is
-//                         st.shared::cluster into every peer's shared memory + barrier.cluster (~0.2 us);
-//                       GRID variant: the group is the whole (cooperative) grid, one CTA per SM; the exchange goes through
-//                         global memory + grid.sync() - for camera counts whose S does not fit one cluster (up to ~300 cameras).
+//   k_dense_pcg<kind> the WHOLE block-Jacobi PCG loop in one launch.  CTA c of the group owns `rows` rows of S (whole cameras);
+//                     per step: q = S p on the owned rows, p.q -> every CTA, alpha, x, r, z = M^-1 r on the owned rows, z and
+//                     r.z -> every CTA, beta, p = z + beta p (every CTA, all rows).  Two exchanges per step.
+//                       kinds 0 / 1: the group is one thread-block cluster (8 or 16 CTAs), S in registers / shared memory; the
+//                         exchange is st.async into every peer's shared memory completing bytes on the peer's mbarrier;
+//                       kind 2: the group is the whole cooperative grid (two cameras per CTA), S in registers; the exchange goes
+//                         through global memory and a counting barrier - for camera counts beyond one cluster (up to 296).
 //                     Same recurrences, stop rule and breakdown handling as k_cg_camera_step; all sums in fixed order.
 #pragma once
 #include "ba_kernels.cuh"
