@@ -41,7 +41,7 @@ namespace b200ba { PinnedPool g_pinned; }
 #define B200BA_PDL_DEFAULT 0
 #endif
 #ifndef B200BA_SLICE_W_NUM
-#define B200BA_SLICE_W_NUM 2
+#define B200BA_SLICE_W_NUM 4
 #endif
 constexpr int SLICE_W_NUM = B200BA_SLICE_W_NUM, SLICE_W_DEN = 3;   // epilogue of a slice, in row bodies
 
@@ -913,7 +913,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     int tab_warps_cap = (n_sm > 0 ? n_sm : 148) * (std::max(std::max(TAB_BLOCK, TAB2_BLOCK), TABC_BLOCK) / 32);
     const int step_grid = cdiv((long long)N * 6, STEP_BLOCK);
     // large-camera-count plan: the packed camera table will not fit one SM's shared memory (same test as `use_tab` below)
-    const bool want_wb = (((size_t)N * TAB_STRIDE * sizeof(double) + 127) & ~(size_t)127) + TABC_RING_BYTES + 256 > (size_t)smem_optin || getenv("B200BA_NO_TAB") != nullptr;
+    const bool want_wb = (((size_t)(N + 1) * TAB_STRIDE * sizeof(double) + 127) & ~(size_t)127) + TABC_RING_BYTES + 256 > (size_t)smem_optin || getenv("B200BA_NO_TAB") != nullptr;
     h->use_wb = want_wb && !h->use_dense && getenv("B200BA_NO_WB") == nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         Arena& A = h->arena;
@@ -932,7 +932,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->cam_seg_beg.take(A, (size_t)N + 1);
         h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)std::max(n_pt_blocks, tab_warps_cap));
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
-        h->ptab.take(A, (size_t)N * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE); h->fin_part.take(A, 4 * (size_t)cdiv(N, FIN_BLOCK) + 4);
+        h->ptab.take(A, (size_t)(N + 1) * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE); h->fin_part.take(A, 4 * (size_t)cdiv(N, FIN_BLOCK) + 4);
         if (o.lm_variant == 1) { h->cam_D0.take(A, n6); h->pt_D0.take(A, 4 * Mp); }
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
@@ -979,7 +979,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (Kp) CU(cudaMemcpyAsync(h->dn_entry_pt.p, dense_entry_pt.data(), sizeof(int) * (size_t)Kp, cudaMemcpyHostToDevice, s));
     }
     if (Kp) {
-        Dev dr{}; dr.o_rec = h->o_rec.p;
+        Dev dr{}; dr.o_rec = h->o_rec.p; dr.ptab = h->ptab.p; dr.N = N;
         k_fill_orows<<<cdiv(Kp / 32, 8), 256, 0, s>>>(dr, h->o_cam.p, Kp / 32);
     }
     if (n_rows) {
@@ -1006,7 +1006,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
 
     lap("upload");
     // ---- execution plan: shared-memory camera table, cooperative camera-side step, CUDA graph ----
-    const size_t tab_bytes = (size_t)N * TAB_STRIDE * sizeof(double);
+    const size_t tab_bytes = (size_t)(N + 1) * TAB_STRIDE * sizeof(double);   // + the padding entries' dummy camera (record N)
     { const char* e = getenv("B200BA_TAB_ILP"); h->tab_ilp = (e && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : B200BA_TAB_ILP_DEFAULT; }
     h->tab_block = h->tab_ilp == 3 ? TABC_BLOCK : h->tab_ilp == 2 ? TAB2_BLOCK : TAB_BLOCK;
     h->tab_smem = ((tab_bytes + 127) & ~(size_t)127) + (h->tab_ilp == 3 ? TABC_RING_BYTES : h->tab_ilp == 2 ? TAB2_RING_BYTES : TAB_RING_BYTES);   // camera table + per-warp stream rings
@@ -1031,11 +1031,12 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         else cudaGetLastError();
     }
     int tab_warps = std::max(1, h->tab_grid) * (h->tab_block / 32);
-    auto warp_headers = [&](int nwarps, int* dst) -> int {
+    auto warp_headers = [&](int nwarps, int warps_per_cta, int* dst) -> int {
         std::vector<int> wr((size_t)nwarps + 1, n_slices);
         // cost of a slice = SLICE_W_NUM / SLICE_W_DEN row bodies for its epilogue + one per row (clock stamps of the sweep's
         // warps at Venice shape: a slice end costs 0.6-0.7 of a row body; weighting it as a whole row left the CTAs that own
         // the long tracks 10 % behind those with the two-observation points)
+        const long long SLICE_W_NUM = getenv("B200BA_SLICE_W") ? atoll(getenv("B200BA_SLICE_W")) : ::SLICE_W_NUM;   // (thirds of a row body)
         long long total = 0; for (int g = 0; g < n_slices; ++g) total += (long long)SLICE_W_DEN * slice_deg[g] + SLICE_W_NUM;
         long long acc = 0; int w = 0; wr[0] = 0;
         for (int g = 0; g < n_slices && w + 1 < nwarps; ++g) {
@@ -1043,17 +1044,23 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
             while (w + 1 < nwarps && acc * nwarps >= total * (long long)(w + 1)) wr[++w] = g + 1;
         }
         for (int q = w + 1; q <= nwarps; ++q) wr[q] = n_slices;
+        // Range q goes to warp (q / grid) of CTA (q % grid): the points are sorted by track length, so contiguous ranges per CTA gave
+        // the first CTAs only long tracks and the last ones only two-observation points, and whatever the cost model missed showed as
+        // a 10 % spread between the CTAs' finish times; with the ranges dealt out round-robin every SM gets the same mix.  Which warp
+        // sweeps a range changes no arithmetic.  (B200BA_XPOSE=0: contiguous ranges per CTA.)
+        const int wpc = std::max(1, warps_per_cta), grid = std::max(1, nwarps / wpc);
+        const bool xpose = nwarps == grid * wpc && (getenv("B200BA_XPOSE") ? atoi(getenv("B200BA_XPOSE")) != 0 : true);
         std::vector<int> hdr((size_t)nwarps * 8, 0);
         for (int q = 0; q < nwarps; ++q) {
             const int g0 = wr[q], g1 = wr[q + 1];
-            int* o = hdr.data() + 8 * (size_t)q;
+            int* o = hdr.data() + 8 * (size_t)(xpose ? (q % grid) * wpc + q / grid : q);
             o[0] = g0; o[1] = g1; o[2] = slice_base[g0]; o[3] = slice_base[g1];
             o[4] = g0 < n_slices ? slice_deg[g0] : 0; o[5] = g0 + 1 < g1 ? slice_deg[g0 + 1] : 0;
         }
         CU(cudaMemcpy(dst, hdr.data(), sizeof(int) * hdr.size(), cudaMemcpyHostToDevice));
         return 0;
     };
-    if (int rc = warp_headers(tab_warps, h->tab_wr.p)) return rc;
+    if (int rc = warp_headers(tab_warps, h->tab_block / 32, h->tab_wr.p)) return rc;
     // ---- optional mixed-precision PCG (options.pcg_fp32): needs the fp32 camera table in shared memory ----
     h->use_f32 = false;
     int tab_warps32 = 0;
@@ -1066,7 +1073,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         CU(cudaFuncSetAttribute(k_cg_camera_pass32, cudaFuncAttributeMaxDynamicSharedMemorySize, CAMPASS32_SMEM));
         h->tab32_grid = std::max(1, std::min(h->num_sms, cdiv(n_slices, TAB32_BLOCK / 32)));
         tab_warps32 = h->tab32_grid * (TAB32_BLOCK / 32);
-        if (int rc = warp_headers(tab_warps32, h->tab_wr32.p)) return rc;
+        if (int rc = warp_headers(tab_warps32, TAB32_BLOCK / 32, h->tab_wr32.p)) return rc;
         h->use_f32 = true;
     }
     if ((size_t)CAMPASS_SMEM > (size_t)smem_optin) return fail(h, B200BA_E_CUDA, "device offers %d bytes of shared memory per block, the by-camera sweep needs %d", smem_optin, CAMPASS_SMEM);

@@ -70,6 +70,10 @@ constexpr int STAGE_BYTES  = CG * REC_BYTES;
 constexpr int CAMPASS_SMEM = CW * CNS * STAGE_BYTES + CW * CNS * 8;
 constexpr int ONE_CTA      = 1024;  // threads of the single-CTA camera-side kernels
 constexpr int TRACE_COLS   = 8;
+#ifndef B200BA_WHATIF
+#define B200BA_WHATIF 0      // bit mask (1, 2, 4, 8, 16, 32): timing experiments on the by-point PCG sweep (tools/gpu_r2d.sh whatif), results are WRONG with them
+#endif
+constexpr double QUAT_SCALE = 1.4142135623730951;   // the camera tables hold sqrt(2) x the unit quaternion: the sandwich's factor 2 comes with the components
 constexpr int TAB_STRIDE   = 14;    // doubles per camera in the packed table: quaternion 4, T 3, p 6, pad 1 (112 B = 7 x 16 B)
 #ifndef B200BA_TAB_BLOCK
 #define B200BA_TAB_BLOCK 608
@@ -933,43 +937,76 @@ __global__ void __launch_bounds__(192) k_precond_invert(Dev d, int precond)
 
 // one observation of the by-point CG sweep against the packed camera table [quaternion 4 | T 3 | p 6 | pad]
 struct TabRow { double h0, h1, h2, qw, qx, qy, qz, t0, t1; };   // t = A~ p is only read by the back-substitution (|J delta|^2)
+// The table carries the rotation as sqrt(2) x the unit quaternion (QUAT_SCALE): every term of the sandwich
+//   r = X + 2 (qw t + qv x t),  t = qv x X
+// is quadratic in q, so the factor 2 comes with the scaled components and each component of r is a chain of three FMAs that
+// starts at X (was: 2 products + 2 FMAs).  Record N of the table (tab_pad_cam) is a dummy camera for SELL padding entries -
+// identity rotation, depth 1e100, zero direction; the padding weights of the row records are 0 (k_fill_orows) - so the row body
+// runs without a select or a divergent branch and contributes exact zeros whatever the point is.
+// The by-point sweep is bound by instruction issue (FP64 = 2 issue cycles): the row body below has 59 FP64 instructions, the
+// first version had 71 (s = p_t + p_w x r as 2 FMAs per component instead of 3 operations; P~^t P~ s through x/z, y/z so that
+// the two off-diagonal entries of P~ are never formed).
 // first half of a row body: forward rotation, projection Jacobian, t = A~ p, h = P~^t t  (table fields die here)
 // GLOBAL = false: the table lives in shared memory (k_cg_point_pass_tab); true: read-only global loads (problems whose
 // camera table does not fit one SM's shared memory: 7 x LDG.128 instead of the 9 of [R|T] + p)
-// pad: the entry is SELL padding - the caller passes camera 0 and weight 0 and the depth is replaced by 1, so the row body
-// runs without a divergent branch and contributes exact zeros
+__device__ __forceinline__ int tab_pad_cam(int cam, int n_cams) { return (int)min((unsigned)cam, (unsigned)n_cams); }   // -1 (padding) -> record N
+__device__ __forceinline__ void tab_row_core(const double2 a0, const double2 a1, const double2 a2, const double2 a3, const double2 a4, const double2 a5,
+                                             const double2 a6, double w, const double X[3], const Intrinsics& in, TabRow& o)
+{
+    const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;      // sqrt(2) x unit quaternion
+    const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];      // t = qv x X
+    const double r0 = fma(qw, tx, fma(qy, tz, fma(-qz, ty, X[0])));                                        // r = X + qw t + qv x t
+    const double r1 = fma(qw, ty, fma(qz, tx, fma(-qx, tz, X[1])));
+    const double r2 = fma(qw, tz, fma(qx, ty, fma(-qy, tx, X[2])));
+    const double x = r0 + a2.x, y = r1 + a2.y, z = r2 + a3.x;
+    const double iz = fast_rcp(z);
+    const double pa = w * in.k00 * iz, pc = in.ar * pa;           // P~ = [[pa, 0, -pa x/z], [0, pc, -pc y/z]]
+    const double xz = x * iz, yz = y * iz;
+    // s = p_t + p_w x r,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x);  t = A~ p = P~ s
+    const double s0 = fma(-a6.x, r1, fma(a5.y, r2, a3.y));
+    const double s1 = fma(-a5.x, r2, fma(a6.x, r0, a4.x));
+    const double s2 = fma(-a5.y, r0, fma(a5.x, r1, a4.y));
+    const double t0 = pa * fma(-xz, s2, s0), t1 = pc * fma(-yz, s2, s1);
+    o.h0 = pa * t0; o.h1 = pc * t1; o.h2 = fma(-yz, o.h1, -(xz * o.h0));
+    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz; o.t0 = t0; o.t1 = t1;
+}
 template <bool GLOBAL>
-__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o, bool pad = false)
+__device__ __forceinline__ void tab_row_fwd(const double2* __restrict__ tab, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
 {
     const double2* t = tab + 7 * cam;
     double2 a0, a1, a2, a3, a4, a5, a6;
     if (GLOBAL) { a0 = __ldg(t); a1 = __ldg(t + 1); a2 = __ldg(t + 2); a3 = __ldg(t + 3); a4 = __ldg(t + 4); a5 = __ldg(t + 5); a6 = __ldg(t + 6); }
     else { a0 = t[0]; a1 = t[1]; a2 = t[2]; a3 = t[3]; a4 = t[4]; a5 = t[5]; a6 = t[6]; }
-    const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
-    // r = R X by the quaternion sandwich  r = X + 2 (qw t + qv x t),  t = qv x X   (no 3x3 matrix in registers)
-    const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];      // t = qv x X
-    const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);                                         // r = X + 2 (qw t + qv x t)
-    const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
-    const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
-    const double x = r0 + a2.x, y = r1 + a2.y, z = pad ? 1.0 : r2 + a3.x;
-    const double iz = fast_rcp(z);
-    const double wf = w * in.k00 * iz;
-    const double pa = wf, pb = -wf * x * iz, pc = in.ar * wf, pd = -in.ar * wf * y * iz;
-    // t = A~ p,  p = (a3.y a4.x a4.y | a5.x a5.y a6.x)
-    const double s0 = a3.y + (a5.y * r2 - a6.x * r1);
-    const double s1 = a4.x + (a6.x * r0 - a5.x * r2);
-    const double s2 = a4.y + (a5.x * r1 - a5.y * r0);
-    const double t0 = pa * s0 + pb * s2, t1 = pc * s1 + pd * s2;
-    o.h0 = pa * t0; o.h1 = pc * t1; o.h2 = pb * t0 + pd * t1;
-    o.qw = qw; o.qx = qx; o.qy = qy; o.qz = qz; o.t0 = t0; o.t1 = t1;
+    tab_row_core(a0, a1, a2, a3, a4, a5, a6, w, X, in, o);
 }
-// second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion
+// the same against a table addressed by its shared-memory window address (tab_smem_base): the base stays in ONE register; through the
+// generic pointer the compiler re-derived it from %cluster_ctaid in every trip of the sweep's loop (S2R + MOV + VIADD + LEA)
+__device__ __forceinline__ double2 lds_d2(uint32_t a) { double2 v; asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t tab_smem_base(const void* smem) { uint32_t a = smem_u32(smem); asm volatile("" : "+r"(a)); return a; }
+__device__ __forceinline__ void tab_row_fwd_s(uint32_t tab_s, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
+{
+    const uint32_t t = tab_s + 112u * (uint32_t)cam;
+#if B200BA_WHATIF & 2         // timing experiment (wrong results): ONE table load per observation instead of seven
+    const double2 a0 = lds_d2(t), a1 = make_double2(a0.y, a0.x), a2 = a0, a3 = a1, a4 = a0, a5 = a1;
+    double2 a6; a6.x = a0.x; a6.y = 0.0;
+#else
+    const double2 a0 = lds_d2(t), a1 = lds_d2(t + 16u), a2 = lds_d2(t + 32u), a3 = lds_d2(t + 48u), a4 = lds_d2(t + 64u), a5 = lds_d2(t + 80u);
+    double2 a6; a6.x = lds_f64(t + 96u); a6.y = 0.0;
+#endif
+#if B200BA_WHATIF & 4         // timing experiment (wrong results): the loads, almost no arithmetic
+    o.h0 = a0.x + a1.x + a2.x + w; o.h1 = a3.x + a4.x + a5.x + X[0]; o.h2 = a6.x + a0.y + a1.y + a2.y + a3.y + a4.y + a5.y;
+    o.qw = o.qx = o.qy = o.qz = o.t0 = o.t1 = 0.0;
+#else
+    tab_row_core(a0, a1, a2, a3, a4, a5, a6, w, X, in, o);
+#endif
+}
+// second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion (same scaled components)
 __device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
 {
     const double gx = o.qz * o.h1 - o.qy * o.h2, gy = o.qx * o.h2 - o.qz * o.h0, gz = o.qy * o.h0 - o.qx * o.h1;   // g = -qv x h
-    u0 += fma(2.0, o.qw * gx + (o.qz * gy - o.qy * gz), o.h0);
-    u1 += fma(2.0, o.qw * gy + (o.qx * gz - o.qz * gx), o.h1);
-    u2 += fma(2.0, o.qw * gz + (o.qy * gx - o.qx * gy), o.h2);
+    u0 = fma(o.qw, gx, fma(o.qz, gy, fma(-o.qy, gz, u0 + o.h0)));
+    u1 = fma(o.qw, gy, fma(o.qx, gz, fma(-o.qz, gx, u1 + o.h1)));
+    u2 = fma(o.qw, gz, fma(o.qy, gx, fma(-o.qx, gy, u2 + o.h2)));
 }
 // ------------------------------------------------------------------------------------------------------
 // K8  cg_point_pass: v_j = (V+lambda I)^-1 u_j with
@@ -1148,17 +1185,17 @@ __device__ __forceinline__ void cam_pass_one(const Cam& cm, const Intrinsics& in
 {
     const double x = r0 + cm.T[0], y = r1 + cm.T[1], z = ok ? r2 + cm.T[2] : 1.0;
     const double iz = fast_rcp(z);
-    const double wf = w * in.k00 * iz, ar = in.ar;
-    const double pa = wf, pb = -wf * x * iz, pc = ar * wf, pd = -ar * wf * y * iz;
+    const double pa = w * in.k00 * iz, pc = in.ar * pa;           // P~ = [[pa, 0, -pa x/z], [0, pc, -pc y/z]] (the off-diagonal entries are never formed)
+    const double xz = x * iz, yz = y * iz;
     const double g0 = cm.R[0] * v[0] + cm.R[1] * v[1] + cm.R[2] * v[2];
     const double g1 = cm.R[3] * v[0] + cm.R[4] * v[1] + cm.R[5] * v[2];
     const double g2 = cm.R[6] * v[0] + cm.R[7] * v[1] + cm.R[8] * v[2];
-    const double y0 = pa * g0 + pb * g2, y1 = pc * g1 + pd * g2;
-    const double h0 = pa * y0, h1 = pc * y1, h2 = pb * y0 + pd * y1;
+    const double y0 = pa * fma(-xz, g2, g0), y1 = pc * fma(-yz, g2, g1);
+    const double h0 = pa * y0, h1 = pc * y1, h2 = fma(-yz, h1, -(xz * h0));
     acc[0] += h0; acc[1] += h1; acc[2] += h2;
-    acc[3] += r1 * h2 - r2 * h1;       // r x h
-    acc[4] += r2 * h0 - r0 * h2;
-    acc[5] += r0 * h1 - r1 * h0;
+    acc[3] = fma(r1, h2, fma(-r2, h1, acc[3]));       // r x h
+    acc[4] = fma(r2, h0, fma(-r0, h2, acc[4]));
+    acc[5] = fma(r0, h1, fma(-r1, h0, acc[5]));
 }
 // the sweep of one warp over its row range (returns early for warps without rows: no CTA-wide barrier inside)
 __device__ __forceinline__ void camera_pass_sweep(const Dev& d, const LMState* st, unsigned char* smem_raw)
@@ -1466,6 +1503,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
 // once per linearisation; the CG kernels keep the p-part current.
 // ------------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int qtab_unit(int c, int f);
+__device__ __forceinline__ void rot_to_quat(const double* s, double q[4]);
 // also_qtab: the compact [quaternion | T] table of the same cameras in the same launch (k_build_qtab(d, 0); its only reader,
 // k_lin_tab, runs under the same `compute` flag)
 __global__ void __launch_bounds__(128) k_build_ptab(Dev d, int also_qtab)
@@ -1476,28 +1514,28 @@ __global__ void __launch_bounds__(128) k_build_ptab(Dev d, int also_qtab)
     int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= d.N) return;
     const double* s = d.rt[st->cur] + 12 * (size_t)i;
-    double R0 = s[0], R1 = s[1], R2 = s[2], R3 = s[4], R4 = s[5], R5 = s[6], R6 = s[8], R7 = s[9], R8 = s[10];
-    double w, x, y, z, tr = R0 + R4 + R8;
-    if (tr > 0) { double q = sqrt(tr + 1.0) * 2.0; w = 0.25 * q; x = (R7 - R5) / q; y = (R2 - R6) / q; z = (R3 - R1) / q; }
-    else if (R0 > R4 && R0 > R8) { double q = sqrt(1.0 + R0 - R4 - R8) * 2.0; w = (R7 - R5) / q; x = 0.25 * q; y = (R1 + R3) / q; z = (R2 + R6) / q; }
-    else if (R4 > R8) { double q = sqrt(1.0 + R4 - R0 - R8) * 2.0; w = (R2 - R6) / q; x = (R1 + R3) / q; y = 0.25 * q; z = (R5 + R7) / q; }
-    else { double q = sqrt(1.0 + R8 - R0 - R4) * 2.0; w = (R3 - R1) / q; x = (R2 + R6) / q; y = (R5 + R7) / q; z = 0.25 * q; }
-    double n = 1.0 / sqrt(w * w + x * x + y * y + z * z);
+    double q[4]; rot_to_quat(s, q);                               // sqrt(2) x unit quaternion (QUAT_SCALE)
     double* o = d.ptab + (size_t)i * TAB_STRIDE;
-    o[0] = w * n; o[1] = x * n; o[2] = y * n; o[3] = z * n; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
+    o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
     if (also_qtab) {
         double2* t = reinterpret_cast<double2*>(d.qtab);
-        t[qtab_unit(i, 0)] = make_double2(w * n, x * n); t[qtab_unit(i, 1)] = make_double2(y * n, z * n);
+        t[qtab_unit(i, 0)] = make_double2(q[0], q[1]); t[qtab_unit(i, 1)] = make_double2(q[2], q[3]);
         t[qtab_unit(i, 2)] = make_double2(s[3], s[7]); t[qtab_unit(i, 3)] = make_double2(s[11], 0.0);
     }
 }
 
-// one warp per point-order row: camera indices into the row record (the weights are written by the linearisation)
+// one warp per point-order row: camera indices into the row record; the weights start at 0 (the linearisation writes those of the
+// real entries, the padding entries keep 0: the table sweeps run them against the dummy camera without a select).  Thread 0
+// also writes that dummy camera, record N of the packed table: identity rotation, depth 1e100, zero direction (tab_row_fwd).
 __global__ void __launch_bounds__(256) k_fill_orows(Dev d, const int* __restrict__ o_cam, int n_orows)
 {
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x < TAB_STRIDE)
+        d.ptab[(size_t)d.N * TAB_STRIDE + threadIdx.x] = threadIdx.x == 0 ? QUAT_SCALE : threadIdx.x == 6 ? 1e100 : 0.0;
     if (r >= n_orows) return;
-    reinterpret_cast<int*>(d.o_rec + (size_t)r * OREC_BYTES)[lane] = o_cam[32 * (size_t)r + lane];
+    unsigned char* rec = d.o_rec + (size_t)r * OREC_BYTES;
+    reinterpret_cast<int*>(rec)[lane] = o_cam[32 * (size_t)r + lane];
+    reinterpret_cast<double*>(rec + 128)[lane] = 0.0;
 }
 
 // ---- device-side build of the camera-order row records (set_problem) ----
@@ -1558,7 +1596,7 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
     const LMState* st = d.st;
     if (st->done || !st->cg_active) return;
     const double2* tab = reinterpret_cast<const double2*>(smem_raw);
-    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+    const uint32_t total = (uint32_t)(d.N + 1) * TAB_STRIDE * 8u;    // + the padding entries' dummy camera
 #ifdef B200BA_STAMPS
     unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
     if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
@@ -1678,8 +1716,7 @@ __global__ void __launch_bounds__(TAB_BLOCK, 1) k_cg_point_pass_tab(Dev d)
         if (++slot == PR) { slot = 0; par ^= 1u; }
         const bool last = (--rows_left == 0);                    // warp-uniform
         TabRow o;
-        const bool pad = cam < 0;                                // padding entries run the body on camera 0 with weight 0: no divergence
-        tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
+        tab_row_fwd<false>(tab, tab_pad_cam(cam, d.N), w, X, d.in, o);
         double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};     // (leaving these uninitialised measured 6 us SLOWER; requesting
         if (last) request(Vi, Xn);                                //  before the forward half 2 us slower)
         tab_row_bwd(o, u0, u1, u2);
@@ -1709,7 +1746,7 @@ __global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
     const LMState* st = d.st;
     if (st->done || !st->cg_active) return;
     const double2* tab = reinterpret_cast<const double2*>(smem_raw);
-    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+    const uint32_t total = (uint32_t)(d.N + 1) * TAB_STRIDE * 8u;    // + the padding entries' dummy camera
 #ifdef B200BA_STAMPS
     unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
     if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
@@ -1819,9 +1856,8 @@ __global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
             r += 2; rows_left -= 2;
             const bool last = rows_left == 0;
             TabRow oA, oB;
-            const bool padA = camA < 0, padB = camB < 0;
-            tab_row_fwd<false>(tab, padA ? 0 : camA, padA ? 0.0 : wA, X, d.in, oA, padA);
-            tab_row_fwd<false>(tab, padB ? 0 : camB, padB ? 0.0 : wB, X, d.in, oB, padB);
+            tab_row_fwd<false>(tab, tab_pad_cam(camA, d.N), wA, X, d.in, oA);
+            tab_row_fwd<false>(tab, tab_pad_cam(camB, d.N), wB, X, d.in, oB);
             double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
             if (last) request(Vi, Xn);
             tab_row_bwd(oA, u0, u1, u2);
@@ -1831,8 +1867,7 @@ __global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
             if (r & 1) rearm = (r >> 1) & 1;
             r += 1; rows_left = 0;
             TabRow oA;
-            const bool padA = camA < 0;
-            tab_row_fwd<false>(tab, padA ? 0 : camA, padA ? 0.0 : wA, X, d.in, oA, padA);
+            tab_row_fwd<false>(tab, tab_pad_cam(camA, d.N), wA, X, d.in, oA);
             double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
             request(Vi, Xn);
             tab_row_bwd(oA, u0, u1, u2);
@@ -1859,7 +1894,16 @@ __global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
 #ifndef B200BA_TABC_ROWS
 #define B200BA_TABC_ROWS 4
 #endif
-constexpr int TABC_BLOCK = B200BA_TABC_BLOCK, TABC_ROWS = B200BA_TABC_ROWS;
+#ifndef B200BA_TABC_PF
+#define B200BA_TABC_PF 0      // rows of the stream kept in L2 ahead of the ring (0 = off; 8 .. 32 measured 0.3 .. 2.4 us SLOWER)
+#endif
+#ifndef B200BA_TABC_EARLY
+#define B200BA_TABC_EARLY 0   // 1: the slice-end loads are requested before the last row body instead of in its middle
+#endif
+#ifndef B200BA_TABC_PFN
+#define B200BA_TABC_PFN 4     // rows per bulk L2 prefetch (power of two)
+#endif
+constexpr int TABC_BLOCK = B200BA_TABC_BLOCK, TABC_ROWS = B200BA_TABC_ROWS, TABC_PF = B200BA_TABC_PF, TABC_PFN = B200BA_TABC_PFN;
 constexpr int TABC_RING_BYTES = (TABC_BLOCK / 32) * (TABC_ROWS * OREC_BYTES);
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
@@ -1870,8 +1914,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
-    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
-    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+    const uint32_t total = (uint32_t)(d.N + 1) * TAB_STRIDE * 8u;    // + the padding entries' dummy camera
 #ifdef B200BA_STAMPS
     unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
     if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
@@ -1894,7 +1937,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     const unsigned char* src_lane = src_rows + 4 * lane;          // camera index of this lane in the row; weight at + 128 + 4 lane more
     int fetched = 0;                                              // rows requested so far
     auto fetch = [&]() {
-        if (fetched < n_rows) {
+        if (fetched < n_rows && !(B200BA_WHATIF & 16)) {          // (16 = timing experiment: no row stream at all)
             const uint32_t dst = ring + (uint32_t)(fetched % TABC_ROWS) * OREC_BYTES + 4u * lane;
             cp_async4(dst, src_lane);
             cp_async8(dst + 128u + 4u * lane, src_lane + 128 + 4 * lane);
@@ -1905,6 +1948,12 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     };
 #pragma unroll
     for (int i = 0; i < TABC_ROWS - 1; ++i) fetch();
+    // The ring holds TABC_ROWS - 1 rows in flight per warp (shared memory is full of camera table): 23 KB per SM against a DRAM
+    // latency of ~0.8 us is 25 GB/s per SM by Little's law - exactly what the sweep ran at, whatever its arithmetic did
+    // (tools/gpu_r2d.sh whatif).  So the stream is pulled into L2 TABC_PF rows ahead of the ring, TABC_PFN rows per bulk prefetch:
+    // the ring's copies then wait for an L2 hit instead of DRAM.
+    if (TABC_PF > 0 && lane == 0 && n_rows > TABC_ROWS - 1)
+        prefetch_l2_bulk(src_rows + (size_t)(TABC_ROWS - 1) * OREC_BYTES, (uint32_t)min(TABC_PF, n_rows - (TABC_ROWS - 1)) * OREC_BYTES);
     double X[3] = {0, 0, 0};
     if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
     // Everything above reads what no PCG kernel writes (slice headers, row records, X): with programmatic dependent launch it runs
@@ -1927,21 +1976,25 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     struct EndStamp { unsigned long long* p; int lane; __device__ ~EndStamp() { if (lane == 0) *p = clock64(); } } end_stamp{stp + 8 + warp, lane};
 #endif
     if (g >= g_end) return;
+    const uint32_t tab_s = tab_smem_base(smem_raw);
     double u0 = 0, u1 = 0, u2 = 0;
     auto request = [&](double Vi[6], double Xn[3]) {
+#if B200BA_WHATIF & 1         // timing experiment (wrong results): no global loads at the end of a slice
+        Vi[0] = Vi[1] = Vi[2] = Vi[3] = Vi[4] = Vi[5] = 1.0; Xn[0] = Xn[1] = Xn[2] = 0.5; return;
+#endif
         if (32 * g + lane < d.M) load6(d.Vinv, 32 * g + lane, Vi);
         if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, policy_evict_last());
     };
     auto finish = [&](const double Vi[6], const double Xn[3]) -> bool {
         const int j = 32 * g + lane;
-        if (j < d.M)
+        if (j < d.M && (!(B200BA_WHATIF & 32) || u0 == 123.456))   // (32 = timing experiment: v is never written)
             store4_keep(d.v + 4 * (size_t)j, Vi[0] * u0 + Vi[1] * u1 + Vi[2] * u2, Vi[1] * u0 + Vi[3] * u1 + Vi[4] * u2,
                         Vi[2] * u0 + Vi[4] * u1 + Vi[5] * u2, 0.0, policy_evict_last());
         if (++g >= g_end) return false;
         rows_left = deg_next; X[0] = Xn[0]; X[1] = Xn[1]; X[2] = Xn[2]; u0 = u1 = u2 = 0;
         if (g + 1 < g_end) {
-            deg_next = __ldg(d.slice_deg + g + 1);
-            if (lane == 0) {
+            deg_next = (B200BA_WHATIF & 128) ? 5 : __ldg(d.slice_deg + g + 1);
+            if (lane == 0 && !(B200BA_WHATIF & 64)) {
                 const int nj = min(32, d.M - 32 * (g + 1));
                 if (nj > 0) { prefetch_l2_bulk(d.Vinv + 6 * (size_t)(32 * (g + 1)), (uint32_t)nj * 48u); prefetch_l2_bulk(Xb + 4 * (size_t)(32 * (g + 1)), (uint32_t)nj * 32u); }
             }
@@ -1949,27 +2002,54 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
         return true;
     };
     int r = 0;                                                    // rows consumed
-    for (;;) {
-        while (rows_left == 0) {
-            double Vi[6], Xn[3];
-            request(Vi, Xn);
-            if (!finish(Vi, Xn)) return;
-        }
+    while (rows_left == 0) {                                      // leading slices without observations
+        double Vi[6], Xn[3];
+        request(Vi, Xn);
+        if (!finish(Vi, Xn)) return;
+    }
+    for (;;) {                                                    // invariant: rows_left > 0 (the common path tests it once per row, below)
         fetch();                                                  // row r + TABC_ROWS - 1 into the slot row r - 1 has left
+#if !(B200BA_WHATIF & 8)     // 8 = timing experiment (wrong results): never wait for the row stream
         cp_async_wait<TABC_ROWS - 1>();                           // all but the newest TABC_ROWS - 1 groups have landed: row r is there
+#endif
         const uint32_t ca = ring + (uint32_t)(r % TABC_ROWS) * OREC_BYTES + 4u * lane;
         const int cam = lds_s32(ca);
         const double w = lds_f64(ca + 128u + 4u * lane);
         ++r;
+        if (TABC_PF > 0 && (r & (TABC_PFN - 1)) == 0 && lane == 0) {        // rows [r + PF + ROWS - 1, + PFN) -> L2
+            const int first = r + TABC_PF + TABC_ROWS - 1;
+            if (first < n_rows) prefetch_l2_bulk(src_rows + (size_t)first * OREC_BYTES, (uint32_t)min(TABC_PFN, n_rows - first) * OREC_BYTES);
+        }
         TabRow o;
-        const bool pad = cam < 0;
-        tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
+#if B200BA_TABC_EARLY
+        if (--rows_left != 0) {                                   // warp-uniform; the common path carries no slice-end state
+            tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
+            tab_row_bwd(o, u0, u1, u2);
+            continue;
+        }
+        {
+            double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+            request(Vi, Xn);                                      // what the END of the slice needs, in flight during the whole last row body
+            tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
+            tab_row_bwd(o, u0, u1, u2);
+            if (!finish(Vi, Xn)) return;
+        }
+#else
+        tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
         if (--rows_left != 0) {                                   // warp-uniform; the common path carries no slice-end state
             tab_row_bwd(o, u0, u1, u2);
-        } else {
+            continue;
+        }
+        {
             double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
             request(Vi, Xn);                                      // what the END of the slice needs, in flight during the back-rotation
             tab_row_bwd(o, u0, u1, u2);
+            if (!finish(Vi, Xn)) return;
+        }
+#endif
+        while (rows_left == 0) {                                  // slices without observations
+            double Vi[6], Xn[3];
+            request(Vi, Xn);
             if (!finish(Vi, Xn)) return;
         }
     }
@@ -1990,7 +2070,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
 constexpr int QTAB_STRIDE = 8;                                   // doubles per camera of the compact table: quaternion 4, T 3, pad
 // physical 16-byte unit of logical field f (0: qw qx, 1: qy qz, 2: T0 T1, 3: T2 pad) of camera c
 __host__ __device__ __forceinline__ int qtab_unit(int c, int f) { return 4 * c + (f ^ ((c >> 1) & 3)); }   // (declared above k_build_ptab)
-// R (row-major 3x3 at stride 4 of an [R|T] record) -> unit quaternion; the conversion of k_build_ptab
+// R (row-major 3x3 at stride 4 of an [R|T] record) -> QUAT_SCALE x unit quaternion (what every camera table carries, see tab_row_fwd)
 __device__ __forceinline__ void rot_to_quat(const double* s, double q[4])
 {
     double R0 = s[0], R1 = s[1], R2 = s[2], R3 = s[4], R4 = s[5], R5 = s[6], R6 = s[8], R7 = s[9], R8 = s[10];
@@ -1999,7 +2079,7 @@ __device__ __forceinline__ void rot_to_quat(const double* s, double q[4])
     else if (R0 > R4 && R0 > R8) { double t = sqrt(1.0 + R0 - R4 - R8) * 2.0; w = (R7 - R5) / t; x = 0.25 * t; y = (R1 + R3) / t; z = (R2 + R6) / t; }
     else if (R4 > R8) { double t = sqrt(1.0 + R4 - R0 - R8) * 2.0; w = (R2 - R6) / t; x = (R1 + R3) / t; y = 0.25 * t; z = (R5 + R7) / t; }
     else { double t = sqrt(1.0 + R8 - R0 - R4) * 2.0; w = (R3 - R1) / t; x = (R2 + R6) / t; y = (R5 + R7) / t; z = 0.25 * t; }
-    double n = 1.0 / sqrt(w * w + x * x + y * y + z * z);
+    double n = QUAT_SCALE / sqrt(w * w + x * x + y * y + z * z);
     q[0] = w * n; q[1] = x * n; q[2] = y * n; q[3] = z * n;
 }
 // compact [quaternion | T] table of camera set `which` (0 / 1 = rt[which]); one thread per camera
@@ -2035,8 +2115,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
     if (st->done || !st->solve_ok) return;
-    const double2* tab = reinterpret_cast<const double2*>(smem_raw);
-    const uint32_t total = (uint32_t)d.N * TAB_STRIDE * 8u;
+    const uint32_t total = (uint32_t)(d.N + 1) * TAB_STRIDE * 8u;    // + the padding entries' dummy camera
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, total);
@@ -2077,6 +2156,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
     if (g < g_end && 32 * g + lane < d.M) load3p(Xb, 32 * g + lane, X);
     __syncthreads();
     mbar_wait(&bar, 0);
+    const uint32_t tab_s = tab_smem_base(smem_raw);
     double d2 = 0, dg = 0, njx = 0;                               // this lane's share of |delta_p|^2, delta_p . g_p, |J delta|^2
     double u0 = 0, u1 = 0, u2 = 0, tt = 0;                        // tt: sum over the point's observations of |A~ delta_c|^2
     const bool pba = st->variant == 1;
@@ -2126,8 +2206,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_backsub_tab(Dev d)
         const double w = lds_f64(ca + 128u + 4u * lane);
         ++r;
         TabRow o;
-        const bool pad = cam < 0;
-        tab_row_fwd<false>(tab, pad ? 0 : cam, pad ? 0.0 : w, X, d.in, o, pad);
+        tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
         if (pba) tt += o.t0 * o.t0 + o.t1 * o.t1;
         if (--rows_left != 0) tab_row_bwd(o, u0, u1, u2);
         else {
@@ -2219,9 +2298,9 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cost_tab(Dev d)
         const double2 a0 = tab[qtab_unit(c, 0)], a1 = tab[qtab_unit(c, 1)], a2 = tab[qtab_unit(c, 2)], a3 = tab[qtab_unit(c, 3)];
         const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
         const double tx = qy * X[2] - qz * X[1], ty = qz * X[0] - qx * X[2], tz = qx * X[1] - qy * X[0];
-        const double r0 = fma(2.0, qw * tx + (qy * tz - qz * ty), X[0]);
-        const double r1 = fma(2.0, qw * ty + (qz * tx - qx * tz), X[1]);
-        const double r2 = fma(2.0, qw * tz + (qx * ty - qy * tx), X[2]);
+        const double r0 = fma(qw, tx, fma(qy, tz, fma(-qz, ty, X[0])));      // scaled quaternion, see tab_row_fwd
+        const double r1 = fma(qw, ty, fma(qz, tx, fma(-qx, tz, X[1])));
+        const double r2 = fma(qw, tz, fma(qx, ty, fma(-qy, tx, X[2])));
         const double x = r0 + a2.x, y = r1 + a2.y, z = pad ? 1.0 : r2 + a3.x;
         const double iz = fast_rcp(z);
         const double uu = x * iz, vv = y * iz;
@@ -2328,11 +2407,11 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_lin_tab(Dev d)
         if (cam >= 0) {                                           // padding entries only occur where track lengths differ inside a slice
             const double2 a0 = tab[qtab_unit(cam, 0)], a1 = tab[qtab_unit(cam, 1)], a2 = tab[qtab_unit(cam, 2)], a3 = tab[qtab_unit(cam, 3)];
             const double qw = a0.x, qx = a0.y, qy = a1.x, qz = a1.y;
-            Cam cm;                                               // R from the unit quaternion
-            const double xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
-            cm.R[0] = 1.0 - 2.0 * (yy + zz); cm.R[1] = 2.0 * (xy - wz); cm.R[2] = 2.0 * (xz + wy);
-            cm.R[3] = 2.0 * (xy + wz); cm.R[4] = 1.0 - 2.0 * (xx + zz); cm.R[5] = 2.0 * (yz - wx);
-            cm.R[6] = 2.0 * (xz - wy); cm.R[7] = 2.0 * (yz + wx); cm.R[8] = 1.0 - 2.0 * (xx + yy);
+            Cam cm;                                               // R from the sqrt(2)-scaled quaternion: the factors 2 come with the components
+            const double wx = qw * qx, wy = qw * qy, wz = qw * qz;
+            cm.R[0] = fma(-qz, qz, fma(-qy, qy, 1.0)); cm.R[1] = fma(qx, qy, -wz); cm.R[2] = fma(qx, qz, wy);
+            cm.R[3] = fma(qx, qy, wz); cm.R[4] = fma(-qz, qz, fma(-qx, qx, 1.0)); cm.R[5] = fma(qy, qz, -wx);
+            cm.R[6] = fma(qx, qz, -wy); cm.R[7] = fma(qy, qz, wx); cm.R[8] = fma(-qy, qy, fma(-qx, qx, 1.0));
             cm.T[0] = a2.x; cm.T[1] = a2.y; cm.T[2] = a3.x;
             Obs o; obs_full(cm, X, m, in, o);
             *wp = o.w;

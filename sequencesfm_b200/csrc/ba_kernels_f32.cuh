@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(128) k_f32_cameras(Dev d)               // rt3
     for (int c = 0; c < 12; ++c) d.rt32[12 * (size_t)i + c] = (float)s[c];
     const double* t = d.ptab + (size_t)i * TAB_STRIDE;
     float* o = d.ptab32 + (size_t)i * TAB32_STRIDE;
-    o[0] = (float)t[0]; o[1] = (float)t[1]; o[2] = (float)t[2]; o[3] = (float)t[3]; o[4] = (float)t[4]; o[5] = (float)t[5]; o[6] = (float)t[6]; o[7] = 0.f;
+    constexpr double us = 1.0 / QUAT_SCALE;                      // ptab holds sqrt(2) x the unit quaternion, the fp32 table the unit one
+    o[0] = (float)(us * t[0]); o[1] = (float)(us * t[1]); o[2] = (float)(us * t[2]); o[3] = (float)(us * t[3]); o[4] = (float)t[4]; o[5] = (float)t[5]; o[6] = (float)t[6]; o[7] = 0.f;
     for (int c = 14; c < 20; ++c) o[c] = 0.f;
 }
 // weights of the point-order rows: one thread per padded entry

@@ -32,3 +32,5 @@ for name, base, nw in (("point_pass_tab", 0, int(os.environ.get("TABW", "19"))),
     print("  warp end after CTA entry (cycles):", q(ends[~np.isnan(ends)]))
     cta_end = np.nanmax(ends, axis=1)
     print("  CTA end (max over warps, cycles):", q(cta_end), "| warp spread inside a CTA (max-min):", q(np.nanmax(ends, axis=1) - np.nanmin(ends, axis=1)))
+    # per-warp-slot finish time (mean over CTAs): which of a CTA's warps (= which band of track lengths) runs longest
+    print("  warp slot mean end (cycles):", " ".join(f"{x:.0f}" for x in np.nanmean(ends, axis=0)))
