@@ -38,7 +38,7 @@ namespace b200ba { PinnedPool g_pinned; }
 #define B200BA_TAB_ILP_DEFAULT 3
 #endif
 #ifndef B200BA_PDL_DEFAULT
-#define B200BA_PDL_DEFAULT 0
+#define B200BA_PDL_DEFAULT 2
 #endif
 #ifndef B200BA_SLICE_W_NUM
 #define B200BA_SLICE_W_NUM 4
@@ -132,10 +132,10 @@ struct b200ba_handle {
     DBuf<unsigned char> sort_tmp;
     DBuf<int2> row_hdr;
     DBuf<unsigned char> c_rec, o_rec;
-    DBuf<double> fin_part, ptab, qtab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
+    DBuf<double> fin_part, ptab, qtab, ctab, part_pq, part_rz, X_init, rt_init, cam_D0, pt_D0;
     double pba_depth_scale = 1.0;                     // normalize = 2: PBA's depth scaling of T and X
     bool use_tab_backsub = false; size_t cost_smem = 0;          // linearisation / back-substitution / trial cost as table sweeps
-    bool use_pdl = false;                            // programmatic dependent launch of the two PCG sweeps (B200BA_PDL=1)
+    int use_pdl = 0;                                 // programmatic dependent launch of the PCG sweeps (B200BA_PDL = 1: both, 2: by-point only, 3: by-camera only)
     bool quat_ok = true;                             // the caller's rotations are orthonormal (checked by b200ba_begin): quaternion tables may stand in for R
     DBuf<unsigned long long> stamps, step_bar;
     DBuf<int> tab_wr, tab_wr32;
@@ -223,7 +223,7 @@ void launch_chain(b200ba_handle* h, void (*kern)(KA...), int grid, int block, si
 // by-point PCG sweep against the shared-memory camera table (one or two rows in flight per trip)
 void launch_point_tab(b200ba_handle* h)
 {
-    if (h->tab_ilp == 3 && h->use_pdl) {
+    if (h->tab_ilp == 3 && (h->use_pdl == 1 || h->use_pdl == 2)) {
         cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
         cfg.gridDim = dim3(h->tab_grid); cfg.blockDim = dim3(TABC_BLOCK); cfg.dynamicSmemBytes = h->tab_smem; cfg.stream = h->stream;
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -314,7 +314,7 @@ int enqueue_cg_init(b200ba_handle* h)
 int enqueue_camera_half(b200ba_handle* h, int rhs_pass)
 {
     Dev& d = h->d;
-    if (h->use_pdl && !rhs_pass) {
+    if ((h->use_pdl == 1 || h->use_pdl == 3) && !rhs_pass) {
         cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[1];
         cfg.gridDim = dim3(h->cam_grid); cfg.blockDim = dim3(CW * 32); cfg.dynamicSmemBytes = CAMPASS_SMEM; cfg.stream = h->stream;
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -614,7 +614,7 @@ void b200ba_destroy(b200ba_handle* h)
     h->X0.release(); h->X1.release(); h->V.release(); h->gp.release(); h->Vinv.release(); h->v.release(); h->o_rec.release();
     h->seg_part.release(); h->pt_part.release(); h->trace.release(); h->o_meas.release(); h->c_meas.release(); h->o_cam.release();
     h->sort_keys.release(); h->sort_vals.release(); h->row_tab.release(); h->sort_tmp.release(); h->row_hdr.release(); h->c_rec.release(); h->cam_seg_beg.release();
-    h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->part_pq.release(); h->part_rz.release();
+    h->st.release(); h->norm_buf.release(); h->slice_base.release(); h->slice_deg.release(); h->ptab.release(); h->ctab.release(); h->part_pq.release(); h->part_rz.release();
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->arena.base) cudaFree(h->arena.base);
     h->tab_wr.release();
@@ -932,7 +932,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         h->cam_seg_beg.take(A, (size_t)N + 1);
         h->seg_part.take(A, (size_t)std::max(n_segs, 1) * PART_STRIDE); h->pt_part.take(A, 4 * (size_t)std::max(n_pt_blocks, tab_warps_cap));
         h->trace.take(A, (size_t)h->trace_cap * TRACE_COLS); h->st.take(A, 1); h->norm_buf.take(A, 16);
-        h->ptab.take(A, (size_t)(N + 1) * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE); h->fin_part.take(A, 4 * (size_t)cdiv(N, FIN_BLOCK) + 4);
+        h->ptab.take(A, (size_t)(N + 1) * TAB_STRIDE); h->qtab.take(A, (size_t)N * QTAB_STRIDE); h->ctab.take(A, (size_t)(N + 1) * QTAB_STRIDE); h->fin_part.take(A, 4 * (size_t)cdiv(N, FIN_BLOCK) + 4);
         if (o.lm_variant == 1) { h->cam_D0.take(A, n6); h->pt_D0.take(A, 4 * Mp); }
         h->X_init.take(A, 4 * Mp); h->rt_init.take(A, 12 * (size_t)N);
         h->tab_wr.take(A, (size_t)tab_warps_cap * 8 + 8);
@@ -979,7 +979,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
         if (Kp) CU(cudaMemcpyAsync(h->dn_entry_pt.p, dense_entry_pt.data(), sizeof(int) * (size_t)Kp, cudaMemcpyHostToDevice, s));
     }
     if (Kp) {
-        Dev dr{}; dr.o_rec = h->o_rec.p; dr.ptab = h->ptab.p; dr.N = N;
+        Dev dr{}; dr.o_rec = h->o_rec.p; dr.ptab = h->ptab.p; dr.ctab = h->ctab.p; dr.N = N;
         k_fill_orows<<<cdiv(Kp / 32, 8), 256, 0, s>>>(dr, h->o_cam.p, Kp / 32);
     }
     if (n_rows) {
@@ -1020,7 +1020,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     }
     // contiguous slice ranges per warp of the persistent CG point sweep, balanced by rows (+1 per slice for the epilogue);
     // one 32-byte header per warp: {first slice, end slice, first entry, end entry, deg(first), deg(first+1), 0, 0}
-    { const char* e = getenv("B200BA_PDL"); h->use_pdl = e ? atoi(e) != 0 : B200BA_PDL_DEFAULT; }
+    { const char* e = getenv("B200BA_PDL"); h->use_pdl = e ? atoi(e) : B200BA_PDL_DEFAULT; }
     h->use_tab_backsub = false;
     if (h->use_tab && h->tab_ilp == 3 && getenv("B200BA_NO_TAB_BACKSUB") == nullptr) {
         h->cost_smem = ((((size_t)N * QTAB_STRIDE * sizeof(double)) + 127) & ~(size_t)127) + COST_RING_BYTES;
@@ -1120,7 +1120,7 @@ static int set_problem_impl(b200ba_handle* h, int32_t N, int32_t M, int32_t K,
     d.ar_lin = h->ar_lin.p; d.ar_q = h->ar_q.p; d.ar_sd = h->ar_sd.p; d.ar_dec = h->ar_dec.p;
     d.X[0] = h->X0.p; d.X[1] = h->X1.p; d.V = h->V.p; d.gp = h->gp.p; d.Vinv = h->Vinv.p; d.v = h->v.p;
     d.o_rec = h->o_rec.p; d.o_meas = h->o_meas.p; d.slice_base = h->slice_base.p; d.slice_deg = h->slice_deg.p;
-    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.obs_B = h->use_wb ? h->obs_B.p : nullptr; d.wtab = h->use_wb ? h->wtab.p : nullptr; d.fin_part = h->fin_part.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
+    d.ptab = h->ptab.p; d.qtab = h->qtab.p; d.ctab = h->ctab.p; d.obs_B = h->use_wb ? h->obs_B.p : nullptr; d.wtab = h->use_wb ? h->wtab.p : nullptr; d.fin_part = h->fin_part.p; d.cam_D0 = h->cam_D0.p; d.pt_D0 = h->pt_D0.p;
     d.tab_wr = h->tab_wr.p; d.tab_warps = tab_warps;
     d.c_rec = h->c_rec.p; d.c_meas = h->c_meas.p;
     d.cam_seg_beg = h->cam_seg_beg.p;

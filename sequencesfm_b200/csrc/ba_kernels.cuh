@@ -166,6 +166,8 @@ struct Dev {
     double* fin_part;   // 4 x blocks of k_cg_finish: camera part of |delta|^2, delta . g, non-finite flag
     double* obs_B;      // large-camera-count plan: per SELL row of 32 entries, the weighted point Jacobian B~ = w dp/dXX R (2 x 3) as 6 x 32 doubles
     double* wtab;       // N x 8: the PCG direction in WORLD axes [R^t p_t | R^t p_w | pad] for k_cg_point_pass_wB
+    double* ctab;       // (N + 1) x 8 compact table [quat 4 | T 3 | pad] of the CURRENT cameras (layout of qtab) + the padding entries' dummy camera:
+                        // the static half of the PCG by-point sweep's shared-memory table (k_cg_point_pass_tabc), written once per linearisation
     double* qtab;       // N x 8 compact table [quat 4 | T 3 | pad] (swizzled, see qtab_unit) of the trial cameras for k_cost_tab
     unsigned char* c_rec;         // n_rows x REC_BYTES camera-order row records (see REC_*)
     double2* c_meas;              // n_rows x 32 normalised measurements in row order
@@ -1000,6 +1002,23 @@ __device__ __forceinline__ void tab_row_fwd_s(uint32_t tab_s, int cam, double w,
     tab_row_core(a0, a1, a2, a3, a4, a5, a6, w, X, in, o);
 #endif
 }
+// the PCG by-point sweep's table in two pieces: the static [quaternion | T] records (layout of qtab: 64 bytes, 16-byte units swizzled with
+// (camera >> 1) & 3) and the direction p as it lies in d.p (48 bytes per camera: odd in 16-byte units) - both keep "bank group of a
+// field = bijection of camera mod 8".  The static piece is staged BEFORE griddepcontrol.wait, i.e. while the camera-side step of the
+// previous PCG step still runs; only the 48-byte piece waits for it.
+__device__ __forceinline__ void tab_row_fwd_split(uint32_t ctab_s, uint32_t p_s, int cam, double w, const double X[3], const Intrinsics& in, TabRow& o)
+{
+    const uint32_t c = (uint32_t)cam, sw = (c << 3) & 0x30u;      // 16 x ((camera >> 1) & 3)
+    const uint32_t tq = ctab_s + 64u * c, tp = p_s + 48u * c;
+    const double2 a0 = lds_d2(tq + sw), a1 = lds_d2(tq + (16u ^ sw)), t01 = lds_d2(tq + (32u ^ sw)), t2 = lds_d2(tq + (48u ^ sw));
+#if B200BA_WHATIF & 2         // timing experiment (wrong results): ONE table load per observation instead of seven
+    const double2 p01 = a0, p23 = a1, p45 = a0;
+#else
+    const double2 p01 = lds_d2(tp), p23 = lds_d2(tp + 16u), p45 = lds_d2(tp + 32u);
+#endif
+    // packed-table field order of tab_row_core: a2 = (T0, T1), a3 = (T2, p0), a4 = (p1, p2), a5 = (p3, p4), a6 = (p5, -)
+    tab_row_core(a0, a1, t01, make_double2(t2.x, p01.x), make_double2(p01.y, p23.x), make_double2(p23.y, p45.x), make_double2(p45.y, 0.0), w, X, in, o);
+}
 // second half: u += R^t h, the inverse rotation = sandwich with the conjugate quaternion (same scaled components)
 __device__ __forceinline__ void tab_row_bwd(const TabRow& o, double& u0, double& u1, double& u2)
 {
@@ -1517,6 +1536,11 @@ __global__ void __launch_bounds__(128) k_build_ptab(Dev d, int also_qtab)
     double q[4]; rot_to_quat(s, q);                               // sqrt(2) x unit quaternion (QUAT_SCALE)
     double* o = d.ptab + (size_t)i * TAB_STRIDE;
     o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; o[4] = s[3]; o[5] = s[7]; o[6] = s[11]; o[13] = 0.0;
+    {
+        double2* t = reinterpret_cast<double2*>(d.ctab);
+        t[qtab_unit(i, 0)] = make_double2(q[0], q[1]); t[qtab_unit(i, 1)] = make_double2(q[2], q[3]);
+        t[qtab_unit(i, 2)] = make_double2(s[3], s[7]); t[qtab_unit(i, 3)] = make_double2(s[11], 0.0);
+    }
     if (also_qtab) {
         double2* t = reinterpret_cast<double2*>(d.qtab);
         t[qtab_unit(i, 0)] = make_double2(q[0], q[1]); t[qtab_unit(i, 1)] = make_double2(q[2], q[3]);
@@ -1532,6 +1556,10 @@ __global__ void __launch_bounds__(256) k_fill_orows(Dev d, const int* __restrict
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x < TAB_STRIDE)
         d.ptab[(size_t)d.N * TAB_STRIDE + threadIdx.x] = threadIdx.x == 0 ? QUAT_SCALE : threadIdx.x == 6 ? 1e100 : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 36) {          // the same dummy camera in the compact table (fields 0 .. 3)
+        const int f = threadIdx.x - 32;
+        reinterpret_cast<double2*>(d.ctab)[qtab_unit(d.N, f)] = make_double2(f == 0 ? QUAT_SCALE : f == 3 ? 1e100 : 0.0, 0.0);
+    }
     if (r >= n_orows) return;
     unsigned char* rec = d.o_rec + (size_t)r * OREC_BYTES;
     reinterpret_cast<int*>(rec)[lane] = o_cam[32 * (size_t)r + lane];
@@ -1915,6 +1943,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     __shared__ __align__(8) uint64_t bar;
     const LMState* st = d.st;
     const uint32_t total = (uint32_t)(d.N + 1) * TAB_STRIDE * 8u;    // + the padding entries' dummy camera
+    const uint32_t q_bytes = (uint32_t)(d.N + 1) * 64u, p_bytes = (uint32_t)d.N * 48u;     // static piece (with the dummy record) | direction (d.p)
 #ifdef B200BA_STAMPS
     unsigned long long* stp = d.stamps + (size_t)blockIdx.x * STAMP_STRIDE;
     if (threadIdx.x == 0) { stp[0] = gtime(); stp[2] = clock64(); }
@@ -1958,17 +1987,21 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     if (g < g_end && 32 * g + lane < d.M) load3p_256_keep(Xb, 32 * g + lane, X, policy_evict_last());
     // Everything above reads what no PCG kernel writes (slice headers, row records, X): with programmatic dependent launch it runs
     // while the camera-side step of the previous PCG step is still in flight.  The control words and the camera table are its output.
-    pdl_wait();
-    if (st->done || !st->cg_active) { cp_async_wait<0>(); return; }         // uniform over the grid
+    // static piece of the table: in flight while the predecessor (the camera-side step of the previous PCG step) still runs
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, total);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ptab);
-        for (uint32_t off = 0; off < total; off += 32768u) {
-            uint32_t n = total - off < 32768u ? total - off : 32768u;
-            bulk_g2s(smem_raw + off, src + off, n, &bar);
-        }
+        fence_proxy_async();                                      // (mbarrier init -> async proxy)
+        mbar_expect_tx(&bar, q_bytes + p_bytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.ctab);
+        for (uint32_t off = 0; off < q_bytes; off += 32768u) bulk_g2s(smem_raw + off, src + off, min(32768u, q_bytes - off), &bar);
+    }
+    if (threadIdx.x < 6) reinterpret_cast<double*>(smem_raw + q_bytes)[6 * d.N + threadIdx.x] = 0.0;      // direction of the dummy camera
+    pdl_wait();
+    if (threadIdx.x == 0) {                                       // (issued even when the sweep is switched off: the barrier must complete)
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(d.p);
+        for (uint32_t off = 0; off < p_bytes; off += 32768u) bulk_g2s(smem_raw + q_bytes + off, src + off, min(32768u, p_bytes - off), &bar);
         pdl_trigger();                                            // the by-camera sweep may take this SM as soon as this CTA leaves it
     }
+    if (st->done || !st->cg_active) { cp_async_wait<0>(); __syncthreads(); mbar_wait(&bar, 0); return; }        // uniform over the grid
     __syncthreads();
     mbar_wait(&bar, 0);
 #ifdef B200BA_STAMPS
@@ -1976,7 +2009,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     struct EndStamp { unsigned long long* p; int lane; __device__ ~EndStamp() { if (lane == 0) *p = clock64(); } } end_stamp{stp + 8 + warp, lane};
 #endif
     if (g >= g_end) return;
-    const uint32_t tab_s = tab_smem_base(smem_raw);
+    const uint32_t tab_s = tab_smem_base(smem_raw), p_s = tab_s + q_bytes;
     double u0 = 0, u1 = 0, u2 = 0;
     auto request = [&](double Vi[6], double Xn[3]) {
 #if B200BA_WHATIF & 1         // timing experiment (wrong results): no global loads at the end of a slice
@@ -2023,19 +2056,19 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
         TabRow o;
 #if B200BA_TABC_EARLY
         if (--rows_left != 0) {                                   // warp-uniform; the common path carries no slice-end state
-            tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
+            tab_row_fwd_split(tab_s, p_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
             tab_row_bwd(o, u0, u1, u2);
             continue;
         }
         {
             double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
             request(Vi, Xn);                                      // what the END of the slice needs, in flight during the whole last row body
-            tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
+            tab_row_fwd_split(tab_s, p_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
             tab_row_bwd(o, u0, u1, u2);
             if (!finish(Vi, Xn)) return;
         }
 #else
-        tab_row_fwd_s(tab_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
+        tab_row_fwd_split(tab_s, p_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
         if (--rows_left != 0) {                                   // warp-uniform; the common path carries no slice-end state
             tab_row_bwd(o, u0, u1, u2);
             continue;
