@@ -143,6 +143,7 @@ struct b200ba_handle {
     bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
     // explicit reduced camera system (small problems): pair lists on the device, S, the per-observation blocks
     bool pdl_chain = false;                          // programmatic dependent launch of every kernel of the iteration (explicit plan)
+    bool fuse_small = false;                         // small kernels of the LM iteration fused (single rank: no all-reduce between them)
     bool use_dense = false; int dense_ctas = 0, dense_kind = -1, dense_threads = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
     DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik, dn_entry_pt;
     DBuf<double> dn_Wobs, dn_Yobs, dn_Tobs, dn_chunk_part, dn_chunk_rhs, dn_S, dn_zg, dn_pq, dn_rz; DBuf<unsigned int> dn_bar;
@@ -254,7 +255,7 @@ int enqueue_linearize(b200ba_handle* h)
 {
     Dev& d = h->d;
     const bool tabs = h->use_tab_backsub && h->quat_ok;
-    const bool fuse = h->use_dense;                               // explicit plan (single rank): fused small kernels, 20 -> 15 launches per iteration
+    const bool fuse = h->fuse_small;                              // single rank: fused small kernels (explicit plan 20 -> 14, matrix-free plan 174 -> 168 launches per iteration)
     const int lin_parts = tabs ? h->tab_grid * (TABC_BLOCK / 32) : d.n_pt_blocks;
     LAUNCH(k_build_ptab, cdiv(d.N, 128), 128, d, (fuse && tabs) ? 1 : 0);
     if (tabs) {                                                  // table plan: by-point linearisation as a shared-memory-table sweep
@@ -284,7 +285,7 @@ int enqueue_linearize(b200ba_handle* h)
 int enqueue_precond(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
+    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d, 1);           // + v = (V + damping)^-1 g_p for enqueue_cg_init
     if (h->use_f32) LAUNCH(k_f32_points, cdiv(d.M, 256), 256, d, 1);
     if (h->opt.precond == 1) {
         LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d);
@@ -302,7 +303,7 @@ const void* dense_pcg_kernel(int kind);
 int enqueue_cg_init(b200ba_handle* h)
 {
     Dev& d = h->d;
-    LAUNCH(k_cg_point_pass<1>, d.n_pt_blocks, PT_BLOCK, d);
+    // (v = (V + damping)^-1 g_p was written by k_point_vinv in enqueue_precond)
     if (int rc = enqueue_camera_half(h, 1)) return rc;
     if (int rc = enqueue_camera_sums(h)) return rc;
     LAUNCH(k_cg_init, h->step_grid, STEP_BLOCK, d, h->part_rz.p);
@@ -381,16 +382,16 @@ void enqueue_backsub(b200ba_handle* h)
 {
     Dev& d = h->d;
     if (h->use_tab_backsub && h->quat_ok) {
-        if (!h->use_dense) {                                     // (explicit plan: both written by k_cg_finish)
+        if (!h->fuse_small) {                                    // (fused: both written by k_cg_finish)
             LAUNCH(k_ptab_set_x, cdiv(6 * (long long)d.N, 256), 256, d);
             LAUNCH(k_build_qtab, cdiv(d.N, 128), 128, d, 1);
         }
         launch_chain(h, k_backsub_tab, h->tab_grid, TABC_BLOCK, h->tab_smem, d);
         launch_chain(h, k_cost_tab, h->tab_grid, TABC_BLOCK, h->cost_smem, d);
-        if (!h->use_dense) LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, h->tab_grid * (TABC_BLOCK / 32));
+        if (!h->fuse_small) LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, h->tab_grid * (TABC_BLOCK / 32));
     } else {
         LAUNCH(k_cg_point_pass<2>, d.n_pt_blocks, PT_BLOCK, d);
-        if (!h->use_dense) LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, -1);
+        if (!h->fuse_small) LAUNCH(k_point_partials_reduce, 1, ONE_CTA, d, 1, -1);
     }
 }
 
@@ -398,11 +399,11 @@ int enqueue_step_and_decide(b200ba_handle* h)
 {
     Dev& d = h->d;
     const bool tabs = h->use_tab_backsub && h->quat_ok;
-    LAUNCH(k_cg_finish, cdiv(d.N, FIN_BLOCK), FIN_BLOCK, d, h->fin_part.p, (h->use_dense && tabs) ? 1 : 0);
+    LAUNCH(k_cg_finish, cdiv(d.N, FIN_BLOCK), FIN_BLOCK, d, h->fin_part.p, (h->fuse_small && tabs) ? 1 : 0);
     enqueue_backsub(h);
     if (int rc = allreduce(h, d.ar_dec, 4, 1)) return rc;
-    const int dec_parts = h->use_dense ? (tabs ? h->tab_grid * (TABC_BLOCK / 32) : d.n_pt_blocks) : -1;
-    const int dec_threads = h->use_dense ? ONE_CTA : 1;
+    const int dec_parts = h->fuse_small ? (tabs ? h->tab_grid * (TABC_BLOCK / 32) : d.n_pt_blocks) : -1;
+    const int dec_threads = h->fuse_small ? ONE_CTA : 1;
     if (h->opt.lm_variant == 1) LAUNCH(k_lm_decide_pba, 1, dec_threads, d, dec_parts); else LAUNCH(k_lm_decide, 1, dec_threads, d, dec_parts);
     return 0;
 }
@@ -595,6 +596,18 @@ int b200ba_create(const b200ba_options* opt, b200ba_handle** out)
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         fail(nullptr, B200BA_E_CUDA, "cannot initialise device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
         delete h; return B200BA_E_CUDA;
+    }
+    {
+        // experiment knob: L2 set-aside for persisting (evict_last) lines, in MB (-1 = the device maximum)
+        const char* e = getenv("B200BA_L2_PERSIST");
+        if (e) {
+            int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            long long want = atoll(e) < 0 ? (long long)maxp : atoll(e) << 20;
+            if (want > maxp) want = maxp;
+            cudaError_t pe = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want);
+            if (getenv("B200BA_VERBOSE")) fprintf(stderr, "[b200ba] persisting L2: max %d bytes, set %lld bytes (%s)\n", maxp, want, cudaGetErrorString(pe));
+            cudaGetLastError();
+        }
     }
     *out = h;
     return 0;
@@ -1334,6 +1347,26 @@ int b200ba_begin(b200ba_handle* h)
     CU(cudaStreamSynchronize(s));
     h->launches = 0; h->ms_solve = 0; h->iters_before_restart = 0; h->accepts_before_restart = 0;
     if (int rc = mean_reproj(h, 0, &h->mean_px[0])) return rc;
+    {
+        const bool fs = h->use_dense || (h->world == 1 && getenv("B200BA_NO_FUSE_SMALL") == nullptr);
+        if (fs != h->fuse_small) { h->fuse_small = fs; if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } }
+    }
+    {
+        // experiment knob: access policy window (persisting hits, streaming misses) on v [, Vinv] of this handle's stream
+        const char* e = getenv("B200BA_L2_WINDOW");
+        if (e && atoi(e) > 0) {
+            cudaStreamAttrValue av = {};
+            char* lo = atoi(e) == 2 ? (char*)h->Vinv.p : (char*)h->v.p;
+            char* hi = (char*)h->v.p + sizeof(double) * 4 * (size_t)h->M;
+            if (atoi(e) == 2 && (char*)h->Vinv.p > (char*)h->v.p) { lo = (char*)h->v.p; hi = (char*)h->Vinv.p + sizeof(double) * 6 * (size_t)h->M; }
+            av.accessPolicyWindow.base_ptr = lo; av.accessPolicyWindow.num_bytes = (size_t)(hi - lo);
+            av.accessPolicyWindow.hitRatio = getenv("B200BA_L2_RATIO") ? (float)atof(getenv("B200BA_L2_RATIO")) : 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaError_t pe = cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            if (getenv("B200BA_VERBOSE")) fprintf(stderr, "[b200ba] L2 window %zu bytes: %s\n", av.accessPolicyWindow.num_bytes, cudaGetErrorString(pe));
+            cudaGetLastError();
+        }
+    }
     h->begun = true; h->finished = false;
     return 0;
 }
@@ -1608,7 +1641,7 @@ int b200ba_debug_schur_matvec(b200ba_handle* h, double lambda, const double* x, 
     st.lambda = lambda; st.done = 0; st.cg_active = 1; st.solve_ok = 1;
     CU(cudaMemcpy(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.p, x, sizeof(double) * n6, cudaMemcpyHostToDevice));
-    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d);
+    LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d, 0);
     {
         // both by-point sweeps read the direction from the packed table: scatter x into its p-slots
         CU(cudaStreamSynchronize(h->stream));
@@ -1740,7 +1773,7 @@ int b200ba_debug_time_kernel(b200ba_handle* h, int32_t which, int32_t reps, doub
         case 4: LAUNCH((k_camera_reduce<6, 6>), cdiv((long long)d.N * 6 * 4, 256), 256, d, d.ar_q, 0); break;
         case 5: LAUNCH(k_cg_update, 1, ONE_CTA, d); CU(cudaMemcpyAsync(h->st.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream)); break;
         case 6: LAUNCH(k_schur_diag_cameras, cdiv(d.n_vwarps, CH_BLOCK / 32), CH_BLOCK, d); break;
-        case 7: LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d); break;
+        case 7: LAUNCH(k_point_vinv, cdiv(d.M, 256), 256, d, 0); break;
         case 8: enqueue_backsub(h); break;
         case 9: LAUNCH(k_precond_invert, cdiv(6ll * d.N, 192), 192, d, h->opt.precond); break;
         }

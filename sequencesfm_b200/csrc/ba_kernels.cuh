@@ -767,7 +767,9 @@ __device__ __forceinline__ bool point_vinv_eval(const double V[6], double l, boo
     Vi[0] = c00 * id; Vi[1] = c01 * id; Vi[2] = c02 * id; Vi[3] = (a * g - c * c) * id; Vi[4] = (b * c - a * f) * id; Vi[5] = (a * e - b * b) * id;
     return ok;
 }
-__global__ void __launch_bounds__(256) k_point_vinv(Dev d)
+// with_rhs: also v_j = (V_j + damping)^-1 g_p,j, the by-point half of the reduced right-hand side (what k_cg_point_pass<1> computes from
+// the stored inverse: one launch and one pass over the inverses less per LM iteration)
+__global__ void __launch_bounds__(256) k_point_vinv(Dev d, int with_rhs)
 {
     pdl_chain_enter();
     LMState* st = d.st;
@@ -784,6 +786,14 @@ __global__ void __launch_bounds__(256) k_point_vinv(Dev d)
     o[1] = make_double2(Vi[2], Vi[3]);
     o[2] = make_double2(Vi[4], Vi[5]);
     if (!ok) st->solve_ok = 0;
+    if (with_rhs) {
+        double g[3]; load3p(d.gp, j, g);
+        const double v0 = Vi[0] * g[0] + Vi[1] * g[1] + Vi[2] * g[2];
+        const double v1 = Vi[1] * g[0] + Vi[3] * g[1] + Vi[4] * g[2];
+        const double v2 = Vi[2] * g[0] + Vi[4] * g[1] + Vi[5] * g[2];
+        double2* w = reinterpret_cast<double2*>(d.v + 4 * (size_t)j);
+        w[0] = make_double2(v0, v1); w[1] = make_double2(v2, 0.0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1928,6 +1938,9 @@ __global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
 #ifndef B200BA_TABC_EARLY
 #define B200BA_TABC_EARLY 0   // 1: the slice-end loads are requested before the last row body instead of in its middle
 #endif
+#ifndef B200BA_TABC_HINT
+#define B200BA_TABC_HINT 0    // bit 1: row stream copied with an L2 evict_first hint, bit 2: (V + damping)^-1 read with evict_last
+#endif
 #ifndef B200BA_TABC_PFN
 #define B200BA_TABC_PFN 4     // rows per bulk L2 prefetch (power of two)
 #endif
@@ -1935,6 +1948,15 @@ constexpr int TABC_BLOCK = B200BA_TABC_BLOCK, TABC_ROWS = B200BA_TABC_ROWS, TABC
 constexpr int TABC_RING_BYTES = (TABC_BLOCK / 32) * (TABC_ROWS * OREC_BYTES);
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async4_hint(uint32_t dst, const void* src, uint64_t pol) { asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory"); }
+__device__ __forceinline__ void cp_async8_hint(uint32_t dst, const void* src, uint64_t pol) { asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory"); }
+__device__ __forceinline__ void load6_hint(const double* __restrict__ base, int i, double v[6], uint64_t pol)
+{
+    const double* s = base + 6 * (size_t)i;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(s), "l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[2]), "=d"(v[3]) : "l"(s + 2), "l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[4]), "=d"(v[5]) : "l"(s + 4), "l"(pol));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
@@ -1965,11 +1987,17 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     // the group arithmetic of wait_group stays uniform)
     const unsigned char* src_lane = src_rows + 4 * lane;          // camera index of this lane in the row; weight at + 128 + 4 lane more
     int fetched = 0;                                              // rows requested so far
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
     auto fetch = [&]() {
         if (fetched < n_rows && !(B200BA_WHATIF & 16)) {          // (16 = timing experiment: no row stream at all)
             const uint32_t dst = ring + (uint32_t)(fetched % TABC_ROWS) * OREC_BYTES + 4u * lane;
+#if B200BA_TABC_HINT & 1
+            cp_async4_hint(dst, src_lane, pol_stream);
+            cp_async8_hint(dst + 128u + 4u * lane, src_lane + 128 + 4 * lane, pol_stream);
+#else
             cp_async4(dst, src_lane);
             cp_async8(dst + 128u + 4u * lane, src_lane + 128 + 4 * lane);
+#endif
             src_lane += OREC_BYTES;
         }
         ++fetched;
@@ -2015,8 +2043,12 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
 #if B200BA_WHATIF & 1         // timing experiment (wrong results): no global loads at the end of a slice
         Vi[0] = Vi[1] = Vi[2] = Vi[3] = Vi[4] = Vi[5] = 1.0; Xn[0] = Xn[1] = Xn[2] = 0.5; return;
 #endif
+#if B200BA_TABC_HINT & 2
+        if (32 * g + lane < d.M) load6_hint(d.Vinv, 32 * g + lane, Vi, pol_keep);
+#else
         if (32 * g + lane < d.M) load6(d.Vinv, 32 * g + lane, Vi);
-        if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, policy_evict_last());
+#endif
+        if (g + 1 < g_end && 32 * (g + 1) + lane < d.M) load3p_256_keep(Xb, 32 * (g + 1) + lane, Xn, pol_keep);
     };
     auto finish = [&](const double Vi[6], const double Xn[3]) -> bool {
         const int j = 32 * g + lane;
@@ -2040,6 +2072,44 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
         request(Vi, Xn);
         if (!finish(Vi, Xn)) return;
     }
+#if B200BA_TABC_EARLY == 2
+    // one row: next ring slot, this lane's camera and weight, forward half of the row body
+    auto next_row = [&](TabRow& o) {
+        fetch();                                                  // row r + TABC_ROWS - 1 into the slot row r - 1 has left
+        cp_async_wait<TABC_ROWS - 1>();                           // all but the newest TABC_ROWS - 1 groups have landed: row r is there
+        const uint32_t ca = ring + (uint32_t)(r % TABC_ROWS) * OREC_BYTES + 4u * lane;
+        const int cam = lds_s32(ca);
+        const double w = lds_f64(ca + 128u + 4u * lane);
+        ++r;
+        tab_row_fwd_split(tab_s, p_s, tab_pad_cam(cam, d.N), w, X, d.in, o);
+    };
+    for (;;) {                                                    // invariant: rows_left > 0
+        TabRow o;
+        if (rows_left > 2) {                                      // warp-uniform; the common path carries no slice-end state
+            next_row(o);
+            tab_row_bwd(o, u0, u1, u2);
+            --rows_left;
+            continue;
+        }
+        // the slice ends within the next two rows: what its END needs ((V + damping)^-1 of its points, X of the next slice) is
+        // requested now and stays in flight during both row bodies (requested in the middle of the last row it was waited for:
+        // 4 us of a 41 us sweep, tools/gpu_r2d.sh whatif)
+        double Vi[6] = {0, 0, 0, 0, 0, 0}, Xn[3] = {0, 0, 0};
+        request(Vi, Xn);
+        if (rows_left == 2) { next_row(o); tab_row_bwd(o, u0, u1, u2); }
+        next_row(o);
+        tab_row_bwd(o, u0, u1, u2);
+        if (!finish(Vi, Xn)) return;
+        while (rows_left == 0) {                                  // slices without observations
+            double Vj[6], Xm[3];
+            request(Vj, Xm);
+            if (!finish(Vj, Xm)) return;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+#else
     for (;;) {                                                    // invariant: rows_left > 0 (the common path tests it once per row, below)
         fetch();                                                  // row r + TABC_ROWS - 1 into the slot row r - 1 has left
 #if !(B200BA_WHATIF & 8)     // 8 = timing experiment (wrong results): never wait for the row stream
@@ -2087,6 +2157,7 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
         }
     }
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------------
 // K9a/K9b  back-substitution and trial cost on the shared-memory camera table (replaces k_cg_point_pass<2> when the table plan
@@ -2496,6 +2567,10 @@ __device__ __forceinline__ void step_barrier(unsigned long long* ctr, unsigned l
 // NT = threads per block; FUSED: called at the end of the by-camera sweep (k_cg_camera_pass_step, NT = 512, only the first
 // STEP_BLOCK threads of the first step_blocks blocks own elements): one more barrier up front ("every segment partial of the
 // sweep is visible") replaces the kernel boundary, and the loads that do not depend on the sweep are in flight while it waits.
+#ifndef B200BA_SEG_BATCH
+#define B200BA_SEG_BATCH 8
+#endif
+constexpr int SEG_BATCH = B200BA_SEG_BATCH;
 template <int NT, bool FUSED>
 __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
                                                    double* part_pq, double* part_rz, int step_blocks, double* sv, double* sm,
@@ -2526,7 +2601,18 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
     double q = 0, s = 0;
     if (on) {
         if (sums_ready == 1) s = d.ar_q[e];
-        else for (int sg = sg0; sg < sg1; ++sg) s += FUSED ? __ldcg(d.seg_part + PART_STRIDE * (size_t)sg + a) : d.seg_part[PART_STRIDE * (size_t)sg + a];
+        else {
+            // the first SEG_BATCH partials are loaded together (a camera has 2.3 x VSPLIT segments on average at Venice shape; the plain loop waited
+            // for one L2 round trip per segment), summed in the same order as before
+            auto ld = [&](int sg) { return FUSED ? __ldcg(d.seg_part + PART_STRIDE * (size_t)sg + a) : d.seg_part[PART_STRIDE * (size_t)sg + a]; };
+            double v[SEG_BATCH];
+#pragma unroll
+            for (int k = 0; k < SEG_BATCH; ++k) v[k] = (sg0 + k < sg1) ? ld(sg0 + k) : 0.0;
+            s = v[0];
+#pragma unroll
+            for (int k = 1; k < SEG_BATCH; ++k) s += v[k];
+            for (int sg = sg0 + SEG_BATCH; sg < sg1; ++sg) s += ld(sg);
+        }
     }
     unsigned long long coll = 0;
     if (sums_ready == 2) {
