@@ -61,7 +61,7 @@ def kernel_models(N: int, M: int, K: int, s: int = 8) -> dict:
 
 def ncu_traffic() -> tuple[dict, str | None]:
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full digest (profiles/)."""
-    for name in ("ncu_r2_final_summary.json", "ncu_r1_final_summary.json"):
+    for name in ("ncu_r2g_summary.json", "ncu_r2_final_summary.json", "ncu_r1_final_summary.json"):
         path = os.path.join(ROOT, "profiles", name)
         try:
             out = {}

@@ -183,7 +183,7 @@ int b200ba_problem_size(const b200ba_handle* h, int32_t* N, int32_t* M, int32_t*
  * code path).  Tests use it to make sure a given plan is the one a parity case exercised. */
 enum {
     B200BA_TABLE_GLOBAL  = 0,   /* packed camera table [quaternion | T | p] read through L2 by every observation        */
-    B200BA_TABLE_SHARED  = 1,   /* whole table staged into one SM's shared memory by TMA bulk copies (<= 2075 cameras)  */
+    B200BA_TABLE_SHARED  = 1,   /* whole table staged into one SM's shared memory by TMA bulk copies (table + row rings <= 227 KB: ~1 797 cameras) */
     B200BA_TABLE_CLUSTER = 2    /* table sharded over the distributed shared memory of a thread-block cluster           */
 };
 typedef struct b200ba_plan {

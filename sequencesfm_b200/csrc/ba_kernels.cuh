@@ -510,7 +510,9 @@ template <int NACC> __device__ __forceinline__ void seg_flush(const Dev& d, int 
 //     bulk copies; the X_j gathers of stage t+1 are in flight while stage t is computed.  (The version that loaded two
 //     rows at a time through registers was latency-bound at 12 warps per SM: 166 us.)
 constexpr int LC_NS = 3;
-constexpr int LC_STAGE_BYTES = CG * (REC_BYTES + 512);           // CG row records, then CG x 32 double2 measurements
+constexpr int LC_HEAD_BYTES = REC_W;                             // what this kernel READS of a row record: header + point indices (144 of 1168 bytes;
+                                                                 // the weight and R X fields are its OUTPUT: staging whole records read 160 MB for nothing)
+constexpr int LC_STAGE_BYTES = CG * (LC_HEAD_BYTES + 512);       // CG record heads, then CG x 32 double2 measurements
 constexpr int LINCAM_SMEM = (CH_BLOCK / 32) * LC_NS * (LC_STAGE_BYTES + 8);
 __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 {
@@ -532,9 +534,11 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
     auto arm = [&](int t) {
         const int sl = t % LC_NS;
         const uint32_t rows = (uint32_t)min(CG, n - t * CG);
-        mbar_expect_tx(&bar[sl], rows * (REC_BYTES + 512));
-        bulk_g2s_hint(buf + sl * LC_STAGE_BYTES, grec + (size_t)t * CG * REC_BYTES, rows * REC_BYTES, &bar[sl], strm);
-        bulk_g2s_hint(buf + sl * LC_STAGE_BYTES + CG * REC_BYTES, gmeas + 32 * (size_t)t * CG, rows * 512, &bar[sl], strm);
+        mbar_expect_tx(&bar[sl], rows * (LC_HEAD_BYTES + 512));
+#pragma unroll
+        for (uint32_t g = 0; g < (uint32_t)CG; ++g)
+            if (g < rows) bulk_g2s_hint(buf + sl * LC_STAGE_BYTES + g * LC_HEAD_BYTES, grec + ((size_t)t * CG + g) * REC_BYTES, LC_HEAD_BYTES, &bar[sl], strm);
+        bulk_g2s_hint(buf + sl * LC_STAGE_BYTES + CG * LC_HEAD_BYTES, gmeas + 32 * (size_t)t * CG, rows * 512, &bar[sl], strm);
     };
     if (lane == 0) {
 #pragma unroll
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
         mbar_wait(&bar[sl], (uint32_t)(t / LC_NS) & 1u);
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
-            jj[g] = (t * CG + g < n) ? reinterpret_cast<const int*>(buf + sl * LC_STAGE_BYTES + g * REC_BYTES + REC_J)[lane] : -1;
+            jj[g] = (t * CG + g < n) ? reinterpret_cast<const int*>(buf + sl * LC_STAGE_BYTES + g * LC_HEAD_BYTES + REC_J)[lane] : -1;
             XX[g][0] = 0.0; XX[g][1] = 0.0; XX[g][2] = 1.0;
             if (jj[g] >= 0) load3p_256(Xb, jj[g], XX[g]);
         }
@@ -568,13 +572,13 @@ __global__ void __launch_bounds__(CH_BLOCK) k_linearize_cameras(Dev d)
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
             if (t * CG + g < n) {                                // warp-uniform
-                const int2 h = *reinterpret_cast<const int2*>(sb + g * REC_BYTES + REC_HDR);
+                const int2 h = *reinterpret_cast<const int2*>(sb + g * LC_HEAD_BYTES + REC_HDR);
                 if (h.y != seg) {
                     if (seg >= 0) seg_flush<27>(d, seg, acc, lane);
                     seg = h.y; cam = h.x; load_cam(rt, cam, cm);
                 }
                 if (jj[g] >= 0 && cam >= d.first_free) {
-                    const double2 m = reinterpret_cast<const double2*>(sb + CG * REC_BYTES + g * 512)[lane];
+                    const double2 m = reinterpret_cast<const double2*>(sb + CG * LC_HEAD_BYTES + g * 512)[lane];
                     Obs o; obs_full(cm, XX[g], m, d.in, o);
                     unsigned char* rec = grec + (size_t)(t * CG + g) * REC_BYTES;          // write-back goes to the record in HBM
                     reinterpret_cast<double*>(rec + REC_W)[lane] = o.w;
