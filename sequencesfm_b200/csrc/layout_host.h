@@ -156,8 +156,22 @@ inline void build_point_layout(int M, int K, const int32_t* obs_cam, const int32
             pkey[j] = kq;
         }
     });
+    // thread boundaries (multiples of 32 points) at equal WORK, not equal point counts: the points are sorted by track length and the
+    // grouping / colouring of a quarter-warp costs about its 8 d observations (+ a constant per point); with equal point counts the
+    // thread that owned the long tracks took 35 ms where the others took 20 - 27 (Venice shape, 8 threads)
+    std::vector<long long> cut((size_t)T + 1, M);
+    {
+        cut[0] = 0;
+        const int pw = getenv("B200BA_LAYOUT_PW") ? atoi(getenv("B200BA_LAYOUT_PW")) : 3;       // cost of a point in observations
+        long long total = 0; for (int j = 0; j < M; ++j) total += deg[(size_t)j] + pw;
+        long long acc = 0; int t = 1;
+        for (long long g = 0; g + 32 <= M && t < T; g += 32) {
+            for (int q = 0; q < 32; ++q) acc += deg[(size_t)(g + q)] + pw;
+            while (t < T && acc * T >= total * t) cut[t++] = g + 32;
+        }
+    }
     host_parallel_for(T, [&](int t, int nt) {
-        const long long a = (long long)(M / 32) * t / nt * 32, b = (t + 1 == nt) ? M : (long long)(M / 32) * (t + 1) / nt * 32;
+        const long long a = nt == T ? cut[t] : (long long)(M / 32) * t / nt * 32, b = (t + 1 == nt) ? M : (nt == T ? cut[t + 1] : (long long)(M / 32) * (t + 1) / nt * 32);
         struct Tm { std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); int t; long long a, b; ~Tm() { if (getenv("B200BA_LAYOUT_TIMES")) fprintf(stderr, "[layout] thread %d points %lld..%lld: %.2f ms\n", t, a, b, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } } tm_; tm_.t = t; tm_.a = a; tm_.b = b;
         std::vector<int> run, out, pool, cams, slot_edge, head, nxt;
         std::vector<uint64_t> key, hkey;

@@ -141,12 +141,13 @@ def test_fifty_step_mode_matches_oracle(shape, seed, kw, opts, plan):
 
 
 @pytest.mark.parametrize("env", ["B200BA_NO_TAB", "B200BA_NO_TAB,B200BA_NO_WB", "B200BA_NO_COOP", "B200BA_NO_GRAPH", "B200BA_NO_LANE_OPT", "B200BA_FUSE_STEP",
-                                 "B200BA_PDL_CHAIN=0"])
+                                 "B200BA_PDL_CHAIN=0", "B200BA_PDL=0", "B200BA_PDL=1", "B200BA_XPOSE=0", "B200BA_NO_FUSE_SMALL", "B200BA_SLICE_W=2"])
 def test_alternative_execution_plans_agree(env, monkeypatch):
     """The engine picks its execution plan at set_problem (shared-memory camera table vs generic by-point sweep through the
     packed table in global memory - the plan for problems with more than ~1800 cameras -, cooperative camera-side step vs
-    single-CTA kernels, CUDA-graph replay vs stream launches, bank-conflict-aware point grouping).  Every plan must reproduce
-    the default one and the oracle."""
+    single-CTA kernels, CUDA-graph replay vs stream launches, bank-conflict-aware point grouping, programmatic dependent launch of
+    the PCG sweeps, slice ranges dealt round-robin over the CTAs vs contiguous, fused vs separate small kernels).  Every plan must
+    reproduce the default one and the oracle."""
     p = make_problem("ladybug", 3, outlier_frac=0.02)
     # (a problem of this size runs the explicit reduced-system plan by default; the plans under test belong to the matrix-free
     #  path - reduced_system = 1 - except the launch mode of the explicit plan's own kernels)
