@@ -805,6 +805,13 @@ __global__ void __launch_bounds__(256) k_point_vinv(Dev d, int with_rhs)
 //     Gives the diagonal blocks of S for the block-Jacobi preconditioner.  Streams the row records (weight, cached
 //     R X) and gathers (V_j + lambda I)^-1.
 // ------------------------------------------------------------------------------------------------------
+#ifndef B200BA_SD_HDR
+#define B200BA_SD_HDR 0
+#endif
+#ifndef B200BA_SD_PF
+#define B200BA_SD_PF 0
+#endif
+constexpr int SD_PF = B200BA_SD_PF;                             // rows of records pulled into L2 ahead of a warp of k_schur_diag_cameras (0 = off: 2 / 3 / 6 rows measured 105 / 107 / 115 us against 89.5 without)
 __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
 {
     pdl_chain_enter();
@@ -867,12 +874,32 @@ __global__ void __launch_bounds__(CH_BLOCK) k_schur_diag_cameras(Dev d)
             }
         };
         // (two rows of loads per trip, as in k_linearize_cameras, measured SLOWER here: 196 vs 112 us at 156 registers)
+        // The warp walks its rows one at a time (16 warps per SM = exactly one wave of the 16 virtual warps per SM; more registers
+        // per warp cost that): per row a DRAM round trip for the record, then the dependent gather of V^-1.  The NEXT row's point
+        // index is loaded one row early, so that its gather can be issued as soon as the row starts: 112 -> 89.5 us at Venice shape.
+        // (Bulk L2 prefetches of the records SD_PF rows ahead, by lane 0, made it slower again.)
+        if (SD_PF > 0 && lane == 0 && rb < re) prefetch_l2_bulk(d.c_rec + (size_t)rb * REC_BYTES, (uint32_t)min(SD_PF, re - rb) * REC_BYTES);
+        int j_next = rb < re ? __ldg(reinterpret_cast<const int*>(d.c_rec + (size_t)rb * REC_BYTES + REC_J) + lane) : -1;
+#if B200BA_SD_HDR
+        int2 h_next = rb < re ? __ldg(reinterpret_cast<const int2*>(d.c_rec + (size_t)rb * REC_BYTES + REC_HDR)) : make_int2(0, -1);
+#endif
         for (int r = rb; r < re; ++r) {
             const unsigned char* rec = d.c_rec + (size_t)r * REC_BYTES;
+            if (SD_PF > 0 && lane == 0 && r + SD_PF < re) prefetch_l2_bulk(rec + (size_t)SD_PF * REC_BYTES, REC_BYTES);
+#if B200BA_SD_HDR
+            const int2 h = h_next;
+#else
             const int2 h = __ldg(reinterpret_cast<const int2*>(rec + REC_HDR));
-            const int j = __ldg(reinterpret_cast<const int*>(rec + REC_J) + lane);
+#endif
+            const int j = j_next;
             double Vi[6] = {0, 0, 0, 0, 0, 0};
             if (j >= 0) load6(d.Vinv, j, Vi);
+            if (r + 1 < re) {
+                j_next = __ldg(reinterpret_cast<const int*>(rec + REC_BYTES + REC_J) + lane);
+#if B200BA_SD_HDR
+                h_next = __ldg(reinterpret_cast<const int2*>(rec + REC_BYTES + REC_HDR));
+#endif
+            }
             do_row(rec, h, j, Vi);
         }
         if (seg >= 0) seg_flush<21>(d, seg, acc, lane);
