@@ -1951,11 +1951,15 @@ __global__ void __launch_bounds__(TAB2_BLOCK, 1) k_cg_point_pass_tab2(Dev d)
 //      will read (4 + 8 bytes per row, coalesced across the warp) into a private ring of TABC_ROWS rows and waits with
 //      cp.async.wait_group: no mbarrier, no elected lane, no bulk-copy issue per stage, rows in flight = TABC_ROWS - 1.
 //      Measured (Venice, round 2): 51.4 us (TMA ring, one row) / 49.4 (TMA ring, two rows) -> 47.4 (this, 608 threads) ->
-//      46.9 (640 threads = 5 warps on every scheduler).  The SASS of the row body is ~155 instructions of which ~71 are FP64
-//      (2 issue cycles each): 5 warps x 57 rows x ~226 issue cycles is what a scheduler spends, i.e. the sweep is bound by
-//      instruction issue, and what helped was fewer instructions per row.  A device-wide chunk queue (guided self-scheduling,
-//      claims by atomicAdd) evened out the warps' finish times (spread 16 % -> 5 %) but cost more than it gained (51-55 us):
-//      every chunk switch drains and refills the ring.
+//      46.9 (640 threads = 5 warps on every scheduler).  A device-wide chunk queue (guided self-scheduling, claims by atomicAdd)
+//      evened out the warps' finish times (spread 16 % -> 5 %) but cost more than it gained (51-55 us): every chunk switch drains
+//      and refills the ring.
+//      Closing sessions of round 2: the sweep is NOT bound by instruction issue - with 17 % fewer issue
+//      cycles per row (101 SASS instructions of which 59 FP64) it ran 2 % faster, with (almost) no arithmetic at all as long
+//      (-DB200BA_WHATIF builds); it is a sum of latencies per warp at 5 warps per scheduler.  What moved it: the slice ranges dealt
+//      round-robin over the CTAs and a slice end weighted 4/3 of a row on the host (46.6 -> 41.1 us), and the launch as a
+//      programmatic dependent of the camera-side step with the static [quaternion | T] piece of the table staged before
+//      griddepcontrol.wait (-> 37.7 us).
 // ------------------------------------------------------------------------------------------------------
 #ifndef B200BA_TABC_BLOCK
 #define B200BA_TABC_BLOCK 640
@@ -2036,10 +2040,9 @@ __global__ void __launch_bounds__(TABC_BLOCK, 1) k_cg_point_pass_tabc(Dev d)
     };
 #pragma unroll
     for (int i = 0; i < TABC_ROWS - 1; ++i) fetch();
-    // The ring holds TABC_ROWS - 1 rows in flight per warp (shared memory is full of camera table): 23 KB per SM against a DRAM
-    // latency of ~0.8 us is 25 GB/s per SM by Little's law - exactly what the sweep ran at, whatever its arithmetic did
-    // (tools/gpu_r2d.sh whatif).  So the stream is pulled into L2 TABC_PF rows ahead of the ring, TABC_PFN rows per bulk prefetch:
-    // the ring's copies then wait for an L2 hit instead of DRAM.
+    // Experiment (TABC_PF > 0, off): the row stream pulled into L2 TABC_PF rows ahead of the ring, TABC_PFN rows per bulk prefetch.
+    // The ring holds TABC_ROWS - 1 rows in flight per warp, and a warp needs ~1200 cycles per row, so a row's copy has landed
+    // long before its turn (never waiting for the ring changes nothing: -DB200BA_WHATIF=8); the prefetches only cost, 0.3 - 2.4 us.
     if (TABC_PF > 0 && lane == 0 && n_rows > TABC_ROWS - 1)
         prefetch_l2_bulk(src_rows + (size_t)(TABC_ROWS - 1) * OREC_BYTES, (uint32_t)min(TABC_PF, n_rows - (TABC_ROWS - 1)) * OREC_BYTES);
     double X[3] = {0, 0, 0};
