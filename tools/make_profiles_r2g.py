@@ -99,6 +99,8 @@ whatif = {
     "unit": "us per launch of k_cg_point_pass_tabc at Venice shape (tools/prof_cg.py: 20 launches back to back, CUDA events)",
     "knob": "-DB200BA_WHATIF=<bit mask>: 1 no global loads at the end of a slice, 2 one table load per observation instead of seven, 4 (almost) no arithmetic, "
             "8 never wait for the row stream, 16 no row stream, 32 v never written, 64 no L2 prefetch of the next slice's X / V^-1 (results are WRONG with any of them)",
+    "keys": "lib_w<mask>.so = library built with -DB200BA_WHATIF=<mask>; lib_whatif1..4.so = the first encoding of the same knob (1 no slice-end loads, "
+            "2 one table load, 3 no arithmetic, 4 never wait for the row stream); 'in-tree' = the library of that call's commit (in the L2-prefetch set: prefetch 16 rows ahead)",
     "before_the_range_balance (contiguous slice ranges per CTA, slice end weighted 2/3 of a row)": {**grab("ab_whatif.log"), **grab("ab_w.log"), **grab("ab_w2.log")},
     "after (ranges dealt round-robin over the CTAs, slice end weighted 4/3)": grab("ab_w3.log"),
     "slice_end_weight_sweep (thirds of a row body)": grab("slicew_x.log"),
