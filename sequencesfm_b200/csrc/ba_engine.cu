@@ -237,7 +237,7 @@ void launch_point_tab(b200ba_handle* h)
     h->launches++;
 }
 
-// by-point PCG sweep: shared-memory camera table (<= 2075 cameras), else B~ records + world-axes direction table
+// by-point PCG sweep: shared-memory camera table (<= ~1 797 cameras), else B~ records + world-axes direction table
 // (k_cg_point_pass_wB; needs orthonormal input rotations like every table plan), else the generic packed-table gathers
 void launch_point_sweep(b200ba_handle* h, bool allow_tab = true)
 {

@@ -1169,7 +1169,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_cg_point_pass(Dev d)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K8w  by-point PCG sweep of the LARGE-CAMERA-COUNT plan (camera table larger than one SM's shared memory: > 2075 cameras).
+// K8w  by-point PCG sweep of the LARGE-CAMERA-COUNT plan (camera table + row rings larger than one SM's shared memory: > ~1 797 cameras).
 //      The generic sweep gathers the packed record [quaternion | T | p] - 7 x LDG.128 = 112 bytes per observation out of L2,
 //      3.2 GB per sweep at Final shape (498 us: L2-gather bound) - and rebuilds R, the projection Jacobian and two rotations
 //      from it (71 fp64 instructions per observation).  Here
@@ -1557,7 +1557,7 @@ __global__ void __launch_bounds__(ONE_CTA) k_cg_update(Dev d)
 //
 // In the by-point sweep every observation needs its camera's R, T and p (18 doubles = 5 sectors of L2 traffic and,
 // worse, 6 uncoalesced LDG.128 per lane = 192 L1 wavefronts per warp: ncu showed the generic sweep bound by L1
-// wavefronts at 70 %).  For problems up to MAX_SMEM / 112 B = 2075 cameras (Venice: 1778) the whole camera side fits
+// wavefronts at 70 %).  For problems up to (MAX_SMEM - row rings) / 112 B = ~1 797 cameras (Venice: 1778) the whole camera side fits
 // in one SM's shared memory once R is carried as a unit quaternion: 14 doubles per camera, staged with TMA bulk
 // copies (cp.async.bulk, one mbarrier), read with 7 LDS.128 per observation.  k_build_ptab converts R -> quaternion
 // once per linearisation; the CG kernels keep the p-part current.

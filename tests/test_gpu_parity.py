@@ -213,7 +213,7 @@ def test_ragged_random_problems_match_oracle(seed):
     q = p.copy(); q.obs_xy, q.obs_cam, q.obs_pt = p.obs_xy[keep], p.obs_cam[keep], p.obs_pt[keep]
     o = oracle.linearize(q)
     x = rng.normal(size=(q.N, 6))
-    # plans: shared-memory camera table; B~ records + world-axes direction table (the > 2075-camera plan, forced); generic
+    # plans: shared-memory camera table; B~ records + world-axes direction table (the large-camera-count plan, forced); generic
     # packed-table gathers; explicit reduced camera system (what a problem of this size runs by default)
     for generic, (env, mode) in enumerate([((), 1), (("B200BA_NO_TAB",), 1), (("B200BA_NO_TAB", "B200BA_NO_WB"), 1), ((), 0)]):
         for e in env:
