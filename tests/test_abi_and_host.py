@@ -251,3 +251,30 @@ def test_explicit_reduced_system_pair_lists():
     assert kinds[296]["kind"] == 2 and kinds[400]["kind"] == -1         # more than two cameras per multiprocessor: matrix-free
     for s in kinds.values():
         assert s["smem"] <= 227 * 1024 and (s["kind"] < 0 or s["rows"] % 6 == 0)
+
+
+def test_committed_bench_line_follows_the_contract():
+    """The bench line committed as closing evidence (profiles/bench_r2g_venice.json = one `python bench.py` run on a B200) carries
+    every key the measurement contract names - metric / value / unit / n_gpus / steps / warmup / ms_per_step / higher_is_better /
+    scaling / vs_baseline / dtype / data / config.workload / clocks / e2e with its byte counts / gpu_launches / roofline / cpu_baseline -
+    and its numbers are consistent with each other and with the byte model."""
+    import json
+    d = json.load(open(os.path.join(ROOT, "profiles", "bench_r2g_venice.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity"):
+        assert k in d, k
+    assert d["metric"] == "lm_iterations_per_s" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["vs_baseline"] is None and "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] * d["ms_per_step"] / 1e3 - 1.0) < 1e-9                      # value = LM iterations per second of the timed steps
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+    e = d["e2e"]
+    assert e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == d["unit"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["algorithmic_bytes_per_launch"] == 5001946 * 48 + 993923 * 96            # SURVEY.md 8(d): K (16 + 4 s) + 12 s M, s = 8
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["ms_per_launch"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["traffic"] is None or r["traffic"] > 0.9 * r["algorithmic_bytes_per_launch"]
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert d["parity"]["pass"] is True and d["parity"]["max_rel_cost_diff"] < d["parity"]["tolerance"] == 1e-9
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
