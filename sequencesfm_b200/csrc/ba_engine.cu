@@ -143,6 +143,7 @@ struct b200ba_handle {
     bool use_f32 = false; int tab32_grid = 0; size_t tab32_smem = 0;
     // explicit reduced camera system (small problems): pair lists on the device, S, the per-observation blocks
     bool pdl_chain = false;                          // programmatic dependent launch of every kernel of the iteration (explicit plan)
+    bool step_pdl = false;                           // camera-side step as a programmatic dependent of the by-camera sweep (single rank)
     bool fuse_small = false;                         // small kernels of the LM iteration fused (single rank: no all-reduce between them)
     bool use_dense = false; int dense_ctas = 0, dense_kind = -1, dense_threads = 0; bool dense_grid = false; size_t dense_smem = 0; long long dense_pairs = 0;
     DBuf<int2> dn_pairs; DBuf<int4> dn_chunks; DBuf<int> dn_blk_chunk_beg, dn_blk_ik, dn_entry_pt;
@@ -338,7 +339,17 @@ int launch_camera_step(b200ba_handle* h, int sums_ready)
     Dev& d = h->d;
     double* ppq = h->part_pq.p; double* prz = h->part_rz.p;
     void* args[] = {(void*)&d, (void*)&sums_ready, (void*)&ppq, (void*)&prz};
-    CU(cudaLaunchCooperativeKernel((const void*)k_cg_camera_step, dim3(h->step_grid), dim3(STEP_BLOCK), args, 0, h->stream));
+    // Single rank: the step is launched as a programmatic dependent of the by-camera sweep (which triggers at its top): its blocks
+    // take the SMs the sweep's CTAs leave and have their loads of U, M^-1, x, r, p in flight when the sweep ends (LM iteration
+    // 5.010 -> 4.984 ms at Venice shape).  B200BA_NO_STEP_PDL=1 or more than one rank: plain cooperative launch.
+    if (h->step_pdl) {
+        cudaLaunchConfig_t cfg = {}; cudaLaunchAttribute at[2];
+        cfg.gridDim = dim3(h->step_grid); cfg.blockDim = dim3(STEP_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        CU(cudaLaunchKernelExC(&cfg, (const void*)k_cg_camera_step, args));
+    } else CU(cudaLaunchCooperativeKernel((const void*)k_cg_camera_step, dim3(h->step_grid), dim3(STEP_BLOCK), args, 0, h->stream));
     h->launches++;
     return 0;
 }
@@ -1349,7 +1360,8 @@ int b200ba_begin(b200ba_handle* h)
     if (int rc = mean_reproj(h, 0, &h->mean_px[0])) return rc;
     {
         const bool fs = h->use_dense || (h->world == 1 && getenv("B200BA_NO_FUSE_SMALL") == nullptr);
-        if (fs != h->fuse_small) { h->fuse_small = fs; if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } }
+        const bool sp = h->world == 1 && (h->use_pdl == 1 || h->use_pdl == 2) && getenv("B200BA_NO_STEP_PDL") == nullptr;
+        if (fs != h->fuse_small || sp != h->step_pdl) { h->fuse_small = fs; h->step_pdl = sp; if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } }
     }
     {
         // experiment knob: access policy window (persisting hits, streaming misses) on v [, Vinv] of this handle's stream

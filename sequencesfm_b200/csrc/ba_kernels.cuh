@@ -1366,6 +1366,7 @@ __global__ void __launch_bounds__(CW * 32, 1) k_cg_camera_pass(Dev d, int rhs_pa
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const LMState* st = d.st;
     pdl_wait();                                                   // (programmatic dependent launch: v and the control words come from the by-point sweep)
+    if (threadIdx.x == 0) pdl_trigger();                          // the camera-side step may be launched as a programmatic dependent of this sweep (single rank)
     if (st->done) return;
     if (rhs_pass ? !st->solve_ok : !st->cg_active) return;
     camera_pass_sweep(d, st, smem_raw);
@@ -2632,6 +2633,8 @@ __device__ __forceinline__ void camera_step_phases(const Dev& d, int sums_ready,
     if (threadIdx.x < STEP_BLOCK) sv[threadIdx.x] = pe;
     __syncthreads();
     if (FUSED) step_barrier(bar, bar_base + gridDim.x);          // the sweep's segment partials of every block are visible
+    if (!FUSED) pdl_wait();                                      // launched as a programmatic dependent of the by-camera sweep (single rank): everything
+                                                                 // above reads what that sweep does not write, the segment partials below are its output
     double q = 0, s = 0;
     if (on) {
         if (sums_ready == 1) s = d.ar_q[e];

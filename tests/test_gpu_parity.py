@@ -141,7 +141,7 @@ def test_fifty_step_mode_matches_oracle(shape, seed, kw, opts, plan):
 
 
 @pytest.mark.parametrize("env", ["B200BA_NO_TAB", "B200BA_NO_TAB,B200BA_NO_WB", "B200BA_NO_COOP", "B200BA_NO_GRAPH", "B200BA_NO_LANE_OPT", "B200BA_FUSE_STEP",
-                                 "B200BA_PDL_CHAIN=0", "B200BA_PDL=0", "B200BA_PDL=1", "B200BA_XPOSE=0", "B200BA_NO_FUSE_SMALL", "B200BA_SLICE_W=2"])
+                                 "B200BA_PDL_CHAIN=0", "B200BA_PDL=0", "B200BA_PDL=1", "B200BA_XPOSE=0", "B200BA_NO_FUSE_SMALL", "B200BA_SLICE_W=2", "B200BA_NO_STEP_PDL"])
 def test_alternative_execution_plans_agree(env, monkeypatch):
     """The engine picks its execution plan at set_problem (shared-memory camera table vs generic by-point sweep through the
     packed table in global memory - the plan for problems with more than ~1800 cameras -, cooperative camera-side step vs
